@@ -1,0 +1,141 @@
+/* nquant_b200.h -- C ABI of the B200 implementation of nQuant's quantizer hot path.
+ *
+ * The reference (mcychan/nQuant.android) is pure Java and has no FFI today; these are the entry
+ * points a JNI / java.lang.foreign binding of its public surface would bind. Each one names the
+ * reference interface it stands in for (paths relative to
+ * nQuant.master/src/main/java/com/android/nQuant/). INTEGRATION.md shows the Java-side stub.
+ *
+ * Pixel layout everywhere: row-major, non-premultiplied 0xAARRGGBB, bidx = x + y*width -- the int[]
+ * the reference fills with Bitmap.getPixels (PnnQuantizer.java:39-44) and hands to
+ * Bitmap.createBitmap (PnnQuantizer.java:455).
+ *
+ * Ownership: the caller owns every buffer; the library keeps no pointer after a call returns.
+ * Threading: one nq_ctx per (thread, GPU). Distinct contexts run concurrently; one context is not
+ * re-entrant (the reference's quantizer instances are not thread-safe either, PnnQuantizer.java:18-33).
+ * Errors: 0 on success, a negative NQ_ERR_* otherwise; nq_last_error() returns the thread's message.
+ * There is no CPU fallback: without a usable CUDA device every call fails with NQ_ERR_CUDA.
+ */
+#ifndef NQUANT_B200_H
+#define NQUANT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NQ_KIND_PNN 0     /* com.android.nQuant.PnnQuantizer    (PnnQuantizer.java:16)    */
+#define NQ_KIND_PNNLAB 1  /* com.android.nQuant.PnnLABQuantizer (PnnLABQuantizer.java:17) */
+
+#define NQ_OK 0
+#define NQ_ERR_CUDA (-1)         /* CUDA runtime failure, or no device                                  */
+#define NQ_ERR_ARG (-2)          /* bad argument (null buffer, size <= 0, nMaxColors < 2 or > 256, ...) */
+#define NQ_ERR_COLOR (-3)        /* the reference would throw: ColorUtils.setAlphaComponent rejects an
+                                    alpha outside 0..255 (CIELABConvertor.java:79)                        */
+#define NQ_ERR_UNSUPPORTED (-4)  /* a branch of the reference this build does not cover yet             */
+#define NQ_ERR_NOMEM (-5)
+
+typedef struct nq_ctx nq_ctx;
+
+/* Number of CUDA devices visible to the process (0 when there is none). */
+int nq_device_count(void);
+
+/* Create / destroy a context bound to one GPU. Stands in for constructing a quantizer object:
+ * `new PnnQuantizer(fname)` (PnnQuantizer.java:35), `new PnnLABQuantizer(fname)`
+ * (PnnLABQuantizer.java:24) -- the pixels themselves are passed per call instead of being read from a
+ * file/Bitmap (PnnQuantizer.java:39-49). Returns NULL on failure. */
+nq_ctx* nq_create(int device);
+void nq_destroy(nq_ctx* ctx);
+
+/* Thread-local message of the last failing call. */
+const char* nq_last_error(void);
+
+/* `Bitmap convert(int nMaxColors, boolean dither) throws Exception` (PnnQuantizer.java:409-456,
+ * inherited by PnnLABQuantizer) on one image held in HOST memory.
+ *   kind          NQ_KIND_PNN or NQ_KIND_PNNLAB
+ *   argb_in       width*height source pixels (never modified; the reference edits its private copy)
+ *   n_max_colors  2..256
+ *   dither        the reference's `dither` flag
+ *   rng_seed      seed of the java.util.Random that PnnLABQuantizer.closestColorIndex draws from
+ *                 (PnnLABQuantizer.java:22,467 -- unseeded and static in the reference, injected here so
+ *                 runs are reproducible); ignored by NQ_KIND_PNN
+ *   argb_out      width*height result pixels: palette colours, i.e. the int[] the reference passes to
+ *                 Bitmap.createBitmap (PnnQuantizer.java:455)
+ *   palette_out   optional, room for 256 entries; the palette `pnnquan` produced
+ *   palette_len   optional
+ *   has_alpha     optional; `boolean hasAlpha()` (PnnQuantizer.java:458-460) after the call */
+int nq_convert(nq_ctx* ctx, int kind, const uint32_t* argb_in, int width, int height, int n_max_colors, int dither,
+               uint64_t rng_seed, uint32_t* argb_out, uint32_t* palette_out, int* palette_len, int* has_alpha);
+
+/* The same call over a batch of equally sized images in HOST memory (one quantizer object per
+ * image in the reference, MainActivity.java:193-194 in a loop). Image i lives at
+ * argb_in + i*width*height; rng_seeds may be NULL (seed 0 for every image). palettes_out (optional)
+ * holds 256 entries per image, palette_lens / has_alpha (optional) one int per image. */
+int nq_convert_batch(nq_ctx* ctx, int kind, const uint32_t* argb_in, int n_images, int width, int height, int n_max_colors,
+                     int dither, const uint64_t* rng_seeds, uint32_t* argb_out, uint32_t* palettes_out, int* palette_lens,
+                     int* has_alpha);
+
+/* As nq_convert_batch, but argb_in / argb_out are DEVICE pointers on the context's GPU (16-byte
+ * aligned). For callers that already hold the pixels in HBM; rng_seeds, palettes_out, palette_lens and
+ * has_alpha stay host pointers. Work is enqueued on the context's stream and the call returns after
+ * the stream has drained. */
+int nq_convert_batch_device(nq_ctx* ctx, int kind, const uint32_t* d_argb_in, int n_images, int width, int height,
+                            int n_max_colors, int dither, const uint64_t* rng_seeds, uint32_t* d_argb_out,
+                            uint32_t* palettes_out, int* palette_lens, int* has_alpha);
+
+/* Stage hook (parity + profiling): GilbertCurve.dither / BlueNoise.dither with a caller-supplied
+ * palette (PnnQuantizer.java:393-407, PnnLABQuantizer.java:492-522). Runs the alpha scan and the
+ * histogram-derived scalars as convert() would, but replaces the palette pnnquan produced by
+ * palette_in before dithering. Host buffers. */
+int nq_dither_with_palette(nq_ctx* ctx, int kind, const uint32_t* argb_in, int width, int height, int n_max_colors,
+                           int dither, uint64_t rng_seed, const uint32_t* palette_in, int palette_len, uint32_t* argb_out);
+
+/* Generalized Hilbert visiting order for a width x height image (GilbertCurve.java:282-334,
+ * 356-365): order_out[n] = x + y*width of the n-th pixel diffusePixel is called on. Host buffer. */
+int nq_gilbert_order(int width, int height, uint32_t* order_out);
+
+/* ---- introspection of the last batch (parity tests, bench counters) --------------------------- */
+
+/* Per-image facts of the last nq_convert* call on this context. */
+typedef struct nq_image_info {
+  int has_semi_transparency;   /* hasSemiTransparency (PnnQuantizer.java:431)  */
+  int transparent_pixel_index; /* m_transparentPixelIndex (PnnQuantizer.java:420) */
+  uint32_t transparent_color;  /* m_transparentColor */
+  int maxbins, quan_rt, texicab, is_nano;
+  double weight, ratio_init, ratio_merge, pr, pg, pb, pa;
+  int g_margin, g_thresold, g_dither_max_q, g_dither_max, g_sorted, g_has_alpha, g_use_saliency;
+  float g_beta;
+  float bn_weight;
+  int palette_len;
+  unsigned long long merges, rescans, pair_tests, rng_draws, heap_pops;
+  int error;
+} nq_image_info;
+int nq_get_image_info(nq_ctx* ctx, int image, nq_image_info* out);
+
+/* When enabled (flag != 0) the next calls keep, per image, the compacted bins before merging, the
+ * initial find_nn results and the merge sequence, retrievable below. Costs memory and a few copies. */
+int nq_set_debug(nq_ctx* ctx, int flag);
+/* bins5: maxbins x 5 doubles (alpha, c1, c2, c3, cnt) -- mean colour (r,g,b or L,A,B) and the count
+ * after getQuanFn, i.e. the state at PnnQuantizer.java:192 / PnnLABQuantizer.java:218. */
+int nq_debug_get_bins(nq_ctx* ctx, int image, double* bins5, float* init_err, int* init_nn);
+/* pairs: merges x 2 ints (tb, nb) in merge order (PnnQuantizer.java:240-254). */
+int nq_debug_get_merges(nq_ctx* ctx, int image, int* pairs);
+/* saliency map of the image (PnnLABQuantizer.java:155-156, 499-508), width*height floats. */
+int nq_debug_get_saliencies(nq_ctx* ctx, int image, float* out);
+
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+unsigned long long nq_kernel_launches(nq_ctx* ctx);
+/* Device-side math probe (tests): evaluates the shared nq_math.h kernels ON THE GPU.
+ * fn: 0 pow(x,y) 1 exp 2 tanh 3 cbrt 4 atan2(x,y) 5 sin 6 cos. n elements, host buffers. */
+int nq_debug_math(nq_ctx* ctx, int fn, const double* x, const double* y, double* out, int n);
+
+/* Fills a device buffer with the synthetic test image of SURVEY.md 8(d) (see
+ * nquant_android_b200/synth.py for the definition) -- used by bench.py so inputs can be created in
+ * HBM. cls: 0 smooth, 1 noisy, 2 rand; alpha_mode: 0 opaque, 1 transparent block, 2 semi. */
+int nq_synth_device(nq_ctx* ctx, uint32_t* d_out, int n_images, int width, int height, int cls, int alpha_mode,
+                    uint64_t seed0);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NQUANT_B200_H */

@@ -1,0 +1,617 @@
+// nq_api.cu -- context, workspace, stage orchestration and the C ABI (include/nquant_b200.h).
+// One translation unit: the stage kernels live in the .cuh files next to this one.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <utility>
+#include <algorithm>
+
+#include "../../include/nquant_b200.h"
+#include "nq_types.h"
+#include "nq_math.h"
+#include "nq_color.h"
+#include "nq_bluenoise_table.h"
+#include "nq_hist.cuh"
+#include "nq_pnn.cuh"
+#include "nq_dither.cuh"
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const std::string& msg) {
+  g_lastError = msg;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(NQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                \
+  } while (0)
+
+const signed char kBlueNoise[4096] = NQ_BLUE_NOISE_INIT;
+
+// ---- generalized Hilbert order (GC:282-334, 356-365), explicit stack -----------------------------
+struct GFrame { int x, y, ax, ay, bx, by; };
+inline int sgn(int v) { return (v > 0) - (v < 0); }
+template <class Emit>
+void gilbert_walk(int width, int height, Emit emit) {
+  std::vector<GFrame> st;
+  st.reserve(256);
+  if (width >= height) st.push_back({0, 0, width, 0, 0, height});
+  else st.push_back({0, 0, 0, height, width, 0});
+  while (!st.empty()) {
+    GFrame f = st.back();
+    st.pop_back();
+    int x = f.x, y = f.y;
+    const int ax = f.ax, ay = f.ay, bx = f.bx, by = f.by;
+    const int w = abs(ax + ay), h = abs(bx + by);
+    const int dax = sgn(ax), day = sgn(ay), dbx = sgn(bx), dby = sgn(by);
+    if (h == 1) { for (int i = 0; i < w; ++i) { emit(x, y); x += dax; y += day; } continue; }
+    if (w == 1) { for (int i = 0; i < h; ++i) { emit(x, y); x += dbx; y += dby; } continue; }
+    int ax2 = ax / 2, ay2 = ay / 2, bx2 = bx / 2, by2 = by / 2;
+    const int w2 = abs(ax2 + ay2), h2 = abs(bx2 + by2);
+    if (2 * w > 3 * h) {
+      if ((w2 % 2) != 0 && w > 2) { ax2 += dax; ay2 += day; }
+      st.push_back({x + ax2, y + ay2, ax - ax2, ay - ay2, bx, by});   // visited second
+      st.push_back({x, y, ax2, ay2, bx, by});                          // visited first
+      continue;
+    }
+    if ((h2 % 2) != 0 && h > 2) { bx2 += dbx; by2 += dby; }
+    st.push_back({x + (ax - dax) + (bx2 - dbx), y + (ay - day) + (by2 - dby), -bx2, -by2, -(ax - ax2), -(ay - ay2)});
+    st.push_back({x + bx2, y + by2, ax, ay, bx - bx2, by - by2});
+    st.push_back({x, y, bx2, by2, ax2, ay2});
+  }
+}
+
+// ---- synthetic images (nquant_android_b200/synth.py) ---------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+__global__ void k_synth(uint32_t* out, int nimg, int width, int height, int cls, int amode, unsigned long long seed0) {
+  const long long npix = (long long)width * height;
+  const long long total = npix * nimg;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(g / npix);
+    const long long idx = g - (long long)img * npix;
+    const int x = (int)(idx % width), y = (int)(idx / width);
+    const unsigned long long seed = seed0 + (unsigned long long)img;
+    int v[3];
+    const int bw = width - 1 > 1 ? width - 1 : 1, bh = height - 1 > 1 ? height - 1 : 1, bs = width + height - 2 > 1 ? width + height - 2 : 1;
+    const int base[3] = {255 * x / bw, 255 * y / bh, 255 * (x + y) / bs};
+    for (int ch = 0; ch < 3; ++ch) {
+      unsigned long long h = mix64(seed ^ (((unsigned long long)idx * 4ULL + (unsigned long long)ch) * 0x9E3779B97F4A7C15ULL));
+      if (cls == 2) v[ch] = (int)(h & 0xFF);
+      else {
+        const int amp = cls == 0 ? 2 : 32;
+        int t = base[ch] + (int)(h % (unsigned long long)(2 * amp + 1)) - amp;
+        v[ch] = t < 0 ? 0 : (t > 255 ? 255 : t);
+      }
+    }
+    int a = 255;
+    if (amode != 0) {
+      if (amode == 2) a = 255 * (width - 1 - x) / bw;
+      if (x < width / 8 && y < height / 8) a = 0;
+    }
+    out[g] = ((uint32_t)a << 24) | ((uint32_t)v[0] << 16) | ((uint32_t)v[1] << 8) | (uint32_t)v[2];
+  }
+}
+
+__global__ void k_math_probe(int fn, const double* x, const double* y, double* out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r = 0;
+  switch (fn) {
+    case 0: r = nqm::nq_pow(x[i], y[i]); break;
+    case 1: r = nqm::nq_exp(x[i]); break;
+    case 2: r = nqm::nq_tanh(x[i]); break;
+    case 3: r = nqm::nq_cbrt(x[i]); break;
+    case 4: r = nqm::nq_atan2(x[i], y[i]); break;
+    case 5: r = nqm::nq_sin(x[i]); break;
+    case 6: r = nqm::nq_cos(x[i]); break;
+  }
+  out[i] = r;
+}
+
+__global__ void k_set_palette(NqImage* imgs, int img, const uint32_t* pal, int plen) {
+  if (threadIdx.x < plen) imgs[img].palette[threadIdx.x] = pal[threadIdx.x];
+  if (threadIdx.x == 0) imgs[img].paletteLen = plen;
+}
+
+struct DebugImage {
+  std::vector<double> bins5;
+  std::vector<float> initErr;
+  std::vector<int> initNn;
+  std::vector<int> merges;
+  std::vector<float> sal;
+};
+
+}  // namespace
+
+struct nq_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int smCount = 148;
+  unsigned long long launches = 0;
+  bool debug = false;
+  // Gilbert orders by (w,h)
+  std::map<std::pair<int, int>, uint32_t*> orders;
+  // workspace
+  unsigned char* ws = nullptr;
+  size_t wsBytes = 0;
+  NqImage* dImgs = nullptr;
+  NqSlot* dSlots = nullptr;
+  int* dLive = nullptr;
+  int* dPos = nullptr;
+  int wsSlots = 0, wsNpix = 0, wsKind = -1;
+  std::vector<NqSlot> hSlots;
+  // staging for host-buffer calls
+  uint32_t* dIn = nullptr;
+  uint32_t* dOut = nullptr;
+  size_t stageBytes = 0;
+  // results of the last batch
+  std::vector<NqImage> lastImgs;
+  std::vector<DebugImage> dbg;
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct SlotLayout {
+  size_t hCnt, hSum, keyOff, sortA, sortB, warpHist, sal, bD, bF, bCnt, bErr, bNn, bTm, bMtm, hErr, hId, mergeLog, memo, total;
+};
+SlotLayout slot_layout(int kind, int npix, bool debug) {
+  SlotLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  L.hCnt = take(NQ_NBINS * 4);
+  L.hSum = take((size_t)4 * NQ_NBINS * 8);
+  L.keyOff = take((NQ_NBINS + 1) * 4);
+  const bool lab = kind == NQ_KIND_LAB;
+  const size_t nruns = ((size_t)npix + NQ_RUN - 1) / NQ_RUN;
+  L.sortA = take(lab ? (size_t)npix * 4 : 0);
+  L.sortB = take(lab ? (size_t)npix * 4 : 0);
+  L.warpHist = take(lab ? nruns * 256 * 4 : 0);
+  L.sal = take(lab ? (size_t)npix * 4 : 0);
+  L.bD = take((size_t)4 * NQ_NBINS * 8);
+  L.bF = take((size_t)4 * NQ_NBINS * 4);
+  L.bCnt = take(NQ_NBINS * 4);
+  L.bErr = take(NQ_NBINS * 4);
+  L.bNn = take(NQ_NBINS * 4);
+  L.bTm = take(NQ_NBINS * 4);
+  L.bMtm = take(NQ_NBINS * 4);
+  L.hErr = take((NQ_NBINS + 1) * 4);
+  L.hId = take((NQ_NBINS + 1) * 4);
+  L.mergeLog = take(debug ? (size_t)2 * NQ_NBINS * 4 : 0);
+  L.memo = take(NQ_NBINS * 2);
+  L.total = o;
+  return L;
+}
+
+int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots) {
+  SlotLayout L = slot_layout(kind, npix, c->debug);
+  size_t freeB = 0, totalB = 0;
+  CU(cudaMemGetInfo(&freeB, &totalB));
+  size_t budget = (size_t)((double)(freeB + c->wsBytes) * 0.85);
+  int maxSlots = (int)std::min<size_t>(budget / (L.total + sizeof(NqImage) + sizeof(NqSlot) + 2 * NQ_NBINS * 4), 4096);
+  if (maxSlots < 1) return fail(NQ_ERR_NOMEM, "not enough device memory for one image workspace");
+  int slots = std::min(wantSlots, maxSlots);
+  static bool dbgFlagLast = false;
+  if (c->ws && c->wsKind == kind && c->wsNpix == npix && c->wsSlots >= slots && dbgFlagLast == c->debug) return NQ_OK;
+  dbgFlagLast = c->debug;
+  if (c->ws) { cudaFree(c->ws); c->ws = nullptr; c->wsBytes = 0; }
+  size_t imgsB = align_up(sizeof(NqImage) * slots, 256), slotsB = align_up(sizeof(NqSlot) * slots, 256);
+  size_t liveB = align_up((size_t)slots * NQ_NBINS * 4, 256);
+  size_t total = imgsB + slotsB + 2 * liveB + L.total * slots;
+  CU(cudaMalloc(&c->ws, total));
+  c->wsBytes = total;
+  unsigned char* p = c->ws;
+  c->dImgs = reinterpret_cast<NqImage*>(p); p += imgsB;
+  c->dSlots = reinterpret_cast<NqSlot*>(p); p += slotsB;
+  c->dLive = reinterpret_cast<int*>(p); p += liveB;
+  c->dPos = reinterpret_cast<int*>(p); p += liveB;
+  c->hSlots.assign(slots, NqSlot{});
+  for (int s = 0; s < slots; ++s) {
+    unsigned char* b = p + L.total * s;
+    NqSlot& S = c->hSlots[s];
+    S.hCnt = reinterpret_cast<unsigned int*>(b + L.hCnt);
+    S.hSum = reinterpret_cast<unsigned long long*>(b + L.hSum);
+    S.keyOff = reinterpret_cast<unsigned int*>(b + L.keyOff);
+    S.sortA = reinterpret_cast<uint32_t*>(b + L.sortA);
+    S.sortB = reinterpret_cast<uint32_t*>(b + L.sortB);
+    S.warpHist = reinterpret_cast<unsigned int*>(b + L.warpHist);
+    S.sal = reinterpret_cast<float*>(b + L.sal);
+    double* bd = reinterpret_cast<double*>(b + L.bD);
+    S.bAc = bd; S.bC1 = bd + NQ_NBINS; S.bC2 = bd + 2 * NQ_NBINS; S.bC3 = bd + 3 * NQ_NBINS;
+    float* bf = reinterpret_cast<float*>(b + L.bF);
+    S.fAc = bf; S.fC1 = bf + NQ_NBINS; S.fC2 = bf + 2 * NQ_NBINS; S.fC3 = bf + 3 * NQ_NBINS;
+    S.bCnt = reinterpret_cast<float*>(b + L.bCnt);
+    S.bErr = reinterpret_cast<float*>(b + L.bErr);
+    S.bNn = reinterpret_cast<int*>(b + L.bNn);
+    S.bTm = reinterpret_cast<int*>(b + L.bTm);
+    S.bMtm = reinterpret_cast<int*>(b + L.bMtm);
+    S.hErr = reinterpret_cast<float*>(b + L.hErr);
+    S.hId = reinterpret_cast<int*>(b + L.hId);
+    S.mergeLog = c->debug ? reinterpret_cast<int*>(b + L.mergeLog) : nullptr;
+    S.memo = reinterpret_cast<unsigned short*>(b + L.memo);
+    S.idx = nullptr;
+  }
+  c->wsSlots = slots; c->wsNpix = npix; c->wsKind = kind;
+  return NQ_OK;
+}
+
+int ensure_order(nq_ctx* c, int w, int h, const uint32_t** out) {
+  auto key = std::make_pair(w, h);
+  auto it = c->orders.find(key);
+  if (it != c->orders.end()) { *out = it->second; return NQ_OK; }
+  if (w > 65535 || h > 65535) return fail(NQ_ERR_ARG, "image side exceeds 65535");
+  std::vector<uint32_t> host;
+  host.reserve((size_t)w * h);
+  gilbert_walk(w, h, [&](int x, int y) { host.push_back((uint32_t)x | ((uint32_t)y << 16)); });
+  if (host.size() != (size_t)w * h) return fail(NQ_ERR_ARG, "gilbert walk size mismatch");
+  uint32_t* d = nullptr;
+  CU(cudaMalloc(&d, host.size() * 4));
+  CU(cudaMemcpy(d, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+  c->orders[key] = d;
+  *out = d;
+  return NQ_OK;
+}
+
+int pixel_grid_x(const nq_ctx* c, int npix, int nimg) {
+  int want = (npix + 256 * 8 - 1) / (256 * 8);
+  int cap = std::max(1, (c->smCount * 8) / std::max(1, nimg));
+  return std::max(1, std::min(want, cap));
+}
+
+// Runs convert() for images [0, n) already resident on the device. palIn != nullptr replaces the
+// palette before dithering (stage hook).
+int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, int w, int h, int nmax, int dither,
+              const uint64_t* seeds, const uint32_t* dPalIn, int palInLen) {
+  const int npix = w * h;
+  const uint32_t* dOrder = nullptr;
+  int rc = ensure_order(c, w, h, &dOrder);
+  if (rc) return rc;
+  cudaStream_t st = c->stream;
+  std::vector<NqImage> hImgs(n);
+  for (int i = 0; i < n; ++i) {
+    NqImage& I = hImgs[i];
+    memset(&I, 0, sizeof(I));
+    I.kind = kind; I.width = w; I.height = h; I.npix = npix; I.nmax = nmax; I.dither = dither;
+    I.seed = seeds ? seeds[i] : 0ULL;
+    I.transIdx = -1;
+    c->hSlots[i].in = dIn + (size_t)i * npix;
+    c->hSlots[i].out = dOut + (size_t)i * npix;
+  }
+  CU(cudaMemcpyAsync(c->dImgs, hImgs.data(), sizeof(NqImage) * n, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(c->dSlots, c->hSlots.data(), sizeof(NqSlot) * n, cudaMemcpyHostToDevice, st));
+  for (int i = 0; i < n; ++i) {
+    const NqSlot& S = c->hSlots[i];
+    CU(cudaMemsetAsync(S.hCnt, 0, NQ_NBINS * 4, st));
+    CU(cudaMemsetAsync(S.hSum, 0, (size_t)4 * NQ_NBINS * 8, st));
+    CU(cudaMemsetAsync(S.memo, 0xFF, NQ_NBINS * 2, st));
+  }
+  const int gx = pixel_grid_x(c, npix, n);
+  const dim3 pg(gx, n);
+  nq::k_alpha_scan<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+  nq::k_setup_scan<<<(n + 127) / 128, 128, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
+  if (nmax > 2) {
+    if (kind == NQ_KIND_RGB) {
+      nq::k_hist_rgb<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_finalize_rgb<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+    } else {
+      const int nruns = (npix + NQ_RUN - 1) / NQ_RUN;
+      const dim3 rg(std::max(1, std::min((nruns + 7) / 8, std::max(1, c->smCount * 8 / n))), n);
+      nq::k_lab_count<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_lab_scan_keys<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_radix_count<0><<<rg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_radix_offsets<<<n, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_radix_scatter<0><<<rg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_radix_count<1><<<rg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_radix_offsets<<<n, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_radix_scatter<1><<<rg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      const dim3 bg(std::max(1, c->smCount * 8 / n), n);
+      nq::k_lab_bin_sum<<<bg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_finalize_lab<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+    }
+    nq::k_find_nn_all<<<c->smCount * 8, 256, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
+    if (c->debug) {
+      CU(cudaStreamSynchronize(st));
+      std::vector<NqImage> tmp(n);
+      CU(cudaMemcpy(tmp.data(), c->dImgs, sizeof(NqImage) * n, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < n; ++i) {
+        DebugImage& D = c->dbg[i];
+        const int mb = tmp[i].maxbins;
+        const NqSlot& S = c->hSlots[i];
+        D.bins5.assign((size_t)mb * 5, 0.0);
+        D.initErr.assign(mb, 0.f); D.initNn.assign(mb, 0);
+        if (mb <= 0) continue;
+        std::vector<double> col(mb);
+        std::vector<float> colf(mb);
+        for (int k = 0; k < 4; ++k) {
+          if (kind == NQ_KIND_RGB) {
+            const double* src = k == 0 ? S.bAc : k == 1 ? S.bC1 : k == 2 ? S.bC2 : S.bC3;
+            CU(cudaMemcpy(col.data(), src, (size_t)mb * 8, cudaMemcpyDeviceToHost));
+          } else {
+            const float* src = k == 0 ? S.fAc : k == 1 ? S.fC1 : k == 2 ? S.fC2 : S.fC3;
+            CU(cudaMemcpy(colf.data(), src, (size_t)mb * 4, cudaMemcpyDeviceToHost));
+            for (int b = 0; b < mb; ++b) col[b] = colf[b];
+          }
+          for (int b = 0; b < mb; ++b) D.bins5[(size_t)b * 5 + k] = col[b];
+        }
+        CU(cudaMemcpy(colf.data(), S.bCnt, (size_t)mb * 4, cudaMemcpyDeviceToHost));
+        for (int b = 0; b < mb; ++b) D.bins5[(size_t)b * 5 + 4] = colf[b];
+        CU(cudaMemcpy(D.initErr.data(), S.bErr, (size_t)mb * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(D.initNn.data(), S.bNn, (size_t)mb * 4, cudaMemcpyDeviceToHost));
+      }
+    }
+    const size_t heapSmem = (size_t)NQ_HEAP_SMEM * 6;
+    nq::k_merge<<<n, NQ_MERGE_THREADS, heapSmem, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
+  }
+  nq::k_dither_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
+  if (dPalIn) {
+    for (int i = 0; i < n; ++i) { k_set_palette<<<1, 256, 0, st>>>(c->dImgs, i, dPalIn, palInLen); ++c->launches; }
+    nq::k_dither_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
+  }
+  if (kind == NQ_KIND_LAB) { nq::k_saliency<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches; }
+  nq::k_dither<<<n, 32, 0, st>>>(c->dImgs, c->dSlots, dOrder); ++c->launches;
+  CU(cudaGetLastError());
+  c->lastImgs.resize(n);
+  CU(cudaMemcpyAsync(c->lastImgs.data(), c->dImgs, sizeof(NqImage) * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (c->debug) {
+    for (int i = 0; i < n; ++i) {
+      DebugImage& D = c->dbg[i];
+      const NqImage& I = c->lastImgs[i];
+      const int merges = (nmax > 2 && I.extbins > 0) ? I.extbins : 0;
+      D.merges.assign((size_t)merges * 2, 0);
+      if (merges && c->hSlots[i].mergeLog) CU(cudaMemcpy(D.merges.data(), c->hSlots[i].mergeLog, (size_t)merges * 8, cudaMemcpyDeviceToHost));
+      D.sal.clear();
+      if (I.gUseSal) { D.sal.resize(npix); CU(cudaMemcpy(D.sal.data(), c->hSlots[i].sal, (size_t)npix * 4, cudaMemcpyDeviceToHost)); }
+    }
+  }
+  return NQ_OK;
+}
+
+int check_args(nq_ctx* c, int kind, const void* in, int n, int w, int h, int nmax, const void* out) {
+  if (!c) return fail(NQ_ERR_ARG, "null context");
+  if (kind != NQ_KIND_PNN && kind != NQ_KIND_PNNLAB) return fail(NQ_ERR_ARG, "kind must be NQ_KIND_PNN or NQ_KIND_PNNLAB");
+  if (!in || !out) return fail(NQ_ERR_ARG, "null pixel buffer");
+  if (n <= 0 || w <= 0 || h <= 0) return fail(NQ_ERR_ARG, "n_images, width and height must be positive");
+  if ((long long)w * h > 0x7fffffffLL / 4) return fail(NQ_ERR_ARG, "image too large");
+  if (nmax < 2) return fail(NQ_ERR_ARG, "n_max_colors must be >= 2 (the reference indexes palette[1], PnnQuantizer.java:446)");
+  if (nmax > NQ_MAXK) return fail(NQ_ERR_UNSUPPORTED, "n_max_colors > 256 is not supported by this build");
+  return NQ_OK;
+}
+
+int collect_results(nq_ctx* c, int base, int n, uint32_t* palettes, int* plens, int* hasAlpha, int* firstErr) {
+  for (int i = 0; i < n; ++i) {
+    const NqImage& I = c->lastImgs[i];
+    if (palettes) memcpy(palettes + (size_t)(base + i) * NQ_MAXK, I.palette, sizeof(uint32_t) * NQ_MAXK);
+    if (plens) plens[base + i] = I.paletteLen;
+    if (hasAlpha) hasAlpha[base + i] = I.transIdx > -1;
+    if (I.error && !*firstErr) *firstErr = I.error;
+  }
+  return NQ_OK;
+}
+
+int convert_device(nq_ctx* c, int kind, const uint32_t* dIn, int n, int w, int h, int nmax, int dither, const uint64_t* seeds,
+                   uint32_t* dOut, uint32_t* palettes, int* plens, int* hasAlpha, const uint32_t* dPalIn, int palInLen) {
+  CU(cudaSetDevice(c->device));
+  const int npix = w * h;
+  int rc = ensure_workspace(c, kind, npix, n);
+  if (rc) return rc;
+  if (c->debug) c->dbg.assign(n, DebugImage{});
+  int firstErr = 0;
+  std::vector<NqImage> all;
+  all.reserve(n);
+  for (int base = 0; base < n; base += c->wsSlots) {
+    const int m = std::min(c->wsSlots, n - base);
+    rc = run_chunk(c, kind, dIn + (size_t)base * npix, dOut + (size_t)base * npix, m, w, h, nmax, dither,
+                   seeds ? seeds + base : nullptr, dPalIn, palInLen);
+    if (rc) return rc;
+    collect_results(c, base, m, palettes, plens, hasAlpha, &firstErr);
+    all.insert(all.end(), c->lastImgs.begin(), c->lastImgs.end());
+  }
+  c->lastImgs.swap(all);
+  if (firstErr == 3) return fail(NQ_ERR_COLOR, "alpha must be between 0 and 255. (ColorUtils.setAlphaComponent)");
+  if (firstErr) return fail(NQ_ERR_UNSUPPORTED, "device-side error " + std::to_string(firstErr));
+  return NQ_OK;
+}
+
+int ensure_stage(nq_ctx* c, size_t bytes) {
+  if (c->stageBytes >= bytes) return NQ_OK;
+  if (c->dIn) cudaFree(c->dIn);
+  if (c->dOut) cudaFree(c->dOut);
+  c->dIn = c->dOut = nullptr; c->stageBytes = 0;
+  CU(cudaMalloc(&c->dIn, bytes));
+  CU(cudaMalloc(&c->dOut, bytes));
+  c->stageBytes = bytes;
+  return NQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nq_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* nq_last_error(void) { return g_lastError.c_str(); }
+
+nq_ctx* nq_create(int device) {
+  int n = nq_device_count();
+  if (device < 0 || device >= n) { fail(NQ_ERR_CUDA, "no such CUDA device (this library has no CPU fallback)"); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { fail(NQ_ERR_CUDA, "cudaSetDevice failed"); return nullptr; }
+  nq_ctx* c = new nq_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->smCount = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(NQ_ERR_CUDA, "cudaStreamCreate failed"); delete c; return nullptr; }
+  signed char* dBn = nullptr;
+  bool ok = cudaMalloc(&dBn, 4096) == cudaSuccess && cudaMemcpy(dBn, kBlueNoise, 4096, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok) {
+    nq::k_init_tables<<<4, 256, 0, c->stream>>>(dBn); ++c->launches;
+    ok = cudaStreamSynchronize(c->stream) == cudaSuccess;
+  }
+  if (dBn) cudaFree(dBn);
+  if (ok) ok = cudaFuncSetAttribute(nq::k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_HEAP_SMEM * 6) == cudaSuccess;
+  if (!ok) {
+    fail(NQ_ERR_CUDA, std::string("context initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+void nq_destroy(nq_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  for (auto& kv : c->orders) cudaFree(kv.second);
+  if (c->ws) cudaFree(c->ws);
+  if (c->dIn) cudaFree(c->dIn);
+  if (c->dOut) cudaFree(c->dOut);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int nq_convert_batch_device(nq_ctx* c, int kind, const uint32_t* d_in, int n, int w, int h, int nmax, int dither,
+                            const uint64_t* seeds, uint32_t* d_out, uint32_t* palettes, int* plens, int* hasAlpha) {
+  int rc = check_args(c, kind, d_in, n, w, h, nmax, d_out);
+  if (rc) return rc;
+  return convert_device(c, kind, d_in, n, w, h, nmax, dither, seeds, d_out, palettes, plens, hasAlpha, nullptr, 0);
+}
+
+int nq_convert_batch(nq_ctx* c, int kind, const uint32_t* in, int n, int w, int h, int nmax, int dither, const uint64_t* seeds,
+                     uint32_t* out, uint32_t* palettes, int* plens, int* hasAlpha) {
+  int rc = check_args(c, kind, in, n, w, h, nmax, out);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)n * w * h * 4;
+  rc = ensure_stage(c, bytes);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(c->dIn, in, bytes, cudaMemcpyHostToDevice, c->stream));
+  rc = convert_device(c, kind, c->dIn, n, w, h, nmax, dither, seeds, c->dOut, palettes, plens, hasAlpha, nullptr, 0);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, c->dOut, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return NQ_OK;
+}
+
+int nq_convert(nq_ctx* c, int kind, const uint32_t* in, int w, int h, int nmax, int dither, uint64_t seed, uint32_t* out,
+               uint32_t* palette, int* plen, int* hasAlpha) {
+  return nq_convert_batch(c, kind, in, 1, w, h, nmax, dither, &seed, out, palette, plen, hasAlpha);
+}
+
+int nq_dither_with_palette(nq_ctx* c, int kind, const uint32_t* in, int w, int h, int nmax, int dither, uint64_t seed,
+                           const uint32_t* palette, int plen, uint32_t* out) {
+  int rc = check_args(c, kind, in, 1, w, h, nmax, out);
+  if (rc) return rc;
+  if (!palette || plen <= 0 || plen > NQ_MAXK) return fail(NQ_ERR_ARG, "palette_len must be 1..256");
+  CU(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)w * h * 4;
+  rc = ensure_stage(c, bytes);
+  if (rc) return rc;
+  uint32_t* dPal = nullptr;
+  CU(cudaMalloc(&dPal, NQ_MAXK * 4));
+  CU(cudaMemcpy(dPal, palette, (size_t)plen * 4, cudaMemcpyHostToDevice));
+  CU(cudaMemcpyAsync(c->dIn, in, bytes, cudaMemcpyHostToDevice, c->stream));
+  rc = convert_device(c, kind, c->dIn, 1, w, h, nmax, dither, &seed, c->dOut, nullptr, nullptr, nullptr, dPal, plen);
+  cudaFree(dPal);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, c->dOut, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return NQ_OK;
+}
+
+int nq_gilbert_order(int w, int h, uint32_t* out) {
+  if (w <= 0 || h <= 0 || !out) return fail(NQ_ERR_ARG, "bad arguments");
+  size_t n = 0;
+  gilbert_walk(w, h, [&](int x, int y) { out[n++] = (uint32_t)(x + y * w); });
+  return n == (size_t)w * h ? NQ_OK : fail(NQ_ERR_ARG, "gilbert walk size mismatch");
+}
+
+int nq_get_image_info(nq_ctx* c, int image, nq_image_info* o) {
+  if (!c || !o || image < 0 || image >= (int)c->lastImgs.size()) return fail(NQ_ERR_ARG, "no such image in the last batch");
+  const NqImage& I = c->lastImgs[image];
+  memset(o, 0, sizeof(*o));
+  o->has_semi_transparency = I.hasSemi; o->transparent_pixel_index = I.transIdx; o->transparent_color = I.transColor;
+  o->maxbins = I.maxbins; o->quan_rt = I.quan_rt; o->texicab = I.texicab; o->is_nano = I.isNano;
+  o->weight = I.weight; o->ratio_init = I.ratio; o->ratio_merge = I.ratioMerge;
+  o->pr = I.PR; o->pg = I.PG; o->pb = I.PB; o->pa = I.PA;
+  o->g_margin = I.gMargin; o->g_thresold = I.gThresold; o->g_dither_max_q = I.gDitherMaxQ; o->g_dither_max = I.gDitherMax;
+  o->g_sorted = I.gSorted; o->g_has_alpha = I.gHasAlpha; o->g_use_saliency = I.gUseSal; o->g_beta = I.gBeta;
+  o->bn_weight = I.bnWeight; o->palette_len = I.paletteLen;
+  o->merges = (I.nmax > 2 && I.extbins > 0) ? (unsigned long long)I.extbins : 0ULL;
+  o->rescans = I.statRescans; o->pair_tests = I.statPairs; o->rng_draws = I.rngDraws; o->heap_pops = I.statHeapPops;
+  o->error = I.error;
+  return NQ_OK;
+}
+
+int nq_set_debug(nq_ctx* c, int flag) {
+  if (!c) return fail(NQ_ERR_ARG, "null context");
+  c->debug = flag != 0;
+  return NQ_OK;
+}
+
+int nq_debug_get_bins(nq_ctx* c, int image, double* bins5, float* initErr, int* initNn) {
+  if (!c || image < 0 || image >= (int)c->dbg.size()) return fail(NQ_ERR_ARG, "no debug record for that image");
+  const DebugImage& D = c->dbg[image];
+  if (bins5) memcpy(bins5, D.bins5.data(), D.bins5.size() * 8);
+  if (initErr) memcpy(initErr, D.initErr.data(), D.initErr.size() * 4);
+  if (initNn) memcpy(initNn, D.initNn.data(), D.initNn.size() * 4);
+  return NQ_OK;
+}
+int nq_debug_get_merges(nq_ctx* c, int image, int* pairs) {
+  if (!c || image < 0 || image >= (int)c->dbg.size()) return fail(NQ_ERR_ARG, "no debug record for that image");
+  const DebugImage& D = c->dbg[image];
+  if (pairs) memcpy(pairs, D.merges.data(), D.merges.size() * 4);
+  return NQ_OK;
+}
+int nq_debug_get_saliencies(nq_ctx* c, int image, float* out) {
+  if (!c || image < 0 || image >= (int)c->dbg.size()) return fail(NQ_ERR_ARG, "no debug record for that image");
+  const DebugImage& D = c->dbg[image];
+  if (D.sal.empty()) return fail(NQ_ERR_ARG, "this image has no saliency map");
+  if (out) memcpy(out, D.sal.data(), D.sal.size() * 4);
+  return NQ_OK;
+}
+
+unsigned long long nq_kernel_launches(nq_ctx* c) { return c ? c->launches : 0ULL; }
+
+int nq_debug_math(nq_ctx* c, int fn, const double* x, const double* y, double* out, int n) {
+  if (!c || !x || !out || n <= 0) return fail(NQ_ERR_ARG, "bad arguments");
+  CU(cudaSetDevice(c->device));
+  double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+  CU(cudaMalloc(&dx, (size_t)n * 8));
+  CU(cudaMalloc(&dy, (size_t)n * 8));
+  CU(cudaMalloc(&dout, (size_t)n * 8));
+  CU(cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+  if (y) CU(cudaMemcpy(dy, y, (size_t)n * 8, cudaMemcpyHostToDevice));
+  else CU(cudaMemset(dy, 0, (size_t)n * 8));
+  k_math_probe<<<(n + 127) / 128, 128, 0, c->stream>>>(fn, dx, dy, dout, n); ++c->launches;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(dx); cudaFree(dy); cudaFree(dout);
+  return NQ_OK;
+}
+
+int nq_synth_device(nq_ctx* c, uint32_t* d_out, int n, int w, int h, int cls, int amode, uint64_t seed0) {
+  if (!c || !d_out || n <= 0 || w <= 0 || h <= 0) return fail(NQ_ERR_ARG, "bad arguments");
+  CU(cudaSetDevice(c->device));
+  k_synth<<<c->smCount * 8, 256, 0, c->stream>>>(d_out, n, w, h, cls, amode, seed0); ++c->launches;
+  CU(cudaStreamSynchronize(c->stream));
+  return NQ_OK;
+}
+
+}  // extern "C"

@@ -904,10 +904,10 @@ class PnnQuantizer {
       trace.merges.push_back(tb->nn);
       float n1 = tb->cnt, n2 = nb.cnt;
       float d = 1.f / (n1 + n2);
-      tb->ac = d * (double)jround(n1 * tb->ac + n2 * nb.ac);
-      tb->rc = d * (double)jround(n1 * tb->rc + n2 * nb.rc);
-      tb->gc = d * (double)jround(n1 * tb->gc + n2 * nb.gc);
-      tb->bc = d * (double)jround(n1 * tb->bc + n2 * nb.bc);
+      tb->ac = d * (float)jround(n1 * tb->ac + n2 * nb.ac);  // float * long -> float (JLS 5.6.2), then widened
+      tb->rc = d * (float)jround(n1 * tb->rc + n2 * nb.rc);  // float * long -> float (JLS 5.6.2), then widened
+      tb->gc = d * (float)jround(n1 * tb->gc + n2 * nb.gc);  // float * long -> float (JLS 5.6.2), then widened
+      tb->bc = d * (float)jround(n1 * tb->bc + n2 * nb.bc);  // float * long -> float (JLS 5.6.2), then widened
       tb->cnt += n2;
       tb->mtm = ++i;
 

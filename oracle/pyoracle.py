@@ -11,8 +11,9 @@ _SO = os.path.join(_HERE, "libnq_oracle.so")
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "nq_oracle.cpp")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "nq_oracle.cpp")] + [os.path.join(_HERE, "..", "nquant_android_b200", "csrc", f)
+                                                      for f in ("nq_math.h", "nq_math_tables.h", "nq_bluenoise_table.h")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []) + ["libnq_oracle.so"],
                               stdout=subprocess.DEVNULL)
     return _SO
@@ -36,8 +37,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()  # no-op unless the .so is missing or older than its source
         L = ctypes.CDLL(_SO)
         vp, ci, cd, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_float
         L.nqo_create.restype = vp
