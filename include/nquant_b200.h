@@ -47,6 +47,11 @@ int nq_device_count(void);
 nq_ctx* nq_create(int device);
 void nq_destroy(nq_ctx* ctx);
 
+/* Run this context's copies and kernels on a caller-owned CUDA stream (a cudaStream_t passed as
+ * void*; NULL restores the context's own stream), so a host framework can order and time them with
+ * its own events. */
+int nq_set_stream(nq_ctx* ctx, void* cuda_stream);
+
 /* Thread-local message of the last failing call. */
 const char* nq_last_error(void);
 
@@ -125,6 +130,10 @@ int nq_debug_get_saliencies(nq_ctx* ctx, int image, float* out);
 
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 unsigned long long nq_kernel_launches(nq_ctx* ctx);
+/* Device time per stage, measured with CUDA events on the context's stream and accumulated over the
+ * calls since the last reset. ms[6] / launches[6]: 0 alpha scan, 1 histogram (+compaction), 2 initial
+ * find_nn sweep, 3 merge loop, 4 dither setup + saliency, 5 dither (Gilbert pass + blue-noise pass). */
+int nq_get_stage_times(nq_ctx* ctx, double* ms, unsigned long long* launches, int reset);
 /* Device-side math probe (tests): evaluates the shared nq_math.h kernels ON THE GPU.
  * fn: 0 pow(x,y) 1 exp 2 tanh 3 cbrt 4 atan2(x,y) 5 sin 6 cos. n elements, host buffers. */
 int nq_debug_math(nq_ctx* ctx, int fn, const double* x, const double* y, double* out, int n);

@@ -11,7 +11,7 @@ SYMBOLS = [
     "nq_device_count", "nq_create", "nq_destroy", "nq_last_error", "nq_convert", "nq_convert_batch",
     "nq_convert_batch_device", "nq_dither_with_palette", "nq_gilbert_order", "nq_get_image_info", "nq_set_debug",
     "nq_debug_get_bins", "nq_debug_get_merges", "nq_debug_get_saliencies", "nq_kernel_launches", "nq_debug_math",
-    "nq_synth_device",
+    "nq_synth_device", "nq_get_stage_times", "nq_set_stream",
 ]
 
 NQ_KIND_PNN, NQ_KIND_PNNLAB = 0, 1
@@ -69,6 +69,8 @@ def load():
     L.nq_kernel_launches.argtypes = [vp]
     L.nq_kernel_launches.restype = ctypes.c_ulonglong
     L.nq_debug_math.argtypes = [vp, ci, vp, vp, vp, ci]
+    L.nq_set_stream.argtypes = [vp, vp]
+    L.nq_get_stage_times.argtypes = [vp, vp, vp, ci]
     L.nq_synth_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, u64]
     for s in SYMBOLS:
         getattr(L, s)

@@ -19,6 +19,8 @@
 #include "nq_pnn.cuh"
 #include "nq_dither.cuh"
 
+#define NQ_NSTAGES 6   // scan, histogram, find_nn sweep, merge, dither setup + saliency, dither
+
 namespace {
 
 thread_local std::string g_lastError;
@@ -138,6 +140,7 @@ struct DebugImage {
 struct nq_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t ownStream = nullptr;
   int smCount = 148;
   unsigned long long launches = 0;
   bool debug = false;
@@ -156,6 +159,10 @@ struct nq_ctx {
   uint32_t* dIn = nullptr;
   uint32_t* dOut = nullptr;
   size_t stageBytes = 0;
+  // per-stage device timing (CUDA events on the context's stream)
+  cudaEvent_t ev[NQ_NSTAGES + 1] = {};
+  double stageMs[NQ_NSTAGES] = {};
+  unsigned long long stageLaunches[NQ_NSTAGES] = {};
   // results of the last batch
   std::vector<NqImage> lastImgs;
   std::vector<DebugImage> dbg;
@@ -300,8 +307,12 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
   }
   const int gx = pixel_grid_x(c, npix, n);
   const dim3 pg(gx, n);
+  unsigned long long l0 = c->launches;
+  auto mark = [&](int k) { cudaEventRecord(c->ev[k], st); if (k > 0) { c->stageLaunches[k - 1] += c->launches - l0; l0 = c->launches; } };
+  mark(0);
   nq::k_alpha_scan<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
   nq::k_setup_scan<<<(n + 127) / 128, 128, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
+  mark(1);
   if (nmax > 2) {
     if (kind == NQ_KIND_RGB) {
       nq::k_hist_rgb<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
@@ -321,7 +332,9 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
       nq::k_lab_bin_sum<<<bg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
       nq::k_finalize_lab<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
     }
+    mark(2);
     nq::k_find_nn_all<<<c->smCount * 8, 256, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
+    mark(3);
     if (c->debug) {
       CU(cudaStreamSynchronize(st));
       std::vector<NqImage> tmp(n);
@@ -354,18 +367,25 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
     }
     const size_t heapSmem = (size_t)NQ_HEAP_SMEM * 6;
     nq::k_merge<<<n, NQ_MERGE_THREADS, heapSmem, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
-  }
+  } else { mark(2); mark(3); }
+  mark(4);
   nq::k_dither_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
   if (dPalIn) {
     for (int i = 0; i < n; ++i) { k_set_palette<<<1, 256, 0, st>>>(c->dImgs, i, dPalIn, palInLen); ++c->launches; }
     nq::k_dither_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
   }
   if (kind == NQ_KIND_LAB) { nq::k_saliency<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches; }
+  mark(5);
   nq::k_dither<<<n, 32, 0, st>>>(c->dImgs, c->dSlots, dOrder); ++c->launches;
+  mark(6);
   CU(cudaGetLastError());
   c->lastImgs.resize(n);
   CU(cudaMemcpyAsync(c->lastImgs.data(), c->dImgs, sizeof(NqImage) * n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  for (int k = 0; k < NQ_NSTAGES; ++k) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1]) == cudaSuccess) c->stageMs[k] += ms;
+  }
   if (c->debug) {
     for (int i = 0; i < n; ++i) {
       DebugImage& D = c->dbg[i];
@@ -457,7 +477,9 @@ nq_ctx* nq_create(int device) {
   c->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->smCount = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(NQ_ERR_CUDA, "cudaStreamCreate failed"); delete c; return nullptr; }
+  if (cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking) == cudaSuccess) c->stream = c->ownStream;
+  else { fail(NQ_ERR_CUDA, "cudaStreamCreate failed"); delete c; return nullptr; }
+  for (int k = 0; k <= NQ_NSTAGES; ++k) cudaEventCreate(&c->ev[k]);
   signed char* dBn = nullptr;
   bool ok = cudaMalloc(&dBn, 4096) == cudaSuccess && cudaMemcpy(dBn, kBlueNoise, 4096, cudaMemcpyHostToDevice) == cudaSuccess;
   if (ok) {
@@ -468,7 +490,7 @@ nq_ctx* nq_create(int device) {
   if (ok) ok = cudaFuncSetAttribute(nq::k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_HEAP_SMEM * 6) == cudaSuccess;
   if (!ok) {
     fail(NQ_ERR_CUDA, std::string("context initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->ownStream);
     delete c;
     return nullptr;
   }
@@ -482,7 +504,8 @@ void nq_destroy(nq_ctx* c) {
   if (c->ws) cudaFree(c->ws);
   if (c->dIn) cudaFree(c->dIn);
   if (c->dOut) cudaFree(c->dOut);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  for (int k = 0; k <= NQ_NSTAGES; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
+  if (c->ownStream) cudaStreamDestroy(c->ownStream);
   delete c;
 }
 
@@ -559,6 +582,12 @@ int nq_get_image_info(nq_ctx* c, int image, nq_image_info* o) {
   return NQ_OK;
 }
 
+int nq_set_stream(nq_ctx* c, void* stream) {
+  if (!c) return fail(NQ_ERR_ARG, "null context");
+  c->stream = stream ? reinterpret_cast<cudaStream_t>(stream) : c->ownStream;
+  return NQ_OK;
+}
+
 int nq_set_debug(nq_ctx* c, int flag) {
   if (!c) return fail(NQ_ERR_ARG, "null context");
   c->debug = flag != 0;
@@ -588,6 +617,16 @@ int nq_debug_get_saliencies(nq_ctx* c, int image, float* out) {
 }
 
 unsigned long long nq_kernel_launches(nq_ctx* c) { return c ? c->launches : 0ULL; }
+
+int nq_get_stage_times(nq_ctx* c, double* ms, unsigned long long* launches, int reset) {
+  if (!c) return fail(NQ_ERR_ARG, "null context");
+  for (int k = 0; k < NQ_NSTAGES; ++k) {
+    if (ms) ms[k] = c->stageMs[k];
+    if (launches) launches[k] = c->stageLaunches[k];
+    if (reset) { c->stageMs[k] = 0; c->stageLaunches[k] = 0; }
+  }
+  return NQ_OK;
+}
 
 int nq_debug_math(nq_ctx* c, int fn, const double* x, const double* y, double* out, int n) {
   if (!c || !x || !out || n <= 0) return fail(NQ_ERR_ARG, "bad arguments");

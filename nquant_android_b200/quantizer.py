@@ -88,6 +88,10 @@ class Context:
                                                    int(seed), _p(palette), len(palette), _p(out)))
         return out
 
+    def set_stream(self, cuda_stream):
+        """Run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None restores our own."""
+        self._check(self._L.nq_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+
     # -- introspection ------------------------------------------------------------------------------
     def set_debug(self, flag):
         self._check(self._L.nq_set_debug(self._h, int(bool(flag))))
@@ -119,6 +123,15 @@ class Context:
 
     def kernel_launches(self):
         return int(self._L.nq_kernel_launches(self._h))
+
+    STAGES = ["alpha_scan", "histogram", "find_nn_sweep", "merge", "dither_setup", "dither"]
+
+    def stage_times(self, reset=False):
+        """{stage: (device ms, launches)} accumulated since the last reset (CUDA events on the stream)."""
+        ms = np.zeros(6, dtype=np.float64)
+        ln = np.zeros(6, dtype=np.uint64)
+        self._check(self._L.nq_get_stage_times(self._h, _p(ms), _p(ln), int(bool(reset))))
+        return {s: (float(ms[i]), int(ln[i])) for i, s in enumerate(self.STAGES)}
 
     def math(self, fn, x, y=None):
         names = ["pow", "exp", "tanh", "cbrt", "atan2", "sin", "cos"]

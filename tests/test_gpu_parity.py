@@ -1,0 +1,191 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libnquant_b200.so), against the
+oracle on the same seeded inputs -- stage by stage (bins, initial find_nn, merge sequence, palette,
+saliency) and end to end (ARGB output). Everything is integer/bit exact: no tolerances anywhere."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from nquant_android_b200.synth import make_image
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).astype("<u4").tobytes()).hexdigest()
+
+
+def test_native_library_is_the_cuda_build(gpu_ctx):
+    from nquant_android_b200 import _lib
+    assert os.path.basename(_lib.SO) == "libnquant_b200.so" and os.path.exists(_lib.SO)
+    assert gpu_ctx.kernel_launches() >= 1
+
+
+def test_device_math_is_bit_identical_to_host(gpu_ctx, oracle):
+    rng = np.random.default_rng(11)
+    n = 4000
+    sets = {
+        "pow": (rng.uniform(0.003, 1.3, n), np.repeat([2.4, 1 / 3.0, 1 / 2.4, 7.0], n // 4)),
+        "exp": (rng.uniform(-40, 5, n), None), "tanh": (rng.uniform(-25, 25, n), None),
+        "cbrt": (rng.integers(1, 1 << 24, n).astype(np.float64), None),
+        "atan2": (rng.uniform(-130, 130, n), rng.uniform(-130, 130, n)),
+        "sin": (rng.uniform(-55, 55, n), None), "cos": (rng.uniform(-55, 55, n), None),
+    }
+    for name, (x, y) in sets.items():
+        got = gpu_ctx.math(name, x, y)
+        ref = np.array([oracle.math_fn(name, float(a), 0.0 if y is None else float(b), 0)
+                        for a, b in zip(x, y if y is not None else np.zeros(n))])
+        assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), name
+
+
+CASES = [
+    # kind, class, alpha, W, H, K, dither
+    (0, "noisy", "opaque", 160, 120, 256, True), (1, "noisy", "opaque", 160, 120, 256, True),
+    (0, "smooth", "opaque", 160, 120, 256, True), (1, "smooth", "opaque", 160, 120, 256, True),
+    (0, "rand", "opaque", 128, 128, 64, True), (1, "rand", "opaque", 128, 128, 64, True),
+    (0, "noisy", "semi", 128, 96, 16, True), (1, "noisy", "semi", 128, 96, 16, True),
+    (0, "noisy", "transparent", 128, 96, 64, True), (1, "noisy", "transparent", 128, 96, 64, True),
+    (0, "noisy", "opaque", 128, 96, 256, False), (0, "noisy", "opaque", 128, 96, 16, False),
+    (1, "noisy", "opaque", 128, 96, 16, False), (1, "smooth", "opaque", 128, 96, 32, True),
+    (0, "smooth", "opaque", 64, 48, 2, True), (1, "smooth", "transparent", 64, 48, 2, True),
+    (1, "smooth", "opaque", 128, 96, 4, True), (0, "noisy", "opaque", 128, 96, 3, True),
+    (0, "noisy", "semi", 96, 64, 256, True), (1, "smooth", "semi", 96, 64, 256, True),
+    (0, "noisy", "opaque", 1, 97, 8, True), (1, "noisy", "opaque", 97, 1, 8, True),
+    (0, "noisy", "opaque", 37, 211, 128, True), (1, "noisy", "opaque", 211, 37, 128, True),
+]
+
+
+@pytest.mark.parametrize("kind,cls,alpha,W,H,K,dither", CASES)
+def test_stage_and_output_parity(gpu_ctx, oracle, kind, cls, alpha, W, H, K, dither):
+    img = make_image(W, H, cls, alpha)
+    seed = 0xC0FFEE + K
+    ref = oracle.convert(kind, img, W, H, K, dither, seed=seed)
+    gpu_ctx.set_debug(True)
+    try:
+        out, pal, plen, ha = gpu_ctx.convert_batch(kind, img[None, :], W, H, K, dither, seeds=[seed])
+        info = gpu_ctx.image_info(0)
+        s = ref.scalars
+        assert info["has_semi_transparency"] == s["hasSemiTransparency"]
+        assert info["transparent_pixel_index"] == s["transparentPixelIndex"]
+        assert bool(ha[0]) == (s["transparentPixelIndex"] >= 0)
+        if K > 2 and len(ref.bins):
+            assert info["maxbins"] == s["maxbins"] and info["quan_rt"] == s["quan_rt"]
+            assert info["weight"] == s["weight"] and info["ratio_merge"] == s["ratio_merge"]
+            bins, ierr, inn = gpu_ctx.debug_bins(0)
+            assert np.array_equal(bins, ref.bins), "histogram bins (means, counts) differ"
+            assert np.array_equal(ierr.view(np.uint32), ref.init_err.view(np.uint32)) and np.array_equal(inn, ref.init_nn)
+            assert np.array_equal(gpu_ctx.debug_merges(0), ref.merges), "merge sequence differs"
+        for g, r in [("g_margin", "margin"), ("g_thresold", "thresold"), ("g_dither_max_q", "DITHER_MAX"),
+                     ("g_dither_max", "ditherMax"), ("g_sorted", "sortedByYDiff"), ("g_has_alpha", "hasAlpha")]:
+            assert info[g] == s[r], g
+        assert np.float32(info["g_beta"]) == np.float32(s["beta"])
+        assert np.array_equal(pal[0, :plen[0]], ref.palette), "palette differs"
+        if len(ref.saliencies):
+            assert np.array_equal(gpu_ctx.debug_saliencies(W * H, 0).view(np.uint32), ref.saliencies.view(np.uint32))
+        assert info["rng_draws"] == s["rng_draws"]
+        assert np.array_equal(out[0], ref.out), f"{int((out[0] != ref.out).sum())} of {W * H} output pixels differ"
+    finally:
+        gpu_ctx.set_debug(False)
+
+
+def test_golden_fixtures(gpu_ctx):
+    cases = json.load(open(os.path.join(HERE, "golden", "oracle_cases.json")))
+    for c in cases:
+        img = make_image(c["w"], c["h"], c["cls"], c["alpha"])
+        out, pal, plen, _ = gpu_ctx.convert_batch(c["kind"], img[None, :], c["w"], c["h"], c["k"], bool(c["dither"]), seeds=[c["seed"]])
+        assert plen[0] == c["palette_len"] and sha(pal[0, :plen[0]]) == c["palette_sha"], c
+        assert sha(out[0]) == c["output_sha"], c
+
+
+def test_reference_config0_512_rgb(gpu_ctx, oracle):
+    """BASELINE.json configs[0]: PnnQuantizer 256 colours, dither on, 512x512 gradient+noise."""
+    W = H = 512
+    img = make_image(W, H, "noisy", "opaque")
+    ref = oracle.convert(0, img, W, H, 256, True, trace=False)
+    out, pal, plen, _ = gpu_ctx.convert_batch(0, img[None, :], W, H, 256, True)
+    assert np.array_equal(pal[0, :plen[0]], ref.palette) and np.array_equal(out[0], ref.out)
+
+
+def test_reference_config1_1080p_lab(gpu_ctx, oracle):
+    """BASELINE.json configs[1]: PnnLABQuantizer 256 colours, dither on, 1920x1080 (smooth class so
+    the oracle finishes in seconds)."""
+    W, H = 1920, 1080
+    img = make_image(W, H, "smooth", "opaque")
+    ref = oracle.convert(1, img, W, H, 256, True, seed=99, trace=False)
+    out, pal, plen, _ = gpu_ctx.convert_batch(1, img[None, :], W, H, 256, True, seeds=[99])
+    assert np.array_equal(pal[0, :plen[0]], ref.palette) and np.array_equal(out[0], ref.out)
+
+
+def test_batch_matches_single_and_device_matches_host(gpu_ctx):
+    import torch
+    W, H, K = 96, 80, 64
+    imgs = np.stack([make_image(W, H, c, "opaque", seed=0x5EED0000 + i) for i, c in enumerate(["noisy", "smooth", "rand", "noisy"])])
+    seeds = np.arange(4, dtype=np.uint64) + 7
+    for kind in (0, 1):
+        out, pal, plen, _ = gpu_ctx.convert_batch(kind, imgs, W, H, K, True, seeds=seeds)
+        for i in range(4):
+            o1, p1, l1, _ = gpu_ctx.convert_batch(kind, imgs[i:i + 1], W, H, K, True, seeds=seeds[i:i + 1])
+            assert np.array_equal(o1[0], out[i]) and np.array_equal(p1[0], pal[i])
+        din = torch.from_numpy(imgs.view(np.int32)).cuda()
+        dout = torch.empty_like(din)
+        gpu_ctx.convert_batch_ptr(kind, din.data_ptr(), dout.data_ptr(), 4, W, H, K, True, seeds=seeds, device=True)
+        assert np.array_equal(dout.cpu().numpy().view(np.uint32), out)
+
+
+def test_device_synth_matches_numpy(gpu_ctx):
+    import torch
+    W, H = 70, 50
+    for cls_i, cls in enumerate(["smooth", "noisy", "rand"]):
+        for am_i, am in enumerate(["opaque", "transparent", "semi"]):
+            d = torch.empty(2 * W * H, dtype=torch.int32, device="cuda")
+            gpu_ctx.synth_device(d.data_ptr(), 2, W, H, cls_i, am_i, 0x5EED0000)
+            got = d.cpu().numpy().view(np.uint32).reshape(2, -1)
+            for i in range(2):
+                assert np.array_equal(got[i], make_image(W, H, cls, am, seed=0x5EED0000 + i)), (cls, am, i)
+
+
+@pytest.mark.parametrize("kind,K,alpha", [(1, 256, "opaque"), (0, 16, "semi")])
+def test_full_size_4k_properties(gpu_ctx, kind, K, alpha):
+    """BASELINE.json configs[2]/[3] at full 3840x2160: size-independent properties (the oracle needs
+    ~1 minute per 4K image, so it is not run here)."""
+    W, H = 3840, 2160
+    img = make_image(W, H, "noisy", alpha)
+    imgs = np.stack([img, img])
+    out, pal, plen, ha = gpu_ctx.convert_batch(kind, imgs, W, H, K, True, seeds=[5, 5])
+    assert plen[0] == K and np.array_equal(pal[0], pal[1])
+    assert np.array_equal(out[0], out[1]), "two copies of one image in a batch must quantize identically"
+    palette = pal[0, :K]
+    assert np.isin(out[0], palette).all(), "every output pixel must be a palette colour (GilbertCurve.java:279)"
+    info = gpu_ctx.image_info(0)
+    assert info["merges"] == info["maxbins"] - K
+    again = gpu_ctx.dither_with_palette(kind, img, W, H, K, True, palette, seed=5)
+    assert np.array_equal(again, out[0]), "stage hook with the same palette must reproduce convert()"
+    err = np.abs(((out[0][:, None] >> np.array([16, 8, 0])) & 255).astype(np.int32) - ((img[:, None] >> np.array([16, 8, 0])) & 255).astype(np.int32))
+    assert err.mean() < 40
+
+
+def test_error_codes(gpu_ctx):
+    from nquant_android_b200.quantizer import NQuantError
+    img = make_image(8, 8)
+    with pytest.raises(NQuantError) as e:
+        gpu_ctx.convert_batch(0, img[None, :], 8, 8, 1, True)
+    assert e.value.code == -2
+    with pytest.raises(NQuantError) as e:
+        gpu_ctx.convert_batch(0, img[None, :], 8, 8, 257, True)
+    assert e.value.code == -4
+    with pytest.raises(NQuantError):
+        gpu_ctx.convert_batch(7, img[None, :], 8, 8, 16, True)
+
+
+def test_mirror_classes(oracle):
+    from nquant_android_b200.quantizer import PnnQuantizer, PnnLABQuantizer
+    W, H = 64, 64
+    img = make_image(W, H, "noisy", "transparent")
+    for cls, kind in ((PnnQuantizer, 0), (PnnLABQuantizer, 1)):
+        q = cls(img, W, H, rng_seed=3)
+        out = q.convert(32, True)
+        ref = oracle.convert(kind, img, W, H, 32, True, seed=3, trace=False)
+        assert q.hasAlpha() and np.array_equal(out, ref.out) and np.array_equal(q.palette, ref.palette)
