@@ -9,6 +9,7 @@
 #include <map>
 #include <utility>
 #include <algorithm>
+#include <mutex>
 
 #include "../../include/nquant_b200.h"
 #include "nq_types.h"
@@ -127,6 +128,11 @@ __global__ void k_set_palette(NqImage* imgs, int img, const uint32_t* pal, int p
   if (threadIdx.x == 0) imgs[img].paletteLen = plen;
 }
 
+// one RGB->Lab table per device, shared by every context on it
+struct LabLutEntry { float4* ptr = nullptr; int refs = 0; };
+std::mutex g_lutMutex;
+std::map<int, LabLutEntry> g_lut;
+
 struct DebugImage {
   std::vector<double> bins5;
   std::vector<float> initErr;
@@ -153,7 +159,8 @@ struct nq_ctx {
   NqSlot* dSlots = nullptr;
   int* dLive = nullptr;
   int* dPos = nullptr;
-  int wsSlots = 0, wsNpix = 0, wsKind = -1;
+  int wsSlots = 0, wsNpix = 0, wsKind = -1, sortPool = 0;
+  bool wsDebug = false;
   std::vector<NqSlot> hSlots;
   // staging for host-buffer calls
   uint32_t* dIn = nullptr;
@@ -183,11 +190,8 @@ SlotLayout slot_layout(int kind, int npix, bool debug) {
   L.hSum = take((size_t)4 * NQ_NBINS * 8);
   L.keyOff = take((NQ_NBINS + 1) * 4);
   const bool lab = kind == NQ_KIND_LAB;
-  const size_t nruns = ((size_t)npix + NQ_RUN - 1) / NQ_RUN;
-  L.sortA = take(lab ? (size_t)npix * 4 : 0);
-  L.sortB = take(lab ? (size_t)npix * 4 : 0);
-  L.warpHist = take(lab ? nruns * 256 * 4 : 0);
-  L.sal = take(lab ? (size_t)npix * 4 : 0);
+  L.sortA = L.sortB = L.warpHist = 0;                 // these live in the sort pool (see ensure_workspace)
+  L.sal = take(lab && debug ? (size_t)npix * 4 : 0);  // the dither kernel derives saliency itself; kept for parity tests
   L.bD = take((size_t)4 * NQ_NBINS * 8);
   L.bF = take((size_t)4 * NQ_NBINS * 4);
   L.bCnt = take(NQ_NBINS * 4);
@@ -203,21 +207,30 @@ SlotLayout slot_layout(int kind, int npix, bool debug) {
   return L;
 }
 
+// Sort scratch of the strict-order CIELAB histogram (2 x npix words + run counters per image) is only
+// needed while an image's histogram is being built, so a small pool of sets is cycled through the
+// batch instead of giving every image its own.
+#define NQ_SORT_POOL 32
+
 int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots) {
   SlotLayout L = slot_layout(kind, npix, c->debug);
+  const bool lab = kind == NQ_KIND_LAB;
+  const size_t nruns = ((size_t)npix + NQ_RUN - 1) / NQ_RUN;
+  const size_t sortSet = lab ? align_up((size_t)npix * 4, 256) * 2 + align_up(nruns * 256 * 4, 256) : 0;
   size_t freeB = 0, totalB = 0;
   CU(cudaMemGetInfo(&freeB, &totalB));
-  size_t budget = (size_t)((double)(freeB + c->wsBytes) * 0.85);
-  int maxSlots = (int)std::min<size_t>(budget / (L.total + sizeof(NqImage) + sizeof(NqSlot) + 2 * NQ_NBINS * 4), 4096);
-  if (maxSlots < 1) return fail(NQ_ERR_NOMEM, "not enough device memory for one image workspace");
-  int slots = std::min(wantSlots, maxSlots);
-  static bool dbgFlagLast = false;
-  if (c->ws && c->wsKind == kind && c->wsNpix == npix && c->wsSlots >= slots && dbgFlagLast == c->debug) return NQ_OK;
-  dbgFlagLast = c->debug;
+  const size_t budget = (size_t)((double)(freeB + c->wsBytes) * 0.85);
+  const size_t perImage = L.total + sizeof(NqImage) + sizeof(NqSlot) + 2 * NQ_NBINS * 4 + 1024;
+  int pool = std::min(wantSlots, NQ_SORT_POOL);
+  while (pool > 1 && pool * sortSet + perImage > budget) pool /= 2;
+  if (pool * sortSet + perImage > budget) return fail(NQ_ERR_NOMEM, "not enough device memory for one image workspace");
+  const int maxSlots = (int)std::min<size_t>((budget - pool * sortSet) / perImage, 8192);
+  const int slots = std::min(wantSlots, maxSlots);
+  if (c->ws && c->wsKind == kind && c->wsNpix == npix && c->wsSlots >= slots && c->wsDebug == c->debug) return NQ_OK;
   if (c->ws) { cudaFree(c->ws); c->ws = nullptr; c->wsBytes = 0; }
-  size_t imgsB = align_up(sizeof(NqImage) * slots, 256), slotsB = align_up(sizeof(NqSlot) * slots, 256);
-  size_t liveB = align_up((size_t)slots * NQ_NBINS * 4, 256);
-  size_t total = imgsB + slotsB + 2 * liveB + L.total * slots;
+  const size_t imgsB = align_up(sizeof(NqImage) * slots, 256), slotsB = align_up(sizeof(NqSlot) * slots, 256);
+  const size_t liveB = align_up((size_t)slots * NQ_NBINS * 4, 256);
+  const size_t total = imgsB + slotsB + 2 * liveB + L.total * slots + sortSet * pool;
   CU(cudaMalloc(&c->ws, total));
   c->wsBytes = total;
   unsigned char* p = c->ws;
@@ -225,6 +238,7 @@ int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots) {
   c->dSlots = reinterpret_cast<NqSlot*>(p); p += slotsB;
   c->dLive = reinterpret_cast<int*>(p); p += liveB;
   c->dPos = reinterpret_cast<int*>(p); p += liveB;
+  unsigned char* poolBase = p; p += sortSet * pool;
   c->hSlots.assign(slots, NqSlot{});
   for (int s = 0; s < slots; ++s) {
     unsigned char* b = p + L.total * s;
@@ -232,10 +246,13 @@ int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots) {
     S.hCnt = reinterpret_cast<unsigned int*>(b + L.hCnt);
     S.hSum = reinterpret_cast<unsigned long long*>(b + L.hSum);
     S.keyOff = reinterpret_cast<unsigned int*>(b + L.keyOff);
-    S.sortA = reinterpret_cast<uint32_t*>(b + L.sortA);
-    S.sortB = reinterpret_cast<uint32_t*>(b + L.sortB);
-    S.warpHist = reinterpret_cast<unsigned int*>(b + L.warpHist);
-    S.sal = reinterpret_cast<float*>(b + L.sal);
+    if (lab) {
+      unsigned char* sp = poolBase + sortSet * (s % pool);
+      S.sortA = reinterpret_cast<uint32_t*>(sp);
+      S.sortB = reinterpret_cast<uint32_t*>(sp + align_up((size_t)npix * 4, 256));
+      S.warpHist = reinterpret_cast<unsigned int*>(sp + 2 * align_up((size_t)npix * 4, 256));
+    }
+    S.sal = (lab && c->debug) ? reinterpret_cast<float*>(b + L.sal) : nullptr;
     double* bd = reinterpret_cast<double*>(b + L.bD);
     S.bAc = bd; S.bC1 = bd + NQ_NBINS; S.bC2 = bd + 2 * NQ_NBINS; S.bC3 = bd + 3 * NQ_NBINS;
     float* bf = reinterpret_cast<float*>(b + L.bF);
@@ -251,7 +268,7 @@ int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots) {
     S.memo = reinterpret_cast<unsigned short*>(b + L.memo);
     S.idx = nullptr;
   }
-  c->wsSlots = slots; c->wsNpix = npix; c->wsKind = kind;
+  c->wsSlots = slots; c->wsNpix = npix; c->wsKind = kind; c->sortPool = pool; c->wsDebug = c->debug;
   return NQ_OK;
 }
 
@@ -319,17 +336,22 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
       nq::k_finalize_rgb<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
     } else {
       const int nruns = (npix + NQ_RUN - 1) / NQ_RUN;
-      const dim3 rg(std::max(1, std::min((nruns + 7) / 8, std::max(1, c->smCount * 8 / n))), n);
       nq::k_lab_count<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
       nq::k_lab_scan_keys<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
-      nq::k_radix_count<0><<<rg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
-      nq::k_radix_offsets<<<n, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
-      nq::k_radix_scatter<0><<<rg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
-      nq::k_radix_count<1><<<rg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
-      nq::k_radix_offsets<<<n, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
-      nq::k_radix_scatter<1><<<rg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
-      const dim3 bg(std::max(1, c->smCount * 8 / n), n);
-      nq::k_lab_bin_sum<<<bg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      for (int g0 = 0; g0 < n; g0 += c->sortPool) {   // images of one group own distinct sort scratch sets
+        const int gn = std::min(c->sortPool, n - g0);
+        NqImage* gi = c->dImgs + g0;
+        NqSlot* gs = c->dSlots + g0;
+        const dim3 rg(std::max(1, std::min((nruns + 7) / 8, std::max(1, c->smCount * 8 / gn))), gn);
+        nq::k_radix_count<0><<<rg, 256, 0, st>>>(gi, gs); ++c->launches;
+        nq::k_radix_offsets<<<gn, 256, 0, st>>>(gi, gs); ++c->launches;
+        nq::k_radix_scatter<0><<<rg, 256, 0, st>>>(gi, gs); ++c->launches;
+        nq::k_radix_count<1><<<rg, 256, 0, st>>>(gi, gs); ++c->launches;
+        nq::k_radix_offsets<<<gn, 256, 0, st>>>(gi, gs); ++c->launches;
+        nq::k_radix_scatter<1><<<rg, 256, 0, st>>>(gi, gs); ++c->launches;
+        const dim3 bg(std::max(1, c->smCount * 8 / gn), gn);
+        nq::k_lab_bin_sum<<<bg, 256, 0, st>>>(gi, gs); ++c->launches;
+      }
       nq::k_finalize_lab<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
     }
     mark(2);
@@ -374,7 +396,7 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
     for (int i = 0; i < n; ++i) { k_set_palette<<<1, 256, 0, st>>>(c->dImgs, i, dPalIn, palInLen); ++c->launches; }
     nq::k_dither_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
   }
-  if (kind == NQ_KIND_LAB) { nq::k_saliency<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches; }
+  if (kind == NQ_KIND_LAB && c->debug) { nq::k_saliency<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches; }
   mark(5);
   nq::k_dither<<<n, 32, 0, st>>>(c->dImgs, c->dSlots, dOrder); ++c->launches;
   mark(6);
@@ -394,7 +416,7 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
       D.merges.assign((size_t)merges * 2, 0);
       if (merges && c->hSlots[i].mergeLog) CU(cudaMemcpy(D.merges.data(), c->hSlots[i].mergeLog, (size_t)merges * 8, cudaMemcpyDeviceToHost));
       D.sal.clear();
-      if (I.gUseSal) { D.sal.resize(npix); CU(cudaMemcpy(D.sal.data(), c->hSlots[i].sal, (size_t)npix * 4, cudaMemcpyDeviceToHost)); }
+      if (I.gUseSal && c->hSlots[i].sal) { D.sal.resize(npix); CU(cudaMemcpy(D.sal.data(), c->hSlots[i].sal, (size_t)npix * 4, cudaMemcpyDeviceToHost)); }
     }
   }
   return NQ_OK;
@@ -487,6 +509,21 @@ nq_ctx* nq_create(int device) {
     ok = cudaStreamSynchronize(c->stream) == cudaSuccess;
   }
   if (dBn) cudaFree(dBn);
+  if (ok) {
+    std::lock_guard<std::mutex> lk(g_lutMutex);
+    LabLutEntry& e = g_lut[device];
+    if (!e.ptr) {
+      ok = cudaMalloc(&e.ptr, sizeof(float4) << 24) == cudaSuccess;
+      if (ok) {
+        nq::k_build_lab_lut<<<65536, 256, 0, c->stream>>>(e.ptr); ++c->launches;
+        const float4* cp = e.ptr;
+        ok = cudaMemcpyToSymbolAsync(nq::g_labLut, &cp, sizeof(cp), 0, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+             cudaStreamSynchronize(c->stream) == cudaSuccess;
+      }
+      if (!ok && e.ptr) { cudaFree(e.ptr); e.ptr = nullptr; }
+    }
+    if (ok) ++e.refs;
+  }
   if (ok) ok = cudaFuncSetAttribute(nq::k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_HEAP_SMEM * 6) == cudaSuccess;
   if (!ok) {
     fail(NQ_ERR_CUDA, std::string("context initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -500,6 +537,11 @@ nq_ctx* nq_create(int device) {
 void nq_destroy(nq_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  {
+    std::lock_guard<std::mutex> lk(g_lutMutex);
+    auto it = g_lut.find(c->device);
+    if (it != g_lut.end() && it->second.refs > 0 && --it->second.refs == 0) { cudaFree(it->second.ptr); g_lut.erase(it); }
+  }
   for (auto& kv : c->orders) cudaFree(kv.second);
   if (c->ws) cudaFree(c->ws);
   if (c->dIn) cudaFree(c->dIn);

@@ -25,6 +25,9 @@ struct WarpShared {
   float q[NQ_MAXQ][4];        // error queue: FIFO ring, or the PriorityQueue backing array
   double qy[16];              // yDiff of PriorityQueue entries
   float w[NQ_MAXQ];           // current weights[]
+  // PnnLABQuantizer.closestColorIndex cost split per channel: T?[v] = cost of a channel difference of
+  // |v| (see closest_lab); Ta only when the image is semi-transparent
+  double Tr[256], Tg[256], Tb[256], Ta[256];
 };
 
 struct Env {
@@ -35,7 +38,6 @@ struct Env {
   double PR, PG, PB, PA, ratio, gWeight, exp15;
   float beta;
   unsigned short* memo;
-  const float* sal;
   JRandom rng;
   unsigned long long draws;
   int width;
@@ -131,13 +133,13 @@ __device__ int closest_rgb(Env& E, uint32_t c, int pos) {
   t2_reduce(t);
   int c0 = t.d0 == T2_NONE ? 0 : t.i0, e0 = t.d0;
   int c1 = t.d1 == T2_NONE ? c0 : t.i1, e1 = t.d1;     // PQ:359-360
-  const int cl[4] = {c0, c1, e0, e1};
   int MAX_ERR = E.plen << 2;
   int idx = (pos + 1) % 2;
   if ((double)e1 * .67 < (double)(e1 - e0)) idx = 0;
   else if (c0 > c1) idx = pos % 2;
-  if (cl[idx + 2] >= MAX_ERR || (E.hasTrans && cl[idx] == 0)) return nearest_rgb(E, c);
-  return cl[idx];
+  const int ci = idx ? c1 : c0, ei = idx ? e1 : e0;
+  if (ei >= MAX_ERR || (E.hasTrans && ci == 0)) return nearest_rgb(E, c);
+  return ci;
 }
 
 // PnnLABQuantizer.nearestColorIndex (PL:329-404)
@@ -155,7 +157,7 @@ __device__ int nearest_lab(Env& E, uint32_t c) {
   if (c_alpha(c) <= 0xF) c = E.transColor;
   if (E.plen > 2 && E.hasTrans && c_alpha(c) > 0xF) k = 1;
   const int ca = c_alpha(c), cr = c_red(c), cg = c_green(c), cb = c_blue(c);
-  const Lab4 l1 = rgb2lab(c, g_gammaLut);
+  const Lab4 l1 = lab_of(c);
   int bi;
   if (E.plen > 4 && !(E.semi || E.plen < 16) && E.plen <= 32) {
     // CIEDE2000 branch (PL:376-395): R_T can be negative, so acceptance depends on the running
@@ -227,48 +229,74 @@ __device__ int nearest_lab(Env& E, uint32_t c) {
   return bi;
 }
 
+// exact cost of palette entry c2 for colour c, in the reference's operation order (PL:421-446)
+__device__ __forceinline__ double closest_lab_err(const Env& E, uint32_t c2, int ca, int cr, int cg, int cb) {
+  const int ir = c_red(c2) - cr, ig = c_green(c2) - cg, ib = c_blue(c2) - cb;
+  double dr = (double)ir, dg = (double)ig, db = (double)ib;
+  double err = E.PR * (1 - E.ratio) * (dr * dr);
+  err += E.PG * (1 - E.ratio) * (dg * dg);
+  err += E.PB * (1 - E.ratio) * (db * db);
+  if (E.semi) { double da = (double)(c_alpha(c2) - ca); err += E.PA * (da * da); }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double t0 = (double)(c_coeffs[i][0] * (float)ir);   // float * int -> float (PL:437)
+    err += E.ratio * (t0 * t0);
+    double t1 = (double)(c_coeffs[i][1] * (float)ig);
+    err += E.ratio * (t1 * t1);
+    double t2 = (double)(c_coeffs[i][2] * (float)ib);
+    err += E.ratio * (t2 * t2);
+  }
+  return err;
+}
+// per-channel cost tables for the fast scan: every term of closest_lab_err depends on ONE channel
+// difference, and all terms are >= 0, so the reference's 12/13-term sequential double sum S and the
+// regrouped sum A = Tr[|dr|] + Tg[|dg|] + Tb[|db|] (+ Ta[|da|]) agree to a few ulp:
+// |S - A| <= 2e-14 * A. Only floor(S) enters the top-2 decision (see Top2), so A decides it unless A
+// lies within 1e-6 (>> 2e-14 * 2^31) of an integer, in which case the exact S is evaluated.
+__device__ void closest_lab_tables(const Env& E) {
+  for (int v = lane_id(); v < 256; v += 32) {
+    const double dv = (double)v;
+    double tr = E.PR * (1 - E.ratio) * (dv * dv), tg = E.PG * (1 - E.ratio) * (dv * dv), tb = E.PB * (1 - E.ratio) * (dv * dv);
+    for (int i = 0; i < 3; ++i) {
+      double t0 = (double)(c_coeffs[i][0] * (float)v), t1 = (double)(c_coeffs[i][1] * (float)v), t2 = (double)(c_coeffs[i][2] * (float)v);
+      tr += E.ratio * (t0 * t0); tg += E.ratio * (t1 * t1); tb += E.ratio * (t2 * t2);
+    }
+    E.sh->Tr[v] = tr; E.sh->Tg[v] = tg; E.sh->Tb[v] = tb;
+    E.sh->Ta[v] = E.semi ? E.PA * (dv * dv) : 0.0;
+  }
+  __syncwarp();
+}
+
 // PnnLABQuantizer.closestColorIndex (PL:406-474)
 __device__ int closest_lab(Env& E, uint32_t c, int pos) {
   if (c_alpha(c) <= 0xF) return nearest_lab(E, c);
   const unsigned lane = lane_id();
   const int ca = c_alpha(c), cr = c_red(c), cg = c_green(c), cb = c_blue(c);
-  const double PRr = E.PR * (1 - E.ratio), PGr = E.PG * (1 - E.ratio), PBr = E.PB * (1 - E.ratio);
   Top2 t = {1 << 30, 1 << 30, T2_NONE, T2_NONE};
   for (int k = lane; k < E.plen; k += 32) {
     const uint32_t c2 = E.sh->pal[k];
-    const int ir = c_red(c2) - cr, ig = c_green(c2) - cg, ib = c_blue(c2) - cb;
-    double dr = (double)ir, dg = (double)ig, db = (double)ib;
-    double err = PRr * (dr * dr);
-    err += PGr * (dg * dg);
-    err += PBr * (db * db);
-    if (E.semi) { double da = (double)(c_alpha(c2) - ca); err += E.PA * (da * da); }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      double t0 = (double)(c_coeffs[i][0] * (float)ir);   // float * int -> float (PL:437)
-      err += E.ratio * (t0 * t0);
-      double t1 = (double)(c_coeffs[i][1] * (float)ig);
-      err += E.ratio * (t1 * t1);
-      double t2 = (double)(c_coeffs[i][2] * (float)ib);
-      err += E.ratio * (t2 * t2);
-    }
-    int d = j2i(err);
+    double a = E.sh->Tr[abs(c_red(c2) - cr)] + E.sh->Tg[abs(c_green(c2) - cg)] + E.sh->Tb[abs(c_blue(c2) - cb)];
+    if (E.semi) a += E.sh->Ta[abs(c_alpha(c2) - ca)];
+    int d = j2i(a);
+    const double fr = a - (double)d;
+    if (fr < 1e-6 || fr > 1.0 - 1e-6) d = j2i(closest_lab_err(E, c2, ca, cr, cg, cb));
     if (d != T2_NONE) t2_insert(t, d, k);
   }
   t2_reduce(t);
-  int c0 = t.d0 == T2_NONE ? 0 : t.i0, e0 = t.d0;
-  int c1 = t.d1 == T2_NONE ? c0 : t.i1, e1 = t.d1;     // PL:460-461
-  const int cl[4] = {c0, c1, e0, e1};
+  const int c0 = t.d0 == T2_NONE ? 0 : t.i0, e0 = t.d0;
+  const int c1 = t.d1 == T2_NONE ? c0 : t.i1, e1 = t.d1;     // PL:460-461
   int idx = 1;
-  if (e0 == 0) idx = 0;                                 // short-circuit: no draw (PL:467)
+  if (e0 == 0) idx = 0;                                       // short-circuit: no draw (PL:467)
   else {
     int r = E.rng.next_int(32767);
     ++E.draws;
     int sum = (int)((unsigned)e1 + (unsigned)e0);
     if ((r % sum) <= e1) idx = 0;
   }
+  const int ci = idx ? c1 : c0, ei = idx ? e1 : e0;
   int MAX_ERR = E.plen;
-  if (cl[idx + 2] >= MAX_ERR || cl[idx] == 0 || c_alpha(E.sh->pal[cl[idx]]) < ca) return nearest_lab(E, c);
-  return cl[idx];
+  if (ei >= MAX_ERR || ci == 0 || c_alpha(E.sh->pal[ci]) < ca) return nearest_lab(E, c);
+  return ci;
 }
 
 // Ditherable.nearestColorIndex as bound by getDitherFn (PQ:377-391, PL:476-490)
@@ -289,12 +317,16 @@ __device__ float normal_distribution(float x, float peak) {
   return (float)dmax(0.0, dmin((double)peak, scaledPdf));
 }
 
-// GilbertCurve.ditherPixel (GC:125-185). qcur = qPixels[bidx] at the time of the call.
-__device__ int dither_pixel(Env& E, int x, int y, uint32_t pixel, uint32_t c2, float beta, int qcur) {
-  const int bidx = x + y * E.width;
+// Y_Diff(pixel, c) with color2Y(pixel) already known (CL:215-227)
+__device__ __forceinline__ double y_diff_pre(double ypix, uint32_t c, const double* lut) {
+  return nqm::fabs_(color_y(c, lut) - ypix) * 100;
+}
+
+// GilbertCurve.ditherPixel (GC:125-185). qcur = qPixels[bidx] at the time of the call; sal =
+// saliencies[bidx]; ypix = color2Y(pixel).
+__device__ int dither_pixel(Env& E, int x, int y, int bidx, uint32_t pixel, float sal, double ypix, uint32_t c2, float beta, int qcur) {
   const int plen = E.plen, margin = E.margin;
   const double weight = E.gWeight;
-  const float sal = E.sal[bidx];
   const uint32_t qcol = E.sh->pal[qcur];
   const signed char* bn = g_blueNoise;
   const double* lut = g_gammaLut;
@@ -303,7 +335,7 @@ __device__ int dither_pixel(Env& E, int x, int y, uint32_t pixel, uint32_t c2, f
   const int acceptedDiff = max(2, plen - margin);
   if (plen <= 4 && sal > .2f && sal < .25f)
     c2 = bn_diffuse(pixel, qcol, beta * 2 / sal, strength, x, y, bn);
-  else if (plen <= 4 || y_diff(pixel, c2, lut) < (double)(2 * acceptedDiff)) {
+  else if (plen <= 4 || y_diff_pre(ypix, c2, lut) < (double)(2 * acceptedDiff)) {
     if (plen > 64) {
       float kappa = sal < .6f ? beta * .15f / sal : beta * .4f / sal;
       c2 = bn_diffuse(pixel, qcol, kappa, strength, x, y, bn);
@@ -314,7 +346,7 @@ __device__ int dither_pixel(Env& E, int x, int y, uint32_t pixel, uint32_t c2, f
   }
 
   double gamma = (plen <= 32 && weight < .01 && weight > .007) ? (double)(1 - beta) : (double)beta;
-  if (plen > 4 && y_diff(pixel, c2, lut) > (gamma * acceptedDiff)) {
+  if (plen > 4 && y_diff_pre(ypix, c2, lut) > (gamma * acceptedDiff)) {
     if (margin > 6 || gamma > (double)beta) {
       float kappa = sal < .4f ? beta * .4f * sal : beta * .4f / sal;
       uint32_t c1 = c_argb(a_pix, r_pix, g_pix, b_pix);
@@ -339,13 +371,40 @@ __device__ int dither_pixel(Env& E, int x, int y, uint32_t pixel, uint32_t c2, f
       c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
   }
 
-  if (E.DM < 16 && plen > 4 && sal < .6f && y_diff(pixel, c2, lut) > (double)(margin - 1))
+  if (E.DM < 16 && plen > 4 && sal < .6f && y_diff_pre(ypix, c2, lut) > (double)(margin - 1))
     c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
   if (plen > 32 && (double)sal > .95) {
     float kappa = beta * fmaxf(.05f, .75f - plen / 128.f) * sal;
     c2 = bn_diffuse(pixel, qcol, kappa, strength, x, y, bn);
   }
   return lookup(E, c2, bidx);
+}
+
+// (float) Math.tanh(x) for the error shaping (GC:255). The double result is only used after narrowing
+// to float, so a plain-double evaluation t with relative error < 1e-13 decides the float whenever
+// (float)(t(1-d)) == (float)(t(1+d)), d = 1e-12 (rounding is monotone); otherwise, and for |x| < 1
+// where 1 - 2/(e^2x + 1) cancels, the double-double kernel runs. Same float as (float)nq_tanh(x).
+__device__ __forceinline__ float tanh_to_float(double x) {
+  const double ax = nqm::fabs_(x);
+  if (ax >= 1.0 && ax < 22.0) {
+    const double y = 2.0 * ax;
+    const double fk = nqm::rint_(y * nqm::INV_LN2_32);
+    const int kk = (int)fk;
+    const double r = (y - fk * nqm::LN2_32_HI) - fk * nqm::LN2_32_LO;
+    double p = 1.0 / 720.0;
+    p = p * r + 1.0 / 120.0;
+    p = p * r + 1.0 / 24.0;
+    p = p * r + 1.0 / 6.0;
+    p = p * r + 0.5;
+    p = p * r + 1.0;
+    p = p * r;                                     // expm1(r), |r| <= 0.011
+    const double T = nqm::exp2_32_tab(kk & 31, 0);
+    const double Ee = (T + T * p) * nqm::pow2i(kk >> 5);
+    const double t = 1.0 - 2.0 / (Ee + 1.0);
+    const float lo = (float)(t * (1.0 - 1e-12)), hi = (float)(t * (1.0 + 1e-12));
+    if (lo == hi) return x < 0 ? -lo : lo;
+  }
+  return (float)nqm::nq_tanh(x);
 }
 
 // java.util.PriorityQueue over the shared arrays, comparator Double.compare(o2.yDiff, o1.yDiff)
@@ -425,6 +484,10 @@ __global__ void k_dither_setup(NqImage* imgs, const NqSlot* slots, int nimg) {
   const int plen = I.paletteLen;
   const bool lab = I.kind == NQ_KIND_LAB;
   const double weight = I.hasSemi ? -I.weight : I.weight;   // PQ:396-397, PL:496-497
+  // PnnQuantizer.nearestColorIndex tests the FIELD `weight > .015` while it carries the sign flip
+  // (PQ:271 after PQ:396-397): a semi-transparent image always uses the reduced memo key there.
+  // PnnLABQuantizer latched isNano inside pnnquan, before the flip (PL:180).
+  if (!lab) I.isNano = !(weight > .015);
   // which saliency map exists (PL:135, PL:499-508)
   const bool salFromPnn = lab && I.nmax > 2 && I.nmax < 128;
   const bool salFromDither = lab && I.dither && !salFromPnn && (plen <= 256 || weight > .99);
@@ -470,7 +533,18 @@ __global__ void k_dither_setup(NqImage* imgs, const NqSlot* slots, int nimg) {
 // -------------------------------------------------------------------------------------------------
 // the serial pass: Gilbert-order error diffusion (GC:187-280), then BlueNoise.dither (BN:207-222)
 // when dither == false and the palette has more than 32 entries. One warp per image.
+//
+// The warp walks the curve in blocks of 32 pixels. Everything that does not depend on the running
+// error is gathered for a whole block at once, one pixel per lane, a block ahead of its use: the
+// visiting order, the source pixel, its saliency (from the Lab table) and its luminance. Results are
+// kept one per lane and written back per block. Only the serial recurrence stays on the chain.
 // -------------------------------------------------------------------------------------------------
+struct PixBlock { uint32_t xy, px; float sal; double ypix; };
+
+__device__ __forceinline__ int chan(uint32_t c, int ch) {   // ErrorBox channel order r, g, b, a (GC:24-31)
+  return (int)((c >> (ch == 3 ? 24 : 16 - 8 * ch)) & 0xFF);
+}
+
 __global__ void __launch_bounds__(32) k_dither(NqImage* imgs, const NqSlot* slots, const uint32_t* order) {
   __shared__ WarpShared sh;
   const int img = blockIdx.x;
@@ -492,7 +566,7 @@ __global__ void __launch_bounds__(32) k_dither(NqImage* imgs, const NqSlot* slot
   E.PR = I.PR; E.PG = I.PG; E.PB = I.PB; E.PA = I.PA; E.ratio = I.ratioMerge; E.gWeight = I.gWeight;
   E.exp15 = E.semi ? nqm::nq_exp(1.5) : 1.0;
   E.beta = I.gBeta;
-  E.memo = S.memo; E.sal = S.sal;
+  E.memo = S.memo;
   E.rng.set_seed(I.seed);
   E.draws = 0;
   E.width = width;
@@ -500,13 +574,14 @@ __global__ void __launch_bounds__(32) k_dither(NqImage* imgs, const NqSlot* slot
   for (int i = lane; i < plen; i += 32) {
     uint32_t pc = I.palette[i];
     sh.pal[i] = pc;
-    if (E.lab) { Lab4 l = rgb2lab(pc, g_gammaLut); sh.palLab[i] = make_float4(l.alpha, l.L, l.A, l.B); }
+    if (E.lab) { Lab4 l = lab_of(pc); sh.palLab[i] = make_float4(l.alpha, l.L, l.A, l.B); }
   }
   const int DM = E.DM;
   if (lane < NQ_MAXQ) sh.w[lane] = lane < (unsigned)DM ? I.gWeights[lane] : 0.f;
   for (int i = lane; i < NQ_MAXQ * 4; i += 32) sh.q[i >> 2][i & 3] = 0.f;
   if (lane < 16) sh.qy[lane] = 0;
   __syncwarp();
+  if (E.lab && plen > 4) closest_lab_tables(E);
 
   const bool sorted = E.sorted, useSal = E.useSal, dither = E.dither, gHasAlpha = E.gHasAlpha;
   const int ch = lane & 3;
@@ -514,135 +589,173 @@ __global__ void __launch_bounds__(32) k_dither(NqImage* imgs, const NqSlot* slot
   const float beta = E.beta;
   const double* lut = g_gammaLut;
   const signed char* bn = g_blueNoise;
-  int head = 0;            // FIFO: slot of the oldest entry (queue always holds DM entries)
+  const bool salReplaced = I.nmax < 128 && I.nmax > 2;   // which pixel feeds getLab for the saliency (PL:141-156 vs PL:503-506)
+  const uint32_t transColor = I.transColor;
+  int head = 0;            // FIFO: slot of the oldest entry (the queue always holds DM entries)
   PQ pq{&sh, 0};
   int wlen = 0;            // weights.length in sorted mode (0, 1, 3, 7)
 
-  for (int n = 0; n < npix; ++n) {
-    const uint32_t xy = order[n];
-    const int x = xy & 0xFFFF, y = xy >> 16, bidx = x + y * width;
-    const uint32_t pixel = eff_pixel(in[bidx], fixA0);
-
-    // ---- error.p = pixel + sum(queue[i].p * weights[i]) in queue order (GC:190-204); lane&3 = channel
-    const int pv[4] = {c_red(pixel), c_green(pixel), c_blue(pixel), c_alpha(pixel)};
-    float acc = (float)pv[ch];
-    float mx = (float)(DM - 1);
-    if (!sorted) {
-      int slot = head;
-      for (int i = 0; i < DM; ++i) {
-        acc += sh.q[slot][ch] * sh.w[i];
-        if (acc > mx) mx = acc;
-        if (++slot == DM) slot = 0;
+  auto fetch = [&](int n0) {
+    PixBlock b;
+    b.xy = 0; b.px = 0; b.sal = 0.f; b.ypix = 0.0;
+    const int n = n0 + (int)lane;
+    if (n < npix) {
+      b.xy = order[n];
+      const int bidx = (int)(b.xy & 0xFFFF) + (int)(b.xy >> 16) * width;
+      b.px = eff_pixel(in[bidx], fixA0);
+      if (useSal) {
+        uint32_t sp = b.px;
+        if (salReplaced && (sp >> 24) <= 0xF) sp = transColor;
+        const Lab4 l = lab_of(sp);
+        const float saliencyBase = .1f;
+        b.sal = saliencyBase + (1 - saliencyBase) * l.L / 100.f * l.alpha / 255.f;
       }
-    } else {
-      int i = wlen - 1;
-      for (int qi = 0; qi < pq.n && i >= 0; ++qi, --i) {
-        acc += sh.q[qi][ch] * sh.w[i];
-        if (acc > mx) mx = acc;
-      }
+      b.ypix = color_y(b.px, lut);
     }
-    mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 2));
-    const float maxErr = mx;
-    const int mine = j2i(dmin(255.0, dmax((double)acc, 0.0)));
-    const int r_pix = __shfl_sync(FULL, mine, 0), g_pix = __shfl_sync(FULL, mine, 1), b_pix = __shfl_sync(FULL, mine, 2), a_pix = __shfl_sync(FULL, mine, 3);
+    return b;
+  };
 
-    // ---- quantize (GC:211-229)
-    uint32_t c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
-    int qi;
-    if (useSal && dither && !sorted && (!gHasAlpha || c_alpha(pixel) < a_pix)) {
-      if ((plen >= 256 && S.sal[bidx] > .99f) || (gHasAlpha && (double)(c_alpha(pixel) - a_pix) < (.5 * margin)))
-        qi = lookup(E, c2, bidx);
-      else
-        qi = dither_pixel(E, x, y, pixel, c2, beta, 0);    // qPixels[bidx] is still 0 here (GC:136,216)
-    } else if (plen <= 32 && a_pix > 0xF0) {
-      qi = lookup(E, c2, bidx);
-      const int acceptedDiff = max(2, plen - margin);
-      if (useSal && (y_diff(pixel, c2, lut) > (double)acceptedDiff || u_diff(pixel, c2) > (double)(2 * acceptedDiff))) {
-        const float strength = 1 / 3.f;
-        c2 = bn_diffuse(pixel, sh.pal[qi], 1 / S.sal[bidx], strength, x, y, bn);
-        qi = lookup(E, c2, bidx);
+  PixBlock nxt = fetch(0);
+  for (int n0 = 0; n0 < npix; n0 += 32) {
+    const PixBlock cur = nxt;
+    if (n0 + 32 < npix) nxt = fetch(n0 + 32);
+    uint32_t myOut = 0;
+    const int cnt = min(32, npix - n0);
+    for (int j = 0; j < cnt; ++j) {
+      const uint32_t xy = __shfl_sync(FULL, cur.xy, j);
+      const uint32_t pixel = __shfl_sync(FULL, cur.px, j);
+      const float sal = __shfl_sync(FULL, cur.sal, j);
+      const double ypix = shfl_d(cur.ypix, j);
+      const int x = xy & 0xFFFF, y = xy >> 16, bidx = x + y * width;
+
+      // ---- error.p = pixel + sum(queue[i].p * weights[i]) in queue order (GC:190-204); lane&3 = channel
+      float acc = (float)chan(pixel, ch);
+      float mx = (float)(DM - 1);
+      if (!sorted) {
+        int slot = head;
+        for (int i = 0; i < DM; ++i) {
+          acc += sh.q[slot][ch] * sh.w[i];
+          if (acc > mx) mx = acc;
+          if (++slot == DM) slot = 0;
+        }
+      } else {
+        int i = wlen - 1;
+        for (int qi = 0; qi < pq.n && i >= 0; ++qi, --i) {
+          acc += sh.q[qi][ch] * sh.w[i];
+          if (acc > mx) mx = acc;
+        }
       }
-    } else
-      qi = lookup(E, c2, bidx);
+      mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 2));
+      const float maxErr = mx;
+      const int mine = j2i(dmin(255.0, dmax((double)acc, 0.0)));
+      const int r_pix = __shfl_sync(FULL, mine, 0), g_pix = __shfl_sync(FULL, mine, 1), b_pix = __shfl_sync(FULL, mine, 2), a_pix = __shfl_sync(FULL, mine, 3);
 
-    // ---- queue maintenance (GC:231-234)
-    if (!sorted) {
-      // size is always DITHER_MAX here: poll() drops the oldest, its slot receives the new error
-    } else {
-      if (pq.n >= DM) pq.poll();
-      else if (pq.n != 0) {
-        const int size = pq.n;                      // initWeights(size): size empty boxes + new weights
-        const float zero[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = 0; k < size; ++k) pq.offer(zero, 0.0);
-        const float* src = size == 1 ? I.gW1 : (size == 3 ? I.gW3 : I.gW7);
-        if (lane < (unsigned)size) sh.w[lane] = src[lane];
-        wlen = size;
+      // ---- quantize (GC:211-229)
+      uint32_t c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
+      int qi;
+      if (useSal && dither && !sorted && (!gHasAlpha || c_alpha(pixel) < a_pix)) {
+        if ((plen >= 256 && sal > .99f) || (gHasAlpha && (double)(c_alpha(pixel) - a_pix) < (.5 * margin)))
+          qi = lookup(E, c2, bidx);
+        else
+          qi = dither_pixel(E, x, y, bidx, pixel, sal, ypix, c2, beta, 0);    // qPixels[bidx] is still 0 here (GC:136,216)
+      } else if (plen <= 32 && a_pix > 0xF0) {
+        qi = lookup(E, c2, bidx);
+        const int acceptedDiff = max(2, plen - margin);
+        if (useSal && (y_diff_pre(ypix, c2, lut) > (double)acceptedDiff || u_diff(pixel, c2) > (double)(2 * acceptedDiff))) {
+          const float strength = 1 / 3.f;
+          c2 = bn_diffuse(pixel, sh.pal[qi], 1 / sal, strength, x, y, bn);
+          qi = lookup(E, c2, bidx);
+        }
+      } else
+        qi = lookup(E, c2, bidx);
+
+      // ---- queue maintenance (GC:231-234). FIFO: the size is always DITHER_MAX, poll() drops the
+      //      oldest entry and its slot receives the new error below.
+      if (sorted) {
+        if (pq.n >= DM) pq.poll();
+        else if (pq.n != 0) {
+          const int size = pq.n;                      // initWeights(size): size empty boxes + new weights
+          const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int k = 0; k < size; ++k) pq.offer(zero, 0.0);
+          const float* src = size == 1 ? I.gW1 : (size == 3 ? I.gW3 : I.gW7);
+          if (lane < (unsigned)size) sh.w[lane] = src[lane];
+          wlen = size;
+          __syncwarp();
+        }
+      }
+
+      // ---- error of this pixel and its shaping (GC:236-264); lanes 0..2 shape r, g, b
+      c2 = sh.pal[qi];
+      const int pixch = ch == 0 ? r_pix : (ch == 1 ? g_pix : (ch == 2 ? b_pix : a_pix));
+      float e = (float)(pixch - chan(c2, ch));
+      const bool denoise = plen > 2;
+      const bool diffuse = bn[bidx & 4095] > thresold;
+      const double yDiff = sorted ? y_diff_pre(ypix, c2, lut) : 1.0;
+      const bool illusion = !diffuse && bn[j2i(yDiff * 4096) & 4095] > thresold;
+      bool unacc = false;
+      if (denoise && ch < 3) {
+        if (fabsf(e) >= (float)ditherMax) {
+          if (sorted && useSal) unacc = true;
+          if (diffuse) e = tanh_to_float((double)(e / maxErr * 20.f)) * (float)(ditherMax - 1);
+          else if (illusion) e = (float)((double)(e / maxErr) * yDiff) * (float)(ditherMax - 1);
+          else e /= (float)(1 + nqm::sqrt_((double)ditherMax));
+        }
+        if (sorted && !useSal && fabsf(e) >= (float)DM) unacc = true;
+      }
+      const bool unaccepted = (__ballot_sync(FULL, unacc) & 7u) != 0;
+
+      if (unaccepted) {   // GC:266-274
+        if (useSal) qi = dither_pixel(E, x, y, bidx, pixel, sal, ypix, c2, beta, qi);
+        else if (y_diff_pre(ypix, c2, lut) > 3 && u_diff(pixel, c2) > 3) {
+          const float strength = 1 / 3.f;
+          c2 = bn_diffuse(pixel, sh.pal[qi], strength, strength, x, y, bn);
+          qi = lookup(E, c2, bidx);
+        }
+      }
+
+      // ---- errorq.add(error) (GC:276)
+      if (!sorted) {
         __syncwarp();
+        if (lane < 4) sh.q[head][ch] = e;
+        if (++head == DM) head = 0;
+        __syncwarp();
+      } else {
+        float p[4];
+        p[0] = __shfl_sync(FULL, e, 0); p[1] = __shfl_sync(FULL, e, 1); p[2] = __shfl_sync(FULL, e, 2); p[3] = __shfl_sync(FULL, e, 3);
+        pq.offer(p, yDiff);
       }
-    }
 
-    // ---- error of this pixel and its shaping (GC:236-264); lanes 0..2 shape r, g, b
-    c2 = sh.pal[qi];
-    const int cv[4] = {c_red(c2), c_green(c2), c_blue(c2), c_alpha(c2)};
-    const int pix4[4] = {r_pix, g_pix, b_pix, a_pix};
-    float e = (float)(pix4[ch] - cv[ch]);
-    const bool denoise = plen > 2;
-    const bool diffuse = bn[bidx & 4095] > thresold;
-    const double yDiff = sorted ? y_diff(pixel, c2, lut) : 1.0;
-    const bool illusion = !diffuse && bn[j2i(yDiff * 4096) & 4095] > thresold;
-    bool unacc = false;
-    if (denoise && ch < 3) {
-      if (fabsf(e) >= (float)ditherMax) {
-        if (sorted && useSal) unacc = true;
-        if (diffuse) e = (float)nqm::nq_tanh((double)(e / maxErr * 20.f)) * (float)(ditherMax - 1);
-        else if (illusion) e = (float)((double)(e / maxErr) * yDiff) * (float)(ditherMax - 1);
-        else e /= (float)(1 + nqm::sqrt_((double)ditherMax));
-      }
-      if (sorted && !useSal && fabsf(e) >= (float)DM) unacc = true;
+      const uint32_t res = (dither || plen <= 32) ? sh.pal[qi] : (uint32_t)qi;   // GC:278-279
+      if ((int)lane == j) myOut = res;
     }
-    const bool unaccepted = (__ballot_sync(FULL, unacc) & 7u) != 0;
-
-    if (unaccepted) {   // GC:266-274
-      if (useSal) qi = dither_pixel(E, x, y, pixel, c2, beta, qi);
-      else if (y_diff(pixel, c2, lut) > 3 && u_diff(pixel, c2) > 3) {
-        const float strength = 1 / 3.f;
-        c2 = bn_diffuse(pixel, sh.pal[qi], strength, strength, x, y, bn);
-        qi = lookup(E, c2, bidx);
-      }
+    if ((int)lane < cnt) {
+      const int bidx = (int)(cur.xy & 0xFFFF) + (int)(cur.xy >> 16) * width;
+      out[bidx] = myOut;
     }
-
-    // ---- errorq.add(error) (GC:276)
-    if (!sorted) {
-      __syncwarp();
-      if (lane < 4) sh.q[head][ch] = e;
-      if (++head == DM) head = 0;
-      __syncwarp();
-    } else {
-      float p[4];
-      p[0] = __shfl_sync(FULL, e, 0); p[1] = __shfl_sync(FULL, e, 1); p[2] = __shfl_sync(FULL, e, 2); p[3] = __shfl_sync(FULL, e, 3);
-      pq.offer(p, yDiff);
-    }
-
-    if (lane == 0) out[bidx] = (dither || plen <= 32) ? sh.pal[qi] : (uint32_t)qi;   // GC:278-279
   }
 
   // ---- BlueNoise.dither second pass (PQ:400-401, PL:511-515, BN:207-222); memo and RNG carry over
   if (!dither && plen > 32) {
     __syncwarp();
+    __threadfence_block();
     const float weight = I.bnWeight, strength = 1 / 3.f;
-    const int height = I.height;
-    for (int y = 0; y < height; ++y)
-      for (int x = 0; x < width; ++x) {
-        const int bidx = x + y * width;
-        const uint32_t pixel = eff_pixel(in[bidx], fixA0);
-        uint32_t qv = 0;
-        if (lane == 0) qv = out[bidx];
-        qv = __shfl_sync(FULL, qv, 0);
-        const uint32_t c1 = bn_diffuse(pixel, sh.pal[qv], weight, strength, x, y, bn);
+    for (int n0 = 0; n0 < npix; n0 += 32) {
+      const int n = n0 + (int)lane;
+      uint32_t px = 0, qv = 0;
+      if (n < npix) { px = eff_pixel(in[n], fixA0); qv = out[n]; }
+      uint32_t myOut = 0;
+      const int cnt = min(32, npix - n0);
+      for (int j = 0; j < cnt; ++j) {
+        const int bidx = n0 + j, x = bidx % width, y = bidx / width;
+        const uint32_t pixel = __shfl_sync(FULL, px, j);
+        const uint32_t q0 = __shfl_sync(FULL, qv, j);
+        const uint32_t c1 = bn_diffuse(pixel, sh.pal[q0], weight, strength, x, y, bn);
         const int qi = lookup(E, c1, bidx);
-        if (lane == 0) out[bidx] = sh.pal[qi];
+        if ((int)lane == j) myOut = sh.pal[qi];
       }
+      if (n < npix) out[n] = myOut;
+    }
   }
   if (lane == 0) I.rngDraws = E.draws;
 }

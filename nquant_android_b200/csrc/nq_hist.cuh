@@ -10,6 +10,23 @@ namespace nq {
 __device__ double g_gammaLut[256];          // gammaToLinear(v), v = 0..255 (CL:71-75)
 __device__ signed char g_blueNoise[4096];   // TELL_BLUE_NOISE (BN:13-178)
 
+// RGB -> CIELAB for every 24-bit colour: (L, A, B, -) as float4. The reference memoizes getLab per colour
+// in a HashMap (PL:34-42); with 180 GB of HBM the whole function fits in a 256 MiB table built once per
+// device, so the pixel passes gather 16 bytes instead of evaluating three pow() per pixel.
+__device__ const float4* g_labLut;
+
+__global__ void __launch_bounds__(256) k_build_lab_lut(float4* lut) {
+  const unsigned c = blockIdx.x * blockDim.x + threadIdx.x;   // 65536 blocks x 256
+  Lab4 l = rgb2lab(0xFF000000u | c, g_gammaLut);
+  lut[c] = make_float4(l.L, l.A, l.B, 0.f);
+}
+__device__ __forceinline__ Lab4 lab_of(uint32_t c) {
+  const float4 v = __ldg(&g_labLut[c & 0xFFFFFFu]);
+  Lab4 o;
+  o.alpha = (float)(c >> 24); o.L = v.x; o.A = v.y; o.B = v.z;
+  return o;
+}
+
 __global__ void k_init_tables(const signed char* bn) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < 256) g_gammaLut[t] = gamma_to_linear(t);
@@ -339,7 +356,7 @@ __global__ void __launch_bounds__(256) k_lab_bin_sum(const NqImage* imgs, const 
     for (unsigned base = beg; base < end; base += 32) {
       const unsigned i = base + lane;
       Lab4 v = {0.f, 0.f, 0.f, 0.f};
-      if (i < end) v = rgb2lab(S.sortB[i], g_gammaLut);
+      if (i < end) v = lab_of(S.sortB[i]);
       const int cnt = (int)min(32u, end - base);
       for (int j = 0; j < cnt; ++j) {
         ac += __shfl_sync(0xffffffffu, v.alpha, j);
@@ -428,7 +445,7 @@ __global__ void __launch_bounds__(1024) k_finalize_lab(NqImage* imgs, const NqSl
 __global__ void __launch_bounds__(256) k_saliency(const NqImage* imgs, const NqSlot* slots) {
   const int img = blockIdx.y;
   const NqImage& I = imgs[img];
-  if (!I.gUseSal) return;
+  if (!I.gUseSal || !slots[img].sal) return;
   const int n = I.npix;
   const uint32_t* in = slots[img].in;
   float* sal = slots[img].sal;
@@ -439,7 +456,7 @@ __global__ void __launch_bounds__(256) k_saliency(const NqImage* imgs, const NqS
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     uint32_t p = eff_pixel(in[i], fixA0);
     if (replaced) p = lab_src_pixel(p, tc);
-    Lab4 l = rgb2lab(p, g_gammaLut);
+    Lab4 l = lab_of(p);
     sal[i] = saliencyBase + (1 - saliencyBase) * l.L / 100.f * l.alpha / 255.f;
   }
 }
