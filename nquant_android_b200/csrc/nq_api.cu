@@ -398,7 +398,9 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
   }
   if (kind == NQ_KIND_LAB && c->debug) { nq::k_saliency<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches; }
   mark(5);
-  nq::k_dither<<<n, 32, 0, st>>>(c->dImgs, c->dSlots, dOrder); ++c->launches;
+  // each kernel returns at once for images of the other queue mode (decided on the device)
+  nq::k_dither_fifo<<<n, 32, 0, st>>>(c->dImgs, c->dSlots, dOrder); ++c->launches;
+  nq::k_dither_sorted<<<n, 32, 0, st>>>(c->dImgs, c->dSlots, dOrder); ++c->launches;
   mark(6);
   CU(cudaGetLastError());
   c->lastImgs.resize(n);

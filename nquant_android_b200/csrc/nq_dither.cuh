@@ -22,12 +22,17 @@ namespace nq {
 struct WarpShared {
   uint32_t pal[NQ_MAXK];
   float4 palLab[NQ_MAXK];     // alpha, L, A, B of palette[i] (getLab(c2), PL:352)
-  float q[NQ_MAXQ][4];        // error queue: FIFO ring, or the PriorityQueue backing array
-  double qy[16];              // yDiff of PriorityQueue entries
-  float w[NQ_MAXQ];           // current weights[]
+  double lut[256];            // gammaToLinear(v) (CL:71-75), copy of g_gammaLut
+  signed char bn[4096];       // TELL_BLUE_NOISE (BN:13-178), copy of g_blueNoise
   // PnnLABQuantizer.closestColorIndex cost split per channel: T?[v] = cost of a channel difference of
   // |v| (see closest_lab); Ta only when the image is semi-transparent
   double Tr[256], Tg[256], Tb[256], Ta[256];
+};
+// java.util.PriorityQueue state of the sortedByYDiff mode (GC:87-94)
+struct SortedShared {
+  float q[16][4];             // backing array of ErrorBoxes
+  double qy[16];              // their yDiff
+  float w[8];                 // current weights[] (length 1, 3 or 7)
 };
 
 struct Env {
@@ -328,8 +333,8 @@ __device__ int dither_pixel(Env& E, int x, int y, int bidx, uint32_t pixel, floa
   const int plen = E.plen, margin = E.margin;
   const double weight = E.gWeight;
   const uint32_t qcol = E.sh->pal[qcur];
-  const signed char* bn = g_blueNoise;
-  const double* lut = g_gammaLut;
+  const signed char* bn = E.sh->bn;
+  const double* lut = E.sh->lut;
   const int r_pix = c_red(c2), g_pix = c_green(c2), b_pix = c_blue(c2), a_pix = c_alpha(c2);
   const float strength = 1 / 3.f;
   const int acceptedDiff = max(2, plen - margin);
@@ -407,54 +412,6 @@ __device__ __forceinline__ float tanh_to_float(double x) {
   return (float)nqm::nq_tanh(x);
 }
 
-// java.util.PriorityQueue over the shared arrays, comparator Double.compare(o2.yDiff, o1.yDiff)
-// (GC:87-94): "x before e" <=> x.yDiff > e.yDiff. All lanes run the same steps; lane 0 stores.
-struct PQ {
-  WarpShared* sh;
-  int n;
-  __device__ __forceinline__ void put(int k, const float* p, double yd) {
-    if (lane_id() == 0) { sh->q[k][0] = p[0]; sh->q[k][1] = p[1]; sh->q[k][2] = p[2]; sh->q[k][3] = p[3]; sh->qy[k] = yd; }
-  }
-  __device__ __forceinline__ void move(int dst, int src) {
-    float p[4] = {sh->q[src][0], sh->q[src][1], sh->q[src][2], sh->q[src][3]};
-    double yd = sh->qy[src];
-    __syncwarp();
-    put(dst, p, yd);
-    __syncwarp();
-  }
-  __device__ void offer(const float* p, double yd) {   // siftUp
-    int k = n++;
-    while (k > 0) {
-      int parent = (k - 1) >> 1;
-      double pe = sh->qy[parent];
-      if (!(yd > pe)) break;            // cmp(x, e) >= 0
-      move(k, parent);
-      k = parent;
-    }
-    __syncwarp();
-    put(k, p, yd);
-    __syncwarp();
-  }
-  __device__ void poll() {              // remove head, siftDown the last element
-    int last = --n;
-    if (last == 0) return;
-    float p[4] = {sh->q[last][0], sh->q[last][1], sh->q[last][2], sh->q[last][3]};
-    double yd = sh->qy[last];
-    __syncwarp();
-    int k = 0, half = last >> 1;
-    while (k < half) {
-      int child = (k << 1) + 1, right = child + 1;
-      double cy = sh->qy[child];
-      if (right < last) { double ry = sh->qy[right]; if (ry > cy) { child = right; cy = ry; } }   // cmp(c, right) > 0
-      if (!(cy > yd)) break;            // cmp(x, c) <= 0
-      move(k, child);
-      k = child;
-    }
-    put(k, p, yd);
-    __syncwarp();
-  }
-};
-
 // -------------------------------------------------------------------------------------------------
 // GilbertCurve constructor constants + initWeights (GC:50-112, 336-354), one thread per image
 // -------------------------------------------------------------------------------------------------
@@ -531,13 +488,16 @@ __global__ void k_dither_setup(NqImage* imgs, const NqSlot* slots, int nimg) {
 }
 
 // -------------------------------------------------------------------------------------------------
-// the serial pass: Gilbert-order error diffusion (GC:187-280), then BlueNoise.dither (BN:207-222)
+// The serial pass: Gilbert-order error diffusion (GC:187-280), then BlueNoise.dither (BN:207-222)
 // when dither == false and the palette has more than 32 entries. One warp per image.
 //
 // The warp walks the curve in blocks of 32 pixels. Everything that does not depend on the running
 // error is gathered for a whole block at once, one pixel per lane, a block ahead of its use: the
-// visiting order, the source pixel, its saliency (from the Lab table) and its luminance. Results are
-// kept one per lane and written back per block. Only the serial recurrence stays on the chain.
+// visiting order, the source pixel, its saliency (from the Lab table) and its luminance.
+//
+// Two kernels share the code below: k_dither_fifo for the ArrayDeque queue (sortedByYDiff == false)
+// and k_dither_sorted for the PriorityQueue queue (GC:87-94). Each returns at once for images of the
+// other mode.
 // -------------------------------------------------------------------------------------------------
 struct PixBlock { uint32_t xy, px; float sal; double ypix; };
 
@@ -545,19 +505,19 @@ __device__ __forceinline__ int chan(uint32_t c, int ch) {   // ErrorBox channel 
   return (int)((c >> (ch == 3 ? 24 : 16 - 8 * ch)) & 0xFF);
 }
 
-__global__ void __launch_bounds__(32) k_dither(NqImage* imgs, const NqSlot* slots, const uint32_t* order) {
-  __shared__ WarpShared sh;
-  const int img = blockIdx.x;
-  NqImage& I = imgs[img];
-  const NqSlot& S = slots[img];
-  const unsigned lane = lane_id();
-  const int npix = I.npix, width = I.width, plen = I.paletteLen;
-  if (plen <= 0 || I.error) return;
-  const uint32_t* in = S.in;
-  uint32_t* out = S.out;
-  const int fixA0 = I.fixA0;
-
+struct DitherCtx {
   Env E;
+  const uint32_t* in;
+  uint32_t* out;
+  int npix, width, fixA0;
+  bool salReplaced;
+};
+
+// common prologue: palette, tables and the constants of the GilbertCurve object
+__device__ __forceinline__ void dither_prologue(NqImage& I, const NqSlot& S, WarpShared& sh, DitherCtx& D) {
+  const unsigned lane = lane_id();
+  Env& E = D.E;
+  const int plen = I.paletteLen;
   E.sh = &sh;
   E.plen = plen; E.margin = I.gMargin; E.thresold = I.gThresold; E.DM = I.gDitherMaxQ; E.ditherMax = I.gDitherMax;
   E.lab = I.kind == NQ_KIND_LAB; E.dither = I.dither != 0; E.semi = I.hasSemi != 0; E.hasTrans = I.transIdx >= 0;
@@ -569,56 +529,430 @@ __global__ void __launch_bounds__(32) k_dither(NqImage* imgs, const NqSlot* slot
   E.memo = S.memo;
   E.rng.set_seed(I.seed);
   E.draws = 0;
-  E.width = width;
-
+  E.width = I.width;
+  D.in = S.in; D.out = S.out; D.npix = I.npix; D.width = I.width; D.fixA0 = I.fixA0;
+  D.salReplaced = I.nmax < 128 && I.nmax > 2;   // which pixel feeds getLab for the saliency (PL:141-156 vs PL:503-506)
+  for (int i = lane; i < 256; i += 32) sh.lut[i] = g_gammaLut[i];
+  for (int i = lane; i < 4096; i += 32) sh.bn[i] = g_blueNoise[i];
   for (int i = lane; i < plen; i += 32) {
     uint32_t pc = I.palette[i];
     sh.pal[i] = pc;
     if (E.lab) { Lab4 l = lab_of(pc); sh.palLab[i] = make_float4(l.alpha, l.L, l.A, l.B); }
   }
-  const int DM = E.DM;
-  if (lane < NQ_MAXQ) sh.w[lane] = lane < (unsigned)DM ? I.gWeights[lane] : 0.f;
-  for (int i = lane; i < NQ_MAXQ * 4; i += 32) sh.q[i >> 2][i & 3] = 0.f;
-  if (lane < 16) sh.qy[lane] = 0;
   __syncwarp();
   if (E.lab && plen > 4) closest_lab_tables(E);
+}
 
-  const bool sorted = E.sorted, useSal = E.useSal, dither = E.dither, gHasAlpha = E.gHasAlpha;
-  const int ch = lane & 3;
-  const int thresold = E.thresold, ditherMax = E.ditherMax, margin = E.margin;
-  const float beta = E.beta;
-  const double* lut = g_gammaLut;
-  const signed char* bn = g_blueNoise;
-  const bool salReplaced = I.nmax < 128 && I.nmax > 2;   // which pixel feeds getLab for the saliency (PL:141-156 vs PL:503-506)
-  const uint32_t transColor = I.transColor;
-  int head = 0;            // FIFO: slot of the oldest entry (the queue always holds DM entries)
-  PQ pq{&sh, 0};
-  int wlen = 0;            // weights.length in sorted mode (0, 1, 3, 7)
-
-  auto fetch = [&](int n0) {
-    PixBlock b;
-    b.xy = 0; b.px = 0; b.sal = 0.f; b.ypix = 0.0;
-    const int n = n0 + (int)lane;
-    if (n < npix) {
-      b.xy = order[n];
-      const int bidx = (int)(b.xy & 0xFFFF) + (int)(b.xy >> 16) * width;
-      b.px = eff_pixel(in[bidx], fixA0);
-      if (useSal) {
-        uint32_t sp = b.px;
-        if (salReplaced && (sp >> 24) <= 0xF) sp = transColor;
-        const Lab4 l = lab_of(sp);
-        const float saliencyBase = .1f;
-        b.sal = saliencyBase + (1 - saliencyBase) * l.L / 100.f * l.alpha / 255.f;
-      }
-      b.ypix = color_y(b.px, lut);
+// one pixel per lane: visiting order, source pixel, saliency, luminance of pixels [n0, n0 + 32)
+__device__ __forceinline__ PixBlock fetch_block(const DitherCtx& D, const uint32_t* order, int n0) {
+  PixBlock b;
+  b.xy = 0; b.px = 0; b.sal = 0.f; b.ypix = 0.0;
+  const int n = n0 + (int)lane_id();
+  if (n < D.npix) {
+    b.xy = order[n];
+    const int bidx = (int)(b.xy & 0xFFFF) + (int)(b.xy >> 16) * D.width;
+    b.px = eff_pixel(D.in[bidx], D.fixA0);
+    if (D.E.useSal) {
+      uint32_t sp = b.px;
+      if (D.salReplaced && (sp >> 24) <= 0xF) sp = D.E.transColor;
+      const Lab4 l = lab_of(sp);
+      const float saliencyBase = .1f;
+      b.sal = saliencyBase + (1 - saliencyBase) * l.L / 100.f * l.alpha / 255.f;
     }
-    return b;
+    b.ypix = color_y(b.px, D.E.sh->lut);
+  }
+  return b;
+}
+
+// the quantization branch of diffusePixel (GC:211-229), warp-cooperative: every lane holds the same
+// arguments. c2 = the error-diffused colour.
+__device__ int quantize_pixel(Env& E, int x, int y, int bidx, uint32_t pixel, float sal, double ypix, uint32_t c2) {
+  const int plen = E.plen, margin = E.margin;
+  const int a_pix = c_alpha(c2);
+  int qi;
+  if (E.useSal && E.dither && !E.sorted && (!E.gHasAlpha || c_alpha(pixel) < a_pix)) {
+    if ((plen >= 256 && sal > .99f) || (E.gHasAlpha && (double)(c_alpha(pixel) - a_pix) < (.5 * margin)))
+      qi = lookup(E, c2, bidx);
+    else
+      qi = dither_pixel(E, x, y, bidx, pixel, sal, ypix, c2, E.beta, 0);    // qPixels[bidx] is still 0 here (GC:136,216)
+  } else if (plen <= 32 && a_pix > 0xF0) {
+    qi = lookup(E, c2, bidx);
+    const int acceptedDiff = max(2, plen - margin);
+    if (E.useSal && (y_diff_pre(ypix, c2, E.sh->lut) > (double)acceptedDiff || u_diff(pixel, c2) > (double)(2 * acceptedDiff))) {
+      const float strength = 1 / 3.f;
+      c2 = bn_diffuse(pixel, E.sh->pal[qi], 1 / sal, strength, x, y, E.sh->bn);
+      qi = lookup(E, c2, bidx);
+    }
+  } else
+    qi = lookup(E, c2, bidx);
+  return qi;
+}
+
+// BlueNoise.dither second pass (PQ:400-401, PL:511-515, BN:207-222); memo and RNG carry over
+__device__ void bluenoise_pass(NqImage& I, DitherCtx& D) {
+  Env& E = D.E;
+  const unsigned lane = lane_id();
+  const int npix = D.npix, width = D.width;
+  __syncwarp();
+  __threadfence_block();
+  const float weight = I.bnWeight, strength = 1 / 3.f;
+  for (int n0 = 0; n0 < npix; n0 += 32) {
+    const int n = n0 + (int)lane;
+    uint32_t px = 0, qv = 0;
+    if (n < npix) { px = eff_pixel(D.in[n], D.fixA0); qv = D.out[n]; }
+    uint32_t myOut = 0;
+    const int cnt = min(32, npix - n0);
+    for (int j = 0; j < cnt; ++j) {
+      const int bidx = n0 + j, x = bidx % width, y = bidx / width;
+      const uint32_t pixel = __shfl_sync(FULL, px, j);
+      const uint32_t q0 = __shfl_sync(FULL, qv, j);
+      const uint32_t c1 = bn_diffuse(pixel, E.sh->pal[q0], weight, strength, x, y, E.sh->bn);
+      const int qi = lookup(E, c1, bidx);
+      if ((int)lane == j) myOut = E.sh->pal[qi];
+    }
+    if (n < npix) D.out[n] = myOut;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// FIFO queue mode. The ArrayDeque always holds DITHER_MAX boxes (initWeights pushes DITHER_MAX
+// empty ones before the first pixel, GC:345,358-359; afterwards every pixel polls one and adds one),
+// so the sum of GC:193-204 for pixel n is
+//     ((pixel_n + e[n-DM] w[0]) + e[n-DM+1] w[1]) + ... + e[n-1] w[DM-1]        (e[t] = 0 for t < 0)
+// in exactly that float order. Only the LAST term depends on the previous pixel. The partial sums are
+// kept in registers as a systolic pipeline: at step n lane k holds the sum of pixel n + DM-1-k through
+// tap k, every lane adds e[n-1] w[k] to what its left neighbour held one step earlier, and the sum of
+// pixel n through tap DM-2 is broadcast before e[n-1] is known. maxErr (max over all partial sums,
+// GC:192,200-201) travels with the sums. Every lane redundantly finishes the four channels of pixel n,
+// so nothing is shuffled on the dependency chain.
+//
+// CIELAB images with a saliency map mostly take GilbertCurve.ditherPixel (GC:125-185), which for
+// palettes with palette.length - margin > 50 replaces the error-diffused colour by
+// BlueNoise.diffuse(pixel, palette[0], kappa) BEFORE the palette lookup: Y_Diff <= 100 < 2 acceptedDiff
+// makes GC:137 always true. The looked-up index then does not depend on the running error at all, so
+// the lookups of a whole block are done one pixel per lane ("pre-lookup"), consuming the
+// java.util.Random stream and the first-seen memo in curve order, and only the error arithmetic
+// stays on the serial chain. Blocks containing a pixel whose lookup does consume the diffused colour
+// fall back to the cooperative per-pixel path.
+// -------------------------------------------------------------------------------------------------
+
+// ditherPixel (GC:125-185) with qPixels[bidx] == 0, evaluated without the error-diffused colour.
+// Returns false when the reference's result would read it. The caller guarantees
+// plen <= 4 || 2 * acceptedDiff > 101 (so GC:137 holds for any c2).
+__device__ bool dither_pixel_pre(const Env& E, int x, int y, uint32_t pixel, float sal, double ypix, uint32_t* out) {
+  const int plen = E.plen, margin = E.margin;
+  const double weight = E.gWeight;
+  const float beta = E.beta;
+  const uint32_t qcol = E.sh->pal[0];
+  const signed char* bn = E.sh->bn;
+  const double* lut = E.sh->lut;
+  const float strength = 1 / 3.f;
+  const int acceptedDiff = max(2, plen - margin);
+  uint32_t c2;
+  if (plen <= 4 && sal > .2f && sal < .25f)
+    c2 = bn_diffuse(pixel, qcol, beta * 2 / sal, strength, x, y, bn);
+  else if (plen > 64) {
+    float kappa = sal < .6f ? beta * .15f / sal : beta * .4f / sal;
+    c2 = bn_diffuse(pixel, qcol, kappa, strength, x, y, bn);
+  } else if (plen > 16 && weight < .005)
+    c2 = bn_diffuse(pixel, qcol, beta * normal_distribution(sal, .5f) + beta, strength, x, y, bn);
+  else
+    c2 = bn_diffuse(pixel, qcol, beta * .5f / sal, strength, x, y, bn);
+
+  const double gamma = (plen <= 32 && weight < .01 && weight > .007) ? (double)(1 - beta) : (double)beta;
+  if (plen > 4 && y_diff_pre(ypix, c2, lut) > (gamma * acceptedDiff)) return false;   // GC:149-172 reads r_pix..a_pix
+  if (E.DM < 16 && plen > 4 && sal < .6f && y_diff_pre(ypix, c2, lut) > (double)(margin - 1)) return false;   // GC:175
+  if (plen > 32 && (double)sal > .95) {
+    float kappa = beta * fmaxf(.05f, .75f - plen / 128.f) * sal;
+    c2 = bn_diffuse(pixel, qcol, kappa, strength, x, y, bn);
+  }
+  *out = c2;
+  return true;
+}
+
+// PnnLABQuantizer.closestColorIndex top-2 scan (PL:418-458), one colour per lane over the whole palette.
+// Keys are floor(err) << 8 | index: the two smallest keys are the reference's closest[0..3].
+#define K2_NONE 0xFFFFFFFFu
+__device__ __forceinline__ void closest_scan_lane(const Env& E, uint32_t c, unsigned& k0, unsigned& k1) {
+  const WarpShared& sh = *E.sh;
+  const int ca = c_alpha(c), cr = c_red(c), cg = c_green(c), cb = c_blue(c);
+  k0 = K2_NONE; k1 = K2_NONE;
+  // a + 1.5 * 2^32 has an ulp of 2^-20: its mantissa is a in 2^-20 fixed point (rounded to nearest)
+  const double MAGIC = 6442450944.0;
+#pragma unroll 4
+  for (int k = 0; k < E.plen; ++k) {
+    const uint32_t c2 = sh.pal[k];
+    double a = sh.Tr[abs(c_red(c2) - cr)] + sh.Tg[abs(c_green(c2) - cg)] + sh.Tb[abs(c_blue(c2) - cb)];
+    if (E.semi) a += sh.Ta[abs(c_alpha(c2) - ca)];
+    const long long bits = __double_as_longlong(a + MAGIC);
+    const unsigned lo = (unsigned)bits, hi = (unsigned)(bits >> 32) & 0x7FFFFu;
+    int d = (int)__funnelshift_r(lo, hi, 20);
+    const unsigned fr = lo & 0xFFFFFu;
+    // the table sum is within 2e-14 relative of the reference's 12/13-term sum (see closest_lab_tables):
+    // only within 2^-19 of an integer can the floors differ
+    if (((fr + 2u) & 0xFFFFFu) < 4u) d = j2i(closest_lab_err(E, c2, ca, cr, cg, cb));
+    const unsigned key = ((unsigned)d << 8) | (unsigned)k;
+    const unsigned t = max(key, k0);
+    k0 = min(key, k0);
+    k1 = min(k1, t);
+  }
+}
+
+// the ordered (n+1)-th accepted value of java.util.Random.nextInt(32767) is a pure function of the seed
+// and n: a block's draws are generated in order by every lane, each lane keeping its own.
+
+__global__ void __launch_bounds__(32) k_dither_fifo(NqImage* imgs, const NqSlot* slots, const uint32_t* order) {
+  __shared__ WarpShared sh;
+  const int img = blockIdx.x;
+  NqImage& I = imgs[img];
+  const NqSlot& S = slots[img];
+  const unsigned lane = lane_id();
+  const int plen = I.paletteLen;
+  if (plen <= 0 || I.error || I.gSorted) return;
+  DitherCtx D;
+  dither_prologue(I, S, sh, D);
+  Env& E = D.E;
+  const int npix = D.npix, width = D.width;
+  uint32_t* out = D.out;
+
+  const int DM = E.DM;
+  const bool useSal = E.useSal, dither = E.dither;
+  const int thresold = E.thresold, ditherMax = E.ditherMax, margin = E.margin;
+  const signed char* bn = sh.bn;
+  const float wk = lane < (unsigned)DM ? I.gWeights[lane] : 0.f;   // this lane's tap
+  const float wLast = I.gWeights[DM - 1];
+  const float fDitherMax = (float)ditherMax, fDitherMax1 = (float)(ditherMax - 1);
+  const float divisor = (float)(1 + nqm::sqrt_((double)ditherMax));
+  const bool denoise = plen > 2;
+  const bool illusion0 = bn[0] > thresold;          // yDiff == 1: bn[(int)(4096.0) & 4095] (GC:251-252)
+  const int acceptedDiff = max(2, plen - margin);
+  // images whose ditherPixel lookups do not read the diffused colour (see above)
+  const bool preImg = E.lab && useSal && dither && !E.gHasAlpha && (plen <= 4 || 2 * acceptedDiff > 101);
+
+  // systolic state: lane k carries the sum of some pixel through tap k, and its running maximum
+  float P0 = 0.f, P1 = 0.f, P2 = 0.f, P3 = 0.f, M = (float)(DM - 1);
+  float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;    // shaped error of the previous pixel (r, g, b, a)
+
+  // one systolic step: inject `px` at lane 0, every lane adds e * w[k]
+  auto advance = [&](uint32_t injectPx) {
+    float q0 = __shfl_up_sync(FULL, P0, 1), q1 = __shfl_up_sync(FULL, P1, 1), q2 = __shfl_up_sync(FULL, P2, 1), q3 = __shfl_up_sync(FULL, P3, 1);
+    float qm = __shfl_up_sync(FULL, M, 1);
+    if (lane == 0) {
+      q0 = (float)c_red(injectPx); q1 = (float)c_green(injectPx); q2 = (float)c_blue(injectPx); q3 = (float)c_alpha(injectPx);
+      qm = (float)(DM - 1);
+    }
+    P0 = q0 + e0 * wk; P1 = q1 + e1 * wk; P2 = q2 + e2 * wk; P3 = q3 + e3 * wk;
+    M = fmaxf(fmaxf(fmaxf(qm, P0), fmaxf(P1, P2)), P3);
   };
 
-  PixBlock nxt = fetch(0);
+  PixBlock nxt = fetch_block(D, order, 0);
+  // fill the pipeline: pixels 0 .. DM-2 enter with zero errors behind them
+  for (int s = 0; s < DM - 1; ++s) advance(__shfl_sync(FULL, nxt.px, s));
+
   for (int n0 = 0; n0 < npix; n0 += 32) {
     const PixBlock cur = nxt;
-    if (n0 + 32 < npix) nxt = fetch(n0 + 32);
+    nxt = fetch_block(D, order, n0 + 32);
+    const int cnt = min(32, npix - n0);
+    const bool mine = (int)lane < cnt;
+    const int myX = cur.xy & 0xFFFF, myY = cur.xy >> 16, myBidx = myX + myY * width;
+    const unsigned diffMask = __ballot_sync(FULL, mine && bn[myBidx & 4095] > thresold);
+
+    // ---- pre-lookup of the whole block (one pixel per lane)
+    bool blockPre = false;
+    uint32_t preCol = 0;
+    if (preImg) {
+      uint32_t c = 0;
+      bool ok = true;
+      if (mine) {
+        if (plen >= 256 && cur.sal > .99f) ok = false;          // GC:214-215: looks up the diffused colour
+        else ok = dither_pixel_pre(E, myX, myY, cur.px, cur.sal, cur.ypix, &c);
+      }
+      blockPre = __all_sync(FULL, ok);
+      if (blockPre) {
+        const int ca = c_alpha(c);
+        const bool viaClosest = mine && plen > 4 && ca > 0xF;    // PL:484-487, PL:407-408
+        unsigned k0 = K2_NONE, k1 = K2_NONE;
+        if (__any_sync(FULL, viaClosest)) closest_scan_lane(E, c, k0, k1);
+        const int c0 = k0 == K2_NONE ? 0 : (int)(k0 & 255u), d0 = k0 == K2_NONE ? T2_NONE : (int)(k0 >> 8);
+        const int c1 = k1 == K2_NONE ? c0 : (int)(k1 & 255u), d1 = k1 == K2_NONE ? T2_NONE : (int)(k1 >> 8);
+        const bool draw = viaClosest && d0 != 0;                  // short-circuit: no draw when closest[2] == 0 (PL:467)
+        const unsigned dm = __ballot_sync(FULL, draw);
+        const int myDraw = __popc(dm & ((1u << lane) - 1u)), total = __popc(dm);
+        int r = 0;
+        for (int t = 0; t < total; ++t) {
+          const int v = E.rng.next_int(32767);
+          if (myDraw == t) r = v;
+        }
+        E.draws += (unsigned long long)total;
+        int idx = 1;
+        if (d0 == 0) idx = 0;
+        else {
+          const int sum = (int)((unsigned)d1 + (unsigned)d0);
+          if ((r % sum) <= d1) idx = 0;
+        }
+        const int ci = idx ? c1 : c0, ei = idx ? d1 : d0;
+        int qi = ci;
+        bool needNear = mine && (!viaClosest || ei >= plen || ci == 0 || c_alpha(sh.pal[ci]) < ca);   // PL:470-472
+        if (E.isNano && needNear) {   // memo entries never change once written: hits can be read out of order
+          const unsigned short got = E.memo[color_index(c, E.semi, E.hasTrans)];
+          if (got != 0xFFFF) { qi = got; needNear = false; }
+        }
+        unsigned nm = __ballot_sync(FULL, needNear);
+        while (nm) {                  // misses in curve order (first-seen colour fixes a bucket, PL:332-335,402)
+          const int L = __ffs(nm) - 1;
+          nm &= nm - 1;
+          const int res = nearest_lab(E, __shfl_sync(FULL, c, L));
+          if ((int)lane == L) qi = res;
+        }
+        preCol = sh.pal[qi];
+      }
+    }
+
+    uint32_t myOut = preCol;
+    for (int j = 0; j < cnt; ++j) {
+      // ---- independent of the previous pixel's error: sum of this pixel through tap DM-2
+      const float b0 = __shfl_sync(FULL, P0, DM - 2), b1 = __shfl_sync(FULL, P1, DM - 2), b2 = __shfl_sync(FULL, P2, DM - 2), b3 = __shfl_sync(FULL, P3, DM - 2);
+      const float bm = __shfl_sync(FULL, M, DM - 2);
+      const uint32_t pixel = __shfl_sync(FULL, cur.px, j);
+      const int jn = j + DM - 1;
+      const uint32_t injA = __shfl_sync(FULL, cur.px, jn & 31), injB = __shfl_sync(FULL, nxt.px, jn & 31);
+      const uint32_t inject = jn < 32 ? injA : injB;
+
+      // ---- last tap, clamp (GC:199-211)
+      const float a0 = b0 + e0 * wLast, a1 = b1 + e1 * wLast, a2 = b2 + e2 * wLast, a3 = b3 + e3 * wLast;
+      const float maxErr = fmaxf(fmaxf(fmaxf(bm, a0), fmaxf(a1, a2)), a3);
+      const int r_pix = j2i(dmin(255.0, dmax((double)a0, 0.0))), g_pix = j2i(dmin(255.0, dmax((double)a1, 0.0)));
+      const int b_pix = j2i(dmin(255.0, dmax((double)a2, 0.0))), a_pix = j2i(dmin(255.0, dmax((double)a3, 0.0)));
+      advance(inject);     // uses e0..e3 of the previous pixel; must precede their update below
+
+      // ---- quantize (GC:211-229)
+      uint32_t pc;
+      if (blockPre) pc = __shfl_sync(FULL, preCol, j);
+      else {
+        const uint32_t xy = __shfl_sync(FULL, cur.xy, j);
+        const int x = xy & 0xFFFF, y = xy >> 16;
+        const int qi = quantize_pixel(E, x, y, x + y * width, pixel, __shfl_sync(FULL, cur.sal, j), shfl_d(cur.ypix, j),
+                                      c_argb(a_pix, r_pix, g_pix, b_pix));
+        pc = sh.pal[qi];
+        const uint32_t res = (dither || plen <= 32) ? pc : (uint32_t)qi;   // GC:278-279
+        if ((int)lane == j) myOut = res;
+      }
+
+      // ---- error of this pixel and its shaping (GC:236-264); yDiff == 1 in this mode
+      e0 = (float)(r_pix - c_red(pc)); e1 = (float)(g_pix - c_green(pc)); e2 = (float)(b_pix - c_blue(pc)); e3 = (float)(a_pix - c_alpha(pc));
+      if (denoise) {
+        const bool s0 = fabsf(e0) >= fDitherMax, s1 = fabsf(e1) >= fDitherMax, s2 = fabsf(e2) >= fDitherMax;
+        if (s0 || s1 || s2) {
+          if ((diffMask >> j) & 1u) {
+            if (s0) e0 = tanh_to_float((double)(e0 / maxErr * 20.f)) * fDitherMax1;
+            if (s1) e1 = tanh_to_float((double)(e1 / maxErr * 20.f)) * fDitherMax1;
+            if (s2) e2 = tanh_to_float((double)(e2 / maxErr * 20.f)) * fDitherMax1;
+          } else if (illusion0) {
+            if (s0) e0 = (float)((double)(e0 / maxErr) * 1.0) * fDitherMax1;
+            if (s1) e1 = (float)((double)(e1 / maxErr) * 1.0) * fDitherMax1;
+            if (s2) e2 = (float)((double)(e2 / maxErr) * 1.0) * fDitherMax1;
+          } else {
+            if (s0) e0 /= divisor;
+            if (s1) e1 /= divisor;
+            if (s2) e2 /= divisor;
+          }
+        }
+      }
+    }
+    if (mine) out[myBidx] = myOut;
+  }
+
+  if (!dither && plen > 32) bluenoise_pass(I, D);
+  if (lane == 0) I.rngDraws = E.draws;
+}
+
+// -------------------------------------------------------------------------------------------------
+// PriorityQueue mode (sortedByYDiff, GC:87-94): the queue is a binary heap ordered by yDiff; the sum
+// of GC:193-204 walks its backing array, so the order of the float additions changes with every
+// sift. The recurrence stays in shared memory and the warp splits only the four channels.
+// Steady state: 15 boxes, weights of length 7 (initWeights is re-run with sizes 1, 3, 7 on pixels
+// 2, 3, 4, each time pushing `size` empty boxes, GC:233-234,345).
+// -------------------------------------------------------------------------------------------------
+struct PQ {
+  SortedShared* sh;
+  int n;
+  __device__ __forceinline__ void put(int k, const float* p, double yd) {
+    if (lane_id() == 0) { sh->q[k][0] = p[0]; sh->q[k][1] = p[1]; sh->q[k][2] = p[2]; sh->q[k][3] = p[3]; sh->qy[k] = yd; }
+  }
+  __device__ __forceinline__ void move(int dst, int src) {
+    float p[4] = {sh->q[src][0], sh->q[src][1], sh->q[src][2], sh->q[src][3]};
+    double yd = sh->qy[src];
+    __syncwarp();
+    put(dst, p, yd);
+    __syncwarp();
+  }
+  __device__ void offer(const float* p, double yd) {   // siftUp; "x before e" <=> x.yDiff > e.yDiff
+    int k = n++;
+    while (k > 0) {
+      int parent = (k - 1) >> 1;
+      double pe = sh->qy[parent];
+      if (!(yd > pe)) break;            // cmp(x, e) >= 0
+      move(k, parent);
+      k = parent;
+    }
+    __syncwarp();
+    put(k, p, yd);
+    __syncwarp();
+  }
+  __device__ void poll() {              // remove head, siftDown the last element
+    int last = --n;
+    if (last == 0) return;
+    float p[4] = {sh->q[last][0], sh->q[last][1], sh->q[last][2], sh->q[last][3]};
+    double yd = sh->qy[last];
+    __syncwarp();
+    int k = 0, half = last >> 1;
+    while (k < half) {
+      int child = (k << 1) + 1, right = child + 1;
+      double cy = sh->qy[child];
+      if (right < last) { double ry = sh->qy[right]; if (ry > cy) { child = right; cy = ry; } }   // cmp(c, right) > 0
+      if (!(cy > yd)) break;            // cmp(x, c) <= 0
+      move(k, child);
+      k = child;
+    }
+    put(k, p, yd);
+    __syncwarp();
+  }
+};
+
+__global__ void __launch_bounds__(32) k_dither_sorted(NqImage* imgs, const NqSlot* slots, const uint32_t* order) {
+  __shared__ WarpShared sh;
+  __shared__ SortedShared qs;
+  const int img = blockIdx.x;
+  NqImage& I = imgs[img];
+  const NqSlot& S = slots[img];
+  const unsigned lane = lane_id();
+  const int plen = I.paletteLen;
+  if (plen <= 0 || I.error || !I.gSorted) return;
+  DitherCtx D;
+  dither_prologue(I, S, sh, D);
+  Env& E = D.E;
+  const int npix = D.npix, width = D.width;
+  uint32_t* out = D.out;
+
+  const int DM = E.DM;
+  for (int i = lane; i < 16 * 4; i += 32) qs.q[i >> 2][i & 3] = 0.f;
+  if (lane < 16) qs.qy[lane] = 0;
+  if (lane < 8) qs.w[lane] = 0.f;
+  __syncwarp();
+
+  const bool useSal = E.useSal, dither = E.dither;
+  const int ch = lane & 3;
+  const int thresold = E.thresold, ditherMax = E.ditherMax;
+  const float beta = E.beta;
+  const double* lut = sh.lut;
+  const signed char* bn = sh.bn;
+  PQ pq{&qs, 0};
+  int wlen = 0;            // weights.length (0, 1, 3, 7)
+
+  PixBlock nxt = fetch_block(D, order, 0);
+  for (int n0 = 0; n0 < npix; n0 += 32) {
+    const PixBlock cur = nxt;
+    if (n0 + 32 < npix) nxt = fetch_block(D, order, n0 + 32);
     uint32_t myOut = 0;
     const int cnt = min(32, npix - n0);
     for (int j = 0; j < cnt; ++j) {
@@ -628,20 +962,14 @@ __global__ void __launch_bounds__(32) k_dither(NqImage* imgs, const NqSlot* slot
       const double ypix = shfl_d(cur.ypix, j);
       const int x = xy & 0xFFFF, y = xy >> 16, bidx = x + y * width;
 
-      // ---- error.p = pixel + sum(queue[i].p * weights[i]) in queue order (GC:190-204); lane&3 = channel
+      // ---- error.p = pixel + sum(queue[i].p * weights[i]), backing-array order, weights from the top
+      //      down (GC:190-204); lane&3 = channel
       float acc = (float)chan(pixel, ch);
       float mx = (float)(DM - 1);
-      if (!sorted) {
-        int slot = head;
-        for (int i = 0; i < DM; ++i) {
-          acc += sh.q[slot][ch] * sh.w[i];
-          if (acc > mx) mx = acc;
-          if (++slot == DM) slot = 0;
-        }
-      } else {
+      {
         int i = wlen - 1;
         for (int qi = 0; qi < pq.n && i >= 0; ++qi, --i) {
-          acc += sh.q[qi][ch] * sh.w[i];
+          acc += qs.q[qi][ch] * qs.w[i];
           if (acc > mx) mx = acc;
         }
       }
@@ -653,36 +981,18 @@ __global__ void __launch_bounds__(32) k_dither(NqImage* imgs, const NqSlot* slot
 
       // ---- quantize (GC:211-229)
       uint32_t c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
-      int qi;
-      if (useSal && dither && !sorted && (!gHasAlpha || c_alpha(pixel) < a_pix)) {
-        if ((plen >= 256 && sal > .99f) || (gHasAlpha && (double)(c_alpha(pixel) - a_pix) < (.5 * margin)))
-          qi = lookup(E, c2, bidx);
-        else
-          qi = dither_pixel(E, x, y, bidx, pixel, sal, ypix, c2, beta, 0);    // qPixels[bidx] is still 0 here (GC:136,216)
-      } else if (plen <= 32 && a_pix > 0xF0) {
-        qi = lookup(E, c2, bidx);
-        const int acceptedDiff = max(2, plen - margin);
-        if (useSal && (y_diff_pre(ypix, c2, lut) > (double)acceptedDiff || u_diff(pixel, c2) > (double)(2 * acceptedDiff))) {
-          const float strength = 1 / 3.f;
-          c2 = bn_diffuse(pixel, sh.pal[qi], 1 / sal, strength, x, y, bn);
-          qi = lookup(E, c2, bidx);
-        }
-      } else
-        qi = lookup(E, c2, bidx);
+      int qi = quantize_pixel(E, x, y, bidx, pixel, sal, ypix, c2);
 
-      // ---- queue maintenance (GC:231-234). FIFO: the size is always DITHER_MAX, poll() drops the
-      //      oldest entry and its slot receives the new error below.
-      if (sorted) {
-        if (pq.n >= DM) pq.poll();
-        else if (pq.n != 0) {
-          const int size = pq.n;                      // initWeights(size): size empty boxes + new weights
-          const float zero[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int k = 0; k < size; ++k) pq.offer(zero, 0.0);
-          const float* src = size == 1 ? I.gW1 : (size == 3 ? I.gW3 : I.gW7);
-          if (lane < (unsigned)size) sh.w[lane] = src[lane];
-          wlen = size;
-          __syncwarp();
-        }
+      // ---- queue maintenance (GC:231-234)
+      if (pq.n >= DM) pq.poll();
+      else if (pq.n != 0) {
+        const int size = pq.n;                      // initWeights(size): size empty boxes + new weights
+        const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < size; ++k) pq.offer(zero, 0.0);
+        const float* src = size == 1 ? I.gW1 : (size == 3 ? I.gW3 : I.gW7);
+        if (lane < (unsigned)size) qs.w[lane] = src[lane];
+        wlen = size;
+        __syncwarp();
       }
 
       // ---- error of this pixel and its shaping (GC:236-264); lanes 0..2 shape r, g, b
@@ -691,17 +1001,17 @@ __global__ void __launch_bounds__(32) k_dither(NqImage* imgs, const NqSlot* slot
       float e = (float)(pixch - chan(c2, ch));
       const bool denoise = plen > 2;
       const bool diffuse = bn[bidx & 4095] > thresold;
-      const double yDiff = sorted ? y_diff_pre(ypix, c2, lut) : 1.0;
+      const double yDiff = y_diff_pre(ypix, c2, lut);
       const bool illusion = !diffuse && bn[j2i(yDiff * 4096) & 4095] > thresold;
       bool unacc = false;
       if (denoise && ch < 3) {
         if (fabsf(e) >= (float)ditherMax) {
-          if (sorted && useSal) unacc = true;
+          if (useSal) unacc = true;
           if (diffuse) e = tanh_to_float((double)(e / maxErr * 20.f)) * (float)(ditherMax - 1);
           else if (illusion) e = (float)((double)(e / maxErr) * yDiff) * (float)(ditherMax - 1);
           else e /= (float)(1 + nqm::sqrt_((double)ditherMax));
         }
-        if (sorted && !useSal && fabsf(e) >= (float)DM) unacc = true;
+        if (!useSal && fabsf(e) >= (float)DM) unacc = true;
       }
       const bool unaccepted = (__ballot_sync(FULL, unacc) & 7u) != 0;
 
@@ -715,16 +1025,9 @@ __global__ void __launch_bounds__(32) k_dither(NqImage* imgs, const NqSlot* slot
       }
 
       // ---- errorq.add(error) (GC:276)
-      if (!sorted) {
-        __syncwarp();
-        if (lane < 4) sh.q[head][ch] = e;
-        if (++head == DM) head = 0;
-        __syncwarp();
-      } else {
-        float p[4];
-        p[0] = __shfl_sync(FULL, e, 0); p[1] = __shfl_sync(FULL, e, 1); p[2] = __shfl_sync(FULL, e, 2); p[3] = __shfl_sync(FULL, e, 3);
-        pq.offer(p, yDiff);
-      }
+      float p[4];
+      p[0] = __shfl_sync(FULL, e, 0); p[1] = __shfl_sync(FULL, e, 1); p[2] = __shfl_sync(FULL, e, 2); p[3] = __shfl_sync(FULL, e, 3);
+      pq.offer(p, yDiff);
 
       const uint32_t res = (dither || plen <= 32) ? sh.pal[qi] : (uint32_t)qi;   // GC:278-279
       if ((int)lane == j) myOut = res;
@@ -735,28 +1038,7 @@ __global__ void __launch_bounds__(32) k_dither(NqImage* imgs, const NqSlot* slot
     }
   }
 
-  // ---- BlueNoise.dither second pass (PQ:400-401, PL:511-515, BN:207-222); memo and RNG carry over
-  if (!dither && plen > 32) {
-    __syncwarp();
-    __threadfence_block();
-    const float weight = I.bnWeight, strength = 1 / 3.f;
-    for (int n0 = 0; n0 < npix; n0 += 32) {
-      const int n = n0 + (int)lane;
-      uint32_t px = 0, qv = 0;
-      if (n < npix) { px = eff_pixel(in[n], fixA0); qv = out[n]; }
-      uint32_t myOut = 0;
-      const int cnt = min(32, npix - n0);
-      for (int j = 0; j < cnt; ++j) {
-        const int bidx = n0 + j, x = bidx % width, y = bidx / width;
-        const uint32_t pixel = __shfl_sync(FULL, px, j);
-        const uint32_t q0 = __shfl_sync(FULL, qv, j);
-        const uint32_t c1 = bn_diffuse(pixel, sh.pal[q0], weight, strength, x, y, bn);
-        const int qi = lookup(E, c1, bidx);
-        if ((int)lane == j) myOut = sh.pal[qi];
-      }
-      if (n < npix) out[n] = myOut;
-    }
-  }
+  if (!dither && plen > 32) bluenoise_pass(I, D);
   if (lane == 0) I.rngDraws = E.draws;
 }
 
