@@ -114,6 +114,10 @@ typedef struct nq_image_info {
   int palette_len;
   unsigned long long merges, rescans, pair_tests, rng_draws, heap_pops;
   int error;
+  unsigned long long full_evals; /* CIELAB merge loop: candidates that reached the trigonometric part of find_nn */
+  /* CIELAB merge loop: SM cycles per phase (heap/top, first 32, block tests, screen, full+resolve, merge+rebuild),
+     blocks that survived their summary test, candidates that survived the screen */
+  unsigned long long merge_cycles[6], live_blocks, screened;
 } nq_image_info;
 int nq_get_image_info(nq_ctx* ctx, int image, nq_image_info* out);
 
@@ -137,6 +141,12 @@ int nq_get_stage_times(nq_ctx* ctx, double* ms, unsigned long long* launches, in
 /* Device-side math probe (tests): evaluates the shared nq_math.h kernels ON THE GPU.
  * fn: 0 pow(x,y) 1 exp 2 tanh 3 cbrt 4 atan2(x,y) 5 sin 6 cos. n elements, host buffers. */
 int nq_debug_math(nq_ctx* ctx, int fn, const double* x, const double* y, double* out, int n);
+
+/* Device-side CIEDE2000 probe (tests): the L', C', H' and R_T terms of find_nn (PnnLABQuantizer.java:86-104,
+ * CIELABConvertor.java:91-194) for n colour pairs, through the SAME routine the merge kernels use (plain-double
+ * filter in front of the correctly rounded kernels). lab1/lab2: n x (L, A, B) floats; out: n x 4 floats;
+ * n_exact (optional): how many pairs needed the exact path. Host buffers. */
+int nq_debug_ciede(nq_ctx* ctx, const float* lab1, const float* lab2, float* out, int* n_exact, int n);
 
 /* Fills a device buffer with the synthetic test image of SURVEY.md 8(d) (see
  * nquant_android_b200/synth.py for the definition) -- used by bench.py so inputs can be created in

@@ -11,7 +11,7 @@ SYMBOLS = [
     "nq_device_count", "nq_create", "nq_destroy", "nq_last_error", "nq_convert", "nq_convert_batch",
     "nq_convert_batch_device", "nq_dither_with_palette", "nq_gilbert_order", "nq_get_image_info", "nq_set_debug",
     "nq_debug_get_bins", "nq_debug_get_merges", "nq_debug_get_saliencies", "nq_kernel_launches", "nq_debug_math",
-    "nq_synth_device", "nq_get_stage_times", "nq_set_stream",
+    "nq_synth_device", "nq_get_stage_times", "nq_set_stream", "nq_debug_ciede",
 ]
 
 NQ_KIND_PNN, NQ_KIND_PNNLAB = 0, 1
@@ -32,10 +32,12 @@ class ImageInfo(ctypes.Structure):
         ("merges", ctypes.c_ulonglong), ("rescans", ctypes.c_ulonglong), ("pair_tests", ctypes.c_ulonglong),
         ("rng_draws", ctypes.c_ulonglong), ("heap_pops", ctypes.c_ulonglong),
         ("error", ctypes.c_int),
+        ("full_evals", ctypes.c_ulonglong),
+        ("merge_cycles", ctypes.c_ulonglong * 6), ("live_blocks", ctypes.c_ulonglong), ("screened", ctypes.c_ulonglong),
     ]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n == "merge_cycles" else getattr(self, n)) for n, _ in self._fields_}
 
 
 _lib = None
@@ -70,6 +72,7 @@ def load():
     L.nq_kernel_launches.restype = ctypes.c_ulonglong
     L.nq_debug_math.argtypes = [vp, ci, vp, vp, vp, ci]
     L.nq_set_stream.argtypes = [vp, vp]
+    L.nq_debug_ciede.argtypes = [vp, vp, vp, vp, vp, ci]
     L.nq_get_stage_times.argtypes = [vp, vp, vp, ci]
     L.nq_synth_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, u64]
     for s in SYMBOLS:

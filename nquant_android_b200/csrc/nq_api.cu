@@ -123,6 +123,23 @@ __global__ void k_math_probe(int fn, const double* x, const double* y, double* o
   out[i] = r;
 }
 
+__global__ void k_ciede_probe(const float* l1, const float* l2, float* out, int* nExact, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float L1 = l1[3 * i], A1 = l1[3 * i + 1], B1 = l1[3 * i + 2], L2 = l2[3 * i], A2 = l2[3 * i + 1], B2 = l2[3 * i + 2];
+  nq::CiedeC cc;
+  const float tL = nq::ciede_L(L1, L2);
+  const float tC = nq::ciede_C(A1, B1, A2, B2, &cc);
+  float tH, tRT;
+  if (!nqf::ciede_HRT_fast(B1, B2, cc, tC, &tH, &tRT)) {
+    double barC, barh;
+    tH = nq::ciede_H(B1, B2, cc, &barC, &barh);
+    tRT = nq::ciede_RT(barC, barh, tC, tH);
+    atomicAdd(nExact, 1);
+  }
+  out[4 * i] = tL; out[4 * i + 1] = tC; out[4 * i + 2] = tH; out[4 * i + 3] = tRT;
+}
+
 __global__ void k_set_palette(NqImage* imgs, int img, const uint32_t* pal, int plen) {
   if (threadIdx.x < plen) imgs[img].palette[threadIdx.x] = pal[threadIdx.x];
   if (threadIdx.x == 0) imgs[img].paletteLen = plen;
@@ -355,7 +372,11 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
       nq::k_finalize_lab<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
     }
     mark(2);
-    nq::k_find_nn_all<<<c->smCount * 8, 256, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
+    if (kind == NQ_KIND_RGB) { nq::k_find_nn_all<<<c->smCount * 8, 256, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches; }
+    else {
+      nq::k_lab_blocks<<<dim3(2, n), 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_find_nn_lab<<<c->smCount * 8, 256, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
+    }
     mark(3);
     if (c->debug) {
       CU(cudaStreamSynchronize(st));
@@ -387,8 +408,11 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
         CU(cudaMemcpy(D.initNn.data(), S.bNn, (size_t)mb * 4, cudaMemcpyDeviceToHost));
       }
     }
-    const size_t heapSmem = (size_t)NQ_HEAP_SMEM * 6;
-    nq::k_merge<<<n, NQ_MERGE_THREADS, heapSmem, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
+    if (kind == NQ_KIND_RGB) {
+      nq::k_merge<<<n, NQ_MERGE_THREADS, (size_t)NQ_HEAP_SMEM * 6, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
+    } else {
+      nq::k_merge_lab<<<n, NQ_LAB_THREADS, (size_t)NQ_LAB_HEAP_SMEM * 6, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
+    }
   } else { mark(2); mark(3); }
   mark(4);
   nq::k_dither_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
@@ -508,6 +532,7 @@ nq_ctx* nq_create(int device) {
   bool ok = cudaMalloc(&dBn, 4096) == cudaSuccess && cudaMemcpy(dBn, kBlueNoise, 4096, cudaMemcpyHostToDevice) == cudaSuccess;
   if (ok) {
     nq::k_init_tables<<<4, 256, 0, c->stream>>>(dBn); ++c->launches;
+    nq::k_init_rtfac<<<1, 256, 0, c->stream>>>(); ++c->launches;
     ok = cudaStreamSynchronize(c->stream) == cudaSuccess;
   }
   if (dBn) cudaFree(dBn);
@@ -527,6 +552,7 @@ nq_ctx* nq_create(int device) {
     if (ok) ++e.refs;
   }
   if (ok) ok = cudaFuncSetAttribute(nq::k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_HEAP_SMEM * 6) == cudaSuccess;
+  if (ok) ok = cudaFuncSetAttribute(nq::k_merge_lab, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_LAB_HEAP_SMEM * 6) == cudaSuccess;
   if (!ok) {
     fail(NQ_ERR_CUDA, std::string("context initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));
     cudaStreamDestroy(c->ownStream);
@@ -622,6 +648,9 @@ int nq_get_image_info(nq_ctx* c, int image, nq_image_info* o) {
   o->bn_weight = I.bnWeight; o->palette_len = I.paletteLen;
   o->merges = (I.nmax > 2 && I.extbins > 0) ? (unsigned long long)I.extbins : 0ULL;
   o->rescans = I.statRescans; o->pair_tests = I.statPairs; o->rng_draws = I.rngDraws; o->heap_pops = I.statHeapPops;
+  o->full_evals = I.statFullEvals;
+  for (int k = 0; k < 6; ++k) o->merge_cycles[k] = I.statCyc[k];
+  o->live_blocks = I.statLiveBlocks; o->screened = I.statScreened;
   o->error = I.error;
   return NQ_OK;
 }
@@ -686,6 +715,28 @@ int nq_debug_math(nq_ctx* c, int fn, const double* x, const double* y, double* o
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaMemcpy(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost));
   cudaFree(dx); cudaFree(dy); cudaFree(dout);
+  return NQ_OK;
+}
+
+int nq_debug_ciede(nq_ctx* c, const float* lab1, const float* lab2, float* out, int* nExact, int n) {
+  if (!c || !lab1 || !lab2 || !out || n <= 0) return fail(NQ_ERR_ARG, "bad arguments");
+  CU(cudaSetDevice(c->device));
+  float *d1 = nullptr, *d2 = nullptr, *dout = nullptr;
+  int* dcnt = nullptr;
+  CU(cudaMalloc(&d1, (size_t)n * 12));
+  CU(cudaMalloc(&d2, (size_t)n * 12));
+  CU(cudaMalloc(&dout, (size_t)n * 16));
+  CU(cudaMalloc(&dcnt, 4));
+  CU(cudaMemcpy(d1, lab1, (size_t)n * 12, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d2, lab2, (size_t)n * 12, cudaMemcpyHostToDevice));
+  CU(cudaMemset(dcnt, 0, 4));
+  k_ciede_probe<<<(n + 127) / 128, 128, 0, c->stream>>>(d1, d2, dout, dcnt, n); ++c->launches;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy(out, dout, (size_t)n * 16, cudaMemcpyDeviceToHost));
+  int cnt = 0;
+  CU(cudaMemcpy(&cnt, dcnt, 4, cudaMemcpyDeviceToHost));
+  if (nExact) *nExact = cnt;
+  cudaFree(d1); cudaFree(d2); cudaFree(dout); cudaFree(dcnt);
   return NQ_OK;
 }
 

@@ -18,6 +18,7 @@
 #include "nq_types.h"
 #include "nq_color.h"
 #include "nq_hist.cuh"
+#include "nq_fastmath.cuh"
 
 namespace nq {
 
@@ -82,8 +83,11 @@ __device__ __forceinline__ double rgb_take(const RgbProbe& P, const RgbCand& c, 
 // against the err at the start of a chunk can be dropped for good. A survivor carries
 // gs (must be < err), gw (must be <= err) and f (the new err).
 // -------------------------------------------------------------------------------------------------
+// upper bound of sqrt(A^2 + B^2) as a float
+__device__ __forceinline__ float chroma_ub(float A, float B) { return sqrtf((A * A) + (B * B)) * 1.000001f; }
+
 struct LabProbe {
-  float n1, a1, L1, A1, B1;
+  float n1, a1, L1, A1, B1, C1;   // C1: upper bound of the chroma sqrt(A1^2 + B1^2)
   double ratio, exp175;
   bool semi, texicab;
 };
@@ -91,6 +95,7 @@ __device__ __forceinline__ LabProbe lab_probe(const NqImage& I, const NqSlot& S,
   LabProbe P;
   P.n1 = S.bCnt[idx];
   P.a1 = S.fAc[idx]; P.L1 = S.fC1[idx]; P.A1 = S.fC2[idx]; P.B1 = S.fC3[idx];
+  P.C1 = chroma_ub(P.A1, P.B1);
   P.ratio = ratio;
   P.semi = I.hasSemi != 0;
   P.exp175 = P.semi ? nqm::nq_exp(1.75) : 1.0;
@@ -99,11 +104,80 @@ __device__ __forceinline__ LabProbe lab_probe(const NqImage& I, const NqSlot& S,
 }
 struct LabCand { double gs, gw, f; };
 
-__device__ __forceinline__ bool lab_eval(const LabProbe& P, const NqSlot& S, int i, double err, LabCand* c) {
-  float n2 = S.bCnt[i];
+// Candidate bins as five position-indexed float arrays plus one summary per 32 positions. For the
+// initial sweep the position is the bin index; inside the merge loop it is the position in the
+// compacted list of surviving bins (cnt < 0 marks a bin that died since the last compaction).
+struct LabView {
+  const float *cnt, *al, *L, *A, *B;
+  const float* C;                       // chroma_ub(A, B) per position
+  const float *bcmin, *blmin, *blmax;   // per block of 32 positions: min count, min L, max L (conservative)
+  int n;
+};
+
+// Lower bound of the cost of EVERY candidate of block `blk`, from the summary alone:
+//   cost >= ratio * nerr2 * L'^2,  nerr2 = n1 n2 / (n1 + n2) increasing in n2,  |L'| = |dL| / S_L, S_L <= 1.7472
+// (CL:91-98: S_L = 1 + .015 d^2 / sqrt(20 + d^2), |d| <= 50). The factors (1 - 1e-6) and (1 - 1e-5) cover
+// the float roundings of the reference's own evaluation. A block may be skipped when even this bound
+// fails the reference's tests against an upper bound U of the running err: nerr2 >= U (PL:57) or the
+// prefix after the L' term > U (PL:88-90; every earlier term is >= 0).
+__device__ __forceinline__ bool lab_block_skip(const LabProbe& P, const LabView& V, int blk, double U) {
+  const float cmin = V.bcmin[blk];
+  if (!(cmin >= 0.f)) return true;                        // block holds no live bin
+  const float lo = V.blmin[blk], hi = V.blmax[blk];
+  const double n2 = (double)cmin, n1 = (double)P.n1;
+  const double nerr2 = (n1 * n2) / (n1 + n2) * (1.0 - 1e-6);
+  if (nerr2 >= U) return true;
+  const float dl = fmaxf(0.f, fmaxf(lo - P.L1, P.L1 - hi));
+  const double t = (double)dl * (1.0 / 1.7472);
+  const double lb = P.ratio * nerr2 * (t * t) * (1.0 - 1e-5);
+  return lb > U;
+}
+
+// 1 - |R_T|max / 2 for barCPrime in [k, k + 1): R_T = -sin(2 dTheta) R_C with |sin(2 dTheta)| <= sin(60 deg) and
+// R_C = 2 sqrt(c^7 / (c^7 + 25^7)) increasing in c (CL:187-194). Filled by k_init_tables.
+__device__ float g_rtFac[256];
+__global__ void k_init_rtfac() {
+  const int k = threadIdx.x;
+  double f = 1.0 - 0.86603 * 1.000001;                    // barCPrime >= 255: R_C < 2
+  if (k < 255) {
+    const double c = (double)(k + 1) / 25.0, c2 = c * c, c7 = c2 * c2 * c2 * c;
+    f = 1.0 - 0.5 * 0.86603 * (2.0 * nqm::sqrt_(c7 / (c7 + 1.0))) * 1.000001;
+  }
+  g_rtFac[k] = (float)f * 0.999999f;
+}
+
+// Per-candidate lower bound of the cost, from float arithmetic only:
+//   L'^2 + C'^2 + H'^2 + R_T C' H' >= (dL / S_L)^2 + (1 - |R_T|/2) (C'^2 + H'^2),
+//   (S_C C')^2 + (S_H H')^2 = dC'^2 + dH'^2 = (a1' - a2')^2 + (b1 - b2)^2 >= da^2 + db^2   (chord identity; a' = (1 + G) a),
+//   S_H <= S_C = 1 + .045 barC', barC' <= .75 (C1 + C2)   (G <= .5).
+// The slack terms cover the float roundings of the reference's own evaluation (the float difference of the two
+// C' values is off by up to 1.3e-7 max(C')). Returns false only if the reference must reject i given err.
+__device__ __forceinline__ bool lab_cheap_keep(const LabProbe& P, const LabView& V, int i, double err) {
+  const float n2 = V.cnt[i];
+  if (!(n2 >= 0.f)) return false;
+  const double nerr2 = (double)((P.n1 * n2) / (P.n1 + n2));       // the reference's own value and test (PL:56-57)
+  if (nerr2 >= err) return false;
+  const float dl = V.L[i] - P.L1, da = V.A[i] - P.A1, db = V.B[i] - P.B1;
+  const float cb = (0.75f * (P.C1 + V.C[i])) * 1.00001f;
+  const float sc = (1.f + (0.045f * cb)) * 1.00001f;
+  const float rf = g_rtFac[min(255, (int)cb)];
+  const float d2 = fmaxf(0.f, (((da * da) + (db * db)) * 0.9999f) - 1e-4f);
+  const double tl = (double)dl * (1.0 / 1.7472);
+  const double q = (tl * tl) + ((double)rf * (double)d2) / ((double)sc * (double)sc);
+  const double lb = (P.ratio * nerr2) * q * (1.0 - 1e-5);
+  return !(lb > err);
+}
+
+// find_nn's tests for candidate i against err (PL:54-108). With STOP_AFTER_C the evaluation ends after
+// the C' term (a cheap screen: two more square roots and a pow(.,7), no trigonometry); it then returns
+// true iff the candidate is still alive there.
+template <bool STOP_AFTER_C>
+__device__ __forceinline__ bool lab_eval_t(const LabProbe& P, const LabView& V, int i, double err, LabCand* c) {
+  const float n2 = V.cnt[i];
+  if (!(n2 >= 0.f)) return false;                         // dead since the last compaction
   double nerr2 = (double)((P.n1 * n2) / (P.n1 + n2));
   if (nerr2 >= err) return false;
-  float a2 = S.fAc[i], L2 = S.fC1[i], A2 = S.fC2[i], B2 = S.fC3[i];
+  const float a2 = V.al[i], L2 = V.L[i], A2 = V.A[i], B2 = V.B[i];
   double alphaDiff = 0;
   if (P.semi) { double d = (double)(a2 - P.a1); alphaDiff = (d * d) / P.exp175; }
   double nerr = nerr2 * alphaDiff;
@@ -136,17 +210,146 @@ __device__ __forceinline__ bool lab_eval(const LabProbe& P, const NqSlot& S, int
   float tC = ciede_C(P.A1, P.B1, A2, B2, &cc);
   nerr += P.ratio * nerr2 * ((double)tC * (double)tC);
   if (nerr > err) return false;
+  if (STOP_AFTER_C) return true;
 
-  double barC, barh;
-  float tH = ciede_H(P.B1, B2, cc, &barC, &barh);
+  float tH, tRT;
+  if (!nqf::ciede_HRT_fast(P.B1, B2, cc, tC, &tH, &tRT)) {   // the filter could not decide both floats
+    double barC, barh;
+    tH = ciede_H(P.B1, B2, cc, &barC, &barh);
+    tRT = ciede_RT(barC, barh, tC, tH);
+  }
   nerr += P.ratio * nerr2 * ((double)tH * (double)tH);
   if (nerr > err) return false;
   double gw = nerr;
 
-  nerr += P.ratio * nerr2 * (double)ciede_RT(barC, barh, tC, tH);
+  nerr += P.ratio * nerr2 * (double)tRT;
   if (nerr > err) return false;
   c->gs = gs; c->gw = nerr > gw ? nerr : gw; c->f = nerr;
   return true;
+}
+
+// ordered acceptance among up to 32 evaluated candidates held one per lane, in lane order: candidate
+// i is taken iff gs < err and gw <= err with the err left by the candidates before it
+__device__ __forceinline__ void lab_accept_in_order(bool alive, const LabCand& c, int id, double& err, int& nn) {
+  unsigned remaining = 0xffffffffu;
+  for (;;) {
+    unsigned m = __ballot_sync(0xffffffffu, alive && c.gs < err && c.gw <= err) & remaining;
+    if (!m) break;
+    int L = __ffs(m) - 1;
+    err = __shfl_sync(0xffffffffu, c.f, L);
+    nn = __shfl_sync(0xffffffffu, id, L);
+    remaining = (L == 31) ? 0u : ~((2u << L) - 1u);
+  }
+}
+
+// find_nn for one bin by ONE warp, streaming over the candidates at positions >= first in order.
+// The first 32 candidates are evaluated unconditionally (err is still infinite; they are the bins
+// with the nearest histogram keys, so err is tight afterwards). From then on whole blocks are dropped
+// by their summary, the candidates of the remaining blocks are screened through the C' term, and the
+// survivors queue up (in order) until 32 of them can be evaluated in full together.
+__device__ void warp_find_nn_lab(const LabProbe& P, const LabView& V, int first, int* sBufA /*[64]*/, int* sBufB /*[64], this warp's*/, double* errOut, int* nnOut) {
+  const unsigned lane = lane_id();
+  double err = 1e100;
+  int nn = -1, nA = 0, nB = 0;
+  const int n = V.n;
+  auto shift = [&](int* buf, int& cnt, int take) {
+    const int rest = cnt - take;
+    const int v = ((int)lane < rest) ? buf[take + lane] : 0;
+    __syncwarp();
+    if ((int)lane < rest) buf[lane] = v;
+    cnt = rest;
+    __syncwarp();
+  };
+  auto flushB = [&](int take) {               // full evaluation + ordered acceptance
+    int i = -1;
+    LabCand c;
+    bool alive = false;
+    if ((int)lane < take) { i = sBufB[lane]; alive = lab_eval_t<false>(P, V, i, err, &c); }
+    lab_accept_in_order(alive, c, i, err, nn);
+    shift(sBufB, nB, take);
+  };
+  auto pushB = [&](bool keep, int i) {
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) sBufB[nB + __popc(m & ((1u << lane) - 1u))] = i;
+    nB += __popc(m);
+    __syncwarp();
+    if (nB >= 32) flushB(32);
+  };
+  auto flushA = [&](int take) {               // screen through the C' term
+    int i = -1;
+    bool keep = false;
+    LabCand dummy;
+    if ((int)lane < take) { i = sBufA[lane]; keep = lab_eval_t<true>(P, V, i, err, &dummy); }
+    shift(sBufA, nA, take);
+    pushB(keep, i);
+  };
+  auto pushA = [&](bool keep, int i) {
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) sBufA[nA + __popc(m & ((1u << lane) - 1u))] = i;
+    nA += __popc(m);
+    __syncwarp();
+    if (nA >= 32) flushA(32);
+  };
+  int pos = first;
+  if (pos < n) {
+    const int i = pos + (int)lane;
+    pushB(i < n && V.cnt[i] >= 0.f, i);
+    if (nB) flushB(nB);
+    pos += 32;
+  }
+  const int stop = first + 32;     // positions below were handled by the unconditional tile
+  for (int blk0 = pos >> 5; (blk0 << 5) < n; blk0 += 32) {
+    const int blk = blk0 + (int)lane;
+    const bool live = (blk << 5) < n && !lab_block_skip(P, V, blk, err);
+    unsigned bm = __ballot_sync(0xffffffffu, live);
+    while (bm) {
+      const int b = __ffs(bm) - 1;
+      bm &= bm - 1;
+      const int i = ((blk0 + b) << 5) + (int)lane;
+      pushA(i >= stop && i < n && lab_cheap_keep(P, V, i, err), i);
+    }
+  }
+  if (nA) flushA(nA);
+  if (nB) flushB(nB);
+  *errOut = err;
+  *nnOut = nn;
+}
+
+// summaries of blocks [0, ceil(n/32)) over position-indexed arrays; one thread per block
+__device__ __forceinline__ void lab_block_summary(const float* cnt, const float* L, int n, int blk, float* bcmin, float* blmin, float* blmax) {
+  float cm = -1.f, lo = 1e30f, hi = -1e30f;
+  const int p0 = blk << 5, p1 = min(n, p0 + 32);
+  for (int p = p0; p < p1; ++p) {
+    const float c = cnt[p];
+    if (!(c >= 0.f)) continue;
+    cm = cm < 0.f ? c : fminf(cm, c);
+    const float l = L[p];
+    lo = fminf(lo, l); hi = fmaxf(hi, l);
+  }
+  bcmin[blk] = cm; blmin[blk] = lo; blmax[blk] = hi;
+}
+
+// scratch carved out of the histogram sum planes (free once the bins are compacted)
+struct LabScratch { float *cnt, *al, *L, *A, *B, *C, *bcmin, *blmin, *blmax; };
+__device__ __forceinline__ LabScratch lab_scratch(const NqSlot& S) {
+  float* f = reinterpret_cast<float*>(S.hSum);
+  LabScratch X;
+  X.cnt = f; X.al = f + NQ_NBINS; X.L = f + 2 * NQ_NBINS; X.A = f + 3 * NQ_NBINS; X.B = f + 4 * NQ_NBINS;
+  X.bcmin = f + 5 * NQ_NBINS; X.blmin = X.bcmin + 2048; X.blmax = X.blmin + 2048;
+  X.C = f + 6 * NQ_NBINS;
+  return X;
+}
+
+__global__ void __launch_bounds__(256) k_lab_blocks(const NqImage* imgs, const NqSlot* slots) {
+  const int img = blockIdx.y;
+  const NqImage& I = imgs[img];
+  if (I.kind != NQ_KIND_LAB || I.nmax <= 2 || I.skipPnn) return;
+  const NqSlot& S = slots[img];
+  const LabScratch X = lab_scratch(S);
+  const int n = I.maxbins, nblk = (n + 31) >> 5;
+  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += gridDim.x * blockDim.x)
+    lab_block_summary(S.bCnt, S.fC1, n, blk, X.bcmin, X.blmin, X.blmax);
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) X.C[b] = chroma_ub(S.fC2[b], S.fC3[b]);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -157,52 +360,59 @@ __global__ void __launch_bounds__(256) k_find_nn_all(NqImage* imgs, const NqSlot
   const int wpb = blockDim.x >> 5;
   for (int img = 0; img < nimg; ++img) {
     NqImage& I = imgs[img];
-    if (I.nmax <= 2 || I.skipPnn) continue;
+    if (I.kind != NQ_KIND_RGB || I.nmax <= 2 || I.skipPnn) continue;
     const NqSlot& S = slots[img];
     const int maxbins = I.maxbins;
     unsigned long long pairs = 0;
     for (int idx = blockIdx.x * wpb + (threadIdx.x >> 5); idx < maxbins; idx += gridDim.x * wpb) {
       double err = 1e100;
       int nn = 0;
-      if (I.kind == NQ_KIND_RGB) {
-        RgbProbe P = rgb_probe(I, S, idx);
-        for (int base = idx + 1; base < maxbins; base += 32) {
-          const int i = base + lane;
-          RgbCand c;
-          double gate = 1e300;
-          if (i < maxbins) gate = rgb_gate(P, S, i, &c);
-          unsigned remaining = 0xffffffffu;
-          for (;;) {
-            unsigned m = __ballot_sync(0xffffffffu, gate < err) & remaining;
-            if (!m) break;
-            int L = __ffs(m) - 1;
-            double e = 0;
-            if ((int)lane == L) e = rgb_take(P, c, err);
-            err = __shfl_sync(0xffffffffu, e, L);
-            nn = base + L;
-            remaining = (L == 31) ? 0u : ~((2u << L) - 1u);
-          }
-        }
-      } else {
-        LabProbe P = lab_probe(I, S, idx, I.ratio);
-        for (int base = idx + 1; base < maxbins; base += 32) {
-          const int i = base + lane;
-          LabCand c;
-          bool alive = false;
-          if (i < maxbins) alive = lab_eval(P, S, i, err, &c);
-          unsigned remaining = 0xffffffffu;
-          for (;;) {
-            unsigned m = __ballot_sync(0xffffffffu, alive && c.gs < err && c.gw <= err) & remaining;
-            if (!m) break;
-            int L = __ffs(m) - 1;
-            err = __shfl_sync(0xffffffffu, c.f, L);
-            nn = base + L;
-            remaining = (L == 31) ? 0u : ~((2u << L) - 1u);
-          }
+      RgbProbe P = rgb_probe(I, S, idx);
+      for (int base = idx + 1; base < maxbins; base += 32) {
+        const int i = base + lane;
+        RgbCand c;
+        double gate = 1e300;
+        if (i < maxbins) gate = rgb_gate(P, S, i, &c);
+        unsigned remaining = 0xffffffffu;
+        for (;;) {
+          unsigned m = __ballot_sync(0xffffffffu, gate < err) & remaining;
+          if (!m) break;
+          int L = __ffs(m) - 1;
+          double e = 0;
+          if ((int)lane == L) e = rgb_take(P, c, err);
+          err = __shfl_sync(0xffffffffu, e, L);
+          nn = base + L;
+          remaining = (L == 31) ? 0u : ~((2u << L) - 1u);
         }
       }
       pairs += (unsigned long long)(maxbins - idx - 1);
       if (lane == 0) { S.bErr[idx] = (float)err; S.bNn[idx] = nn; }
+    }
+    if (lane == 0 && pairs) atomicAdd(&I.statPairs, pairs);
+  }
+}
+
+// CIELAB: one warp per bin, streaming with block summaries (warp_find_nn_lab). Bins are dealt out
+// interleaved so that every warp gets a mix of long (small idx) and short candidate lists.
+__global__ void __launch_bounds__(256) k_find_nn_lab(NqImage* imgs, const NqSlot* slots, int nimg) {
+  __shared__ int sBufA[8][64], sBufB[8][64];
+  const unsigned lane = lane_id();
+  const int w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int img = 0; img < nimg; ++img) {
+    NqImage& I = imgs[img];
+    if (I.kind != NQ_KIND_LAB || I.nmax <= 2 || I.skipPnn) continue;
+    const NqSlot& S = slots[img];
+    const LabScratch X = lab_scratch(S);
+    const int maxbins = I.maxbins;
+    const LabView V{S.bCnt, S.fAc, S.fC1, S.fC2, S.fC3, X.C, X.bcmin, X.blmin, X.blmax, maxbins};
+    unsigned long long pairs = 0;
+    for (int idx = blockIdx.x * wpb + w; idx < maxbins; idx += gridDim.x * wpb) {
+      const LabProbe P = lab_probe(I, S, idx, I.ratio);
+      double err;
+      int nn;
+      warp_find_nn_lab(P, V, idx + 1, sBufA[w], sBufB[w], &err, &nn);
+      pairs += (unsigned long long)(maxbins - idx - 1);
+      if (lane == 0) { S.bErr[idx] = (float)err; S.bNn[idx] = nn < 0 ? 0 : nn; }
     }
     if (lane == 0 && pairs) atomicAdd(&I.statPairs, pairs);
   }
@@ -214,13 +424,14 @@ __global__ void __launch_bounds__(256) k_find_nn_all(NqImage* imgs, const NqSlot
 #define NQ_MERGE_THREADS 1024
 #define NQ_HEAP_SMEM 32768     // heap slots kept in shared memory (err f32 + id u16 = 6 B each = 192 KB)
 
+template <int HS>
 struct HeapView {
-  float* sErr; unsigned short* sId;   // shared part, slots [0, NQ_HEAP_SMEM)
+  float* sErr; unsigned short* sId;   // shared part, slots [0, HS)
   float* gErr; int* gId;              // global spill for the deepest level(s)
-  __device__ __forceinline__ float err(int l) const { return l < NQ_HEAP_SMEM ? sErr[l] : gErr[l]; }
-  __device__ __forceinline__ int id(int l) const { return l < NQ_HEAP_SMEM ? (int)sId[l] : gId[l]; }
+  __device__ __forceinline__ float err(int l) const { return l < HS ? sErr[l] : gErr[l]; }
+  __device__ __forceinline__ int id(int l) const { return l < HS ? (int)sId[l] : gId[l]; }
   __device__ __forceinline__ void set(int l, int id_, float e) {
-    if (l < NQ_HEAP_SMEM) { sErr[l] = e; sId[l] = (unsigned short)id_; } else { gErr[l] = e; gId[l] = id_; }
+    if (l < HS) { sErr[l] = e; sId[l] = (unsigned short)id_; } else { gErr[l] = e; gId[l] = id_; }
   }
   // "push slot down" (PQ:228-236): sift (b1, e1) down from the root of a heap with heapN entries
   __device__ __forceinline__ void sift_down(int b1, float e1, int heapN) {
@@ -260,7 +471,7 @@ __global__ void __launch_bounds__(NQ_MERGE_THREADS, 1) k_merge(NqImage* imgs, co
 
   const int img = blockIdx.x;
   NqImage& I = imgs[img];
-  if (I.nmax <= 2 || I.skipPnn) return;
+  if (I.kind != NQ_KIND_RGB || I.nmax <= 2 || I.skipPnn) return;   // CIELAB images: k_merge_lab
   const NqSlot& S = slots[img];
   const int t = threadIdx.x;
   const unsigned lane = lane_id(), w = t >> 5;
@@ -268,7 +479,7 @@ __global__ void __launch_bounds__(NQ_MERGE_THREADS, 1) k_merge(NqImage* imgs, co
   const bool rgb = I.kind == NQ_KIND_RGB;
   int* live = liveBuf + (size_t)img * NQ_NBINS;
   int* posOf = posBuf + (size_t)img * NQ_NBINS;
-  HeapView H{sErr, sId, S.hErr, S.hId};
+  HeapView<NQ_HEAP_SMEM> H{sErr, sId, S.hErr, S.hId};
 
   // ---- heap build: sequential pushes in bin order (PQ:196-207). Warp 0 replays them; every lane
   //      follows the same scalar steps (values prefetched 32 at a time), lane 0 does the stores.
@@ -298,7 +509,6 @@ __global__ void __launch_bounds__(NQ_MERGE_THREADS, 1) k_merge(NqImage* imgs, co
   int liveAtRebuild = liveLen, iterAtRebuild = 0;
   unsigned long long rescans = 0, pairs = 0;
   unsigned pops = 0;
-  const double ratioMerge = I.ratioMerge;
 
   for (;;) {
     // ---- thread 0: look at the heap top (PQ:214-226)
@@ -360,34 +570,6 @@ __global__ void __launch_bounds__(NQ_MERGE_THREADS, 1) k_merge(NqImage* imgs, co
             unsigned mm = __shfl_sync(0xffffffffu, mine, fw);
             int winner = fw * 32 + (__ffs(mm) - 1);
             if (t == winner) { sErrCur = rgb_take(P, c, err); sNnCur = i; }
-            __syncthreads();
-            err = sErrCur; nn = sNnCur;
-            lastP = base + winner;
-          }
-        }
-      } else {
-        LabProbe P = lab_probe(I, S, b1, ratioMerge);
-        for (int base = p0; base < liveLen; base += NQ_MERGE_THREADS) {
-          const int p = base + t;
-          int i = -1;
-          LabCand c;
-          bool ok = false;
-          if (p < liveLen) {
-            i = live[p];
-            if (S.bMtm[i] != NQ_DELETED) ok = lab_eval(P, S, i, err, &c);
-          }
-          int lastP = -1;
-          for (;;) {
-            unsigned m = __ballot_sync(0xffffffffu, ok && p > lastP && c.gs < err && c.gw <= err);
-            if (lane == 0) sMask[w] = m;
-            __syncthreads();
-            unsigned mine = sMask[lane];
-            unsigned wm = __ballot_sync(0xffffffffu, mine != 0);
-            if (!wm) { __syncthreads(); break; }
-            int fw = __ffs(wm) - 1;
-            unsigned mm = __shfl_sync(0xffffffffu, mine, fw);
-            int winner = fw * 32 + (__ffs(mm) - 1);
-            if (t == winner) { sErrCur = c.f; sNnCur = i; }
             __syncthreads();
             err = sErrCur; nn = sNnCur;
             lastP = base + winner;
@@ -455,5 +637,337 @@ __global__ void __launch_bounds__(NQ_MERGE_THREADS, 1) k_merge(NqImage* imgs, co
     I.statRescans = rescans; I.statPairs += pairs; I.statHeapPops = pops;
   }
 }
+
+// -------------------------------------------------------------------------------------------------
+// CIELAB merge loop. A full find_nn test costs a few thousand double-precision instructions
+// (CIEDE2000 with correctly rounded atan2/sin/cos/exp/pow), so the kernel is organised around
+// evaluating as FEW candidates in full as the reference's own early exits allow:
+//   1. warp 0 evaluates the first 32 surviving bins after b1 in full (err is infinite there) and
+//      resolves them in order -> err, the exact running error after 32 candidates;
+//   2. all threads test the 32-bin block summaries of the rest against err (lab_block_skip);
+//   3. the bins of the remaining blocks are screened through the C' term (lab_eval_t<true>);
+//   4. the screened bins are evaluated in full, packed one per thread, and resolved in list order.
+// Every test is the reference's test against an err that is >= the err the sequential scan would hold
+// at that candidate, so nothing the reference would take is dropped, and step 4 replays its decisions.
+// 128 threads and 48 KB of heap per CTA: several images share an SM and fill each other's serial gaps.
+// -------------------------------------------------------------------------------------------------
+#define NQ_LAB_THREADS 128
+#define NQ_LAB_HEAP_SMEM 7680   // 45 KB of heap: four CTAs fit one SM
+
+__device__ __forceinline__ int block_excl_scan_128(int v, int* total, int* sScan /*[8]*/) {
+  const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= (unsigned)o) x += y;
+  }
+  if (lane == 31) sScan[w] = x;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int k = 0; k < NQ_LAB_THREADS / 32; ++k) { const int c = sScan[k]; if (k < (int)w) base += c; tot += c; }
+  *total = tot;
+  __syncthreads();
+  return base + x - v;
+}
+
+// rebuild the ascending list of live bins, their compacted copies and the block summaries
+__device__ __forceinline__ int rebuild_live_lab(const NqSlot& S, const LabScratch& X, int maxbins, int* live, int* posOf, int* sScan) {
+  const int t = threadIdx.x;
+  const int per = (maxbins + NQ_LAB_THREADS - 1) / NQ_LAB_THREADS;
+  const int b0 = min(maxbins, t * per), b1 = min(maxbins, b0 + per);
+  int c = 0;
+  for (int b = b0; b < b1; ++b) c += S.bMtm[b] != NQ_DELETED;
+  int total, j = block_excl_scan_128(c, &total, sScan);
+  for (int b = b0; b < b1; ++b)
+    if (S.bMtm[b] != NQ_DELETED) {
+      live[j] = b; posOf[b] = j;
+      X.cnt[j] = S.bCnt[b]; X.al[j] = S.fAc[b]; X.L[j] = S.fC1[b]; X.A[j] = S.fC2[b]; X.B[j] = S.fC3[b];
+      X.C[j] = chroma_ub(S.fC2[b], S.fC3[b]);
+      ++j;
+    }
+  __syncthreads();
+  const int nblk = (total + 31) >> 5;
+  for (int blk = t; blk < nblk; blk += NQ_LAB_THREADS) lab_block_summary(X.cnt, X.L, total, blk, X.bcmin, X.blmin, X.blmax);
+  __syncthreads();
+  return total;
+}
+
+__global__ void __launch_bounds__(NQ_LAB_THREADS) k_merge_lab(NqImage* imgs, const NqSlot* slots, int* liveBuf, int* posBuf, int logMerges) {
+  extern __shared__ unsigned char smemRaw[];
+  float* sErr = reinterpret_cast<float*>(smemRaw);
+  unsigned short* sId = reinterpret_cast<unsigned short*>(smemRaw + (size_t)NQ_LAB_HEAP_SMEM * 4);
+  __shared__ int sScan[8];
+  __shared__ unsigned sBits[64];             // live blocks of this rescan, one bit per block
+  __shared__ unsigned short sBlk[2048];      // the same as an ordered list
+  __shared__ unsigned sMaskA[32];            // bins that passed the cheap bound, per block of the current batch
+  __shared__ unsigned sMaskB[32];            // ... of those, the ones that passed the screen, per 32 list entries
+  __shared__ int sOffA[33], sOffB[33];
+  __shared__ double sGs[NQ_LAB_THREADS], sGw[NQ_LAB_THREADS], sF[NQ_LAB_THREADS];
+  __shared__ int sPos[NQ_LAB_THREADS];       // position of a fully evaluated survivor, -1 = rejected
+  __shared__ double sErrCur;
+  __shared__ int sNnCur, sAction, sB1, sHeapN, sIter, sNLive;
+
+  const int img = blockIdx.x;
+  NqImage& I = imgs[img];
+  if (I.kind != NQ_KIND_LAB || I.nmax <= 2 || I.skipPnn) return;
+  const NqSlot& S = slots[img];
+  const LabScratch X = lab_scratch(S);
+  const int t = threadIdx.x;
+  const unsigned lane = lane_id(), w = t >> 5;
+  const int W = NQ_LAB_THREADS / 32;
+  const int maxbins = I.maxbins, extbins = I.extbins;
+  int* live = liveBuf + (size_t)img * NQ_NBINS;
+  int* posOf = posBuf + (size_t)img * NQ_NBINS;
+  HeapView<NQ_LAB_HEAP_SMEM> H{sErr, sId, S.hErr, S.hId};
+
+  // ---- heap build: sequential pushes in bin order (PL:246-257), replayed by warp 0
+  if (w == 0) {
+    int heapN = 0;
+    for (int base = 0; base < maxbins; base += 32) {
+      float e = (base + (int)lane < maxbins) ? S.bErr[base + lane] : 0.f;
+      const int cnt = min(32, maxbins - base);
+      for (int j = 0; j < cnt; ++j) {
+        const float err = __shfl_sync(0xffffffffu, e, j);
+        int l = ++heapN, l2;
+        for (; l > 1; l = l2) {
+          l2 = l >> 1;
+          float pe = H.err(l2);
+          if (pe <= err) break;
+          int pid = H.id(l2);
+          if (lane == 0) H.set(l, pid, pe);
+        }
+        if (lane == 0) H.set(l, base + j, err);
+        __syncwarp();
+      }
+    }
+    if (lane == 0) { sHeapN = heapN; sIter = 0; }
+  }
+  __syncthreads();
+  int liveLen = rebuild_live_lab(S, X, maxbins, live, posOf, sScan);
+  int liveAtRebuild = liveLen, iterAtRebuild = 0;
+  unsigned long long rescans = 0, pairs = 0, fulls = 0, liveBlocks = 0, screened = 0;
+  unsigned pops = 0;
+  const double ratioMerge = I.ratioMerge;
+  long long cyc[6] = {0, 0, 0, 0, 0, 0};
+  long long tk = clock64();
+  auto tick = [&](int k) { const long long now = clock64(); cyc[k] += now - tk; tk = now; };
+
+  for (;;) {
+    // ---- thread 0: look at the heap top (PL:271-283)
+    if (t == 0) {
+      int action = 0;  // 0 = merge, 1 = rescan, 2 = finished
+      if (sIter >= extbins) action = 2;
+      else {
+        int heapN = sHeapN;
+        for (;;) {
+          int b1 = H.id(1);
+          int tm = S.bTm[b1], mtm = S.bMtm[b1];
+          if (tm >= mtm && S.bMtm[S.bNn[b1]] <= tm) { action = 0; sB1 = b1; break; }
+          if (mtm == NQ_DELETED) {
+            b1 = H.id(heapN);
+            float e1 = H.err(heapN);
+            --heapN;
+            ++pops;
+            H.sift_down(b1, e1, heapN);
+            continue;
+          }
+          action = 1; sB1 = b1;
+          break;
+        }
+        sHeapN = heapN;
+      }
+      sAction = action;
+    }
+    if (t < 64) sBits[t] = 0u;
+    __syncthreads();
+    tick(0);
+    const int action = sAction;
+    if (action == 2) break;
+    const int b1 = sB1;
+
+    if (action == 1) {
+      ++rescans;
+      const int first = posOf[b1] + 1;
+      const LabView V{X.cnt, X.al, X.L, X.A, X.B, X.C, X.bcmin, X.blmin, X.blmax, liveLen};
+      const LabProbe P = lab_probe(I, S, b1, ratioMerge);
+      double err = 1e100;
+      int nn = -1;                              // position in the live list
+      // -- 1. the first 32 candidates in full
+      if (w == 0) {
+        const int i = first + (int)lane;
+        LabCand c;
+        const bool alive = i < liveLen && lab_eval_t<false>(P, V, i, err, &c);
+        lab_accept_in_order(alive, c, i, err, nn);
+        fulls += i < liveLen;
+        if (lane == 0) { sErrCur = err; sNnCur = nn; }
+      }
+      __syncthreads();
+      tick(1);
+      err = sErrCur; nn = sNnCur;
+      // -- 2. block summaries of everything behind them
+      const int stop = first + 32;
+      const int blkBeg = stop >> 5, nblk = (liveLen + 31) >> 5;
+      for (int blk = blkBeg + t; blk < nblk; blk += NQ_LAB_THREADS)
+        if (!lab_block_skip(P, V, blk, err)) atomicOr(&sBits[blk >> 5], 1u << (blk & 31));
+      __syncthreads();
+      if (w == 0) {                             // bit set -> ordered list
+        const unsigned m0 = sBits[2 * lane], m1 = sBits[2 * lane + 1];
+        const int c = __popc(m0) + __popc(m1);
+        int x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+        int at = x - c;
+        for (unsigned m = m0; m; m &= m - 1) sBlk[at++] = (unsigned short)(64 * lane + (__ffs(m) - 1));
+        for (unsigned m = m1; m; m &= m - 1) sBlk[at++] = (unsigned short)(64 * lane + 32 + (__ffs(m) - 1));
+        if (lane == 31) sNLive = x;
+      }
+      __syncthreads();
+      tick(2);
+      const int nLive = sNLive;
+      liveBlocks += nLive;
+      for (int g0 = 0; g0 < nLive; g0 += 32) {  // batches of 32 live blocks (<= 1024 bins), in list order
+        const int gn = min(32, nLive - g0);
+        // -- 3a. per-candidate lower bound (lab_cheap_keep): one warp per block, one lane per bin
+        if (t < 32) { sMaskA[t] = 0u; sMaskB[t] = 0u; }
+        __syncthreads();
+        for (int r = w; r < gn; r += W) {
+          const int i = ((int)sBlk[g0 + r] << 5) + (int)lane;
+          const bool keep = i >= stop && i < liveLen && lab_cheap_keep(P, V, i, err);
+          const unsigned m = __ballot_sync(0xffffffffu, keep);
+          if (lane == 0) sMaskA[r] = m;
+        }
+        __syncthreads();
+        if (w == 0) {
+          const int c = __popc(sMaskA[lane]);
+          int x = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+          sOffA[lane + 1] = x;
+          if (lane == 0) sOffA[0] = 0;
+        }
+        __syncthreads();
+        const int totalA = sOffA[32];
+        // the s-th bin that passed 3a, in list order
+        auto posA = [&](int sIdx) {
+          int lo = 0, hi = 32;                    // largest r with sOffA[r] <= sIdx
+          while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sOffA[mid] <= sIdx) lo = mid; else hi = mid; }
+          return ((int)sBlk[g0 + lo] << 5) + (int)__fns(sMaskA[lo], 0, sIdx - sOffA[lo] + 1);
+        };
+        // -- 3b. screen through the C' term, packed one bin per thread
+        for (int base = 0; base < totalA; base += NQ_LAB_THREADS) {
+          const int sIdx = base + t;
+          LabCand dummy;
+          const bool keep = sIdx < totalA && lab_eval_t<true>(P, V, posA(sIdx), err, &dummy);
+          const unsigned m = __ballot_sync(0xffffffffu, keep);
+          if (lane == 0) sMaskB[(base >> 5) + w] = m;
+        }
+        __syncthreads();
+        if (w == 0) {
+          const int c = __popc(sMaskB[lane]);
+          int x = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+          sOffB[lane + 1] = x;
+          if (lane == 0) sOffB[0] = 0;
+        }
+        __syncthreads();
+        tick(3);
+        const int total = sOffB[32];
+        screened += total;
+        // -- 4. survivors in full, packed; then resolved in order
+        for (int base = 0; base < total; base += NQ_LAB_THREADS) {
+          const int uIdx = base + t;
+          int pos = -1;
+          if (uIdx < total) {
+            int lo = 0, hi = 32;                  // largest word with sOffB[word] <= uIdx
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sOffB[mid] <= uIdx) lo = mid; else hi = mid; }
+            const int sIdx = (lo << 5) + (int)__fns(sMaskB[lo], 0, uIdx - sOffB[lo] + 1);   // index into the 3a list
+            const int i = posA(sIdx);
+            LabCand c;
+            if (lab_eval_t<false>(P, V, i, err, &c)) { pos = i; sGs[t] = c.gs; sGw[t] = c.gw; sF[t] = c.f; }
+          }
+          sPos[t] = pos;
+          fulls += uIdx < total;
+          __syncthreads();
+          if (w == 0) {
+            const int cnt = min(NQ_LAB_THREADS, total - base);
+            for (int q = 0; q < cnt; q += 32) {
+              const int k = q + (int)lane;
+              LabCand c{0, 0, 0};
+              int pp = -1;
+              if (k < cnt) { pp = sPos[k]; if (pp >= 0) { c.gs = sGs[k]; c.gw = sGw[k]; c.f = sF[k]; } }
+              lab_accept_in_order(pp >= 0, c, pp, err, nn);
+            }
+            if (lane == 0) { sErrCur = err; sNnCur = nn; }
+          }
+          __syncthreads();
+          tick(4);
+          err = sErrCur; nn = sNnCur;
+        }
+      }
+      pairs += (unsigned long long)max(0, liveLen - first);
+      if (t == 0) {
+        // tb.tm = i; push slot down (PL:281-293)
+        float e1 = (float)err;
+        S.bErr[b1] = e1; S.bNn[b1] = nn < 0 ? 0 : live[nn]; S.bTm[b1] = sIter;
+        H.sift_down(b1, e1, sHeapN);
+      }
+      __syncthreads();
+      tick(0);
+      continue;
+    }
+
+    // ---- merge tb <- tb + nb (PL:297-311)
+    if (t == 0) {
+      const int nbI = S.bNn[b1];
+      const float n1 = S.bCnt[b1], n2 = S.bCnt[nbI];
+      const float d = 1.0f / (n1 + n2);
+      const float na = d * (n1 * S.fAc[b1] + n2 * S.fAc[nbI]);
+      const float nL = d * (n1 * S.fC1[b1] + n2 * S.fC1[nbI]);
+      const float nA = d * (n1 * S.fC2[b1] + n2 * S.fC2[nbI]);
+      const float nB = d * (n1 * S.fC3[b1] + n2 * S.fC3[nbI]);
+      S.fAc[b1] = na; S.fC1[b1] = nL; S.fC2[b1] = nA; S.fC3[b1] = nB;
+      S.bCnt[b1] = n1 + n2;
+      const int i = sIter + 1;
+      S.bMtm[b1] = i;
+      S.bMtm[nbI] = NQ_DELETED;
+      // compacted copies and the summary of tb's block (the count only grows, L may leave the old range)
+      const int pt = posOf[b1], pn = posOf[nbI];
+      X.cnt[pt] = n1 + n2; X.al[pt] = na; X.L[pt] = nL; X.A[pt] = nA; X.B[pt] = nB; X.C[pt] = chroma_ub(nA, nB);
+      X.cnt[pn] = -1.f;
+      X.blmin[pt >> 5] = fminf(X.blmin[pt >> 5], nL);
+      X.blmax[pt >> 5] = fmaxf(X.blmax[pt >> 5], nL);
+      if (logMerges && S.mergeLog) { S.mergeLog[2 * (i - 1)] = b1; S.mergeLog[2 * (i - 1) + 1] = nbI; }
+      sIter = i;
+    }
+    __syncthreads();
+    const int it = sIter;
+    if ((it - iterAtRebuild) * 4 > liveAtRebuild) {
+      liveLen = rebuild_live_lab(S, X, maxbins, live, posOf, sScan);
+      liveAtRebuild = liveLen; iterAtRebuild = it;
+    }
+    tick(5);
+  }
+
+  // ---- palette fill (PL:315-324): the k-th live bin in ascending order
+  liveLen = rebuild_live_lab(S, X, maxbins, live, posOf, sScan);
+  const int plen = extbins > 0 ? I.nmax : maxbins;
+  for (int k = t; k < plen; k += NQ_LAB_THREADS) {
+    const int b = live[k];
+    uint32_t colr;
+    if (!lab2rgb(j2i((double)S.fAc[b]), S.fC1[b], S.fC2[b], S.fC3[b], &colr)) { colr = 0; I.error = 3; }
+    I.palette[k] = colr;
+  }
+  if (t == 0) {
+    I.paletteLen = plen;
+    I.statRescans = rescans; I.statPairs += pairs; I.statHeapPops = pops;
+    for (int k = 0; k < 6; ++k) I.statCyc[k] = (unsigned long long)cyc[k];
+    I.statLiveBlocks = liveBlocks; I.statScreened = screened;
+  }
+  if (fulls) atomicAdd(&I.statFullEvals, fulls);
+}
+
 
 }  // namespace nq

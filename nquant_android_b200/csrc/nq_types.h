@@ -37,8 +37,10 @@ struct NqImage {
   float bnWeight;          // weight of the BlueNoise second pass
   int error;               // 0 ok, else NQ_ERR_* raised on the device
   // statistics
-  unsigned long long statRescans, statPairs, rngDraws;
+  unsigned long long statRescans, statPairs, rngDraws, statFullEvals;
   unsigned int statHeapPops;
+  // merge-loop phase clocks (SM cycles, thread 0): 0 heap/top, 1 first-32, 2 block tests, 3 screen, 4 full+resolve, 5 merge+rebuild
+  unsigned long long statCyc[6], statLiveBlocks, statScreened;
 };
 
 // Per-image slot of the workspace (device pointers into one big allocation).

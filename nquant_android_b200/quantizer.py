@@ -141,6 +141,15 @@ class Context:
         self._check(self._L.nq_debug_math(self._h, names.index(fn), _p(x), _p(y), _p(out), x.size))
         return out
 
+    def ciede(self, lab1, lab2):
+        """(n, 3) float32 (L, A, B) pairs -> ((n, 4) float32 L', C', H', R_T terms, pairs that took the exact path)."""
+        a = np.ascontiguousarray(lab1, dtype=np.float32).reshape(-1, 3)
+        b = np.ascontiguousarray(lab2, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros((a.shape[0], 4), dtype=np.float32)
+        cnt = ctypes.c_int(0)
+        self._check(self._L.nq_debug_ciede(self._h, _p(a), _p(b), _p(out), ctypes.byref(cnt), a.shape[0]))
+        return out, cnt.value
+
     def synth_device(self, out_ptr, n, width, height, cls, alpha_mode, seed0):
         self._check(self._L.nq_synth_device(self._h, ctypes.c_void_p(out_ptr), n, width, height, cls, alpha_mode, seed0))
 

@@ -1629,6 +1629,10 @@ void nqo_ciede_parts(const float* lab1, const float* lab2, int math_mode, float*
   out4[2] = CIELAB::H_prime_div_k_L_S_L(a, b, a1, a2, c1, c2, bc, bh);
   out4[3] = CIELAB::R_T(bc, bh, out4[1], out4[2]);
 }
+// n pairs: lab1/lab2 hold n x (L, A, B), out n x 4 (L', C', H', R_T terms)
+void nqo_ciede_parts_batch(const float* lab1, const float* lab2, int n, int math_mode, float* out) {
+  for (int i = 0; i < n; ++i) nqo_ciede_parts(lab1 + 3 * (size_t)i, lab2 + 3 * (size_t)i, math_mode, out + 4 * (size_t)i);
+}
 int nqo_java_random_next_int(uint64_t seed, int bound, int n, int* out) {
   JRandom r(seed);
   for (int i = 0; i < n; ++i) out[i] = r.nextInt(bound);

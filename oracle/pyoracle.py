@@ -56,6 +56,7 @@ def lib():
         L.nqo_lab2rgb.argtypes = [cf] * 4 + [ci]
         L.nqo_lab2rgb.restype = ctypes.c_uint32
         L.nqo_ciede_parts.argtypes = [vp, vp, ci, vp]
+        L.nqo_ciede_parts_batch.argtypes = [vp, vp, ci, ci, vp]
         L.nqo_java_random_next_int.argtypes = [ctypes.c_uint64, ci, ci, vp]
         L.nqo_hashmap_order.argtypes = [vp, ci, vp]
         L.nqo_math.argtypes = [ci, cd, cd, ci]
@@ -156,6 +157,15 @@ def ciede_parts(lab1, lab2, math_mode=0):
     b = np.asarray(lab2, dtype=np.float32)
     out = np.zeros(4, dtype=np.float32)
     lib().nqo_ciede_parts(_p(a), _p(b), math_mode, _p(out))
+    return out
+
+
+def ciede_parts_batch(lab1, lab2, math_mode=0):
+    """lab1, lab2: (n, 3) float32 arrays of (L, A, B). Returns (n, 4) float32: L', C', H', R_T terms."""
+    a = np.ascontiguousarray(lab1, dtype=np.float32).reshape(-1, 3)
+    b = np.ascontiguousarray(lab2, dtype=np.float32).reshape(-1, 3)
+    out = np.zeros((a.shape[0], 4), dtype=np.float32)
+    lib().nqo_ciede_parts_batch(_p(a), _p(b), a.shape[0], math_mode, _p(out))
     return out
 
 

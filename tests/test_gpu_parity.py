@@ -41,6 +41,58 @@ def test_device_math_is_bit_identical_to_host(gpu_ctx, oracle):
         assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), name
 
 
+
+def _lab_pairs(rng, n):
+    """Lab pairs shaped like histogram bins: random, near-duplicates, opposite/equal hues, axis cases."""
+    L = rng.uniform(0, 100, (n, 2)).astype(np.float32)
+    A = rng.uniform(-110, 110, (n, 2)).astype(np.float32)
+    B = rng.uniform(-110, 110, (n, 2)).astype(np.float32)
+    k = n // 8
+    # neighbours (what find_nn mostly sees): second colour = first + small step
+    A[:k, 1] = A[:k, 0] + rng.normal(0, 1.5, k).astype(np.float32)
+    B[:k, 1] = B[:k, 0] + rng.normal(0, 1.5, k).astype(np.float32)
+    # same hue, different chroma (dh ~ 0) and exactly opposite hues (|dh| ~ pi, hsum ~ 2 pi)
+    s = rng.uniform(0.1, 3.0, k).astype(np.float32)
+    A[k:2 * k, 1] = A[k:2 * k, 0] * s
+    B[k:2 * k, 1] = B[k:2 * k, 0] * s
+    A[2 * k:3 * k, 1] = -A[2 * k:3 * k, 0] * s
+    B[2 * k:3 * k, 1] = -B[2 * k:3 * k, 0] * s
+    A[3 * k:4 * k, 1] = A[3 * k:4 * k, 0]
+    B[3 * k:4 * k, 1] = -B[3 * k:4 * k, 0]
+    # axis cases and greys
+    A[4 * k:4 * k + k // 4, 0] = 0
+    B[4 * k + k // 4:4 * k + k // 2, 1] = 0
+    A[4 * k + k // 2:5 * k, :] = 0
+    B[4 * k + k // 2:4 * k + 3 * k // 4, :] = 0
+    # tiny chroma
+    A[5 * k:6 * k] *= 1e-3
+    B[5 * k:6 * k] *= 1e-3
+    lab1 = np.stack([L[:, 0], A[:, 0], B[:, 0]], axis=1)
+    lab2 = np.stack([L[:, 1], A[:, 1], B[:, 1]], axis=1)
+    return lab1, lab2
+
+
+def test_ciede_filter_never_changes_a_float(gpu_ctx, oracle):
+    """The plain-double filter in front of the correctly rounded CIEDE2000 kernels (nq_fastmath.cuh) must
+    return exactly the floats of the exact path (oracle: CIELABConvertor.java:91-194 restated)."""
+    rng = np.random.default_rng(2024)
+    n = 400000
+    lab1, lab2 = _lab_pairs(rng, n)
+    got, n_exact = gpu_ctx.ciede(lab1, lab2)
+    ref = oracle.ciede_parts_batch(lab1, lab2)
+    bad = np.nonzero((got.view(np.uint32) != ref.view(np.uint32)).any(axis=1))[0]
+    assert bad.size == 0, (bad[:5], lab1[bad[:5]], lab2[bad[:5]], got[bad[:5]], ref[bad[:5]])
+    # 3/8 of that set is built to defeat the filter; on bin-like pairs it must decide nearly everything
+    m = 100000
+    L = rng.uniform(0, 100, (m, 2)).astype(np.float32)
+    A = rng.uniform(-110, 110, (m, 1)).astype(np.float32) + rng.normal(0, 3, (m, 2)).astype(np.float32)
+    B = rng.uniform(-110, 110, (m, 1)).astype(np.float32) + rng.normal(0, 3, (m, 2)).astype(np.float32)
+    l1, l2 = np.stack([L[:, 0], A[:, 0], B[:, 0]], axis=1), np.stack([L[:, 1], A[:, 1], B[:, 1]], axis=1)
+    got, n_exact = gpu_ctx.ciede(l1, l2)
+    assert np.array_equal(got.view(np.uint32), oracle.ciede_parts_batch(l1, l2).view(np.uint32))
+    assert n_exact < m // 100, f"exact path used for {n_exact} of {m} neighbouring pairs"
+
+
 CASES = [
     # kind, class, alpha, W, H, K, dither
     (0, "noisy", "opaque", 160, 120, 256, True), (1, "noisy", "opaque", 160, 120, 256, True),

@@ -27,7 +27,12 @@ def main():
         st = ctx.stage_times()
         info = ctx.image_info(0)
         print(f"kind={kind} cls={cls} {W}x{H} K={K} dither={dither} batch={batch}: {dt:.3f}s  {batch*npix/dt/1e6:.2f} Mpix/s  "
-              f"bins={info['maxbins']} rescans={info['rescans']} pairs={info['pair_tests']}", flush=True)
+              f"bins={info['maxbins']} rescans={info['rescans']} pairs={info['pair_tests']} full_evals={info['full_evals']}", flush=True)
         print("   " + "  ".join(f"{k}={v[0]:.1f}ms" for k, v in st.items()), flush=True)
+        if kind == 1:
+            mc = info["merge_cycles"]
+            names = ["heap", "first32", "blocktest", "screen", "full", "merge"]
+            print("   merge Mcycles: " + "  ".join(f"{n}={c / 1e6:.0f}" for n, c in zip(names, mc)) +
+                  f"  live_blocks={info['live_blocks']} screened={info['screened']}", flush=True)
 
 main()
