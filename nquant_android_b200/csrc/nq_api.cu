@@ -197,7 +197,7 @@ namespace {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SlotLayout {
-  size_t hCnt, hSum, keyOff, sortA, sortB, warpHist, sal, bD, bF, bCnt, bErr, bNn, bTm, bMtm, hErr, hId, mergeLog, memo, total;
+  size_t hCnt, hSum, keyOff, sortA, sortB, warpHist, sal, bD, bF, bCnt, bErr, bNn, bTm, bMtm, hErr, hId, mergeLog, memo, cells, total;
 };
 SlotLayout slot_layout(int kind, int npix, bool debug) {
   SlotLayout L;
@@ -220,6 +220,7 @@ SlotLayout slot_layout(int kind, int npix, bool debug) {
   L.hId = take((NQ_NBINS + 1) * 4);
   L.mergeLog = take(debug ? (size_t)2 * NQ_NBINS * 4 : 0);
   L.memo = take(NQ_NBINS * 2);
+  L.cells = take(lab ? (size_t)32768 * 32 : 0);
   L.total = o;
   return L;
 }
@@ -283,6 +284,7 @@ int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots) {
     S.hId = reinterpret_cast<int*>(b + L.hId);
     S.mergeLog = c->debug ? reinterpret_cast<int*>(b + L.mergeLog) : nullptr;
     S.memo = reinterpret_cast<unsigned short*>(b + L.memo);
+    S.cells = lab ? b + L.cells : nullptr;
     S.idx = nullptr;
   }
   c->wsSlots = slots; c->wsNpix = npix; c->wsKind = kind; c->sortPool = pool; c->wsDebug = c->debug;
@@ -421,9 +423,10 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
     nq::k_dither_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
   }
   if (kind == NQ_KIND_LAB && c->debug) { nq::k_saliency<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches; }
+  if (kind == NQ_KIND_LAB) { nq::k_build_cells<<<dim3(std::max(1, std::min(128, c->smCount * 8 / n)), n), 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches; }
   mark(5);
   // each kernel returns at once for images of the other queue mode (decided on the device)
-  nq::k_dither_fifo<<<n, 32, 0, st>>>(c->dImgs, c->dSlots, dOrder); ++c->launches;
+  nq::k_dither_fifo<<<n, 64, 0, st>>>(c->dImgs, c->dSlots, dOrder); ++c->launches;
   nq::k_dither_sorted<<<n, 32, 0, st>>>(c->dImgs, c->dSlots, dOrder); ++c->launches;
   mark(6);
   CU(cudaGetLastError());

@@ -27,6 +27,8 @@ struct WarpShared {
   // PnnLABQuantizer.closestColorIndex cost split per channel: T?[v] = cost of a channel difference of
   // |v| (see closest_lab); Ta only when the image is semi-transparent
   double Tr[256], Tg[256], Tb[256], Ta[256];
+  // java.util.Random jump-ahead: seed after k more steps = jmpA[k] * seed + jmpC[k] (mod 2^48), k = 0..32
+  unsigned long long jmpA[33], jmpC[33];
 };
 // java.util.PriorityQueue state of the sortedByYDiff mode (GC:87-94)
 struct SortedShared {
@@ -43,6 +45,7 @@ struct Env {
   double PR, PG, PB, PA, ratio, gWeight, exp15;
   float beta;
   unsigned short* memo;
+  const uint4* cells;         // candidate lists of the closest-colour scan, 32 B per 5-5-5 RGB cell (k_build_cells)
   JRandom rng;
   unsigned long long draws;
   int width;
@@ -258,17 +261,20 @@ __device__ __forceinline__ double closest_lab_err(const Env& E, uint32_t c2, int
 // regrouped sum A = Tr[|dr|] + Tg[|dg|] + Tb[|db|] (+ Ta[|da|]) agree to a few ulp:
 // |S - A| <= 2e-14 * A. Only floor(S) enters the top-2 decision (see Top2), so A decides it unless A
 // lies within 1e-6 (>> 2e-14 * 2^31) of an integer, in which case the exact S is evaluated.
-__device__ void closest_lab_tables(const Env& E) {
-  for (int v = lane_id(); v < 256; v += 32) {
-    const double dv = (double)v;
-    double tr = E.PR * (1 - E.ratio) * (dv * dv), tg = E.PG * (1 - E.ratio) * (dv * dv), tb = E.PB * (1 - E.ratio) * (dv * dv);
-    for (int i = 0; i < 3; ++i) {
-      double t0 = (double)(c_coeffs[i][0] * (float)v), t1 = (double)(c_coeffs[i][1] * (float)v), t2 = (double)(c_coeffs[i][2] * (float)v);
-      tr += E.ratio * (t0 * t0); tg += E.ratio * (t1 * t1); tb += E.ratio * (t2 * t2);
-    }
-    E.sh->Tr[v] = tr; E.sh->Tg[v] = tg; E.sh->Tb[v] = tb;
-    E.sh->Ta[v] = E.semi ? E.PA * (dv * dv) : 0.0;
+__device__ __forceinline__ void closest_lab_table_entry(double PR, double PG, double PB, double PA, double ratio, bool semi, int v,
+                                                        double* tr, double* tg, double* tb, double* ta) {
+  const double dv = (double)v;
+  double r = PR * (1 - ratio) * (dv * dv), g = PG * (1 - ratio) * (dv * dv), b = PB * (1 - ratio) * (dv * dv);
+  for (int i = 0; i < 3; ++i) {
+    double t0 = (double)(c_coeffs[i][0] * (float)v), t1 = (double)(c_coeffs[i][1] * (float)v), t2 = (double)(c_coeffs[i][2] * (float)v);
+    r += ratio * (t0 * t0); g += ratio * (t1 * t1); b += ratio * (t2 * t2);
   }
+  *tr = r; *tg = g; *tb = b;
+  *ta = semi ? PA * (dv * dv) : 0.0;
+}
+__device__ void closest_lab_tables(const Env& E) {
+  for (int v = lane_id(); v < 256; v += 32)
+    closest_lab_table_entry(E.PR, E.PG, E.PB, E.PA, E.ratio, E.semi, v, &E.sh->Tr[v], &E.sh->Tg[v], &E.sh->Tb[v], &E.sh->Ta[v]);
   __syncwarp();
 }
 
@@ -513,9 +519,8 @@ struct DitherCtx {
   bool salReplaced;
 };
 
-// common prologue: palette, tables and the constants of the GilbertCurve object
-__device__ __forceinline__ void dither_prologue(NqImage& I, const NqSlot& S, WarpShared& sh, DitherCtx& D) {
-  const unsigned lane = lane_id();
+// common prologue, register part: the constants of the GilbertCurve object
+__device__ __forceinline__ void dither_prologue_regs(NqImage& I, const NqSlot& S, WarpShared& sh, DitherCtx& D) {
   Env& E = D.E;
   const int plen = I.paletteLen;
   E.sh = &sh;
@@ -527,17 +532,34 @@ __device__ __forceinline__ void dither_prologue(NqImage& I, const NqSlot& S, War
   E.exp15 = E.semi ? nqm::nq_exp(1.5) : 1.0;
   E.beta = I.gBeta;
   E.memo = S.memo;
+  E.cells = reinterpret_cast<const uint4*>(S.cells);
   E.rng.set_seed(I.seed);
   E.draws = 0;
   E.width = I.width;
   D.in = S.in; D.out = S.out; D.npix = I.npix; D.width = I.width; D.fixA0 = I.fixA0;
   D.salReplaced = I.nmax < 128 && I.nmax > 2;   // which pixel feeds getLab for the saliency (PL:141-156 vs PL:503-506)
+}
+// ... and the shared tables (one warp)
+__device__ __forceinline__ void dither_prologue(NqImage& I, const NqSlot& S, WarpShared& sh, DitherCtx& D) {
+  dither_prologue_regs(I, S, sh, D);
+  const unsigned lane = lane_id();
+  Env& E = D.E;
+  const int plen = I.paletteLen;
   for (int i = lane; i < 256; i += 32) sh.lut[i] = g_gammaLut[i];
   for (int i = lane; i < 4096; i += 32) sh.bn[i] = g_blueNoise[i];
   for (int i = lane; i < plen; i += 32) {
     uint32_t pc = I.palette[i];
     sh.pal[i] = pc;
     if (E.lab) { Lab4 l = lab_of(pc); sh.palLab[i] = make_float4(l.alpha, l.L, l.A, l.B); }
+  }
+  if (lane == 0) {
+    unsigned long long a = 1ULL, c = 0ULL;
+    const unsigned long long MASK = (1ULL << 48) - 1;
+    for (int k = 0; k <= 32; ++k) {
+      sh.jmpA[k] = a; sh.jmpC[k] = c;
+      a = (a * 0x5DEECE66DULL) & MASK;
+      c = (c * 0x5DEECE66DULL + 0xBULL) & MASK;
+    }
   }
   __syncwarp();
   if (E.lab && plen > 4) closest_lab_tables(E);
@@ -698,11 +720,184 @@ __device__ __forceinline__ void closest_scan_lane(const Env& E, uint32_t c, unsi
   }
 }
 
-// the ordered (n+1)-th accepted value of java.util.Random.nextInt(32767) is a pure function of the seed
-// and n: a block's draws are generated in order by every lane, each lane keeping its own.
+// -------------------------------------------------------------------------------------------------
+// Candidate lists for the closest-colour scan. The cost of palette entry p for colour c is separable,
+// S_p(c) = Tr[|dr|] + Tg[|dg|] + Tb[|db|] with every table increasing, so over a cell of 8x8x8 colours
+// (5-5-5 bits of r, g, b) it lies in [lo_p, hi_p] with lo/hi taken at the nearest/farthest corner. With
+// D2 = the second smallest floor(hi_p), an entry with floor(lo_p) > D2 can never be one of the two smallest
+// (floor(err), index) pairs the scan keeps (PL:418-458). Each cell stores up to 31 candidates (byte 0 =
+// count, 255 = too many: scan the whole palette). Only used for images without semi-transparency.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_build_cells(const NqImage* imgs, const NqSlot* slots) {
+  __shared__ double Tr[256], Tg[256], Tb[256];
+  __shared__ uint32_t pal[NQ_MAXK];
+  const int img = blockIdx.y;
+  const NqImage& I = imgs[img];
+  const int plen = I.paletteLen;
+  if (I.kind != NQ_KIND_LAB || !I.gUseSal || !I.dither || I.gSorted || I.gHasAlpha || plen <= 4 || I.error || !slots[img].cells) return;
+  const int t = threadIdx.x;
+  {
+    double ta;
+    closest_lab_table_entry(I.PR, I.PG, I.PB, I.PA, I.ratioMerge, false, t, &Tr[t], &Tg[t], &Tb[t], &ta);
+    if (t < plen) pal[t] = I.palette[t];
+  }
+  __syncthreads();
+  unsigned char* out = slots[img].cells;
+  for (int cell = blockIdx.x * blockDim.x + t; cell < 32768; cell += gridDim.x * blockDim.x) {
+    const int r0 = (cell >> 10) << 3, g0 = ((cell >> 5) & 31) << 3, b0 = (cell & 31) << 3;
+    // pass 1: the two smallest floor(hi)
+    int h0 = 0x7fffffff, h1 = 0x7fffffff;
+    for (int k = 0; k < plen; ++k) {
+      const uint32_t pc = pal[k];
+      const int pr = c_red(pc), pg = c_green(pc), pb = c_blue(pc);
+      const double hi = Tr[max(abs(pr - r0), abs(pr - r0 - 7))] + Tg[max(abs(pg - g0), abs(pg - g0 - 7))] + Tb[max(abs(pb - b0), abs(pb - b0 - 7))];
+      const int d = j2i(hi * (1.0 + 1e-12) + 1e-9);
+      if (d < h0) { h1 = h0; h0 = d; } else if (d < h1) h1 = d;
+    }
+    // pass 2: everything that can still reach the top two
+    unsigned words[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+    for (int k = 0; k < plen; ++k) {
+      const uint32_t pc = pal[k];
+      const int pr = c_red(pc), pg = c_green(pc), pb = c_blue(pc);
+      const double lo = Tr[max(0, max(r0 - pr, pr - r0 - 7))] + Tg[max(0, max(g0 - pg, pg - g0 - 7))] + Tb[max(0, max(b0 - pb, pb - b0 - 7))];
+      const int d = j2i(lo * (1.0 - 1e-12) - 1e-9);
+      if (d <= h1) {
+        ++cnt;
+        if (cnt <= 31) words[cnt >> 2] |= (unsigned)k << (8 * (cnt & 3));
+      }
+    }
+    words[0] |= cnt > 31 ? 255u : (unsigned)cnt;
+    uint4* o = reinterpret_cast<uint4*>(out + (size_t)cell * 32);
+    o[0] = make_uint4(words[0], words[1], words[2], words[3]);
+    o[1] = make_uint4(words[4], words[5], words[6], words[7]);
+  }
+}
 
-__global__ void __launch_bounds__(32) k_dither_fifo(NqImage* imgs, const NqSlot* slots, const uint32_t* order) {
+// top-2 scan of one colour per lane over its cell's candidate list (see k_build_cells); false if any
+// lane's cell overflowed (the caller then scans the whole palette)
+__device__ __forceinline__ bool closest_scan_cells(const Env& E, uint32_t c, bool active, unsigned& k0, unsigned& k1) {
+  const WarpShared& sh = *E.sh;
+  const int ca = c_alpha(c), cr = c_red(c), cg = c_green(c), cb = c_blue(c);
+  k0 = K2_NONE; k1 = K2_NONE;
+  unsigned w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    const uint4* p = E.cells + 2 * (size_t)(((cr >> 3) << 10) | ((cg >> 3) << 5) | (cb >> 3));
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  }
+  const int cnt = (int)(w[0] & 255u);
+  if (__any_sync(FULL, cnt == 255)) return false;
+  const int maxCnt = __reduce_max_sync(FULL, cnt);
+  const double MAGIC = 6442450944.0;
+#pragma unroll
+  for (int j = 1; j < 32; ++j) {
+    if (j > maxCnt) break;
+    const int k = (int)((w[j >> 2] >> (8 * (j & 3))) & 255u);
+    const uint32_t c2 = sh.pal[k];
+    double a = sh.Tr[abs(c_red(c2) - cr)] + sh.Tg[abs(c_green(c2) - cg)] + sh.Tb[abs(c_blue(c2) - cb)];
+    const long long bits = __double_as_longlong(a + MAGIC);
+    const unsigned lo = (unsigned)bits, hi = (unsigned)(bits >> 32) & 0x7FFFFu;
+    int d = (int)__funnelshift_r(lo, hi, 20);
+    const unsigned fr = lo & 0xFFFFFu;
+    if (((fr + 2u) & 0xFFFFFu) < 4u) d = j2i(closest_lab_err(E, c2, ca, cr, cg, cb));
+    const unsigned key = j <= cnt ? (((unsigned)d << 8) | (unsigned)k) : K2_NONE;
+    const unsigned t = max(key, k0);
+    k0 = min(key, k0);
+    k1 = min(k1, t);
+  }
+  return true;
+}
+
+// Ring between the producer warp (gathers pixels, does the pre-lookups) and the consumer warp (the
+// serial error recurrence). Block b lives in slot b & 3. Counters only grow: `fetched` blocks have their
+// pixels in the ring, `looked` blocks their pre-lookup result (or the note that there is none),
+// `consumed` blocks are finished. The java.util.Random state and the draw counter travel through the
+// ring too: whoever does lookups (producer for pre-lookup blocks, consumer for the others) owns them,
+// and the producer never commits a block before every earlier non-pre block has been consumed.
+#define NQ_RING 4
+struct DitherRing {
+  uint32_t px[NQ_RING][32], xy[NQ_RING][32], pre[NQ_RING][32];
+  float sal[NQ_RING][32];
+  double ypix[NQ_RING][32];
+  unsigned diffMask[NQ_RING];
+  int blockPre[NQ_RING];
+  int fetched, looked, consumed;
+  unsigned long long rngSeed, draws;
+};
+__device__ __forceinline__ void ring_wait(const int* p, int v) {
+  const volatile int* vp = p;
+  while (*vp < v) __nanosleep(40);
+  __syncwarp();
+  __threadfence_block();
+}
+__device__ __forceinline__ void ring_signal(int* p, int v) {
+  __syncwarp();
+  __threadfence_block();
+  if (lane_id() == 0) *(volatile int*)p = v;
+}
+
+// pre-lookup of one block: colour c per lane (dither_pixel_pre), top-2 scan, java.util.Random draws and
+// nearest fallbacks in curve order. Returns the palette colour chosen for this lane's pixel.
+__device__ uint32_t prelookup_commit(Env& E, uint32_t c, bool mine) {
+  WarpShared& sh = *E.sh;
+  const unsigned lane = lane_id();
+  const int plen = E.plen;
+  const int ca = c_alpha(c);
+  const bool viaClosest = mine && plen > 4 && ca > 0xF;    // PL:484-487, PL:407-408
+  unsigned k0 = K2_NONE, k1 = K2_NONE;
+  if (__any_sync(FULL, viaClosest)) {
+    if (!E.cells || E.semi || !closest_scan_cells(E, c, viaClosest, k0, k1)) closest_scan_lane(E, c, k0, k1);
+  }
+  const int c0 = k0 == K2_NONE ? 0 : (int)(k0 & 255u), d0 = k0 == K2_NONE ? T2_NONE : (int)(k0 >> 8);
+  const int c1 = k1 == K2_NONE ? c0 : (int)(k1 & 255u), d1 = k1 == K2_NONE ? T2_NONE : (int)(k1 >> 8);
+  const bool draw = viaClosest && d0 != 0;                  // short-circuit: no draw when closest[2] == 0 (PL:467)
+  const unsigned dm = __ballot_sync(FULL, draw);
+  const int myDraw = __popc(dm & ((1u << lane) - 1u)), total = __popc(dm);
+  int r = 0;
+  if (total) {
+    // jump ahead: this lane's draw is step myDraw + 1 from the current seed, unless a nextInt in the block
+    // rejected its first value (probability 1.5e-5 per draw), in which case the block is replayed in order
+    const unsigned long long MASK = (1ULL << 48) - 1;
+    const unsigned long long sd = (sh.jmpA[myDraw + 1] * E.rng.seed + sh.jmpC[myDraw + 1]) & MASK;
+    const int u = (int)(sd >> 17);
+    r = u % 32767;
+    const bool rejected = draw && (int)((unsigned)(u - r) + 32766u) < 0;
+    if (__any_sync(FULL, rejected)) {
+      for (int t = 0; t < total; ++t) {
+        const int v = E.rng.next_int(32767);
+        if (myDraw == t) r = v;
+      }
+    } else
+      E.rng.seed = (sh.jmpA[total] * E.rng.seed + sh.jmpC[total]) & MASK;
+  }
+  E.draws += (unsigned long long)total;
+  int idx = 1;
+  if (d0 == 0) idx = 0;
+  else {
+    const int sum = (int)((unsigned)d1 + (unsigned)d0);
+    if ((r % sum) <= d1) idx = 0;
+  }
+  const int ci = idx ? c1 : c0, ei = idx ? d1 : d0;
+  int qi = ci;
+  bool needNear = mine && (!viaClosest || ei >= plen || ci == 0 || c_alpha(sh.pal[ci]) < ca);   // PL:470-472
+  if (E.isNano && needNear) {   // memo entries never change once written: hits can be read out of order
+    const unsigned short got = *(volatile unsigned short*)&E.memo[color_index(c, E.semi, E.hasTrans)];
+    if (got != 0xFFFF) { qi = got; needNear = false; }
+  }
+  unsigned nm = __ballot_sync(FULL, needNear);
+  while (nm) {                  // misses in curve order (first-seen colour fixes a bucket, PL:332-335,402)
+    const int L = __ffs(nm) - 1;
+    nm &= nm - 1;
+    const int res = nearest_lab(E, __shfl_sync(FULL, c, L));
+    if ((int)lane == L) qi = res;
+  }
+  return sh.pal[qi];
+}
+
+__global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot* slots, const uint32_t* order) {
   __shared__ WarpShared sh;
+  __shared__ DitherRing ring;
   const int img = blockIdx.x;
   NqImage& I = imgs[img];
   const NqSlot& S = slots[img];
@@ -710,24 +905,74 @@ __global__ void __launch_bounds__(32) k_dither_fifo(NqImage* imgs, const NqSlot*
   const int plen = I.paletteLen;
   if (plen <= 0 || I.error || I.gSorted) return;
   DitherCtx D;
-  dither_prologue(I, S, sh, D);
+  const bool producer = threadIdx.x >= 32;
+  if (!producer) {
+    dither_prologue(I, S, sh, D);
+    if (lane == 0) { ring.fetched = 0; ring.looked = 0; ring.consumed = 0; ring.rngSeed = D.E.rng.seed; ring.draws = 0; }
+  }
+  __syncthreads();
+  if (producer) dither_prologue_regs(I, S, sh, D);      // same registers, shared tables already filled
   Env& E = D.E;
   const int npix = D.npix, width = D.width;
-  uint32_t* out = D.out;
+  const int nblocks = (npix + 31) >> 5;
 
   const int DM = E.DM;
   const bool useSal = E.useSal, dither = E.dither;
-  const int thresold = E.thresold, ditherMax = E.ditherMax, margin = E.margin;
+  const int thresold = E.thresold, margin = E.margin;
   const signed char* bn = sh.bn;
+  const int acceptedDiff = max(2, plen - margin);
+  // images whose ditherPixel lookups do not read the diffused colour (see above)
+  const bool preImg = E.lab && useSal && dither && !E.gHasAlpha && (plen <= 4 || 2 * acceptedDiff > 101);
+
+  if (producer) {
+    // =========================== producer warp ===========================
+    int lastSlow = -1;                           // last block left to the consumer's own lookups
+    for (int b = 0; b < nblocks; ++b) {
+      const int slot = b & (NQ_RING - 1);
+      ring_wait(&ring.consumed, b - (NQ_RING - 1));
+      const PixBlock cur = fetch_block(D, order, b << 5);
+      const int cnt = min(32, npix - (b << 5));
+      const bool mine = (int)lane < cnt;
+      const int myX = cur.xy & 0xFFFF, myY = cur.xy >> 16, myBidx = myX + myY * width;
+      const unsigned diffMask = __ballot_sync(FULL, mine && bn[myBidx & 4095] > thresold);
+      ring.px[slot][lane] = cur.px; ring.xy[slot][lane] = cur.xy; ring.sal[slot][lane] = cur.sal; ring.ypix[slot][lane] = cur.ypix;
+      if (lane == 0) ring.diffMask[slot] = diffMask;
+      ring_signal(&ring.fetched, b + 1);
+
+      bool blockPre = false;
+      uint32_t preCol = 0;
+      if (preImg) {
+        uint32_t c = 0;
+        bool ok = true;
+        if (mine) {
+          if (plen >= 256 && cur.sal > .99f) ok = false;          // GC:214-215: looks up the diffused colour
+          else ok = dither_pixel_pre(E, myX, myY, cur.px, cur.sal, cur.ypix, &c);
+        }
+        blockPre = __all_sync(FULL, ok);
+        if (blockPre) {
+          ring_wait(&ring.consumed, lastSlow + 1);   // the consumer is done drawing for every earlier block
+          E.rng.seed = ring.rngSeed; E.draws = ring.draws;
+          preCol = prelookup_commit(E, c, mine);
+          if (lane == 0) { ring.rngSeed = E.rng.seed; ring.draws = E.draws; }
+        }
+      }
+      if (!blockPre) lastSlow = b;
+      ring.pre[slot][lane] = preCol;
+      if (lane == 0) ring.blockPre[slot] = blockPre ? 1 : 0;
+      ring_signal(&ring.looked, b + 1);
+    }
+    return;
+  }
+
+  // =========================== consumer warp ===========================
+  uint32_t* out = D.out;
+  const int ditherMax = E.ditherMax;
   const float wk = lane < (unsigned)DM ? I.gWeights[lane] : 0.f;   // this lane's tap
   const float wLast = I.gWeights[DM - 1];
   const float fDitherMax = (float)ditherMax, fDitherMax1 = (float)(ditherMax - 1);
   const float divisor = (float)(1 + nqm::sqrt_((double)ditherMax));
   const bool denoise = plen > 2;
   const bool illusion0 = bn[0] > thresold;          // yDiff == 1: bn[(int)(4096.0) & 4095] (GC:251-252)
-  const int acceptedDiff = max(2, plen - margin);
-  // images whose ditherPixel lookups do not read the diffused colour (see above)
-  const bool preImg = E.lab && useSal && dither && !E.gHasAlpha && (plen <= 4 || 2 * acceptedDiff > 101);
 
   // systolic state: lane k carries the sum of some pixel through tap k, and its running maximum
   float P0 = 0.f, P1 = 0.f, P2 = 0.f, P3 = 0.f, M = (float)(DM - 1);
@@ -745,93 +990,56 @@ __global__ void __launch_bounds__(32) k_dither_fifo(NqImage* imgs, const NqSlot*
     M = fmaxf(fmaxf(fmaxf(qm, P0), fmaxf(P1, P2)), P3);
   };
 
-  PixBlock nxt = fetch_block(D, order, 0);
+  ring_wait(&ring.fetched, 1);
+  uint32_t nxtPx = ring.px[0][lane];
   // fill the pipeline: pixels 0 .. DM-2 enter with zero errors behind them
-  for (int s = 0; s < DM - 1; ++s) advance(__shfl_sync(FULL, nxt.px, s));
+  for (int s = 0; s < DM - 1; ++s) advance(__shfl_sync(FULL, nxtPx, s));
 
-  for (int n0 = 0; n0 < npix; n0 += 32) {
-    const PixBlock cur = nxt;
-    nxt = fetch_block(D, order, n0 + 32);
+  for (int b = 0; b < nblocks; ++b) {
+    const int slot = b & (NQ_RING - 1), n0 = b << 5;
+    ring_wait(&ring.looked, b + 1);
+    ring_wait(&ring.fetched, min(b + 2, nblocks));
+    const uint32_t curPx = nxtPx;
+    nxtPx = b + 1 < nblocks ? ring.px[(b + 1) & (NQ_RING - 1)][lane] : 0u;
+    const uint32_t curXy = ring.xy[slot][lane];
+    const uint32_t preCol = ring.pre[slot][lane];
+    const bool blockPre = ring.blockPre[slot] != 0;
+    const unsigned diffMask = ring.diffMask[slot];
+    float curSal = 0.f;
+    double curY = 0.0;
+    if (!blockPre) {
+      curSal = ring.sal[slot][lane]; curY = ring.ypix[slot][lane];
+      E.rng.seed = ring.rngSeed; E.draws = ring.draws;
+    }
     const int cnt = min(32, npix - n0);
     const bool mine = (int)lane < cnt;
-    const int myX = cur.xy & 0xFFFF, myY = cur.xy >> 16, myBidx = myX + myY * width;
-    const unsigned diffMask = __ballot_sync(FULL, mine && bn[myBidx & 4095] > thresold);
-
-    // ---- pre-lookup of the whole block (one pixel per lane)
-    bool blockPre = false;
-    uint32_t preCol = 0;
-    if (preImg) {
-      uint32_t c = 0;
-      bool ok = true;
-      if (mine) {
-        if (plen >= 256 && cur.sal > .99f) ok = false;          // GC:214-215: looks up the diffused colour
-        else ok = dither_pixel_pre(E, myX, myY, cur.px, cur.sal, cur.ypix, &c);
-      }
-      blockPre = __all_sync(FULL, ok);
-      if (blockPre) {
-        const int ca = c_alpha(c);
-        const bool viaClosest = mine && plen > 4 && ca > 0xF;    // PL:484-487, PL:407-408
-        unsigned k0 = K2_NONE, k1 = K2_NONE;
-        if (__any_sync(FULL, viaClosest)) closest_scan_lane(E, c, k0, k1);
-        const int c0 = k0 == K2_NONE ? 0 : (int)(k0 & 255u), d0 = k0 == K2_NONE ? T2_NONE : (int)(k0 >> 8);
-        const int c1 = k1 == K2_NONE ? c0 : (int)(k1 & 255u), d1 = k1 == K2_NONE ? T2_NONE : (int)(k1 >> 8);
-        const bool draw = viaClosest && d0 != 0;                  // short-circuit: no draw when closest[2] == 0 (PL:467)
-        const unsigned dm = __ballot_sync(FULL, draw);
-        const int myDraw = __popc(dm & ((1u << lane) - 1u)), total = __popc(dm);
-        int r = 0;
-        for (int t = 0; t < total; ++t) {
-          const int v = E.rng.next_int(32767);
-          if (myDraw == t) r = v;
-        }
-        E.draws += (unsigned long long)total;
-        int idx = 1;
-        if (d0 == 0) idx = 0;
-        else {
-          const int sum = (int)((unsigned)d1 + (unsigned)d0);
-          if ((r % sum) <= d1) idx = 0;
-        }
-        const int ci = idx ? c1 : c0, ei = idx ? d1 : d0;
-        int qi = ci;
-        bool needNear = mine && (!viaClosest || ei >= plen || ci == 0 || c_alpha(sh.pal[ci]) < ca);   // PL:470-472
-        if (E.isNano && needNear) {   // memo entries never change once written: hits can be read out of order
-          const unsigned short got = E.memo[color_index(c, E.semi, E.hasTrans)];
-          if (got != 0xFFFF) { qi = got; needNear = false; }
-        }
-        unsigned nm = __ballot_sync(FULL, needNear);
-        while (nm) {                  // misses in curve order (first-seen colour fixes a bucket, PL:332-335,402)
-          const int L = __ffs(nm) - 1;
-          nm &= nm - 1;
-          const int res = nearest_lab(E, __shfl_sync(FULL, c, L));
-          if ((int)lane == L) qi = res;
-        }
-        preCol = sh.pal[qi];
-      }
-    }
+    const int myBidx = (int)(curXy & 0xFFFF) + (int)(curXy >> 16) * width;
 
     uint32_t myOut = preCol;
     for (int j = 0; j < cnt; ++j) {
       // ---- independent of the previous pixel's error: sum of this pixel through tap DM-2
       const float b0 = __shfl_sync(FULL, P0, DM - 2), b1 = __shfl_sync(FULL, P1, DM - 2), b2 = __shfl_sync(FULL, P2, DM - 2), b3 = __shfl_sync(FULL, P3, DM - 2);
       const float bm = __shfl_sync(FULL, M, DM - 2);
-      const uint32_t pixel = __shfl_sync(FULL, cur.px, j);
+      const uint32_t pixel = __shfl_sync(FULL, curPx, j);
       const int jn = j + DM - 1;
-      const uint32_t injA = __shfl_sync(FULL, cur.px, jn & 31), injB = __shfl_sync(FULL, nxt.px, jn & 31);
+      const uint32_t injA = __shfl_sync(FULL, curPx, jn & 31), injB = __shfl_sync(FULL, nxtPx, jn & 31);
       const uint32_t inject = jn < 32 ? injA : injB;
 
       // ---- last tap, clamp (GC:199-211)
       const float a0 = b0 + e0 * wLast, a1 = b1 + e1 * wLast, a2 = b2 + e2 * wLast, a3 = b3 + e3 * wLast;
       const float maxErr = fmaxf(fmaxf(fmaxf(bm, a0), fmaxf(a1, a2)), a3);
-      const int r_pix = j2i(dmin(255.0, dmax((double)a0, 0.0))), g_pix = j2i(dmin(255.0, dmax((double)a1, 0.0)));
-      const int b_pix = j2i(dmin(255.0, dmax((double)a2, 0.0))), a_pix = j2i(dmin(255.0, dmax((double)a3, 0.0)));
+      // (int) Math.min(BYTE_MAX, Math.max(error.p[j], 0.0)): widening the float is exact, so the clamp can stay in float
+      const int r_pix = __float2int_rz(fminf(255.f, fmaxf(a0, 0.f))), g_pix = __float2int_rz(fminf(255.f, fmaxf(a1, 0.f)));
+      const int b_pix = __float2int_rz(fminf(255.f, fmaxf(a2, 0.f))), a_pix = __float2int_rz(fminf(255.f, fmaxf(a3, 0.f)));
       advance(inject);     // uses e0..e3 of the previous pixel; must precede their update below
 
       // ---- quantize (GC:211-229)
       uint32_t pc;
       if (blockPre) pc = __shfl_sync(FULL, preCol, j);
       else {
-        const uint32_t xy = __shfl_sync(FULL, cur.xy, j);
+        const uint32_t xy = __shfl_sync(FULL, curXy, j);
         const int x = xy & 0xFFFF, y = xy >> 16;
-        const int qi = quantize_pixel(E, x, y, x + y * width, pixel, __shfl_sync(FULL, cur.sal, j), shfl_d(cur.ypix, j),
+        const int qi = quantize_pixel(E, x, y, x + y * width, pixel, __shfl_sync(FULL, curSal, j), shfl_d(curY, j),
                                       c_argb(a_pix, r_pix, g_pix, b_pix));
         pc = sh.pal[qi];
         const uint32_t res = (dither || plen <= 32) ? pc : (uint32_t)qi;   // GC:278-279
@@ -860,8 +1068,11 @@ __global__ void __launch_bounds__(32) k_dither_fifo(NqImage* imgs, const NqSlot*
       }
     }
     if (mine) out[myBidx] = myOut;
+    if (!blockPre && lane == 0) { ring.rngSeed = E.rng.seed; ring.draws = E.draws; }
+    ring_signal(&ring.consumed, b + 1);
   }
 
+  E.rng.seed = ring.rngSeed; E.draws = ring.draws;
   if (!dither && plen > 32) bluenoise_pass(I, D);
   if (lane == 0) I.rngDraws = E.draws;
 }

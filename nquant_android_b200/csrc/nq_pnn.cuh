@@ -104,12 +104,12 @@ __device__ __forceinline__ LabProbe lab_probe(const NqImage& I, const NqSlot& S,
 }
 struct LabCand { double gs, gw, f; };
 
-// Candidate bins as five position-indexed float arrays plus one summary per 32 positions. For the
+// Candidate bins as position-indexed records plus one summary per 32 positions. For the
 // initial sweep the position is the bin index; inside the merge loop it is the position in the
 // compacted list of surviving bins (cnt < 0 marks a bin that died since the last compaction).
 struct LabView {
-  const float *cnt, *al, *L, *A, *B;
-  const float* C;                       // chroma_ub(A, B) per position
+  const float4* q;                      // {cnt, L, A, B} per position: one 16-byte load per candidate
+  const float* al;                      // alpha per position (read only for semi-transparent images)
   const float *bcmin, *blmin, *blmax;   // per block of 32 positions: min count, min L, max L (conservative)
   int n;
 };
@@ -152,13 +152,17 @@ __global__ void k_init_rtfac() {
 //   S_H <= S_C = 1 + .045 barC', barC' <= .75 (C1 + C2)   (G <= .5).
 // The slack terms cover the float roundings of the reference's own evaluation (the float difference of the two
 // C' values is off by up to 1.3e-7 max(C')). Returns false only if the reference must reject i given err.
+__device__ __forceinline__ bool lab_cheap_keep_q(const LabProbe& P, const float4 cq, double err);
 __device__ __forceinline__ bool lab_cheap_keep(const LabProbe& P, const LabView& V, int i, double err) {
-  const float n2 = V.cnt[i];
+  return lab_cheap_keep_q(P, V.q[i], err);
+}
+__device__ __forceinline__ bool lab_cheap_keep_q(const LabProbe& P, const float4 cq, double err) {
+  const float n2 = cq.x;
   if (!(n2 >= 0.f)) return false;
   const double nerr2 = (double)((P.n1 * n2) / (P.n1 + n2));       // the reference's own value and test (PL:56-57)
   if (nerr2 >= err) return false;
-  const float dl = V.L[i] - P.L1, da = V.A[i] - P.A1, db = V.B[i] - P.B1;
-  const float cb = (0.75f * (P.C1 + V.C[i])) * 1.00001f;
+  const float dl = cq.y - P.L1, da = cq.z - P.A1, db = cq.w - P.B1;
+  const float cb = (0.75f * (P.C1 + chroma_ub(cq.z, cq.w))) * 1.00001f;
   const float sc = (1.f + (0.045f * cb)) * 1.00001f;
   const float rf = g_rtFac[min(255, (int)cb)];
   const float d2 = fmaxf(0.f, (((da * da) + (db * db)) * 0.9999f) - 1e-4f);
@@ -173,13 +177,14 @@ __device__ __forceinline__ bool lab_cheap_keep(const LabProbe& P, const LabView&
 // true iff the candidate is still alive there.
 template <bool STOP_AFTER_C>
 __device__ __forceinline__ bool lab_eval_t(const LabProbe& P, const LabView& V, int i, double err, LabCand* c) {
-  const float n2 = V.cnt[i];
+  const float4 cq = V.q[i];
+  const float n2 = cq.x;
   if (!(n2 >= 0.f)) return false;                         // dead since the last compaction
   double nerr2 = (double)((P.n1 * n2) / (P.n1 + n2));
   if (nerr2 >= err) return false;
-  const float a2 = V.al[i], L2 = V.L[i], A2 = V.A[i], B2 = V.B[i];
+  const float L2 = cq.y, A2 = cq.z, B2 = cq.w;
   double alphaDiff = 0;
-  if (P.semi) { double d = (double)(a2 - P.a1); alphaDiff = (d * d) / P.exp175; }
+  if (P.semi) { double d = (double)(V.al[i] - P.a1); alphaDiff = (d * d) / P.exp175; }
   double nerr = nerr2 * alphaDiff;
   if (nerr >= err) return false;
   double gs = nerr2;
@@ -293,7 +298,7 @@ __device__ void warp_find_nn_lab(const LabProbe& P, const LabView& V, int first,
   int pos = first;
   if (pos < n) {
     const int i = pos + (int)lane;
-    pushB(i < n && V.cnt[i] >= 0.f, i);
+    pushB(i < n && V.q[i].x >= 0.f, i);
     if (nB) flushB(nB);
     pos += 32;
   }
@@ -316,27 +321,25 @@ __device__ void warp_find_nn_lab(const LabProbe& P, const LabView& V, int first,
 }
 
 // summaries of blocks [0, ceil(n/32)) over position-indexed arrays; one thread per block
-__device__ __forceinline__ void lab_block_summary(const float* cnt, const float* L, int n, int blk, float* bcmin, float* blmin, float* blmax) {
+__device__ __forceinline__ void lab_block_summary(const float4* q, int n, int blk, float* bcmin, float* blmin, float* blmax) {
   float cm = -1.f, lo = 1e30f, hi = -1e30f;
   const int p0 = blk << 5, p1 = min(n, p0 + 32);
   for (int p = p0; p < p1; ++p) {
-    const float c = cnt[p];
-    if (!(c >= 0.f)) continue;
-    cm = cm < 0.f ? c : fminf(cm, c);
-    const float l = L[p];
-    lo = fminf(lo, l); hi = fmaxf(hi, l);
+    const float4 v = q[p];
+    if (!(v.x >= 0.f)) continue;
+    cm = cm < 0.f ? v.x : fminf(cm, v.x);
+    lo = fminf(lo, v.y); hi = fmaxf(hi, v.y);
   }
   bcmin[blk] = cm; blmin[blk] = lo; blmax[blk] = hi;
 }
 
 // scratch carved out of the histogram sum planes (free once the bins are compacted)
-struct LabScratch { float *cnt, *al, *L, *A, *B, *C, *bcmin, *blmin, *blmax; };
+struct LabScratch { float4* q; float *al, *bcmin, *blmin, *blmax; };
 __device__ __forceinline__ LabScratch lab_scratch(const NqSlot& S) {
   float* f = reinterpret_cast<float*>(S.hSum);
   LabScratch X;
-  X.cnt = f; X.al = f + NQ_NBINS; X.L = f + 2 * NQ_NBINS; X.A = f + 3 * NQ_NBINS; X.B = f + 4 * NQ_NBINS;
+  X.q = reinterpret_cast<float4*>(f); X.al = f + 4 * NQ_NBINS;
   X.bcmin = f + 5 * NQ_NBINS; X.blmin = X.bcmin + 2048; X.blmax = X.blmin + 2048;
-  X.C = f + 6 * NQ_NBINS;
   return X;
 }
 
@@ -347,10 +350,26 @@ __global__ void __launch_bounds__(256) k_lab_blocks(const NqImage* imgs, const N
   const NqSlot& S = slots[img];
   const LabScratch X = lab_scratch(S);
   const int n = I.maxbins, nblk = (n + 31) >> 5;
-  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += gridDim.x * blockDim.x)
-    lab_block_summary(S.bCnt, S.fC1, n, blk, X.bcmin, X.blmin, X.blmax);
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) X.C[b] = chroma_ub(S.fC2[b], S.fC3[b]);
+  // one warp per block of 32 bins: pack the records and reduce the summary
+  const unsigned lane = lane_id();
+  for (int blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < nblk; blk += gridDim.x * (blockDim.x >> 5)) {
+    const int b = (blk << 5) + (int)lane;
+    float c = 3e38f, lo = 1e30f, hi = -1e30f;
+    if (b < n) {
+      const float4 v = make_float4(S.bCnt[b], S.fC1[b], S.fC2[b], S.fC3[b]);
+      X.q[b] = v; X.al[b] = S.fAc[b];
+      c = v.x; lo = v.y; hi = v.y;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      c = fminf(c, __shfl_xor_sync(0xffffffffu, c, o));
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { X.bcmin[blk] = c; X.blmin[blk] = lo; X.blmax[blk] = hi; }
+  }
 }
+
 
 // -------------------------------------------------------------------------------------------------
 // initial sweep: find_nn for every bin (PQ:196-197, PL:246-247). One warp per bin.
@@ -404,7 +423,7 @@ __global__ void __launch_bounds__(256) k_find_nn_lab(NqImage* imgs, const NqSlot
     const NqSlot& S = slots[img];
     const LabScratch X = lab_scratch(S);
     const int maxbins = I.maxbins;
-    const LabView V{S.bCnt, S.fAc, S.fC1, S.fC2, S.fC3, X.C, X.bcmin, X.blmin, X.blmax, maxbins};
+    const LabView V{X.q, X.al, X.bcmin, X.blmin, X.blmax, maxbins};
     unsigned long long pairs = 0;
     for (int idx = blockIdx.x * wpb + w; idx < maxbins; idx += gridDim.x * wpb) {
       const LabProbe P = lab_probe(I, S, idx, I.ratio);
@@ -672,24 +691,33 @@ __device__ __forceinline__ int block_excl_scan_128(int v, int* total, int* sScan
   return base + x - v;
 }
 
-// rebuild the ascending list of live bins, their compacted copies and the block summaries
+// rebuild the ascending list of live bins, their compacted records and the block summaries. Each warp
+// owns a contiguous range of bins and walks it 32 at a time (coalesced), ranking survivors by ballot.
 __device__ __forceinline__ int rebuild_live_lab(const NqSlot& S, const LabScratch& X, int maxbins, int* live, int* posOf, int* sScan) {
   const int t = threadIdx.x;
-  const int per = (maxbins + NQ_LAB_THREADS - 1) / NQ_LAB_THREADS;
-  const int b0 = min(maxbins, t * per), b1 = min(maxbins, b0 + per);
+  const unsigned lane = lane_id(), w = t >> 5;
+  const int W = NQ_LAB_THREADS / 32;
+  const int per = (((maxbins + W - 1) / W) + 31) & ~31;
+  const int b0 = min(maxbins, (int)w * per), b1 = min(maxbins, b0 + per);
   int c = 0;
-  for (int b = b0; b < b1; ++b) c += S.bMtm[b] != NQ_DELETED;
+  for (int b = b0 + (int)lane; b < b1; b += 32) c += S.bMtm[b] != NQ_DELETED;
   int total, j = block_excl_scan_128(c, &total, sScan);
-  for (int b = b0; b < b1; ++b)
-    if (S.bMtm[b] != NQ_DELETED) {
-      live[j] = b; posOf[b] = j;
-      X.cnt[j] = S.bCnt[b]; X.al[j] = S.fAc[b]; X.L[j] = S.fC1[b]; X.A[j] = S.fC2[b]; X.B[j] = S.fC3[b];
-      X.C[j] = chroma_ub(S.fC2[b], S.fC3[b]);
-      ++j;
+  j = __shfl_sync(0xffffffffu, j, 0);          // this warp's first output slot
+  for (int base = b0; base < b1; base += 32) {
+    const int b = base + (int)lane;
+    const bool alive = b < b1 && S.bMtm[b] != NQ_DELETED;
+    const unsigned m = __ballot_sync(0xffffffffu, alive);
+    if (alive) {
+      const int p = j + __popc(m & ((1u << lane) - 1u));
+      live[p] = b; posOf[b] = p;
+      X.q[p] = make_float4(S.bCnt[b], S.fC1[b], S.fC2[b], S.fC3[b]);
+      X.al[p] = S.fAc[b];
     }
+    j += __popc(m);
+  }
   __syncthreads();
   const int nblk = (total + 31) >> 5;
-  for (int blk = t; blk < nblk; blk += NQ_LAB_THREADS) lab_block_summary(X.cnt, X.L, total, blk, X.bcmin, X.blmin, X.blmax);
+  for (int blk = t; blk < nblk; blk += NQ_LAB_THREADS) lab_block_summary(X.q, total, blk, X.bcmin, X.blmin, X.blmax);
   __syncthreads();
   return total;
 }
@@ -790,7 +818,7 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS) k_merge_lab(NqImage* imgs, con
     if (action == 1) {
       ++rescans;
       const int first = posOf[b1] + 1;
-      const LabView V{X.cnt, X.al, X.L, X.A, X.B, X.C, X.bcmin, X.blmin, X.blmax, liveLen};
+      const LabView V{X.q, X.al, X.bcmin, X.blmin, X.blmax, liveLen};
       const LabProbe P = lab_probe(I, S, b1, ratioMerge);
       double err = 1e100;
       int nn = -1;                              // position in the live list
@@ -935,8 +963,8 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS) k_merge_lab(NqImage* imgs, con
       S.bMtm[nbI] = NQ_DELETED;
       // compacted copies and the summary of tb's block (the count only grows, L may leave the old range)
       const int pt = posOf[b1], pn = posOf[nbI];
-      X.cnt[pt] = n1 + n2; X.al[pt] = na; X.L[pt] = nL; X.A[pt] = nA; X.B[pt] = nB; X.C[pt] = chroma_ub(nA, nB);
-      X.cnt[pn] = -1.f;
+      X.q[pt] = make_float4(n1 + n2, nL, nA, nB); X.al[pt] = na;
+      X.q[pn].x = -1.f;
       X.blmin[pt >> 5] = fminf(X.blmin[pt >> 5], nL);
       X.blmax[pt >> 5] = fmaxf(X.blmax[pt >> 5], nL);
       if (logMerges && S.mergeLog) { S.mergeLog[2 * (i - 1)] = b1; S.mergeLog[2 * (i - 1) + 1] = nbI; }

@@ -67,4 +67,5 @@ struct NqSlot {
   // dither
   unsigned short* memo;            // [65536] nearestMap for reduced keys (0xFFFF = absent)
   unsigned short* idx;             // [npix] palette indices of pass 1 when a second pass follows
+  unsigned char* cells;            // [32768][32] candidate lists of the CIELAB closest-colour scan (k_build_cells)
 };
