@@ -39,7 +39,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("NQ_BENCH_BATCH", "592")), help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("NQ_BENCH_BATCH", "444")),
+                    help="images per GPU per step (444 = 3 merge CTAs on each of the 148 SMs)")
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--kind", default="lab", choices=list(KINDS))
@@ -49,11 +50,17 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-workers", type=int, default=0, help="reference arm: worker processes (0 = all cores)")
+    ap.add_argument("--cpu-width", type=int, default=1920, help="CPU legs: width of the bounded sample image")
+    ap.add_argument("--cpu-height", type=int, default=1080, help="CPU legs: height of the bounded sample image")
     return ap.parse_args()
 
 
+def workload_quantizer(a):
+    return "PnnLABQuantizer" if a.kind == "lab" else "PnnQuantizer"
+
+
 def workload_name(a):
-    q = "PnnLABQuantizer" if a.kind == "lab" else "PnnQuantizer"
+    q = workload_quantizer(a)
     return f"{q} {a.colors} colors, dither {'on' if a.dither else 'off'}, batch of {a.batch} synthetic {a.cls} {a.width}x{a.height} ARGB images per GPU"
 
 
@@ -121,17 +128,22 @@ def _cpu_one(job):
 
 
 def cpu_single(a):
-    """one image, one thread: the like-for-like figure (the reference creates no threads)"""
+    """one image, one thread: the like-for-like figure (the reference creates no threads). Bounded sample: one
+    image of the workload's class and quantizer at --cpu-width x --cpu-height (a 4K CIELAB image costs the oracle
+    about a minute; Mpixels/s is the unit, so the sample scales)."""
     from oracle import pyoracle
     pyoracle.build()
-    dt = _cpu_one((KINDS[a.kind], a.cls, a.width, a.height, a.colors, a.dither, 0xC0FFEE, 0))
-    return {"value": a.width * a.height / dt / 1e6, "unit": "Mpixels/s", "cores": 1, "kind": "port",
-            "sample": f"1 image of the workload ({a.width}x{a.height} {a.cls}), oracle/nq_oracle.cpp -O2, 1 thread, {dt:.1f} s; "
-                      "C++ restatement of the Java core (no JVM in the image)"}
+    w, h = min(a.cpu_width, a.width), min(a.cpu_height, a.height)
+    dt = _cpu_one((KINDS[a.kind], a.cls, w, h, a.colors, a.dither, 0xC0FFEE, 0))
+    return {"value": w * h / dt / 1e6, "unit": "Mpixels/s", "cores": 1, "kind": "port",
+            "sample": f"1 image of the workload's class ({a.cls}, {workload_quantizer(a)}, {a.colors} colours, dither {a.dither}) at {w}x{h}, "
+                      f"oracle/nq_oracle.cpp -O2, 1 thread, {dt:.1f} s; C++ restatement of the Java core (no JVM in the image)"}
 
 
 def run_reference(a, rank):
-    """--impl reference: every step converts one workload image per worker process, all host cores."""
+    """--impl reference: the oracle (C++ restatement of the reference's Java core) on all host cores. Every step
+    converts one bounded-sample image (--cpu-width x --cpu-height, the workload's class/quantizer/colours) per
+    worker process."""
     if rank != 0:
         return
     import multiprocessing as mp
@@ -139,17 +151,19 @@ def run_reference(a, rank):
     pyoracle.build()
     workers = a.cpu_workers or (os.cpu_count() or 1)
     kind = KINDS[a.kind]
+    w, h = min(a.cpu_width, a.width), min(a.cpu_height, a.height)
     ctx = mp.get_context("fork")
     with ctx.Pool(workers) as pool:
         for _ in range(a.warmup):   # untimed, on a small sample
             pool.map(_cpu_one, [(kind, a.cls, 256, 256, a.colors, a.dither, 0xC0FFEE, i) for i in range(workers)])
         t0 = time.perf_counter()
         for s in range(a.steps):
-            pool.map(_cpu_one, [(kind, a.cls, a.width, a.height, a.colors, a.dither, 0xC0FFEE, s * workers + i) for i in range(workers)])
+            pool.map(_cpu_one, [(kind, a.cls, w, h, a.colors, a.dither, 0xC0FFEE, s * workers + i) for i in range(workers)])
         dt = time.perf_counter() - t0
-    px = a.steps * workers * a.width * a.height
+    px = a.steps * workers * w * h
     val = px / dt / 1e6
-    sample = f"{workers} images per step (one per worker process) of the workload's {a.width}x{a.height} {a.cls} class; warm-up steps use 256x256 images"
+    sample = (f"{workers} images per step (one per worker process) of the workload's class at {w}x{h} "
+              f"({a.cls}, {workload_quantizer(a)}, {a.colors} colours, dither {a.dither}); warm-up steps use 256x256 images")
     line = {"metric": METRIC, "value": val, "unit": "Mpixels/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference",

@@ -351,7 +351,11 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
   mark(1);
   if (nmax > 2) {
     if (kind == NQ_KIND_RGB) {
-      nq::k_hist_rgb<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      {  // contiguous tiles per CTA; enough CTAs to fill the machine twice over
+        const int ntiles = (npix + NQ_HTILE - 1) / NQ_HTILE;
+        const dim3 hg(std::max(1, std::min(ntiles, std::max(1, c->smCount * 4 / n))), n);
+        nq::k_hist_rgb<<<hg, 256, sizeof(nq::HistTable), st>>>(c->dImgs, c->dSlots); ++c->launches;
+      }
       nq::k_finalize_rgb<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
     } else {
       const int nruns = (npix + NQ_RUN - 1) / NQ_RUN;
@@ -411,9 +415,9 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
       }
     }
     if (kind == NQ_KIND_RGB) {
-      nq::k_merge<<<n, NQ_MERGE_THREADS, (size_t)NQ_HEAP_SMEM * 6, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
+      nq::k_merge<<<n, NQ_MERGE_THREADS, (size_t)NQ_HEAP_SMEM * 8, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
     } else {
-      nq::k_merge_lab<<<n, NQ_LAB_THREADS, (size_t)NQ_LAB_HEAP_SMEM * 6, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
+      nq::k_merge_lab<<<n, NQ_LAB_THREADS, (size_t)NQ_LAB_HEAP_SMEM * 8, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
     }
   } else { mark(2); mark(3); }
   mark(4);
@@ -554,8 +558,9 @@ nq_ctx* nq_create(int device) {
     }
     if (ok) ++e.refs;
   }
-  if (ok) ok = cudaFuncSetAttribute(nq::k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_HEAP_SMEM * 6) == cudaSuccess;
-  if (ok) ok = cudaFuncSetAttribute(nq::k_merge_lab, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_LAB_HEAP_SMEM * 6) == cudaSuccess;
+  if (ok) ok = cudaFuncSetAttribute(nq::k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_HEAP_SMEM * 8) == cudaSuccess;
+  if (ok) ok = cudaFuncSetAttribute(nq::k_hist_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nq::HistTable)) == cudaSuccess;
+  if (ok) ok = cudaFuncSetAttribute(nq::k_merge_lab, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_LAB_HEAP_SMEM * 8) == cudaSuccess;
   if (!ok) {
     fail(NQ_ERR_CUDA, std::string("context initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));
     cudaStreamDestroy(c->ownStream);

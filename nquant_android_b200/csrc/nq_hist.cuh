@@ -98,8 +98,45 @@ __global__ void k_setup_scan(NqImage* imgs, const NqSlot* slots, int nimg) {
   I.keyTransp = (I.nmax < 64) || (I.transIdx >= 0);
 }
 
-// ---- RGB histogram (PQ:140-154): integer-exact sums, one 64-bit reduction per channel ------------
+// ---- RGB histogram (PQ:140-154): integer-exact sums -----------------------------------------------
+// 65 536 bins x 5 accumulators do not fit in shared memory, but a stretch of neighbouring pixels only
+// touches a few thousand of them. Each CTA walks contiguous tiles of NQ_HTILE pixels (128-bit loads, four
+// pixels per thread per load) and combines them in a shared-memory hash table of NQ_HSLOTS entries
+// (key tag + count + four channel sums, integer atomics); after every tile the occupied slots are
+// flushed with global atomics. Pixels whose slot (and its neighbour) belongs to another key go to global
+// memory directly. Sums are integers, so the result does not depend on any of this.
+#define NQ_HSLOTS 4096
+#define NQ_HTILE 16384
+struct HistTable { unsigned tag[NQ_HSLOTS], cnt[NQ_HSLOTS], sa[NQ_HSLOTS], sr[NQ_HSLOTS], sg[NQ_HSLOTS], sb[NQ_HSLOTS]; };
+
+__device__ __forceinline__ void hist_rgb_add(HistTable& T, unsigned int* hc, unsigned long long* hs, uint32_t p, bool semi, bool tr) {
+  const unsigned key = (unsigned)color_index(p, semi, tr);
+  unsigned slot = (key ^ (key >> 7) ^ (key >> 12)) & (NQ_HSLOTS - 1);
+  const unsigned tagv = key + 1u;
+#pragma unroll
+  for (int probe = 0; probe < 2; ++probe) {
+    unsigned t = T.tag[slot];
+    if (t == 0u) t = atomicCAS(&T.tag[slot], 0u, tagv), t = t == 0u ? tagv : t;
+    if (t == tagv) {
+      atomicAdd(&T.cnt[slot], 1u);
+      atomicAdd(&T.sa[slot], p >> 24);
+      atomicAdd(&T.sr[slot], (p >> 16) & 0xFFu);
+      atomicAdd(&T.sg[slot], (p >> 8) & 0xFFu);
+      atomicAdd(&T.sb[slot], p & 0xFFu);
+      return;
+    }
+    slot = (slot + 1u) & (NQ_HSLOTS - 1);
+  }
+  atomicAdd(&hc[key], 1u);
+  atomicAdd(&hs[key], (unsigned long long)(p >> 24));
+  atomicAdd(&hs[NQ_NBINS + key], (unsigned long long)((p >> 16) & 0xFF));
+  atomicAdd(&hs[2 * NQ_NBINS + key], (unsigned long long)((p >> 8) & 0xFF));
+  atomicAdd(&hs[3 * NQ_NBINS + key], (unsigned long long)(p & 0xFF));
+}
+
 __global__ void __launch_bounds__(256) k_hist_rgb(const NqImage* imgs, const NqSlot* slots) {
+  extern __shared__ unsigned char histSmem[];
+  HistTable& T = *reinterpret_cast<HistTable*>(histSmem);
   const int img = blockIdx.y;
   const NqImage& I = imgs[img];
   if (I.kind != NQ_KIND_RGB || I.nmax <= 2) return;
@@ -109,15 +146,52 @@ __global__ void __launch_bounds__(256) k_hist_rgb(const NqImage* imgs, const NqS
   unsigned long long* hs = slots[img].hSum;
   const bool semi = I.hasSemi, tr = I.keyTransp;
   const uint32_t tc = I.transColor;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    uint32_t p = in[i];
-    if ((p >> 24) <= 0xF) p = tc;
-    int key = color_index(p, semi, tr);
-    atomicAdd(&hc[key], 1u);
-    atomicAdd(&hs[key], (unsigned long long)(p >> 24));
-    atomicAdd(&hs[NQ_NBINS + key], (unsigned long long)((p >> 16) & 0xFF));
-    atomicAdd(&hs[2 * NQ_NBINS + key], (unsigned long long)((p >> 8) & 0xFF));
-    atomicAdd(&hs[3 * NQ_NBINS + key], (unsigned long long)(p & 0xFF));
+  const bool vec = ((uintptr_t)in & 15) == 0;
+  const int t = threadIdx.x;
+  for (int s = t; s < NQ_HSLOTS; s += 256) { T.tag[s] = 0u; T.cnt[s] = 0u; T.sa[s] = 0u; T.sr[s] = 0u; T.sg[s] = 0u; T.sb[s] = 0u; }
+  __syncthreads();
+  const int ntiles = (n + NQ_HTILE - 1) / NQ_HTILE;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int beg = tile * NQ_HTILE, end = min(n, beg + NQ_HTILE);
+    if (vec) {
+      const int q0 = beg >> 2, q1 = end >> 2;      // beg is a multiple of 4
+      for (int q = q0 + t; q < q1; q += 256) {
+        const uint4 v = ld_stream4(in + 4 * (size_t)q);
+        uint32_t px[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t p = px[k];
+          if ((p >> 24) <= 0xF) p = tc;
+          hist_rgb_add(T, hc, hs, p, semi, tr);
+        }
+      }
+      for (int i = (q1 << 2) + t; i < end; i += 256) {
+        uint32_t p = in[i];
+        if ((p >> 24) <= 0xF) p = tc;
+        hist_rgb_add(T, hc, hs, p, semi, tr);
+      }
+    } else {
+      for (int i = beg + t; i < end; i += 256) {
+        uint32_t p = in[i];
+        if ((p >> 24) <= 0xF) p = tc;
+        hist_rgb_add(T, hc, hs, p, semi, tr);
+      }
+    }
+    __syncthreads();
+    // flush the occupied slots and clear them for the next tile
+    for (int s = t; s < NQ_HSLOTS; s += 256) {
+      const unsigned tg = T.tag[s];
+      if (tg) {
+        const unsigned key = tg - 1u;
+        atomicAdd(&hc[key], T.cnt[s]);
+        atomicAdd(&hs[key], (unsigned long long)T.sa[s]);
+        atomicAdd(&hs[NQ_NBINS + key], (unsigned long long)T.sr[s]);
+        atomicAdd(&hs[2 * NQ_NBINS + key], (unsigned long long)T.sg[s]);
+        atomicAdd(&hs[3 * NQ_NBINS + key], (unsigned long long)T.sb[s]);
+        T.tag[s] = 0u; T.cnt[s] = 0u; T.sa[s] = 0u; T.sr[s] = 0u; T.sg[s] = 0u; T.sb[s] = 0u;
+      }
+    }
+    __syncthreads();
   }
 }
 

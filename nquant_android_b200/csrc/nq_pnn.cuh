@@ -441,29 +441,34 @@ __global__ void __launch_bounds__(256) k_find_nn_lab(NqImage* imgs, const NqSlot
 // merge loop: one persistent CTA per image.
 // -------------------------------------------------------------------------------------------------
 #define NQ_MERGE_THREADS 1024
-#define NQ_HEAP_SMEM 32768     // heap slots kept in shared memory (err f32 + id u16 = 6 B each = 192 KB)
+#define NQ_HEAP_SMEM 24576     // heap slots kept in shared memory (err f32 + id|nn u32 = 8 B each = 192 KB)
 
+// The heap of bin ids keyed by err (PQ:195-236). A slot also carries a copy of the bin's err (a bin's err only
+// changes while it sits at heap[1]) and of its nn (likewise), so the top can be validated with ONE round trip
+// to global memory: tm/mtm of the bin and mtm of its nn are loaded together.
 template <int HS>
 struct HeapView {
-  float* sErr; unsigned short* sId;   // shared part, slots [0, HS)
-  float* gErr; int* gId;              // global spill for the deepest level(s)
+  float* sErr; unsigned* sIdNn;       // shared part, slots [0, HS): err, id | nn << 16
+  float* gErr; int* gIdNn;            // global spill for the deepest level(s)
   __device__ __forceinline__ float err(int l) const { return l < HS ? sErr[l] : gErr[l]; }
-  __device__ __forceinline__ int id(int l) const { return l < HS ? (int)sId[l] : gId[l]; }
-  __device__ __forceinline__ void set(int l, int id_, float e) {
-    if (l < HS) { sErr[l] = e; sId[l] = (unsigned short)id_; } else { gErr[l] = e; gId[l] = id_; }
+  __device__ __forceinline__ unsigned idnn(int l) const { return l < HS ? sIdNn[l] : (unsigned)gIdNn[l]; }
+  __device__ __forceinline__ int id(int l) const { return (int)(idnn(l) & 0xFFFFu); }
+  __device__ __forceinline__ void set(int l, unsigned idnn_, float e) {
+    if (l < HS) { sErr[l] = e; sIdNn[l] = idnn_; } else { gErr[l] = e; gIdNn[l] = (int)idnn_; }
   }
   // "push slot down" (PQ:228-236): sift (b1, e1) down from the root of a heap with heapN entries
-  __device__ __forceinline__ void sift_down(int b1, float e1, int heapN) {
+  __device__ __forceinline__ void sift_down(unsigned idnn1, float e1, int heapN) {
     int l = 1, l2;
     for (; (l2 = l + l) <= heapN; l = l2) {
       float ea = err(l2);
       if (l2 < heapN) { float eb = err(l2 + 1); if (ea > eb) { ++l2; ea = eb; } }
       if (e1 <= ea) break;
-      set(l, id(l2), ea);
+      set(l, idnn(l2), ea);
     }
-    set(l, b1, e1);
+    set(l, idnn1, e1);
   }
 };
+__device__ __forceinline__ unsigned pack_idnn(int id, int nn) { return (unsigned)id | ((unsigned)nn << 16); }
 
 // rebuild the ascending list of live bins; returns its length (block-wide, all threads call)
 __device__ __forceinline__ int rebuild_live(const NqSlot& S, int maxbins, int* live, int* posOf, int* sWarp) {
@@ -482,7 +487,7 @@ __device__ __forceinline__ int rebuild_live(const NqSlot& S, int maxbins, int* l
 __global__ void __launch_bounds__(NQ_MERGE_THREADS, 1) k_merge(NqImage* imgs, const NqSlot* slots, int* liveBuf, int* posBuf, int logMerges) {
   extern __shared__ unsigned char smemRaw[];
   float* sErr = reinterpret_cast<float*>(smemRaw);
-  unsigned short* sId = reinterpret_cast<unsigned short*>(smemRaw + (size_t)NQ_HEAP_SMEM * 4);
+  unsigned* sId = reinterpret_cast<unsigned*>(smemRaw + (size_t)NQ_HEAP_SMEM * 4);
   __shared__ int sWarp[33];
   __shared__ unsigned sMask[32];
   __shared__ double sErrCur;
@@ -506,18 +511,20 @@ __global__ void __launch_bounds__(NQ_MERGE_THREADS, 1) k_merge(NqImage* imgs, co
     int heapN = 0;
     for (int base = 0; base < maxbins; base += 32) {
       float e = (base + (int)lane < maxbins) ? S.bErr[base + lane] : 0.f;
+      const int nnv = (base + (int)lane < maxbins) ? S.bNn[base + lane] : 0;
       const int cnt = min(32, maxbins - base);
       for (int j = 0; j < cnt; ++j) {
         const float err = __shfl_sync(0xffffffffu, e, j);
+        const int nnj = __shfl_sync(0xffffffffu, nnv, j);
         int l = ++heapN, l2;
         for (; l > 1; l = l2) {
           l2 = l >> 1;
           float pe = H.err(l2);
           if (pe <= err) break;
-          int pid = H.id(l2);
+          unsigned pid = H.idnn(l2);
           if (lane == 0) H.set(l, pid, pe);
         }
-        if (lane == 0) H.set(l, base + j, err);
+        if (lane == 0) H.set(l, pack_idnn(base + j, nnj), err);
         __syncwarp();
       }
     }
@@ -537,15 +544,16 @@ __global__ void __launch_bounds__(NQ_MERGE_THREADS, 1) k_merge(NqImage* imgs, co
       else {
         int heapN = sHeapN;
         for (;;) {
-          int b1 = H.id(1);
-          int tm = S.bTm[b1], mtm = S.bMtm[b1];
-          if (tm >= mtm && S.bMtm[S.bNn[b1]] <= tm) { action = 0; sB1 = b1; break; }
+          const unsigned top = H.idnn(1);
+          int b1 = (int)(top & 0xFFFFu);
+          const int tm = S.bTm[b1], mtm = S.bMtm[b1], nmtm = S.bMtm[top >> 16];   // three independent loads
+          if (tm >= mtm && nmtm <= tm) { action = 0; sB1 = b1; break; }
           if (mtm == NQ_DELETED) {   // deleted node: b1 = heap[1] = heap[heap[0]--], then push down
-            b1 = H.id(heapN);
+            const unsigned last = H.idnn(heapN);
             float e1 = H.err(heapN);
             --heapN;
             ++pops;
-            H.sift_down(b1, e1, heapN);
+            H.sift_down(last, e1, heapN);
             continue;
           }
           action = 1; sB1 = b1;
@@ -600,7 +608,7 @@ __global__ void __launch_bounds__(NQ_MERGE_THREADS, 1) k_merge(NqImage* imgs, co
         // tb.tm = i; push slot down (PQ:224-236)
         float e1 = (float)err;
         S.bErr[b1] = e1; S.bNn[b1] = nn; S.bTm[b1] = sIter;
-        H.sift_down(b1, e1, sHeapN);
+        H.sift_down(pack_idnn(b1, nn), e1, sHeapN);
       }
       __syncthreads();
       continue;
@@ -671,7 +679,7 @@ __global__ void __launch_bounds__(NQ_MERGE_THREADS, 1) k_merge(NqImage* imgs, co
 // 128 threads and 48 KB of heap per CTA: several images share an SM and fill each other's serial gaps.
 // -------------------------------------------------------------------------------------------------
 #define NQ_LAB_THREADS 128
-#define NQ_LAB_HEAP_SMEM 7680   // 45 KB of heap: four CTAs fit one SM
+#define NQ_LAB_HEAP_SMEM 8192   // 64 KB of heap: three CTAs fit one SM
 
 __device__ __forceinline__ int block_excl_scan_128(int v, int* total, int* sScan /*[8]*/) {
   const unsigned lane = lane_id(), w = threadIdx.x >> 5;
@@ -722,10 +730,10 @@ __device__ __forceinline__ int rebuild_live_lab(const NqSlot& S, const LabScratc
   return total;
 }
 
-__global__ void __launch_bounds__(NQ_LAB_THREADS) k_merge_lab(NqImage* imgs, const NqSlot* slots, int* liveBuf, int* posBuf, int logMerges) {
+__global__ void __launch_bounds__(NQ_LAB_THREADS, 3) k_merge_lab(NqImage* imgs, const NqSlot* slots, int* liveBuf, int* posBuf, int logMerges) {
   extern __shared__ unsigned char smemRaw[];
   float* sErr = reinterpret_cast<float*>(smemRaw);
-  unsigned short* sId = reinterpret_cast<unsigned short*>(smemRaw + (size_t)NQ_LAB_HEAP_SMEM * 4);
+  unsigned* sId = reinterpret_cast<unsigned*>(smemRaw + (size_t)NQ_LAB_HEAP_SMEM * 4);
   __shared__ int sScan[8];
   __shared__ unsigned sBits[64];             // live blocks of this rescan, one bit per block
   __shared__ unsigned short sBlk[2048];      // the same as an ordered list
@@ -755,18 +763,20 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS) k_merge_lab(NqImage* imgs, con
     int heapN = 0;
     for (int base = 0; base < maxbins; base += 32) {
       float e = (base + (int)lane < maxbins) ? S.bErr[base + lane] : 0.f;
+      const int nnv = (base + (int)lane < maxbins) ? S.bNn[base + lane] : 0;
       const int cnt = min(32, maxbins - base);
       for (int j = 0; j < cnt; ++j) {
         const float err = __shfl_sync(0xffffffffu, e, j);
+        const int nnj = __shfl_sync(0xffffffffu, nnv, j);
         int l = ++heapN, l2;
         for (; l > 1; l = l2) {
           l2 = l >> 1;
           float pe = H.err(l2);
           if (pe <= err) break;
-          int pid = H.id(l2);
+          unsigned pid = H.idnn(l2);
           if (lane == 0) H.set(l, pid, pe);
         }
-        if (lane == 0) H.set(l, base + j, err);
+        if (lane == 0) H.set(l, pack_idnn(base + j, nnj), err);
         __syncwarp();
       }
     }
@@ -790,15 +800,16 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS) k_merge_lab(NqImage* imgs, con
       else {
         int heapN = sHeapN;
         for (;;) {
-          int b1 = H.id(1);
-          int tm = S.bTm[b1], mtm = S.bMtm[b1];
-          if (tm >= mtm && S.bMtm[S.bNn[b1]] <= tm) { action = 0; sB1 = b1; break; }
+          const unsigned top = H.idnn(1);
+          int b1 = (int)(top & 0xFFFFu);
+          const int tm = S.bTm[b1], mtm = S.bMtm[b1], nmtm = S.bMtm[top >> 16];   // three independent loads
+          if (tm >= mtm && nmtm <= tm) { action = 0; sB1 = b1; break; }
           if (mtm == NQ_DELETED) {
-            b1 = H.id(heapN);
+            const unsigned last = H.idnn(heapN);
             float e1 = H.err(heapN);
             --heapN;
             ++pops;
-            H.sift_down(b1, e1, heapN);
+            H.sift_down(last, e1, heapN);
             continue;
           }
           action = 1; sB1 = b1;
@@ -860,11 +871,20 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS) k_merge_lab(NqImage* imgs, con
         // -- 3a. per-candidate lower bound (lab_cheap_keep): one warp per block, one lane per bin
         if (t < 32) { sMaskA[t] = 0u; sMaskB[t] = 0u; }
         __syncthreads();
-        for (int r = w; r < gn; r += W) {
-          const int i = ((int)sBlk[g0 + r] << 5) + (int)lane;
-          const bool keep = i >= stop && i < liveLen && lab_cheap_keep(P, V, i, err);
-          const unsigned m = __ballot_sync(0xffffffffu, keep);
-          if (lane == 0) sMaskA[r] = m;
+        for (int r0 = w; r0 < gn; r0 += 4 * W) {     // four records in flight per lane: the loads come from L2
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * W;
+            const int i = r < gn ? ((int)sBlk[g0 + r] << 5) + (int)lane : -1;
+            v[u] = (i >= stop && i < liveLen) ? X.q[i] : make_float4(-1.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * W;
+            const unsigned m = __ballot_sync(0xffffffffu, lab_cheap_keep_q(P, v[u], err));
+            if (lane == 0 && r < gn) sMaskA[r] = m;
+          }
         }
         __syncthreads();
         if (w == 0) {
@@ -939,8 +959,9 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS) k_merge_lab(NqImage* imgs, con
       if (t == 0) {
         // tb.tm = i; push slot down (PL:281-293)
         float e1 = (float)err;
-        S.bErr[b1] = e1; S.bNn[b1] = nn < 0 ? 0 : live[nn]; S.bTm[b1] = sIter;
-        H.sift_down(b1, e1, sHeapN);
+        const int nnBin = nn < 0 ? 0 : live[nn];
+        S.bErr[b1] = e1; S.bNn[b1] = nnBin; S.bTm[b1] = sIter;
+        H.sift_down(pack_idnn(b1, nnBin), e1, sHeapN);
       }
       __syncthreads();
       tick(0);
