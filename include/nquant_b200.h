@@ -118,6 +118,9 @@ typedef struct nq_image_info {
   /* CIELAB merge loop: SM cycles per phase (heap/top, first 32, block tests, screen, full+resolve, merge+rebuild),
      blocks that survived their summary test, candidates that survived the screen */
   unsigned long long merge_cycles[6], live_blocks, screened;
+  /* FIFO dither kernel: SM cycles of the serial (consumer) warp, of which waiting for the producer warp, and cycles the
+     producer warp waited for ring space */
+  unsigned long long dither_cycles[3];
 } nq_image_info;
 int nq_get_image_info(nq_ctx* ctx, int image, nq_image_info* out);
 

@@ -34,10 +34,11 @@ class ImageInfo(ctypes.Structure):
         ("error", ctypes.c_int),
         ("full_evals", ctypes.c_ulonglong),
         ("merge_cycles", ctypes.c_ulonglong * 6), ("live_blocks", ctypes.c_ulonglong), ("screened", ctypes.c_ulonglong),
+        ("dither_cycles", ctypes.c_ulonglong * 3),
     ]
 
     def as_dict(self):
-        return {n: (list(getattr(self, n)) if n == "merge_cycles" else getattr(self, n)) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n in ("merge_cycles", "dither_cycles") else getattr(self, n)) for n, _ in self._fields_}
 
 
 _lib = None

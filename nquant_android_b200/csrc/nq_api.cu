@@ -352,7 +352,7 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
   if (nmax > 2) {
     if (kind == NQ_KIND_RGB) {
       {  // contiguous tiles per CTA; enough CTAs to fill the machine twice over
-        const int ntiles = (npix + NQ_HTILE - 1) / NQ_HTILE;
+        const int ntiles = ((w + NQ_HTW - 1) / NQ_HTW) * ((h + NQ_HTW - 1) / NQ_HTW);
         const dim3 hg(std::max(1, std::min(ntiles, std::max(1, c->smCount * 4 / n))), n);
         nq::k_hist_rgb<<<hg, 256, sizeof(nq::HistTable), st>>>(c->dImgs, c->dSlots); ++c->launches;
       }
@@ -659,6 +659,7 @@ int nq_get_image_info(nq_ctx* c, int image, nq_image_info* o) {
   o->full_evals = I.statFullEvals;
   for (int k = 0; k < 6; ++k) o->merge_cycles[k] = I.statCyc[k];
   o->live_blocks = I.statLiveBlocks; o->screened = I.statScreened;
+  for (int k = 0; k < 3; ++k) o->dither_cycles[k] = I.statDither[k];
   o->error = I.error;
   return NQ_OK;
 }

@@ -418,6 +418,38 @@ __device__ __forceinline__ float tanh_to_float(double x) {
   return (float)nqm::nq_tanh(x);
 }
 
+// Straight-line variant for the serial chain: explicit fma, Estrin evaluation and a reciprocal instead of the
+// division (the chain is latency bound; the decision logic is the same interval test, so the float it
+// returns with `true` is again exactly (float)nq_tanh(x)). (float)tanh(x) == 1.0f for x >= 9.0109.
+__device__ __forceinline__ bool tanh_fast(double x, float* out) {
+  const double ax = nqm::fabs_(x);
+  const double y = 2.0 * (ax < 9.5 ? ax : 9.5);
+  const double fk = nqm::rint_(y * nqm::INV_LN2_32);
+  const int kk = (int)fk;
+  double r = __fma_rn(-fk, nqm::LN2_32_HI, y);
+  r = __fma_rn(-fk, nqm::LN2_32_LO, r);
+  const double r2 = r * r;
+  const double u0 = __fma_rn(r, 1.0 / 6.0, 0.5), u1 = __fma_rn(r, 1.0 / 120.0, 1.0 / 24.0);
+  const double u2 = __fma_rn(r2, 1.0 / 720.0, u1);
+  const double q = __fma_rn(r2, u2, u0);
+  const double p = __fma_rn(r2, q, r);                    // expm1(r), |r| <= 0.011
+  const double T = nqm::exp2_32_tab(kk & 31, 0);
+  const double Ee = __fma_rn(T, p, T) * nqm::pow2i(kk >> 5);
+  // 1 / (Ee + 1) by two Newton steps from the hardware estimate: no special-case branch (Ee + 1 is in [8, 2^28]),
+  // relative error ~2e-16, far inside the 1e-12 interval below
+  const double d = Ee + 1.0;
+  double rc;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(d));
+  rc = __fma_rn(rc, __fma_rn(-d, rc, 1.0), rc);
+  rc = __fma_rn(rc, __fma_rn(-d, rc, 1.0), rc);
+  const double t = __fma_rn(-2.0, rc, 1.0);
+  const float lo = (float)(t * (1.0 - 1e-12)), hi = (float)(t * (1.0 + 1e-12));
+  const bool sat = ax >= 9.02;
+  const float v = sat ? 1.0f : lo;
+  *out = x < 0 ? -v : v;
+  return sat || (ax >= 1.0 && lo == hi);
+}
+
 // -------------------------------------------------------------------------------------------------
 // GilbertCurve constructor constants + initWeights (GC:50-112, 336-354), one thread per image
 // -------------------------------------------------------------------------------------------------
@@ -825,9 +857,13 @@ struct DitherRing {
   int fetched, looked, consumed;
   unsigned long long rngSeed, draws;
 };
-__device__ __forceinline__ void ring_wait(const int* p, int v) {
+__device__ __forceinline__ void ring_wait(const int* p, int v, long long* waited = nullptr) {
   const volatile int* vp = p;
-  while (*vp < v) __nanosleep(40);
+  if (*vp < v) {
+    const long long t0 = clock64();
+    while (*vp < v) __nanosleep(40);
+    if (waited) *waited += clock64() - t0;
+  }
   __syncwarp();
   __threadfence_block();
 }
@@ -927,9 +963,10 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
   if (producer) {
     // =========================== producer warp ===========================
     int lastSlow = -1;                           // last block left to the consumer's own lookups
+    long long pwait = 0;
     for (int b = 0; b < nblocks; ++b) {
       const int slot = b & (NQ_RING - 1);
-      ring_wait(&ring.consumed, b - (NQ_RING - 1));
+      ring_wait(&ring.consumed, b - (NQ_RING - 1), &pwait);
       const PixBlock cur = fetch_block(D, order, b << 5);
       const int cnt = min(32, npix - (b << 5));
       const bool mine = (int)lane < cnt;
@@ -961,6 +998,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
       if (lane == 0) ring.blockPre[slot] = blockPre ? 1 : 0;
       ring_signal(&ring.looked, b + 1);
     }
+    if (lane == 0) I.statDither[2] = (unsigned long long)pwait;
     return;
   }
 
@@ -990,6 +1028,8 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
     M = fmaxf(fmaxf(fmaxf(qm, P0), fmaxf(P1, P2)), P3);
   };
 
+  long long cwait = 0;
+  const long long cstart = clock64();
   ring_wait(&ring.fetched, 1);
   uint32_t nxtPx = ring.px[0][lane];
   // fill the pipeline: pixels 0 .. DM-2 enter with zero errors behind them
@@ -997,8 +1037,8 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
 
   for (int b = 0; b < nblocks; ++b) {
     const int slot = b & (NQ_RING - 1), n0 = b << 5;
-    ring_wait(&ring.looked, b + 1);
-    ring_wait(&ring.fetched, min(b + 2, nblocks));
+    ring_wait(&ring.looked, b + 1, &cwait);
+    ring_wait(&ring.fetched, min(b + 2, nblocks), &cwait);
     const uint32_t curPx = nxtPx;
     nxtPx = b + 1 < nblocks ? ring.px[(b + 1) & (NQ_RING - 1)][lane] : 0u;
     const uint32_t curXy = ring.xy[slot][lane];
@@ -1021,6 +1061,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
       const float b0 = __shfl_sync(FULL, P0, DM - 2), b1 = __shfl_sync(FULL, P1, DM - 2), b2 = __shfl_sync(FULL, P2, DM - 2), b3 = __shfl_sync(FULL, P3, DM - 2);
       const float bm = __shfl_sync(FULL, M, DM - 2);
       const uint32_t pixel = __shfl_sync(FULL, curPx, j);
+      const uint32_t pcPre = __shfl_sync(FULL, preCol, j);
       const int jn = j + DM - 1;
       const uint32_t injA = __shfl_sync(FULL, curPx, jn & 31), injB = __shfl_sync(FULL, nxtPx, jn & 31);
       const uint32_t inject = jn < 32 ? injA : injB;
@@ -1035,7 +1076,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
 
       // ---- quantize (GC:211-229)
       uint32_t pc;
-      if (blockPre) pc = __shfl_sync(FULL, preCol, j);
+      if (blockPre) pc = pcPre;
       else {
         const uint32_t xy = __shfl_sync(FULL, curXy, j);
         const int x = xy & 0xFFFF, y = xy >> 16;
@@ -1052,9 +1093,20 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
         const bool s0 = fabsf(e0) >= fDitherMax, s1 = fabsf(e1) >= fDitherMax, s2 = fabsf(e2) >= fDitherMax;
         if (s0 || s1 || s2) {
           if ((diffMask >> j) & 1u) {
-            if (s0) e0 = tanh_to_float((double)(e0 / maxErr * 20.f)) * fDitherMax1;
-            if (s1) e1 = tanh_to_float((double)(e1 / maxErr * 20.f)) * fDitherMax1;
-            if (s2) e2 = tanh_to_float((double)(e2 / maxErr * 20.f)) * fDitherMax1;
+            // lanes 0, 1, 2 shape r, g, b at the same time (the other lanes mirror b); the exact kernel only if undecided
+            const float eL = lane == 0 ? e0 : (lane == 1 ? e1 : e2);
+            const bool sL = lane == 0 ? s0 : (lane == 1 ? s1 : s2);
+            const double xL = (double)(eL / maxErr * 20.f);
+            float vL;
+            const bool kL = tanh_fast(xL, &vL);
+            if (__any_sync(FULL, sL && !kL)) {
+              if (sL && !kL) vL = (float)nqm::nq_tanh(xL);
+            }
+            const float rL = vL * fDitherMax1;
+            const float r0 = __shfl_sync(FULL, rL, 0), r1 = __shfl_sync(FULL, rL, 1), r2 = __shfl_sync(FULL, rL, 2);
+            if (s0) e0 = r0;
+            if (s1) e1 = r1;
+            if (s2) e2 = r2;
           } else if (illusion0) {
             if (s0) e0 = (float)((double)(e0 / maxErr) * 1.0) * fDitherMax1;
             if (s1) e1 = (float)((double)(e1 / maxErr) * 1.0) * fDitherMax1;
@@ -1072,6 +1124,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
     ring_signal(&ring.consumed, b + 1);
   }
 
+  if (lane == 0) { I.statDither[0] = (unsigned long long)(clock64() - cstart); I.statDither[1] = (unsigned long long)cwait; }
   E.rng.seed = ring.rngSeed; E.draws = ring.draws;
   if (!dither && plen > 32) bluenoise_pass(I, D);
   if (lane == 0) I.rngDraws = E.draws;

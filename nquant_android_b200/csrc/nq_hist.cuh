@@ -100,13 +100,13 @@ __global__ void k_setup_scan(NqImage* imgs, const NqSlot* slots, int nimg) {
 
 // ---- RGB histogram (PQ:140-154): integer-exact sums -----------------------------------------------
 // 65 536 bins x 5 accumulators do not fit in shared memory, but a stretch of neighbouring pixels only
-// touches a few thousand of them. Each CTA walks contiguous tiles of NQ_HTILE pixels (128-bit loads, four
+// touches a few thousand of them. Each CTA walks NQ_HTW x NQ_HTW pixel tiles (128-bit loads, four
 // pixels per thread per load) and combines them in a shared-memory hash table of NQ_HSLOTS entries
 // (key tag + count + four channel sums, integer atomics); after every tile the occupied slots are
 // flushed with global atomics. Pixels whose slot (and its neighbour) belongs to another key go to global
 // memory directly. Sums are integers, so the result does not depend on any of this.
 #define NQ_HSLOTS 4096
-#define NQ_HTILE 16384
+#define NQ_HTW 128          // tile side in pixels
 struct HistTable { unsigned tag[NQ_HSLOTS], cnt[NQ_HSLOTS], sa[NQ_HSLOTS], sr[NQ_HSLOTS], sg[NQ_HSLOTS], sb[NQ_HSLOTS]; };
 
 __device__ __forceinline__ void hist_rgb_add(HistTable& T, unsigned int* hc, unsigned long long* hs, uint32_t p, bool semi, bool tr) {
@@ -140,7 +140,6 @@ __global__ void __launch_bounds__(256) k_hist_rgb(const NqImage* imgs, const NqS
   const int img = blockIdx.y;
   const NqImage& I = imgs[img];
   if (I.kind != NQ_KIND_RGB || I.nmax <= 2) return;
-  const int n = I.npix;
   const uint32_t* in = slots[img].in;
   unsigned int* hc = slots[img].hCnt;
   unsigned long long* hs = slots[img].hSum;
@@ -150,13 +149,19 @@ __global__ void __launch_bounds__(256) k_hist_rgb(const NqImage* imgs, const NqS
   const int t = threadIdx.x;
   for (int s = t; s < NQ_HSLOTS; s += 256) { T.tag[s] = 0u; T.cnt[s] = 0u; T.sa[s] = 0u; T.sr[s] = 0u; T.sg[s] = 0u; T.sb[s] = 0u; }
   __syncthreads();
-  const int ntiles = (n + NQ_HTILE - 1) / NQ_HTILE;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int beg = tile * NQ_HTILE, end = min(n, beg + NQ_HTILE);
-    if (vec) {
-      const int q0 = beg >> 2, q1 = end >> 2;      // beg is a multiple of 4
-      for (int q = q0 + t; q < q1; q += 256) {
-        const uint4 v = ld_stream4(in + 4 * (size_t)q);
+  // square tiles: neighbouring pixels in BOTH directions share colours, a strip of full rows does not
+  const int width = I.width, height = I.height;
+  const int tx = (width + NQ_HTW - 1) / NQ_HTW, ty = (height + NQ_HTW - 1) / NQ_HTW;
+  const bool vec4 = vec && (width & 3) == 0;
+  for (int tile = blockIdx.x; tile < tx * ty; tile += gridDim.x) {
+    const int x0 = (tile % tx) * NQ_HTW, y0 = (tile / tx) * NQ_HTW;
+    const int x1 = min(width, x0 + NQ_HTW), y1 = min(height, y0 + NQ_HTW);
+    if (vec4) {
+      const int qw = (x1 - x0) >> 2;                 // quads per tile row (x0 and width are multiples of 4)
+      const int total = qw * (y1 - y0);
+      for (int e = t; e < total; e += 256) {
+        const int ry = e / qw, rq = e - ry * qw;
+        const uint4 v = ld_stream4(in + (size_t)(y0 + ry) * width + x0 + 4 * rq);
         uint32_t px[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -165,14 +170,11 @@ __global__ void __launch_bounds__(256) k_hist_rgb(const NqImage* imgs, const NqS
           hist_rgb_add(T, hc, hs, p, semi, tr);
         }
       }
-      for (int i = (q1 << 2) + t; i < end; i += 256) {
-        uint32_t p = in[i];
-        if ((p >> 24) <= 0xF) p = tc;
-        hist_rgb_add(T, hc, hs, p, semi, tr);
-      }
     } else {
-      for (int i = beg + t; i < end; i += 256) {
-        uint32_t p = in[i];
+      const int tw = x1 - x0, total = tw * (y1 - y0);
+      for (int e = t; e < total; e += 256) {
+        const int ry = e / tw, rx = e - ry * tw;
+        uint32_t p = in[(size_t)(y0 + ry) * width + x0 + rx];
         if ((p >> 24) <= 0xF) p = tc;
         hist_rgb_add(T, hc, hs, p, semi, tr);
       }

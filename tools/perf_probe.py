@@ -29,6 +29,8 @@ def main():
         print(f"kind={kind} cls={cls} {W}x{H} K={K} dither={dither} batch={batch}: {dt:.3f}s  {batch*npix/dt/1e6:.2f} Mpix/s  "
               f"bins={info['maxbins']} rescans={info['rescans']} pairs={info['pair_tests']} full_evals={info['full_evals']}", flush=True)
         print("   " + "  ".join(f"{k}={v[0]:.1f}ms" for k, v in st.items()), flush=True)
+        dc = info["dither_cycles"]
+        print(f"   dither Mcycles: consumer={dc[0] / 1e6:.0f} (waiting {dc[1] / 1e6:.0f})  producer waiting={dc[2] / 1e6:.0f}", flush=True)
         if kind == 1:
             mc = info["merge_cycles"]
             names = ["heap", "first32", "blocktest", "screen", "full", "merge"]
