@@ -177,7 +177,7 @@ struct nq_ctx {
   int* dLive = nullptr;
   int* dPos = nullptr;
   int wsSlots = 0, wsNpix = 0, wsKind = -1, sortPool = 0;
-  bool wsDebug = false;
+  bool wsDebug = false, wsBits = false;
   std::vector<NqSlot> hSlots;
   // staging for host-buffer calls
   uint32_t* dIn = nullptr;
@@ -197,9 +197,9 @@ namespace {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SlotLayout {
-  size_t hCnt, hSum, keyOff, sortA, sortB, warpHist, sal, bD, bF, bCnt, bErr, bNn, bTm, bMtm, hErr, hId, mergeLog, memo, cells, total;
+  size_t hCnt, hSum, keyOff, sortA, sortB, warpHist, sal, bD, bF, bCnt, bErr, bNn, bTm, bMtm, hErr, hId, mergeLog, memo, cells, bits, total;
 };
-SlotLayout slot_layout(int kind, int npix, bool debug) {
+SlotLayout slot_layout(int kind, int npix, bool debug, bool needBits) {
   SlotLayout L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
@@ -221,6 +221,7 @@ SlotLayout slot_layout(int kind, int npix, bool debug) {
   L.mergeLog = take(debug ? (size_t)2 * NQ_NBINS * 4 : 0);
   L.memo = take(NQ_NBINS * 2);
   L.cells = take(lab ? (size_t)32768 * 32 : 0);
+  L.bits = take(needBits ? ((size_t)1 << 29) : 0);      // one bit per ARGB value
   L.total = o;
   return L;
 }
@@ -230,8 +231,8 @@ SlotLayout slot_layout(int kind, int npix, bool debug) {
 // batch instead of giving every image its own.
 #define NQ_SORT_POOL 32
 
-int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots) {
-  SlotLayout L = slot_layout(kind, npix, c->debug);
+int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots, bool needBits) {
+  SlotLayout L = slot_layout(kind, npix, c->debug, needBits);
   const bool lab = kind == NQ_KIND_LAB;
   const size_t nruns = ((size_t)npix + NQ_RUN - 1) / NQ_RUN;
   const size_t sortSet = lab ? align_up((size_t)npix * 4, 256) * 2 + align_up(nruns * 256 * 4, 256) : 0;
@@ -244,7 +245,7 @@ int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots) {
   if (pool * sortSet + perImage > budget) return fail(NQ_ERR_NOMEM, "not enough device memory for one image workspace");
   const int maxSlots = (int)std::min<size_t>((budget - pool * sortSet) / perImage, 8192);
   const int slots = std::min(wantSlots, maxSlots);
-  if (c->ws && c->wsKind == kind && c->wsNpix == npix && c->wsSlots >= slots && c->wsDebug == c->debug) return NQ_OK;
+  if (c->ws && c->wsKind == kind && c->wsNpix == npix && c->wsSlots >= slots && c->wsDebug == c->debug && c->wsBits == needBits) return NQ_OK;
   if (c->ws) { cudaFree(c->ws); c->ws = nullptr; c->wsBytes = 0; }
   const size_t imgsB = align_up(sizeof(NqImage) * slots, 256), slotsB = align_up(sizeof(NqSlot) * slots, 256);
   const size_t liveB = align_up((size_t)slots * NQ_NBINS * 4, 256);
@@ -285,9 +286,10 @@ int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots) {
     S.mergeLog = c->debug ? reinterpret_cast<int*>(b + L.mergeLog) : nullptr;
     S.memo = reinterpret_cast<unsigned short*>(b + L.memo);
     S.cells = lab ? b + L.cells : nullptr;
+    S.bits = needBits ? reinterpret_cast<unsigned int*>(b + L.bits) : nullptr;
     S.idx = nullptr;
   }
-  c->wsSlots = slots; c->wsNpix = npix; c->wsKind = kind; c->sortPool = pool; c->wsDebug = c->debug;
+  c->wsSlots = slots; c->wsNpix = npix; c->wsKind = kind; c->sortPool = pool; c->wsDebug = c->debug; c->wsBits = needBits;
   return NQ_OK;
 }
 
@@ -340,6 +342,7 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
     CU(cudaMemsetAsync(S.hCnt, 0, NQ_NBINS * 4, st));
     CU(cudaMemsetAsync(S.hSum, 0, (size_t)4 * NQ_NBINS * 8, st));
     CU(cudaMemsetAsync(S.memo, 0xFF, NQ_NBINS * 2, st));
+    if (S.bits) CU(cudaMemsetAsync(S.bits, 0, (size_t)1 << 29, st));
   }
   const int gx = pixel_grid_x(c, npix, n);
   const dim3 pg(gx, n);
@@ -376,6 +379,7 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
         nq::k_lab_bin_sum<<<bg, 256, 0, st>>>(gi, gs); ++c->launches;
       }
       nq::k_finalize_lab<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_lab_fewcolors<<<n, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
     }
     mark(2);
     if (kind == NQ_KIND_RGB) { nq::k_find_nn_all<<<c->smCount * 8, 256, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches; }
@@ -481,7 +485,9 @@ int convert_device(nq_ctx* c, int kind, const uint32_t* dIn, int n, int w, int h
                    uint32_t* dOut, uint32_t* palettes, int* plens, int* hasAlpha, const uint32_t* dPalIn, int palInLen) {
   CU(cudaSetDevice(c->device));
   const int npix = w * h;
-  int rc = ensure_workspace(c, kind, npix, n);
+  // the BlueNoise second pass of PnnLABQuantizer weighs by pixelMap.size() (PL:511-513): track it only then
+  const bool needBits = kind == NQ_KIND_LAB && !dither && nmax > 32;
+  int rc = ensure_workspace(c, kind, npix, n, needBits);
   if (rc) return rc;
   if (c->debug) c->dbg.assign(n, DebugImage{});
   int firstErr = 0;
@@ -497,6 +503,7 @@ int convert_device(nq_ctx* c, int kind, const uint32_t* dIn, int n, int w, int h
   }
   c->lastImgs.swap(all);
   if (firstErr == 3) return fail(NQ_ERR_COLOR, "alpha must be between 0 and 255. (ColorUtils.setAlphaComponent)");
+  if (firstErr == 4) return fail(NQ_ERR_UNSUPPORTED, "PnnLABQuantizer with dither == false, more than 32 colours and semi-transparent pixels is not covered");
   if (firstErr) return fail(NQ_ERR_UNSUPPORTED, "device-side error " + std::to_string(firstErr));
   return NQ_OK;
 }

@@ -45,6 +45,8 @@ struct Env {
   double PR, PG, PB, PA, ratio, gWeight, exp15;
   float beta;
   unsigned short* memo;
+  unsigned int* bits;         // pixelMap as a bit set (see NqSlot::bits), with its size counter
+  unsigned int* distinct;
   const uint4* cells;         // candidate lists of the closest-colour scan, 32 B per 5-5-5 RGB cell (k_build_cells)
   JRandom rng;
   unsigned long long draws;
@@ -166,6 +168,10 @@ __device__ int nearest_lab(Env& E, uint32_t c) {
   if (E.plen > 2 && E.hasTrans && c_alpha(c) > 0xF) k = 1;
   const int ca = c_alpha(c), cr = c_red(c), cg = c_green(c), cb = c_blue(c);
   const Lab4 l1 = lab_of(c);
+  if (E.bits) {   // getLab(c) and, without semi-transparency, getLab(palette[i]) for every i >= k (PL:345-352)
+    pixelmap_add(E.bits, E.distinct, c, lane == 0);
+    for (int i0 = k; i0 < E.plen; i0 += 32) pixelmap_add(E.bits, E.distinct, i0 + (int)lane < E.plen ? E.sh->pal[i0 + lane] : 0u, i0 + (int)lane < E.plen);
+  }
   int bi;
   if (E.plen > 4 && !(E.semi || E.plen < 16) && E.plen <= 32) {
     // CIEDE2000 branch (PL:376-395): R_T can be negative, so acceptance depends on the running
@@ -523,6 +529,8 @@ __global__ void k_dither_setup(NqImage* imgs, const NqSlot* slots, int nimg) {
   init_weights(I.gW3, 3);
   init_weights(I.gW7, 7);
   I.bnWeight = 1.0f;
+  // pixelMap.size() is only tracked exactly when getLab's call pattern does not depend on the scan order (PL:347-349)
+  if (lab && !I.dither && plen > 32 && I.hasSemi && !I.error) I.error = 4;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -565,6 +573,7 @@ __device__ __forceinline__ void dither_prologue_regs(NqImage& I, const NqSlot& S
   E.beta = I.gBeta;
   E.memo = S.memo;
   E.cells = reinterpret_cast<const uint4*>(S.cells);
+  E.bits = S.bits; E.distinct = &I.distinctColors;
   E.rng.set_seed(I.seed);
   E.draws = 0;
   E.width = I.width;
@@ -649,7 +658,15 @@ __device__ void bluenoise_pass(NqImage& I, DitherCtx& D) {
   const int npix = D.npix, width = D.width;
   __syncwarp();
   __threadfence_block();
-  const float weight = I.bnWeight, strength = 1 / 3.f;
+  float weight = 1.0f;
+  const float strength = 1 / 3.f;
+  if (E.lab) {   // PL:511-513: depends on how many colours getLab has seen by now
+    __threadfence();
+    const double size = (double)*(volatile unsigned int*)E.distinct;
+    const double delta = ((double)E.plen * (double)E.plen) / size;
+    weight = delta > 0.023 ? 1.0f : (float)(37.013 * delta + 0.906);
+  }
+  if (lane == 0) I.bnWeight = weight;
   for (int n0 = 0; n0 < npix; n0 += 32) {
     const int n = n0 + (int)lane;
     uint32_t px = 0, qv = 0;

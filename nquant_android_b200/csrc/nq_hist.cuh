@@ -296,17 +296,36 @@ __global__ void __launch_bounds__(1024) k_finalize_rgb(NqImage* imgs, const NqSl
 
 __device__ __forceinline__ uint32_t lab_src_pixel(uint32_t p, uint32_t tc) { return ((p >> 24) <= 0xF) ? tc : p; }
 
-__global__ void __launch_bounds__(256) k_lab_count(const NqImage* imgs, const NqSlot* slots) {
+// pixelMap.put(c, ...) (PL:34-42) as a bit set over all ARGB values; returns nothing, counts first insertions
+__device__ __forceinline__ void pixelmap_add(unsigned int* bits, unsigned int* counter, uint32_t c, bool active) {
+  bool fresh = false;
+  if (active) {
+    const unsigned m = 1u << (c & 31u);
+    fresh = !(atomicOr(&bits[c >> 5], m) & m);
+  }
+  const unsigned f = __ballot_sync(__activemask(), fresh);
+  if (f && (threadIdx.x & 31) == (unsigned)(__ffs(f) - 1)) atomicAdd(counter, (unsigned)__popc(f));
+}
+
+__global__ void __launch_bounds__(256) k_lab_count(NqImage* imgs, const NqSlot* slots) {
   const int img = blockIdx.y;
-  const NqImage& I = imgs[img];
+  NqImage& I = imgs[img];
   if (I.kind != NQ_KIND_LAB || I.nmax <= 2) return;
   const int n = I.npix;
   const uint32_t* in = slots[img].in;
   unsigned int* hc = slots[img].hCnt;
   const bool semi = I.hasSemi, tr = I.keyTransp;
   const uint32_t tc = I.transColor;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    atomicAdd(&hc[color_index(lab_src_pixel(in[i], tc), semi, tr)], 1u);
+  unsigned int* bits = slots[img].bits;
+  for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+    const int i = i0 + (int)threadIdx.x;
+    uint32_t p = 0;
+    if (i < n) {
+      p = lab_src_pixel(in[i], tc);
+      atomicAdd(&hc[color_index(p, semi, tr)], 1u);
+    }
+    if (bits) pixelmap_add(bits, &I.distinctColors, p, i < n);     // getLab(pixel) in the histogram loop (PL:148)
+  }
 }
 
 // exclusive scan of the 65536 key counts -> keyOff[0..65536]
@@ -511,10 +530,88 @@ __global__ void __launch_bounds__(1024) k_finalize_lab(NqImage* imgs, const NqSl
     }
     I.maxbins = maxbins; I.quan_rt = quan_rt; I.extbins = maxbins - nmax; I.texicab = texicab;
     I.ratio = ratio; I.ratioMerge = ratioMerge;
+    // pixelMap.size() <= nMaxColors needs maxbins <= nMaxColors: leave the decision to k_lab_fewcolors (PL:193-206)
+    I.skipPnn = maxbins <= nmax ? 2 : 0;
   }
   __syncthreads();
   const int maxbins = I.maxbins, quan_rt = I.quan_rt, nmax = I.nmax;
   for (int b = t; b < maxbins; b += 1024) S.bCnt[b] = quan_lab(nmax, quan_rt, S.bCnt[b]);   // PL:210-217
+}
+
+// ---- few-colours shortcut (PL:193-206): when the image holds at most nMaxColors distinct colours the palette is
+//      pixelMap.keySet() in java.util.HashMap iteration order, a fully transparent colour swapped to slot 0.
+//      One CTA per candidate image (skipPnn == 2, i.e. at most nMaxColors occupied bins): a 1024-slot shared hash
+//      set collects the distinct colours with the index of their first pixel (= insertion order of pixelMap).
+__global__ void __launch_bounds__(256) k_lab_fewcolors(NqImage* imgs, const NqSlot* slots) {
+  __shared__ unsigned long long sKey[1024];
+  __shared__ int sFirst[1024];
+  __shared__ int sCount, sOverflow;
+  __shared__ uint32_t sCol[NQ_MAXK];
+  __shared__ int sIdx[NQ_MAXK];
+  const int img = blockIdx.x;
+  NqImage& I = imgs[img];
+  if (I.kind != NQ_KIND_LAB || I.nmax <= 2 || I.skipPnn != 2) return;
+  const int t = threadIdx.x, n = I.npix, nmax = I.nmax;
+  const uint32_t* in = slots[img].in;
+  const uint32_t tc = I.transColor;
+  for (int s = t; s < 1024; s += 256) { sKey[s] = ~0ULL; sFirst[s] = 0x7fffffff; }
+  if (t == 0) { sCount = 0; sOverflow = 0; }
+  __syncthreads();
+  for (int i0 = 0; i0 < n; i0 += 256) {
+    const int i = i0 + t;
+    if (i < n) {
+      const uint32_t p = lab_src_pixel(in[i], tc);
+      unsigned slot = (p ^ (p >> 11) ^ (p >> 22)) & 1023u;
+      for (int probe = 0; probe < 1024; ++probe) {
+        unsigned long long k = sKey[slot];
+        if (k == ~0ULL) {
+          k = atomicCAS(&sKey[slot], ~0ULL, (unsigned long long)p);
+          if (k == ~0ULL) { k = p; if (atomicAdd(&sCount, 1) >= nmax) sOverflow = 1; }
+        }
+        if (k == (unsigned long long)p) { atomicMin(&sFirst[slot], i); break; }
+        slot = (slot + 1) & 1023u;
+      }
+    }
+    if ((i0 & 0xFFFF) == 0) {          // every 256 rounds: stop early once there are too many colours
+      __syncthreads();
+      if (sOverflow) break;
+    }
+  }
+  __syncthreads();
+  if (sOverflow || sCount > nmax) { if (t == 0) I.skipPnn = 0; return; }
+  if (t == 0) {
+    // insertion order = order of first occurrence
+    int cnt = 0;
+    for (int s = 0; s < 1024; ++s)
+      if (sKey[s] != ~0ULL) {
+        const uint32_t col = (uint32_t)sKey[s];
+        const int fi = sFirst[s];
+        int j = cnt++;
+        while (j > 0 && sIdx[j - 1] > fi) { sCol[j] = sCol[j - 1]; sIdx[j] = sIdx[j - 1]; --j; }
+        sCol[j] = col; sIdx[j] = fi;
+      }
+    // java.util.HashMap<Integer, ...>: table of 16, doubled when size exceeds 3/4 of it, or when a 9th node lands
+    // in one bucket of a table smaller than 64 (treeifyBin resizes instead); buckets keep insertion order and
+    // a resize splits them in order, so the final order is (bucket under the final capacity, insertion order)
+    int cap = 16, thr = 12, size = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const uint32_t h = sCol[i] ^ (sCol[i] >> 16);
+      int chain = 1;
+      for (int j = 0; j < i; ++j) chain += ((sCol[j] ^ (sCol[j] >> 16)) & (unsigned)(cap - 1)) == (h & (unsigned)(cap - 1));
+      if (chain >= 9 && cap < 64) { cap *= 2; thr = cap * 3 / 4; }
+      if (++size > thr) { cap *= 2; thr = cap * 3 / 4; }
+    }
+    int k = 0;
+    for (int b = 0; b < cap; ++b)
+      for (int i = 0; i < cnt; ++i)
+        if (((sCol[i] ^ (sCol[i] >> 16)) & (unsigned)(cap - 1)) == (unsigned)b) {
+          const uint32_t pixel = sCol[i];
+          I.palette[k++] = pixel;
+          if (k > 1 && (pixel >> 24) == 0) { I.palette[k - 1] = I.palette[0]; I.palette[0] = pixel; }   // PL:200-202
+        }
+    I.paletteLen = cnt;
+    I.skipPnn = 1;
+  }
 }
 
 // ---- saliency map (PL:155-156 inside pnnquan for nMaxColors < 128; PL:499-508 inside dither) ------

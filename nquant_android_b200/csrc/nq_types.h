@@ -39,6 +39,7 @@ struct NqImage {
   // statistics
   unsigned long long statRescans, statPairs, rngDraws, statFullEvals;
   unsigned int statHeapPops;
+  unsigned int distinctColors;     // pixelMap.size() so far (only tracked when NqSlot::bits is set)
   // merge-loop phase clocks (SM cycles, thread 0): 0 heap/top, 1 first-32, 2 block tests, 3 screen, 4 full+resolve, 5 merge+rebuild
   unsigned long long statCyc[6], statLiveBlocks, statScreened;
   unsigned long long statDither[3];   // FIFO dither: consumer cycles, consumer cycles waiting for the producer, producer cycles waiting
@@ -69,4 +70,6 @@ struct NqSlot {
   unsigned short* memo;            // [65536] nearestMap for reduced keys (0xFFFF = absent)
   unsigned short* idx;             // [npix] palette indices of pass 1 when a second pass follows
   unsigned char* cells;            // [32768][32] candidate lists of the CIELAB closest-colour scan (k_build_cells)
+  unsigned int* bits;              // [2^27] one bit per ARGB colour ever passed to getLab (pixelMap, PL:34-42); only when the
+                                   // BlueNoise second pass needs pixelMap.size() (PL:511-513)
 };

@@ -3,13 +3,14 @@ generator here and the CUDA generator (csrc/nq_synth.cuh) produce identical byte
 
   h(seed, idx, ch) = mix64(seed ^ ((idx*4 + ch) * 0x9E3779B97F4A7C15))
   base gradient   R = 255*x//(W-1), G = 255*y//(H-1), B = 255*(x+y)//(W+H-2)
-  classes         smooth: amp 2, noisy: amp 32 (noise uniform in [-amp, amp], clamped), rand: uniform bytes
+  classes         smooth: amp 2, noisy: amp 32 (noise uniform in [-amp, amp], clamped), rand: uniform bytes,
+                  few (numpy only): rand posterised to 2 levels of r, 3 of g, 2 of b = at most 12 colours
   alpha modes     opaque: 255; transparent: 255 with A=0 in the top-left (W/8 x H/8) block;
                   semi: A = 255*(W-1-x)//(W-1) with A=0 in the same block
 """
 import numpy as np
 
-CLASSES = {"smooth": 0, "noisy": 1, "rand": 2}
+CLASSES = {"smooth": 0, "noisy": 1, "rand": 2, "few": 3}
 ALPHA = {"opaque": 0, "transparent": 1, "semi": 2}
 AMP = {0: 2, 1: 32, 2: 0}
 GOLDEN = np.uint64(0x9E3779B97F4A7C15)
@@ -31,7 +32,11 @@ def make_image(width, height, cls="noisy", alpha="opaque", seed=0x5EED0000):
     y = (idx // np.uint64(width)).astype(np.int64)
     with np.errstate(over="ignore"):
         hs = [_mix64(np.uint64(seed) ^ ((idx * np.uint64(4) + np.uint64(ch)) * GOLDEN)) for ch in range(3)]
-    if kls == 2:
+    if kls == 3:   # icon-like: a handful of flat colours (exercises PnnLABQuantizer's few-colours shortcut)
+        r = ((hs[0] & np.uint64(1)).astype(np.int64)) * 200 + 30
+        g = ((hs[1] % np.uint64(3)).astype(np.int64)) * 100 + 20
+        b = ((hs[2] & np.uint64(1)).astype(np.int64)) * 180 + 40
+    elif kls == 2:
         r, g, b = [(h & np.uint64(0xFF)).astype(np.int64) for h in hs]
     else:
         amp = AMP[kls]

@@ -107,6 +107,16 @@ CASES = [
     (0, "noisy", "semi", 96, 64, 256, True), (1, "smooth", "semi", 96, 64, 256, True),
     (0, "noisy", "opaque", 1, 97, 8, True), (1, "noisy", "opaque", 97, 1, 8, True),
     (0, "noisy", "opaque", 37, 211, 128, True), (1, "noisy", "opaque", 211, 37, 128, True),
+    # dither == false with more than 32 colours: Gilbert pass + BlueNoise.dither second pass; for PnnLABQuantizer its
+    # weight depends on pixelMap.size() (PnnLABQuantizer.java:511-513)
+    (1, "noisy", "opaque", 160, 120, 64, False), (1, "noisy", "opaque", 160, 120, 256, False),
+    (1, "rand", "opaque", 400, 300, 64, False), (1, "noisy", "transparent", 128, 96, 64, False),
+    (0, "noisy", "transparent", 128, 96, 64, False), (1, "smooth", "opaque", 160, 120, 256, False),
+    (1, "smooth", "opaque", 640, 480, 64, False), (1, "smooth", "opaque", 800, 600, 40, False),   # weight != 1
+    # at most 12 (13 with the transparent one) distinct colours: PnnLABQuantizer returns pixelMap.keySet() in HashMap
+    # order (PnnLABQuantizer.java:193-206); PnnQuantizer keeps its bins
+    (1, "few", "opaque", 96, 64, 32, True), (1, "few", "transparent", 96, 64, 32, True), (1, "few", "opaque", 96, 64, 16, False),
+    (1, "few", "opaque", 96, 64, 8, True), (0, "few", "transparent", 96, 64, 32, True), (1, "few", "semi", 64, 48, 256, True),
 ]
 
 
@@ -138,6 +148,8 @@ def test_stage_and_output_parity(gpu_ctx, oracle, kind, cls, alpha, W, H, K, dit
         if len(ref.saliencies):
             assert np.array_equal(gpu_ctx.debug_saliencies(W * H, 0).view(np.uint32), ref.saliencies.view(np.uint32))
         assert info["rng_draws"] == s["rng_draws"]
+        if kind == 1 and not dither and plen[0] > 32:
+            assert np.float32(info["bn_weight"]) == np.float32(s["bn_weight"]), (info["bn_weight"], s["bn_weight"], s["pixelMapSize"])
         assert np.array_equal(out[0], ref.out), f"{int((out[0] != ref.out).sum())} of {W * H} output pixels differ"
     finally:
         gpu_ctx.set_debug(False)
@@ -221,6 +233,9 @@ def test_full_size_4k_properties(gpu_ctx, kind, K, alpha):
 
 def test_error_codes(gpu_ctx):
     from nquant_android_b200.quantizer import NQuantError
+    with pytest.raises(NQuantError) as e:   # pixelMap.size() is not tracked when getLab's calls depend on scan order
+        gpu_ctx.convert_batch(1, make_image(96, 64, "noisy", "semi")[None, :], 96, 64, 64, False)
+    assert e.value.code == -4
     img = make_image(8, 8)
     with pytest.raises(NQuantError) as e:
         gpu_ctx.convert_batch(0, img[None, :], 8, 8, 1, True)
