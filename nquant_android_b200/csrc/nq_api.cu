@@ -356,7 +356,7 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
     if (kind == NQ_KIND_RGB) {
       {  // contiguous tiles per CTA; enough CTAs to fill the machine twice over
         const int ntiles = ((w + NQ_HTW - 1) / NQ_HTW) * ((h + NQ_HTW - 1) / NQ_HTW);
-        const dim3 hg(std::max(1, std::min(ntiles, std::max(1, c->smCount * 4 / n))), n);
+        const dim3 hg(std::max(1, std::min(ntiles, std::max(1, c->smCount * 8 / n))), n);
         nq::k_hist_rgb<<<hg, 256, sizeof(nq::HistTable), st>>>(c->dImgs, c->dSlots); ++c->launches;
       }
       nq::k_finalize_rgb<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
@@ -419,7 +419,7 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
       }
     }
     if (kind == NQ_KIND_RGB) {
-      nq::k_merge<<<n, NQ_MERGE_THREADS, (size_t)NQ_HEAP_SMEM * 8, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
+      nq::k_merge_rgb<<<n, NQ_RGB_THREADS, (size_t)NQ_RGB_HEAP_SMEM * 8, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
     } else {
       nq::k_merge_lab<<<n, NQ_LAB_THREADS, (size_t)NQ_LAB_HEAP_SMEM * 8, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
     }
@@ -565,7 +565,7 @@ nq_ctx* nq_create(int device) {
     }
     if (ok) ++e.refs;
   }
-  if (ok) ok = cudaFuncSetAttribute(nq::k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_HEAP_SMEM * 8) == cudaSuccess;
+  if (ok) ok = cudaFuncSetAttribute(nq::k_merge_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_RGB_HEAP_SMEM * 8) == cudaSuccess;
   if (ok) ok = cudaFuncSetAttribute(nq::k_hist_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nq::HistTable)) == cudaSuccess;
   if (ok) ok = cudaFuncSetAttribute(nq::k_merge_lab, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_LAB_HEAP_SMEM * 8) == cudaSuccess;
   if (!ok) {

@@ -105,8 +105,8 @@ __global__ void k_setup_scan(NqImage* imgs, const NqSlot* slots, int nimg) {
 // (key tag + count + four channel sums, integer atomics); after every tile the occupied slots are
 // flushed with global atomics. Pixels whose slot (and its neighbour) belongs to another key go to global
 // memory directly. Sums are integers, so the result does not depend on any of this.
-#define NQ_HSLOTS 4096
-#define NQ_HTW 128          // tile side in pixels
+#define NQ_HSLOTS 2048
+#define NQ_HTW 64           // tile side in pixels
 struct HistTable { unsigned tag[NQ_HSLOTS], cnt[NQ_HSLOTS], sa[NQ_HSLOTS], sr[NQ_HSLOTS], sg[NQ_HSLOTS], sb[NQ_HSLOTS]; };
 
 __device__ __forceinline__ void hist_rgb_add(HistTable& T, unsigned int* hc, unsigned long long* hs, uint32_t p, bool semi, bool tr) {

@@ -440,8 +440,6 @@ __global__ void __launch_bounds__(256) k_find_nn_lab(NqImage* imgs, const NqSlot
 // -------------------------------------------------------------------------------------------------
 // merge loop: one persistent CTA per image.
 // -------------------------------------------------------------------------------------------------
-#define NQ_MERGE_THREADS 1024
-#define NQ_HEAP_SMEM 24576     // heap slots kept in shared memory (err f32 + id|nn u32 = 8 B each = 192 KB)
 
 // The heap of bin ids keyed by err (PQ:195-236). A slot also carries a copy of the bin's err (a bin's err only
 // changes while it sits at heap[1]) and of its nn (likewise), so the top can be validated with ONE round trip
@@ -469,201 +467,6 @@ struct HeapView {
   }
 };
 __device__ __forceinline__ unsigned pack_idnn(int id, int nn) { return (unsigned)id | ((unsigned)nn << 16); }
-
-// rebuild the ascending list of live bins; returns its length (block-wide, all threads call)
-__device__ __forceinline__ int rebuild_live(const NqSlot& S, int maxbins, int* live, int* posOf, int* sWarp) {
-  const int t = threadIdx.x;
-  const int per = (maxbins + NQ_MERGE_THREADS - 1) / NQ_MERGE_THREADS;
-  const int b0 = min(maxbins, t * per), b1 = min(maxbins, b0 + per);
-  int c = 0;
-  for (int b = b0; b < b1; ++b) c += S.bMtm[b] != NQ_DELETED;
-  int total, j = block_excl_scan_1024(c, &total, sWarp);
-  for (int b = b0; b < b1; ++b)
-    if (S.bMtm[b] != NQ_DELETED) { live[j] = b; posOf[b] = j; ++j; }
-  __syncthreads();
-  return total;
-}
-
-__global__ void __launch_bounds__(NQ_MERGE_THREADS, 1) k_merge(NqImage* imgs, const NqSlot* slots, int* liveBuf, int* posBuf, int logMerges) {
-  extern __shared__ unsigned char smemRaw[];
-  float* sErr = reinterpret_cast<float*>(smemRaw);
-  unsigned* sId = reinterpret_cast<unsigned*>(smemRaw + (size_t)NQ_HEAP_SMEM * 4);
-  __shared__ int sWarp[33];
-  __shared__ unsigned sMask[32];
-  __shared__ double sErrCur;
-  __shared__ int sNnCur, sAction, sB1, sHeapN, sIter;
-
-  const int img = blockIdx.x;
-  NqImage& I = imgs[img];
-  if (I.kind != NQ_KIND_RGB || I.nmax <= 2 || I.skipPnn) return;   // CIELAB images: k_merge_lab
-  const NqSlot& S = slots[img];
-  const int t = threadIdx.x;
-  const unsigned lane = lane_id(), w = t >> 5;
-  const int maxbins = I.maxbins, extbins = I.extbins;
-  const bool rgb = I.kind == NQ_KIND_RGB;
-  int* live = liveBuf + (size_t)img * NQ_NBINS;
-  int* posOf = posBuf + (size_t)img * NQ_NBINS;
-  HeapView<NQ_HEAP_SMEM> H{sErr, sId, S.hErr, S.hId};
-
-  // ---- heap build: sequential pushes in bin order (PQ:196-207). Warp 0 replays them; every lane
-  //      follows the same scalar steps (values prefetched 32 at a time), lane 0 does the stores.
-  if (w == 0) {
-    int heapN = 0;
-    for (int base = 0; base < maxbins; base += 32) {
-      float e = (base + (int)lane < maxbins) ? S.bErr[base + lane] : 0.f;
-      const int nnv = (base + (int)lane < maxbins) ? S.bNn[base + lane] : 0;
-      const int cnt = min(32, maxbins - base);
-      for (int j = 0; j < cnt; ++j) {
-        const float err = __shfl_sync(0xffffffffu, e, j);
-        const int nnj = __shfl_sync(0xffffffffu, nnv, j);
-        int l = ++heapN, l2;
-        for (; l > 1; l = l2) {
-          l2 = l >> 1;
-          float pe = H.err(l2);
-          if (pe <= err) break;
-          unsigned pid = H.idnn(l2);
-          if (lane == 0) H.set(l, pid, pe);
-        }
-        if (lane == 0) H.set(l, pack_idnn(base + j, nnj), err);
-        __syncwarp();
-      }
-    }
-    if (lane == 0) { sHeapN = heapN; sIter = 0; }
-  }
-  __syncthreads();
-  int liveLen = rebuild_live(S, maxbins, live, posOf, sWarp);
-  int liveAtRebuild = liveLen, iterAtRebuild = 0;
-  unsigned long long rescans = 0, pairs = 0;
-  unsigned pops = 0;
-
-  for (;;) {
-    // ---- thread 0: look at the heap top (PQ:214-226)
-    if (t == 0) {
-      int action = 0;  // 0 = merge, 1 = rescan, 2 = finished
-      if (sIter >= extbins) action = 2;
-      else {
-        int heapN = sHeapN;
-        for (;;) {
-          const unsigned top = H.idnn(1);
-          int b1 = (int)(top & 0xFFFFu);
-          const int tm = S.bTm[b1], mtm = S.bMtm[b1], nmtm = S.bMtm[top >> 16];   // three independent loads
-          if (tm >= mtm && nmtm <= tm) { action = 0; sB1 = b1; break; }
-          if (mtm == NQ_DELETED) {   // deleted node: b1 = heap[1] = heap[heap[0]--], then push down
-            const unsigned last = H.idnn(heapN);
-            float e1 = H.err(heapN);
-            --heapN;
-            ++pops;
-            H.sift_down(last, e1, heapN);
-            continue;
-          }
-          action = 1; sB1 = b1;
-          break;
-        }
-        sHeapN = heapN;
-      }
-      sAction = action;
-    }
-    __syncthreads();
-    const int action = sAction;
-    if (action == 2) break;
-    const int b1 = sB1;
-
-    if (action == 1) {
-      // ---- cooperative find_nn(b1) over the live bins after b1
-      ++rescans;
-      const int p0 = posOf[b1] + 1;
-      double err = 1e100;
-      int nn = 0;
-      if (rgb) {
-        RgbProbe P = rgb_probe(I, S, b1);
-        for (int base = p0; base < liveLen; base += NQ_MERGE_THREADS) {
-          const int p = base + t;
-          int i = -1;
-          RgbCand c;
-          double gate = 1e300;
-          if (p < liveLen) {
-            i = live[p];
-            if (S.bMtm[i] != NQ_DELETED) gate = rgb_gate(P, S, i, &c); else i = -1;
-          }
-          int lastP = -1;
-          for (;;) {
-            unsigned m = __ballot_sync(0xffffffffu, i >= 0 && p > lastP && gate < err);
-            if (lane == 0) sMask[w] = m;
-            __syncthreads();
-            unsigned mine = sMask[lane];
-            unsigned wm = __ballot_sync(0xffffffffu, mine != 0);
-            if (!wm) { __syncthreads(); break; }
-            int fw = __ffs(wm) - 1;
-            unsigned mm = __shfl_sync(0xffffffffu, mine, fw);
-            int winner = fw * 32 + (__ffs(mm) - 1);
-            if (t == winner) { sErrCur = rgb_take(P, c, err); sNnCur = i; }
-            __syncthreads();
-            err = sErrCur; nn = sNnCur;
-            lastP = base + winner;
-          }
-        }
-      }
-      pairs += (unsigned long long)max(0, liveLen - p0);
-      if (t == 0) {
-        // tb.tm = i; push slot down (PQ:224-236)
-        float e1 = (float)err;
-        S.bErr[b1] = e1; S.bNn[b1] = nn; S.bTm[b1] = sIter;
-        H.sift_down(pack_idnn(b1, nn), e1, sHeapN);
-      }
-      __syncthreads();
-      continue;
-    }
-
-    // ---- merge tb <- tb + nb (PQ:240-254, PL:297-311)
-    if (t == 0) {
-      const int nbI = S.bNn[b1];
-      const float n1 = S.bCnt[b1], n2 = S.bCnt[nbI];
-      if (rgb) {
-        const float d = 1.f / (n1 + n2);
-        S.bAc[b1] = (double)(d * (float)jround((double)n1 * S.bAc[b1] + (double)n2 * S.bAc[nbI]));   // float * long -> float
-        S.bC1[b1] = (double)(d * (float)jround((double)n1 * S.bC1[b1] + (double)n2 * S.bC1[nbI]));   // float * long -> float
-        S.bC2[b1] = (double)(d * (float)jround((double)n1 * S.bC2[b1] + (double)n2 * S.bC2[nbI]));   // float * long -> float
-        S.bC3[b1] = (double)(d * (float)jround((double)n1 * S.bC3[b1] + (double)n2 * S.bC3[nbI]));   // float * long -> float
-      } else {
-        const float d = 1.0f / (n1 + n2);
-        S.fAc[b1] = d * (n1 * S.fAc[b1] + n2 * S.fAc[nbI]);
-        S.fC1[b1] = d * (n1 * S.fC1[b1] + n2 * S.fC1[nbI]);
-        S.fC2[b1] = d * (n1 * S.fC2[b1] + n2 * S.fC2[nbI]);
-        S.fC3[b1] = d * (n1 * S.fC3[b1] + n2 * S.fC3[nbI]);
-      }
-      S.bCnt[b1] = n1 + n2;
-      const int i = sIter + 1;
-      S.bMtm[b1] = i;
-      S.bMtm[nbI] = NQ_DELETED;
-      if (logMerges && S.mergeLog) { S.mergeLog[2 * (i - 1)] = b1; S.mergeLog[2 * (i - 1) + 1] = nbI; }
-      sIter = i;
-    }
-    __syncthreads();
-    // compact the live list once a quarter of it has died since the last rebuild
-    const int it = sIter;
-    if ((it - iterAtRebuild) * 4 > liveAtRebuild) {
-      liveLen = rebuild_live(S, maxbins, live, posOf, sWarp);
-      liveAtRebuild = liveLen; iterAtRebuild = it;
-    }
-  }
-
-  // ---- palette fill (PQ:258-264, PL:315-324): the k-th live bin in ascending order
-  liveLen = rebuild_live(S, maxbins, live, posOf, sWarp);
-  const int plen = extbins > 0 ? I.nmax : maxbins;
-  for (int k = t; k < plen; k += NQ_MERGE_THREADS) {
-    const int b = live[k];
-    uint32_t colr;
-    if (rgb) colr = c_argb(j2i(S.bAc[b]), j2i(S.bC1[b]), j2i(S.bC2[b]), j2i(S.bC3[b]));
-    else {
-      if (!lab2rgb(j2i((double)S.fAc[b]), S.fC1[b], S.fC2[b], S.fC3[b], &colr)) { colr = 0; I.error = 3; }
-    }
-    I.palette[k] = colr;
-  }
-  if (t == 0) {
-    I.paletteLen = plen;
-    I.statRescans = rescans; I.statPairs += pairs; I.statHeapPops = pops;
-  }
-}
 
 // -------------------------------------------------------------------------------------------------
 // CIELAB merge loop. A full find_nn test costs a few thousand double-precision instructions
@@ -1016,6 +819,363 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 3) k_merge_lab(NqImage* imgs, 
     I.statLiveBlocks = liveBlocks; I.statScreened = screened;
   }
   if (fulls) atomicAdd(&I.statFullEvals, fulls);
+}
+
+
+// -------------------------------------------------------------------------------------------------
+// RGB merge loop, same organisation as k_merge_lab: compacted records of the surviving bins, 32-bin
+// block summaries, 128 threads per image and several images per SM.
+// RGB's find_nn differs in one respect that matters here: a candidate that passes the four `continue`
+// tests is taken with err := the first partial sum that reaches the old err (the `break` of PQ:97-108
+// falls through to PQ:111), so the running err can GROW, and no candidate can be dismissed for good by
+// comparing against the current err. The kernel therefore prunes against U = 4 x (err after the first
+// 32 candidates): blocks and candidates whose gate max(nerr2, q0) is >= U cannot be taken while err < U.
+// The survivors are replayed in list order with the exact err; if err ever reaches U the rescan is
+// redone without pruning (U = infinity), which is the reference's own scan.
+// -------------------------------------------------------------------------------------------------
+#define NQ_RGB_THREADS 128
+#define NQ_RGB_HEAP_SMEM 6144
+
+struct RgbScratch {
+  double2* rg;          // {r, g} per position
+  double2* bc;          // {b, cnt} per position; cnt < 0 marks a bin that died since the last compaction
+  double* al;           // alpha per position (semi-transparent images)
+  double *cmin, *lo, *hi;   // per block of 32 positions: min count, and min / max of r, g, b (3 planes of 2048 each)
+};
+__device__ __forceinline__ RgbScratch rgb_scratch(const NqSlot& S) {
+  RgbScratch X;
+  X.rg = reinterpret_cast<double2*>(S.hSum);                       // 2 MiB of histogram sums, free after compaction
+  X.bc = X.rg + NQ_NBINS;
+  double* f = reinterpret_cast<double*>(S.fAc);                    // the CIELAB float planes (1 MiB), unused for RGB
+  X.al = f;
+  X.cmin = f + NQ_NBINS; X.lo = X.cmin + 2048; X.hi = X.lo + 3 * 2048;
+  return X;
+}
+
+__device__ __forceinline__ double rgb_gate_rec(const RgbProbe& P, const double2 rg, const double2 bc, double al, RgbCand* c) {
+  const double n2 = bc.y;
+  double nerr2 = ((double)P.n1 * n2) / ((double)P.n1 + n2);
+  double nerr = 0.0;
+  if (P.semi) { double d = al - P.wa; nerr += nerr2 * P.PA * (d * d); }
+  double dr = rg.x - P.wr, dg = rg.y - P.wg, db = bc.x - P.wb;
+  nerr += nerr2 * (1 - P.ratio) * P.PR * (dr * dr);
+  nerr += nerr2 * (1 - P.ratio) * P.PG * (dg * dg);
+  nerr += nerr2 * (1 - P.ratio) * P.PB * (db * db);
+  c->nerr2 = nerr2; c->q0 = nerr; c->dr = dr; c->dg = dg; c->db = db;
+  return nerr2 > nerr ? nerr2 : nerr;
+}
+
+// true when no bin of the block can have a gate below U (the alpha term is >= 0 and left out)
+__device__ __forceinline__ bool rgb_block_skip(const RgbProbe& P, const RgbScratch& X, int blk, double U) {
+  const double cmin = X.cmin[blk];
+  if (!(cmin >= 0.0)) return true;
+  const double n1 = (double)P.n1;
+  const double nerr2 = (n1 * cmin) / (n1 + cmin) * (1.0 - 1e-12);
+  if (nerr2 >= U) return true;
+  const double dr = fmax(0.0, fmax(X.lo[blk] - P.wr, P.wr - X.hi[blk]));
+  const double dg = fmax(0.0, fmax(X.lo[2048 + blk] - P.wg, P.wg - X.hi[2048 + blk]));
+  const double db = fmax(0.0, fmax(X.lo[4096 + blk] - P.wb, P.wb - X.hi[4096 + blk]));
+  const double q0 = nerr2 * (1 - P.ratio) * (P.PR * (dr * dr) + P.PG * (dg * dg) + P.PB * (db * db)) * (1.0 - 1e-12);
+  return q0 >= U;
+}
+
+__device__ __forceinline__ void rgb_block_summary(const RgbScratch& X, int n, int blk) {
+  double cm = -1.0, lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  const int p0 = blk << 5, p1 = min(n, p0 + 32);
+  for (int p = p0; p < p1; ++p) {
+    const double2 bc = X.bc[p];
+    if (!(bc.y >= 0.0)) continue;
+    const double2 rg = X.rg[p];
+    cm = cm < 0.0 ? bc.y : fmin(cm, bc.y);
+    lo[0] = fmin(lo[0], rg.x); hi[0] = fmax(hi[0], rg.x);
+    lo[1] = fmin(lo[1], rg.y); hi[1] = fmax(hi[1], rg.y);
+    lo[2] = fmin(lo[2], bc.x); hi[2] = fmax(hi[2], bc.x);
+  }
+  X.cmin[blk] = cm;
+  for (int k = 0; k < 3; ++k) { X.lo[k * 2048 + blk] = lo[k]; X.hi[k * 2048 + blk] = hi[k]; }
+}
+
+__device__ __forceinline__ int rebuild_live_rgb(const NqSlot& S, const RgbScratch& X, int maxbins, int* live, int* posOf, int* sScan) {
+  const int t = threadIdx.x;
+  const unsigned lane = lane_id(), w = t >> 5;
+  const int W = NQ_RGB_THREADS / 32;
+  const int per = (((maxbins + W - 1) / W) + 31) & ~31;
+  const int b0 = min(maxbins, (int)w * per), b1 = min(maxbins, b0 + per);
+  int c = 0;
+  for (int b = b0 + (int)lane; b < b1; b += 32) c += S.bMtm[b] != NQ_DELETED;
+  int total, j = block_excl_scan_128(c, &total, sScan);
+  j = __shfl_sync(0xffffffffu, j, 0);
+  for (int base = b0; base < b1; base += 32) {
+    const int b = base + (int)lane;
+    const bool alive = b < b1 && S.bMtm[b] != NQ_DELETED;
+    const unsigned m = __ballot_sync(0xffffffffu, alive);
+    if (alive) {
+      const int p = j + __popc(m & ((1u << lane) - 1u));
+      live[p] = b; posOf[b] = p;
+      X.rg[p] = make_double2(S.bC1[b], S.bC2[b]);
+      X.bc[p] = make_double2(S.bC3[b], (double)S.bCnt[b]);
+      X.al[p] = S.bAc[b];
+    }
+    j += __popc(m);
+  }
+  __syncthreads();
+  const int nblk = (total + 31) >> 5;
+  for (int blk = t; blk < nblk; blk += NQ_RGB_THREADS) rgb_block_summary(X, total, blk);
+  __syncthreads();
+  return total;
+}
+
+// replay of up to 32 candidates held one per lane, in lane order (PQ:73-112)
+__device__ __forceinline__ void rgb_accept_in_order(const RgbProbe& P, double gate, const RgbCand& c, int id, double& err, int& nn, double& errMax) {
+  const unsigned lane = lane_id();
+  unsigned remaining = 0xffffffffu;
+  for (;;) {
+    const unsigned m = __ballot_sync(0xffffffffu, gate < err) & remaining;
+    if (!m) break;
+    const int L = __ffs(m) - 1;
+    double e = 0;
+    if ((int)lane == L) e = rgb_take(P, c, err);
+    err = __shfl_sync(0xffffffffu, e, L);
+    nn = __shfl_sync(0xffffffffu, id, L);
+    errMax = err > errMax ? err : errMax;
+    remaining = (L == 31) ? 0u : ~((2u << L) - 1u);
+  }
+}
+
+static_assert(NQ_RGB_THREADS == NQ_LAB_THREADS, "block_excl_scan_128 is shared");
+
+__global__ void __launch_bounds__(NQ_RGB_THREADS, 4) k_merge_rgb(NqImage* imgs, const NqSlot* slots, int* liveBuf, int* posBuf, int logMerges) {
+  extern __shared__ unsigned char smemRaw[];
+  float* sErr = reinterpret_cast<float*>(smemRaw);
+  unsigned* sId = reinterpret_cast<unsigned*>(smemRaw + (size_t)NQ_RGB_HEAP_SMEM * 4);
+  __shared__ int sScan[8];
+  __shared__ unsigned sBits[64];
+  __shared__ unsigned short sBlk[2048];
+  __shared__ unsigned sMaskA[32];
+  __shared__ int sOffA[33];
+  __shared__ double sErrCur, sErrMax;
+  __shared__ int sNnCur, sAction, sB1, sHeapN, sIter, sNLive;
+
+  const int img = blockIdx.x;
+  NqImage& I = imgs[img];
+  if (I.kind != NQ_KIND_RGB || I.nmax <= 2 || I.skipPnn) return;
+  const NqSlot& S = slots[img];
+  const RgbScratch X = rgb_scratch(S);
+  const int t = threadIdx.x;
+  const unsigned lane = lane_id(), w = t >> 5;
+  const int W = NQ_RGB_THREADS / 32;
+  const int maxbins = I.maxbins, extbins = I.extbins;
+  int* live = liveBuf + (size_t)img * NQ_NBINS;
+  int* posOf = posBuf + (size_t)img * NQ_NBINS;
+  HeapView<NQ_RGB_HEAP_SMEM> H{sErr, sId, S.hErr, S.hId};
+
+  // ---- heap build: sequential pushes in bin order (PQ:196-207), replayed by warp 0
+  if (w == 0) {
+    int heapN = 0;
+    for (int base = 0; base < maxbins; base += 32) {
+      float e = (base + (int)lane < maxbins) ? S.bErr[base + lane] : 0.f;
+      const int nnv = (base + (int)lane < maxbins) ? S.bNn[base + lane] : 0;
+      const int cnt = min(32, maxbins - base);
+      for (int j = 0; j < cnt; ++j) {
+        const float err = __shfl_sync(0xffffffffu, e, j);
+        const int nnj = __shfl_sync(0xffffffffu, nnv, j);
+        int l = ++heapN, l2;
+        for (; l > 1; l = l2) {
+          l2 = l >> 1;
+          float pe = H.err(l2);
+          if (pe <= err) break;
+          unsigned pid = H.idnn(l2);
+          if (lane == 0) H.set(l, pid, pe);
+        }
+        if (lane == 0) H.set(l, pack_idnn(base + j, nnj), err);
+        __syncwarp();
+      }
+    }
+    if (lane == 0) { sHeapN = heapN; sIter = 0; }
+  }
+  __syncthreads();
+  int liveLen = rebuild_live_rgb(S, X, maxbins, live, posOf, sScan);
+  int liveAtRebuild = liveLen, iterAtRebuild = 0;
+  unsigned long long rescans = 0, pairs = 0, redone = 0;
+  unsigned pops = 0;
+
+  for (;;) {
+    // ---- thread 0: look at the heap top (PQ:214-226)
+    if (t == 0) {
+      int action = 0;  // 0 = merge, 1 = rescan, 2 = finished
+      if (sIter >= extbins) action = 2;
+      else {
+        int heapN = sHeapN;
+        for (;;) {
+          const unsigned top = H.idnn(1);
+          int b1 = (int)(top & 0xFFFFu);
+          const int tm = S.bTm[b1], mtm = S.bMtm[b1], nmtm = S.bMtm[top >> 16];   // three independent loads
+          if (tm >= mtm && nmtm <= tm) { action = 0; sB1 = b1; break; }
+          if (mtm == NQ_DELETED) {   // deleted node: b1 = heap[1] = heap[heap[0]--], then push down
+            const unsigned last = H.idnn(heapN);
+            float e1 = H.err(heapN);
+            --heapN;
+            ++pops;
+            H.sift_down(last, e1, heapN);
+            continue;
+          }
+          action = 1; sB1 = b1;
+          break;
+        }
+        sHeapN = heapN;
+      }
+      sAction = action;
+    }
+    __syncthreads();
+    const int action = sAction;
+    if (action == 2) break;
+    const int b1 = sB1;
+
+    if (action == 1) {
+      ++rescans;
+      const int first = posOf[b1] + 1;
+      const RgbProbe P = rgb_probe(I, S, b1);
+      double err = 1e100, errMax = 0.0;
+      int nn = -1;                              // position in the live list
+      // -- 1. the first 32 candidates, exactly
+      if (w == 0) {
+        const int i = first + (int)lane;
+        RgbCand c;
+        double gate = 1e300;
+        if (i < liveLen) { const double2 bc = X.bc[i]; if (bc.y >= 0.0) gate = rgb_gate_rec(P, X.rg[i], bc, P.semi ? X.al[i] : 0.0, &c); }
+        rgb_accept_in_order(P, gate, c, i, err, nn, errMax);
+        if (lane == 0) { sErrCur = err; sNnCur = nn; }
+      }
+      __syncthreads();
+      const double err32 = sErrCur;
+      const int nn32 = sNnCur;
+      const int stop = first + 32;
+      const int blkBeg = stop >> 5, nblk = (liveLen + 31) >> 5;
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        // attempt 0 prunes against U = 4 err32; attempt 1 (only if err reached U) is the plain scan
+        const double U = attempt == 0 ? (err32 < 1e99 ? 4.0 * err32 : 1e300) : 1e300;
+        err = err32; nn = nn32; errMax = err32 < 1e99 ? err32 : 0.0;
+        if (t < 64) sBits[t] = 0u;
+        __syncthreads();
+        for (int blk = blkBeg + t; blk < nblk; blk += NQ_RGB_THREADS)
+          if (!rgb_block_skip(P, X, blk, U)) atomicOr(&sBits[blk >> 5], 1u << (blk & 31));
+        __syncthreads();
+        if (w == 0) {                             // bit set -> ordered list
+          const unsigned m0 = sBits[2 * lane], m1 = sBits[2 * lane + 1];
+          const int c = __popc(m0) + __popc(m1);
+          int x = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+          int at = x - c;
+          for (unsigned m = m0; m; m &= m - 1) sBlk[at++] = (unsigned short)(64 * lane + (__ffs(m) - 1));
+          for (unsigned m = m1; m; m &= m - 1) sBlk[at++] = (unsigned short)(64 * lane + 32 + (__ffs(m) - 1));
+          if (lane == 31) sNLive = x;
+        }
+        __syncthreads();
+        const int nLive = sNLive;
+        for (int g0 = 0; g0 < nLive; g0 += 32) {  // batches of 32 live blocks, in list order
+          const int gn = min(32, nLive - g0);
+          if (t < 32) sMaskA[t] = 0u;
+          __syncthreads();
+          // -- 2. gates of the bins of the live blocks: one warp per block, one lane per bin
+          for (int r = w; r < gn; r += W) {
+            const int i = ((int)sBlk[g0 + r] << 5) + (int)lane;
+            bool keep = false;
+            if (i >= stop && i < liveLen) {
+              const double2 bc = X.bc[i];
+              RgbCand c;
+              if (bc.y >= 0.0) keep = rgb_gate_rec(P, X.rg[i], bc, P.semi ? X.al[i] : 0.0, &c) < U;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) sMaskA[r] = m;
+          }
+          __syncthreads();
+          // -- 3. warp 0 replays the kept bins in list order with the exact err
+          if (w == 0) {
+            const int c = __popc(sMaskA[lane]);
+            int x = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+            sOffA[lane + 1] = x;
+            if (lane == 0) sOffA[0] = 0;
+            __syncwarp();
+            const int totalA = sOffA[32];
+            for (int base = 0; base < totalA; base += 32) {
+              const int sIdx = base + (int)lane;
+              RgbCand c;
+              double gate = 1e300;
+              int i = -1;
+              if (sIdx < totalA) {
+                int lo = 0, hi = 32;
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sOffA[mid] <= sIdx) lo = mid; else hi = mid; }
+                i = ((int)sBlk[g0 + lo] << 5) + (int)__fns(sMaskA[lo], 0, sIdx - sOffA[lo] + 1);
+                gate = rgb_gate_rec(P, X.rg[i], X.bc[i], P.semi ? X.al[i] : 0.0, &c);
+              }
+              rgb_accept_in_order(P, gate, c, i, err, nn, errMax);
+            }
+          }
+          __syncthreads();
+        }
+        if (w == 0 && lane == 0) { sErrCur = err; sNnCur = nn; sErrMax = errMax; }
+        __syncthreads();
+        if (!(sErrMax >= U)) break;               // err never reached U: the pruning was sound
+        ++redone;
+      }
+      err = sErrCur; nn = sNnCur;
+      pairs += (unsigned long long)max(0, liveLen - first);
+      if (t == 0) {
+        // tb.tm = i; push slot down (PQ:224-236)
+        float e1 = (float)err;
+        const int nnBin = nn < 0 ? 0 : live[nn];
+        S.bErr[b1] = e1; S.bNn[b1] = nnBin; S.bTm[b1] = sIter;
+        H.sift_down(pack_idnn(b1, nnBin), e1, sHeapN);
+      }
+      __syncthreads();
+      continue;
+    }
+
+    // ---- merge tb <- tb + nb (PQ:240-254)
+    if (t == 0) {
+      const int nbI = S.bNn[b1];
+      const float n1 = S.bCnt[b1], n2 = S.bCnt[nbI];
+      const float d = 1.f / (n1 + n2);
+      const double na = (double)(d * (float)jround((double)n1 * S.bAc[b1] + (double)n2 * S.bAc[nbI]));   // float * long -> float
+      const double nr = (double)(d * (float)jround((double)n1 * S.bC1[b1] + (double)n2 * S.bC1[nbI]));
+      const double ng = (double)(d * (float)jround((double)n1 * S.bC2[b1] + (double)n2 * S.bC2[nbI]));
+      const double nb = (double)(d * (float)jround((double)n1 * S.bC3[b1] + (double)n2 * S.bC3[nbI]));
+      S.bAc[b1] = na; S.bC1[b1] = nr; S.bC2[b1] = ng; S.bC3[b1] = nb;
+      S.bCnt[b1] = n1 + n2;
+      const int i = sIter + 1;
+      S.bMtm[b1] = i;
+      S.bMtm[nbI] = NQ_DELETED;
+      const int pt = posOf[b1], pn = posOf[nbI], bt = pt >> 5;
+      X.rg[pt] = make_double2(nr, ng); X.bc[pt] = make_double2(nb, (double)(n1 + n2)); X.al[pt] = na;
+      X.bc[pn].y = -1.0;
+      X.lo[bt] = fmin(X.lo[bt], nr); X.hi[bt] = fmax(X.hi[bt], nr);
+      X.lo[2048 + bt] = fmin(X.lo[2048 + bt], ng); X.hi[2048 + bt] = fmax(X.hi[2048 + bt], ng);
+      X.lo[4096 + bt] = fmin(X.lo[4096 + bt], nb); X.hi[4096 + bt] = fmax(X.hi[4096 + bt], nb);
+      if (logMerges && S.mergeLog) { S.mergeLog[2 * (i - 1)] = b1; S.mergeLog[2 * (i - 1) + 1] = nbI; }
+      sIter = i;
+    }
+    __syncthreads();
+    const int it = sIter;
+    if ((it - iterAtRebuild) * 4 > liveAtRebuild) {
+      liveLen = rebuild_live_rgb(S, X, maxbins, live, posOf, sScan);
+      liveAtRebuild = liveLen; iterAtRebuild = it;
+    }
+  }
+
+  // ---- palette fill (PQ:258-264): the k-th live bin in ascending order
+  liveLen = rebuild_live_rgb(S, X, maxbins, live, posOf, sScan);
+  const int plen = extbins > 0 ? I.nmax : maxbins;
+  for (int k = t; k < plen; k += NQ_RGB_THREADS) {
+    const int b = live[k];
+    I.palette[k] = c_argb(j2i(S.bAc[b]), j2i(S.bC1[b]), j2i(S.bC2[b]), j2i(S.bC3[b]));
+  }
+  if (t == 0) {
+    I.paletteLen = plen;
+    I.statRescans = rescans; I.statPairs += pairs; I.statHeapPops = pops; I.statFullEvals = redone;
+  }
 }
 
 
