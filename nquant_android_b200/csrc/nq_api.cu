@@ -382,7 +382,10 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
       nq::k_lab_fewcolors<<<n, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
     }
     mark(2);
-    if (kind == NQ_KIND_RGB) { nq::k_find_nn_all<<<c->smCount * 8, 256, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches; }
+    if (kind == NQ_KIND_RGB) {
+      nq::k_rgb_blocks<<<dim3(2, n), 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_find_nn_all<<<c->smCount * 8, 256, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
+    }
     else {
       nq::k_lab_blocks<<<dim3(2, n), 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
       nq::k_find_nn_lab<<<c->smCount * 8, 256, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;

@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(1024) k_finalize_rgb(NqImage* imgs, const NqSl
 // replaced) pixels by bin key with a two-pass LSD radix sort and let one warp per bin add its
 // run sequentially. Counts come from integer atomics.
 // =================================================================================================
-#define NQ_RUN 2048   // pixels per warp run in the radix passes
+#define NQ_RUN 8192   // pixels per warp run in the radix passes
 
 __device__ __forceinline__ uint32_t lab_src_pixel(uint32_t p, uint32_t tc) { return ((p >> 24) <= 0xF) ? tc : p; }
 
@@ -385,10 +385,13 @@ __global__ void __launch_bounds__(256) k_radix_offsets(const NqImage* imgs, cons
   const int nruns = (I.npix + NQ_RUN - 1) / NQ_RUN;
   const int d = threadIdx.x;
   unsigned acc = 0;
-  for (int r = 0; r < nruns; ++r) {
-    unsigned c = S.warpHist[(size_t)r * 256 + d];
-    S.warpHist[(size_t)r * 256 + d] = acc;
-    acc += c;
+  for (int r0 = 0; r0 < nruns; r0 += 8) {      // eight loads in flight: the counters come from L2
+    unsigned c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) c[u] = r0 + u < nruns ? S.warpHist[(size_t)(r0 + u) * 256 + d] : 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (r0 + u < nruns) { S.warpHist[(size_t)(r0 + u) * 256 + d] = acc; acc += c[u]; }
   }
   sTot[d] = acc;
   __syncthreads();
@@ -398,7 +401,14 @@ __global__ void __launch_bounds__(256) k_radix_offsets(const NqImage* imgs, cons
   }
   __syncthreads();
   const unsigned base = sTot[d];
-  for (int r = 0; r < nruns; ++r) S.warpHist[(size_t)r * 256 + d] += base;
+  for (int r0 = 0; r0 < nruns; r0 += 8) {
+    unsigned c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) c[u] = r0 + u < nruns ? S.warpHist[(size_t)(r0 + u) * 256 + d] : 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (r0 + u < nruns) S.warpHist[(size_t)(r0 + u) * 256 + d] = c[u] + base;
+  }
 }
 
 // radix pass, step 3: stable scatter.

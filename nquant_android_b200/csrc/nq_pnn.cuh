@@ -120,10 +120,12 @@ struct LabView {
 // the float roundings of the reference's own evaluation. A block may be skipped when even this bound
 // fails the reference's tests against an upper bound U of the running err: nerr2 >= U (PL:57) or the
 // prefix after the L' term > U (PL:88-90; every earlier term is >= 0).
+__device__ __forceinline__ bool lab_block_skip_v(const LabProbe& P, float cmin, float lo, float hi, double U);
 __device__ __forceinline__ bool lab_block_skip(const LabProbe& P, const LabView& V, int blk, double U) {
-  const float cmin = V.bcmin[blk];
+  return lab_block_skip_v(P, V.bcmin[blk], V.blmin[blk], V.blmax[blk], U);
+}
+__device__ __forceinline__ bool lab_block_skip_v(const LabProbe& P, float cmin, float lo, float hi, double U) {
   if (!(cmin >= 0.f)) return true;                        // block holds no live bin
-  const float lo = V.blmin[blk], hi = V.blmax[blk];
   const double n2 = (double)cmin, n1 = (double)P.n1;
   const double nerr2 = (n1 * n2) / (n1 + n2) * (1.0 - 1e-6);
   if (nerr2 >= U) return true;
@@ -303,10 +305,17 @@ __device__ void warp_find_nn_lab(const LabProbe& P, const LabView& V, int first,
     pos += 32;
   }
   const int stop = first + 32;     // positions below were handled by the unconditional tile
-  for (int blk0 = pos >> 5; (blk0 << 5) < n; blk0 += 32) {
-    const int blk = blk0 + (int)lane;
-    const bool live = (blk << 5) < n && !lab_block_skip(P, V, blk, err);
-    unsigned bm = __ballot_sync(0xffffffffu, live);
+  // the summaries of the next 32 blocks are loaded while the current ones are processed (they come from L2)
+  const int nblk = (n + 31) >> 5;
+  int blk0 = pos >> 5;
+  float sc = -1.f, sl = 0.f, sh = 0.f;
+  if (blk0 + (int)lane < nblk) { sc = V.bcmin[blk0 + lane]; sl = V.blmin[blk0 + lane]; sh = V.blmax[blk0 + lane]; }
+  for (; blk0 < nblk; blk0 += 32) {
+    const float c0 = sc, l0 = sl, h0 = sh;
+    const int nb = blk0 + 32 + (int)lane;
+    sc = -1.f;
+    if (nb < nblk) { sc = V.bcmin[nb]; sl = V.blmin[nb]; sh = V.blmax[nb]; }
+    unsigned bm = __ballot_sync(0xffffffffu, !lab_block_skip_v(P, c0, l0, h0, err));
     while (bm) {
       const int b = __ffs(bm) - 1;
       bm &= bm - 1;
@@ -374,43 +383,6 @@ __global__ void __launch_bounds__(256) k_lab_blocks(const NqImage* imgs, const N
 // -------------------------------------------------------------------------------------------------
 // initial sweep: find_nn for every bin (PQ:196-197, PL:246-247). One warp per bin.
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_find_nn_all(NqImage* imgs, const NqSlot* slots, int nimg) {
-  const unsigned lane = lane_id();
-  const int wpb = blockDim.x >> 5;
-  for (int img = 0; img < nimg; ++img) {
-    NqImage& I = imgs[img];
-    if (I.kind != NQ_KIND_RGB || I.nmax <= 2 || I.skipPnn) continue;
-    const NqSlot& S = slots[img];
-    const int maxbins = I.maxbins;
-    unsigned long long pairs = 0;
-    for (int idx = blockIdx.x * wpb + (threadIdx.x >> 5); idx < maxbins; idx += gridDim.x * wpb) {
-      double err = 1e100;
-      int nn = 0;
-      RgbProbe P = rgb_probe(I, S, idx);
-      for (int base = idx + 1; base < maxbins; base += 32) {
-        const int i = base + lane;
-        RgbCand c;
-        double gate = 1e300;
-        if (i < maxbins) gate = rgb_gate(P, S, i, &c);
-        unsigned remaining = 0xffffffffu;
-        for (;;) {
-          unsigned m = __ballot_sync(0xffffffffu, gate < err) & remaining;
-          if (!m) break;
-          int L = __ffs(m) - 1;
-          double e = 0;
-          if ((int)lane == L) e = rgb_take(P, c, err);
-          err = __shfl_sync(0xffffffffu, e, L);
-          nn = base + L;
-          remaining = (L == 31) ? 0u : ~((2u << L) - 1u);
-        }
-      }
-      pairs += (unsigned long long)(maxbins - idx - 1);
-      if (lane == 0) { S.bErr[idx] = (float)err; S.bNn[idx] = nn; }
-    }
-    if (lane == 0 && pairs) atomicAdd(&I.statPairs, pairs);
-  }
-}
-
 // CIELAB: one warp per bin, streaming with block summaries (warp_find_nn_lab). Bins are dealt out
 // interleaved so that every warp gets a mix of long (small idx) and short candidate lists.
 __global__ void __launch_bounds__(256) k_find_nn_lab(NqImage* imgs, const NqSlot* slots, int nimg) {
@@ -482,7 +454,7 @@ __device__ __forceinline__ unsigned pack_idnn(int id, int nn) { return (unsigned
 // 128 threads and 48 KB of heap per CTA: several images share an SM and fill each other's serial gaps.
 // -------------------------------------------------------------------------------------------------
 #define NQ_LAB_THREADS 128
-#define NQ_LAB_HEAP_SMEM 8192   // 64 KB of heap: three CTAs fit one SM
+#define NQ_LAB_HEAP_SMEM 5632   // 44 KB of heap: four CTAs fit one SM
 
 __device__ __forceinline__ int block_excl_scan_128(int v, int* total, int* sScan /*[8]*/) {
   const unsigned lane = lane_id(), w = threadIdx.x >> 5;
@@ -533,7 +505,7 @@ __device__ __forceinline__ int rebuild_live_lab(const NqSlot& S, const LabScratc
   return total;
 }
 
-__global__ void __launch_bounds__(NQ_LAB_THREADS, 3) k_merge_lab(NqImage* imgs, const NqSlot* slots, int* liveBuf, int* posBuf, int logMerges) {
+__global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, const NqSlot* slots, int* liveBuf, int* posBuf, int logMerges) {
   extern __shared__ unsigned char smemRaw[];
   float* sErr = reinterpret_cast<float*>(smemRaw);
   unsigned* sId = reinterpret_cast<unsigned*>(smemRaw + (size_t)NQ_LAB_HEAP_SMEM * 4);
@@ -1178,5 +1150,83 @@ __global__ void __launch_bounds__(NQ_RGB_THREADS, 4) k_merge_rgb(NqImage* imgs, 
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// RGB initial sweep (PQ:196-197): one warp per bin over bin-indexed records (k_rgb_blocks), the first 32
+// candidates exactly, then blocks pruned against U = 4 x that err and the rest replayed in order with the
+// exact err; a bin whose err reached U is redone unpruned (see k_merge_rgb).
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rgb_blocks(const NqImage* imgs, const NqSlot* slots) {
+  const int img = blockIdx.y;
+  const NqImage& I = imgs[img];
+  if (I.kind != NQ_KIND_RGB || I.nmax <= 2 || I.skipPnn) return;
+  const NqSlot& S = slots[img];
+  const RgbScratch X = rgb_scratch(S);
+  const int n = I.maxbins, nblk = (n + 31) >> 5;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
+    X.rg[b] = make_double2(S.bC1[b], S.bC2[b]);
+    X.bc[b] = make_double2(S.bC3[b], (double)S.bCnt[b]);
+    X.al[b] = S.bAc[b];
+  }
+  // summaries straight from the bins (the records above are written by other threads)
+  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += gridDim.x * blockDim.x) {
+    double cm = 1e300, lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int b = blk << 5; b < min(n, (blk << 5) + 32); ++b) {
+      cm = fmin(cm, (double)S.bCnt[b]);
+      const double v[3] = {S.bC1[b], S.bC2[b], S.bC3[b]};
+      for (int k = 0; k < 3; ++k) { lo[k] = fmin(lo[k], v[k]); hi[k] = fmax(hi[k], v[k]); }
+    }
+    X.cmin[blk] = cm;
+    for (int k = 0; k < 3; ++k) { X.lo[k * 2048 + blk] = lo[k]; X.hi[k * 2048 + blk] = hi[k]; }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_find_nn_all(NqImage* imgs, const NqSlot* slots, int nimg) {
+  const unsigned lane = lane_id();
+  const int wpb = blockDim.x >> 5;
+  for (int img = 0; img < nimg; ++img) {
+    NqImage& I = imgs[img];
+    if (I.kind != NQ_KIND_RGB || I.nmax <= 2 || I.skipPnn) continue;
+    const NqSlot& S = slots[img];
+    const RgbScratch X = rgb_scratch(S);
+    const int maxbins = I.maxbins;
+    unsigned long long pairs = 0;
+    for (int idx = blockIdx.x * wpb + (threadIdx.x >> 5); idx < maxbins; idx += gridDim.x * wpb) {
+      const RgbProbe P = rgb_probe(I, S, idx);
+      double err = 1e100, errMax = 0.0;
+      int nn = 0;
+      {   // the first 32 candidates
+        const int i = idx + 1 + (int)lane;
+        RgbCand c;
+        double gate = 1e300;
+        if (i < maxbins) gate = rgb_gate_rec(P, X.rg[i], X.bc[i], P.semi ? X.al[i] : 0.0, &c);
+        rgb_accept_in_order(P, gate, c, i, err, nn, errMax);
+      }
+      const double err32 = err;
+      const int nn32 = nn, stop = idx + 33;
+      for (int attempt = 0; attempt < 2; ++attempt) {
+        const double U = attempt == 0 ? (err32 < 1e99 ? 4.0 * err32 : 1e300) : 1e300;
+        err = err32; nn = nn32; errMax = err32 < 1e99 ? err32 : 0.0;
+        for (int blk0 = stop >> 5; (blk0 << 5) < maxbins; blk0 += 32) {
+          const int blk = blk0 + (int)lane;
+          unsigned bm = __ballot_sync(0xffffffffu, (blk << 5) < maxbins && !rgb_block_skip(P, X, blk, U));
+          while (bm) {
+            const int b = __ffs(bm) - 1;
+            bm &= bm - 1;
+            const int i = ((blk0 + b) << 5) + (int)lane;
+            RgbCand c;
+            double gate = 1e300;
+            if (i >= stop && i < maxbins) gate = rgb_gate_rec(P, X.rg[i], X.bc[i], P.semi ? X.al[i] : 0.0, &c);
+            rgb_accept_in_order(P, gate, c, i, err, nn, errMax);
+          }
+        }
+        if (!(errMax >= U)) break;
+      }
+      pairs += (unsigned long long)(maxbins - idx - 1);
+      if (lane == 0) { S.bErr[idx] = (float)err; S.bNn[idx] = nn; }
+    }
+    if (lane == 0 && pairs) atomicAdd(&I.statPairs, pairs);
+  }
+}
 
 }  // namespace nq
