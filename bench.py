@@ -39,8 +39,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("NQ_BENCH_BATCH", "444")),
-                    help="images per GPU per step (444 = 3 merge CTAs on each of the 148 SMs)")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("NQ_BENCH_BATCH", "592")),
+                    help="images per GPU per step (592 = 4 merge CTAs on each of the 148 SMs)")
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--kind", default="lab", choices=list(KINDS))

@@ -88,6 +88,7 @@ __device__ __forceinline__ float chroma_ub(float A, float B) { return sqrtf((A *
 
 struct LabProbe {
   float n1, a1, L1, A1, B1, C1;   // C1: upper bound of the chroma sqrt(A1^2 + B1^2)
+  float ratioLo;                  // ratio rounded down to float (lower bounds only)
   double ratio, exp175;
   bool semi, texicab;
 };
@@ -97,6 +98,7 @@ __device__ __forceinline__ LabProbe lab_probe(const NqImage& I, const NqSlot& S,
   P.a1 = S.fAc[idx]; P.L1 = S.fC1[idx]; P.A1 = S.fC2[idx]; P.B1 = S.fC3[idx];
   P.C1 = chroma_ub(P.A1, P.B1);
   P.ratio = ratio;
+  P.ratioLo = __double2float_rd(ratio);
   P.semi = I.hasSemi != 0;
   P.exp175 = P.semi ? nqm::nq_exp(1.75) : 1.0;
   P.texicab = I.texicab != 0;
@@ -110,7 +112,8 @@ struct LabCand { double gs, gw, f; };
 struct LabView {
   const float4* q;                      // {cnt, L, A, B} per position: one 16-byte load per candidate
   const float* al;                      // alpha per position (read only for semi-transparent images)
-  const float *bcmin, *blmin, *blmax;   // per block of 32 positions: min count, min L, max L (conservative)
+  const float4* bs;                     // per block of 32 positions, two float4: {min count, min L, max L, max chroma},
+                                        // {min A, max A, min B, max B} (conservative: never tightened between compactions)
   int n;
 };
 
@@ -120,24 +123,35 @@ struct LabView {
 // the float roundings of the reference's own evaluation. A block may be skipped when even this bound
 // fails the reference's tests against an upper bound U of the running err: nerr2 >= U (PL:57) or the
 // prefix after the L' term > U (PL:88-90; every earlier term is >= 0).
-__device__ __forceinline__ bool lab_block_skip_v(const LabProbe& P, float cmin, float lo, float hi, double U);
-__device__ __forceinline__ bool lab_block_skip(const LabProbe& P, const LabView& V, int blk, double U) {
-  return lab_block_skip_v(P, V.bcmin[blk], V.blmin[blk], V.blmax[blk], U);
-}
-__device__ __forceinline__ bool lab_block_skip_v(const LabProbe& P, float cmin, float lo, float hi, double U) {
+__device__ float g_rtFac[256];   // see below (k_init_rtfac)
+__device__ __forceinline__ float chroma_ub(float A, float B);
+// s0 = {min count, min L, max L, max chroma}, s1 = {min A, max A, min B, max B} of the block. The bound is the
+// per-candidate one of lab_cheap_keep_q with every quantity replaced by its most favourable value in the block.
+__device__ __forceinline__ bool lab_block_skip_v(const LabProbe& P, const float4 s0, const float4 s1, double U) {
+  const float cmin = s0.x;
   if (!(cmin >= 0.f)) return true;                        // block holds no live bin
-  const double n2 = (double)cmin, n1 = (double)P.n1;
-  const double nerr2 = (n1 * n2) / (n1 + n2) * (1.0 - 1e-6);
-  if (nerr2 >= U) return true;
-  const float dl = fmaxf(0.f, fmaxf(lo - P.L1, P.L1 - hi));
-  const double t = (double)dl * (1.0 / 1.7472);
-  const double lb = P.ratio * nerr2 * (t * t) * (1.0 - 1e-5);
-  return lb > U;
+  // float arithmetic throughout: a dozen roundings (6e-8 each) against the 1e-4 deflations; Uup >= U
+  const float Uup = __double2float_ru(U);
+  const float nerr2 = ((P.n1 * cmin) / (P.n1 + cmin)) * 0.9999f;
+  if (nerr2 >= Uup) return true;
+  const float dl = fmaxf(0.f, fmaxf(s0.y - P.L1, P.L1 - s0.z));
+  const float da = fmaxf(0.f, fmaxf(s1.x - P.A1, P.A1 - s1.y));
+  const float db = fmaxf(0.f, fmaxf(s1.z - P.B1, P.B1 - s1.w));
+  const float cb = (0.75f * (P.C1 + s0.w)) * 1.00001f;
+  const float sc = (1.f + (0.045f * cb)) * 1.00001f;
+  const float rf = g_rtFac[min(255, (int)cb)];
+  const float d2 = fmaxf(0.f, (((da * da) + (db * db)) * 0.9999f) - 1e-4f);
+  const float t = dl * 0.57234f;                           // 1 / 1.7472 rounded down
+  const float q = (t * t) + (rf * d2) / ((sc * sc) * 1.00001f);
+  const float lb = (P.ratioLo * nerr2) * q * 0.9999f;
+  return lb > Uup;
+}
+__device__ __forceinline__ bool lab_block_skip(const LabProbe& P, const LabView& V, int blk, double U) {
+  return lab_block_skip_v(P, V.bs[2 * blk], V.bs[2 * blk + 1], U);
 }
 
 // 1 - |R_T|max / 2 for barCPrime in [k, k + 1): R_T = -sin(2 dTheta) R_C with |sin(2 dTheta)| <= sin(60 deg) and
-// R_C = 2 sqrt(c^7 / (c^7 + 25^7)) increasing in c (CL:187-194). Filled by k_init_tables.
-__device__ float g_rtFac[256];
+// R_C = 2 sqrt(c^7 / (c^7 + 25^7)) increasing in c (CL:187-194), so the table decreases.
 __global__ void k_init_rtfac() {
   const int k = threadIdx.x;
   double f = 1.0 - 0.86603 * 1.000001;                    // barCPrime >= 255: R_C < 2
@@ -161,17 +175,19 @@ __device__ __forceinline__ bool lab_cheap_keep(const LabProbe& P, const LabView&
 __device__ __forceinline__ bool lab_cheap_keep_q(const LabProbe& P, const float4 cq, double err) {
   const float n2 = cq.x;
   if (!(n2 >= 0.f)) return false;
-  const double nerr2 = (double)((P.n1 * n2) / (P.n1 + n2));       // the reference's own value and test (PL:56-57)
-  if (nerr2 >= err) return false;
+  const float nerr2 = (P.n1 * n2) / (P.n1 + n2);                  // the reference's own value and test (PL:56-57)
+  if ((double)nerr2 >= err) return false;
+  // the bound itself in float: a dozen roundings (6e-8 each) against the 1e-4 deflations; errUp >= err
+  const float errUp = __double2float_ru(err);
   const float dl = cq.y - P.L1, da = cq.z - P.A1, db = cq.w - P.B1;
   const float cb = (0.75f * (P.C1 + chroma_ub(cq.z, cq.w))) * 1.00001f;
   const float sc = (1.f + (0.045f * cb)) * 1.00001f;
   const float rf = g_rtFac[min(255, (int)cb)];
   const float d2 = fmaxf(0.f, (((da * da) + (db * db)) * 0.9999f) - 1e-4f);
-  const double tl = (double)dl * (1.0 / 1.7472);
-  const double q = (tl * tl) + ((double)rf * (double)d2) / ((double)sc * (double)sc);
-  const double lb = (P.ratio * nerr2) * q * (1.0 - 1e-5);
-  return !(lb > err);
+  const float tl = dl * 0.57234f;                                  // 1 / 1.7472 rounded down
+  const float q = (tl * tl) + (rf * d2) / ((sc * sc) * 1.00001f);
+  const float lb = (P.ratioLo * nerr2) * q * 0.9999f;
+  return !(lb > errUp);
 }
 
 // find_nn's tests for candidate i against err (PL:54-108). With STOP_AFTER_C the evaluation ends after
@@ -308,14 +324,15 @@ __device__ void warp_find_nn_lab(const LabProbe& P, const LabView& V, int first,
   // the summaries of the next 32 blocks are loaded while the current ones are processed (they come from L2)
   const int nblk = (n + 31) >> 5;
   int blk0 = pos >> 5;
-  float sc = -1.f, sl = 0.f, sh = 0.f;
-  if (blk0 + (int)lane < nblk) { sc = V.bcmin[blk0 + lane]; sl = V.blmin[blk0 + lane]; sh = V.blmax[blk0 + lane]; }
+  const float4 none = make_float4(-1.f, 0.f, 0.f, 0.f);
+  float4 n0 = none, n1 = none;
+  if (blk0 + (int)lane < nblk) { n0 = V.bs[2 * (blk0 + lane)]; n1 = V.bs[2 * (blk0 + lane) + 1]; }
   for (; blk0 < nblk; blk0 += 32) {
-    const float c0 = sc, l0 = sl, h0 = sh;
+    const float4 s0 = n0, s1 = n1;
     const int nb = blk0 + 32 + (int)lane;
-    sc = -1.f;
-    if (nb < nblk) { sc = V.bcmin[nb]; sl = V.blmin[nb]; sh = V.blmax[nb]; }
-    unsigned bm = __ballot_sync(0xffffffffu, !lab_block_skip_v(P, c0, l0, h0, err));
+    n0 = none;
+    if (nb < nblk) { n0 = V.bs[2 * nb]; n1 = V.bs[2 * nb + 1]; }
+    unsigned bm = __ballot_sync(0xffffffffu, !lab_block_skip_v(P, s0, s1, err));
     while (bm) {
       const int b = __ffs(bm) - 1;
       bm &= bm - 1;
@@ -330,25 +347,29 @@ __device__ void warp_find_nn_lab(const LabProbe& P, const LabView& V, int first,
 }
 
 // summaries of blocks [0, ceil(n/32)) over position-indexed arrays; one thread per block
-__device__ __forceinline__ void lab_block_summary(const float4* q, int n, int blk, float* bcmin, float* blmin, float* blmax) {
-  float cm = -1.f, lo = 1e30f, hi = -1e30f;
+__device__ __forceinline__ void lab_block_summary(const float4* q, int n, int blk, float4* bs) {
+  float cm = -1.f, lo = 1e30f, hi = -1e30f, ch = 0.f, alo = 1e30f, ahi = -1e30f, blo = 1e30f, bhi = -1e30f;
   const int p0 = blk << 5, p1 = min(n, p0 + 32);
   for (int p = p0; p < p1; ++p) {
     const float4 v = q[p];
     if (!(v.x >= 0.f)) continue;
     cm = cm < 0.f ? v.x : fminf(cm, v.x);
     lo = fminf(lo, v.y); hi = fmaxf(hi, v.y);
+    alo = fminf(alo, v.z); ahi = fmaxf(ahi, v.z);
+    blo = fminf(blo, v.w); bhi = fmaxf(bhi, v.w);
+    ch = fmaxf(ch, chroma_ub(v.z, v.w));
   }
-  bcmin[blk] = cm; blmin[blk] = lo; blmax[blk] = hi;
+  bs[2 * blk] = make_float4(cm, lo, hi, ch);
+  bs[2 * blk + 1] = make_float4(alo, ahi, blo, bhi);
 }
 
 // scratch carved out of the histogram sum planes (free once the bins are compacted)
-struct LabScratch { float4* q; float *al, *bcmin, *blmin, *blmax; };
+struct LabScratch { float4* q; float* al; float4* bs; };
 __device__ __forceinline__ LabScratch lab_scratch(const NqSlot& S) {
   float* f = reinterpret_cast<float*>(S.hSum);
   LabScratch X;
   X.q = reinterpret_cast<float4*>(f); X.al = f + 4 * NQ_NBINS;
-  X.bcmin = f + 5 * NQ_NBINS; X.blmin = X.bcmin + 2048; X.blmax = X.blmin + 2048;
+  X.bs = reinterpret_cast<float4*>(f + 5 * NQ_NBINS);
   return X;
 }
 
@@ -363,19 +384,9 @@ __global__ void __launch_bounds__(256) k_lab_blocks(const NqImage* imgs, const N
   const unsigned lane = lane_id();
   for (int blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < nblk; blk += gridDim.x * (blockDim.x >> 5)) {
     const int b = (blk << 5) + (int)lane;
-    float c = 3e38f, lo = 1e30f, hi = -1e30f;
-    if (b < n) {
-      const float4 v = make_float4(S.bCnt[b], S.fC1[b], S.fC2[b], S.fC3[b]);
-      X.q[b] = v; X.al[b] = S.fAc[b];
-      c = v.x; lo = v.y; hi = v.y;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      c = fminf(c, __shfl_xor_sync(0xffffffffu, c, o));
-      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    if (lane == 0) { X.bcmin[blk] = c; X.blmin[blk] = lo; X.blmax[blk] = hi; }
+    if (b < n) { X.q[b] = make_float4(S.bCnt[b], S.fC1[b], S.fC2[b], S.fC3[b]); X.al[b] = S.fAc[b]; }
+    __syncwarp();
+    if (lane == 0) lab_block_summary(X.q, n, blk, X.bs);
   }
 }
 
@@ -395,7 +406,7 @@ __global__ void __launch_bounds__(256) k_find_nn_lab(NqImage* imgs, const NqSlot
     const NqSlot& S = slots[img];
     const LabScratch X = lab_scratch(S);
     const int maxbins = I.maxbins;
-    const LabView V{X.q, X.al, X.bcmin, X.blmin, X.blmax, maxbins};
+    const LabView V{X.q, X.al, X.bs, maxbins};
     unsigned long long pairs = 0;
     for (int idx = blockIdx.x * wpb + w; idx < maxbins; idx += gridDim.x * wpb) {
       const LabProbe P = lab_probe(I, S, idx, I.ratio);
@@ -500,7 +511,7 @@ __device__ __forceinline__ int rebuild_live_lab(const NqSlot& S, const LabScratc
   }
   __syncthreads();
   const int nblk = (total + 31) >> 5;
-  for (int blk = t; blk < nblk; blk += NQ_LAB_THREADS) lab_block_summary(X.q, total, blk, X.bcmin, X.blmin, X.blmax);
+  for (int blk = t; blk < nblk; blk += NQ_LAB_THREADS) lab_block_summary(X.q, total, blk, X.bs);
   __syncthreads();
   return total;
 }
@@ -604,7 +615,7 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
     if (action == 1) {
       ++rescans;
       const int first = posOf[b1] + 1;
-      const LabView V{X.q, X.al, X.bcmin, X.blmin, X.blmax, liveLen};
+      const LabView V{X.q, X.al, X.bs, liveLen};
       const LabProbe P = lab_probe(I, S, b1, ratioMerge);
       double err = 1e100;
       int nn = -1;                              // position in the live list
@@ -761,8 +772,12 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
       const int pt = posOf[b1], pn = posOf[nbI];
       X.q[pt] = make_float4(n1 + n2, nL, nA, nB); X.al[pt] = na;
       X.q[pn].x = -1.f;
-      X.blmin[pt >> 5] = fminf(X.blmin[pt >> 5], nL);
-      X.blmax[pt >> 5] = fmaxf(X.blmax[pt >> 5], nL);
+      {   // widen the summary of tb's block (the count only grows)
+        float4 s0 = X.bs[2 * (pt >> 5)], s1 = X.bs[2 * (pt >> 5) + 1];
+        s0.y = fminf(s0.y, nL); s0.z = fmaxf(s0.z, nL); s0.w = fmaxf(s0.w, chroma_ub(nA, nB));
+        s1.x = fminf(s1.x, nA); s1.y = fmaxf(s1.y, nA); s1.z = fminf(s1.z, nB); s1.w = fmaxf(s1.w, nB);
+        X.bs[2 * (pt >> 5)] = s0; X.bs[2 * (pt >> 5) + 1] = s1;
+      }
       if (logMerges && S.mergeLog) { S.mergeLog[2 * (i - 1)] = b1; S.mergeLog[2 * (i - 1) + 1] = nbI; }
       sIter = i;
     }
