@@ -437,7 +437,10 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
   if (kind == NQ_KIND_LAB) { nq::k_build_cells<<<dim3(std::max(1, std::min(128, c->smCount * 8 / n)), n), 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches; }
   mark(5);
   // each kernel returns at once for images of the other queue mode (decided on the device)
-  nq::k_dither_fifo<<<n, 64, 0, st>>>(c->dImgs, c->dSlots, dOrder); ++c->launches;
+  {  // images whose lookups stay on the serial chain (PnnQuantizer; dither == false) get a shared-memory memo cache
+    const int cacheBytes = (kind == NQ_KIND_RGB || !dither) ? 32768 : 0;
+    nq::k_dither_fifo<<<n, 64, cacheBytes, st>>>(c->dImgs, c->dSlots, dOrder, cacheBytes); ++c->launches;
+  }
   nq::k_dither_sorted<<<n, 32, 0, st>>>(c->dImgs, c->dSlots, dOrder); ++c->launches;
   mark(6);
   CU(cudaGetLastError());
@@ -570,6 +573,7 @@ nq_ctx* nq_create(int device) {
   }
   if (ok) ok = cudaFuncSetAttribute(nq::k_merge_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_RGB_HEAP_SMEM * 8) == cudaSuccess;
   if (ok) ok = cudaFuncSetAttribute(nq::k_hist_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nq::HistTable)) == cudaSuccess;
+  if (ok) ok = cudaFuncSetAttribute(nq::k_dither_fifo, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768) == cudaSuccess;
   if (ok) ok = cudaFuncSetAttribute(nq::k_merge_lab, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_LAB_HEAP_SMEM * 8) == cudaSuccess;
   if (!ok) {
     fail(NQ_ERR_CUDA, std::string("context initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));

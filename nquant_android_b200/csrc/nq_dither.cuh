@@ -45,6 +45,7 @@ struct Env {
   double PR, PG, PB, PA, ratio, gWeight, exp15;
   float beta;
   unsigned short* memo;
+  unsigned short* mcache;     // optional shared-memory cache of memo (consumer warp of k_dither_fifo only)
   unsigned int* bits;         // pixelMap as a bit set (see NqSlot::bits), with its size counter
   unsigned int* distinct;
   const uint4* cells;         // candidate lists of the closest-colour scan, 32 B per 5-5-5 RGB cell (k_build_cells)
@@ -65,16 +66,38 @@ __device__ __forceinline__ void warp_min_last(double& d, int& i) {
   }
 }
 
+// nearestMap for reduced keys (PQ:271-274, PL:332-335): 65 536 x u16 in global memory, 0xFFFF = absent. An
+// entry never changes once written, so the serial consumer may keep copies in a direct-mapped shared-memory
+// cache (E.mcache: bits 0-8 = value + 1, bits 9-10 = key >> 14): a hit costs a shared load instead of a trip to L2.
+__device__ __forceinline__ int memo_get(const Env& E, int key) {
+  if (E.mcache) {
+    const unsigned e = E.mcache[key & 0x3FFF];
+    if ((e & 0x1FFu) != 0u && (e >> 9) == (unsigned)(key >> 14)) return (int)(e & 0x1FFu) - 1;
+  }
+  unsigned short got = 0;
+  if (lane_id() == 0) got = E.memo[key];
+  got = __shfl_sync(FULL, got, 0);
+  if (got == 0xFFFF) return -1;
+  if (E.mcache && lane_id() == 0) E.mcache[key & 0x3FFF] = (unsigned short)(((unsigned)(key >> 14) << 9) | ((unsigned)got + 1u));
+  __syncwarp();
+  return got;
+}
+__device__ __forceinline__ void memo_put(const Env& E, int key, int value) {
+  if (lane_id() == 0) {
+    E.memo[key] = (unsigned short)value;
+    if (E.mcache) E.mcache[key & 0x3FFF] = (unsigned short)(((unsigned)(key >> 14) << 9) | ((unsigned)value + 1u));
+  }
+  __syncwarp();
+}
+
 // PnnQuantizer.nearestColorIndex (PQ:269-311)
 __device__ int nearest_rgb(Env& E, uint32_t c) {
   const unsigned lane = lane_id();
   int offset = 0;
   if (E.isNano) {
     offset = color_index(c, E.semi, E.hasTrans);
-    unsigned short got = 0;
-    if (lane == 0) got = E.memo[offset];
-    got = __shfl_sync(FULL, got, 0);
-    if (got != 0xFFFF) return got;
+    const int got = memo_get(E, offset);
+    if (got >= 0) return got;
   }
   int k = 0;
   if (c_alpha(c) <= 0xF) c = E.transColor;
@@ -95,10 +118,7 @@ __device__ int nearest_rgb(Env& E, uint32_t c) {
   }
   warp_min_last(best, bi);
   if (!(best <= 2147483647.0) || bi < 0) bi = k;   // mindist starts at Integer.MAX_VALUE (PQ:286)
-  if (E.isNano) {
-    if (lane == 0) E.memo[offset] = (unsigned short)bi;
-    __syncwarp();
-  }
+  if (E.isNano) memo_put(E, offset, bi);
   return bi;
 }
 
@@ -158,10 +178,8 @@ __device__ int nearest_lab(Env& E, uint32_t c) {
   int offset = 0;
   if (E.isNano) {
     offset = color_index(c, E.semi, E.hasTrans);
-    unsigned short got = 0;
-    if (lane == 0) got = E.memo[offset];
-    got = __shfl_sync(FULL, got, 0);
-    if (got != 0xFFFF) return got;
+    const int got = memo_get(E, offset);
+    if (got >= 0) return got;
   }
   int k = 0;
   if (c_alpha(c) <= 0xF) c = E.transColor;
@@ -236,10 +254,7 @@ __device__ int nearest_lab(Env& E, uint32_t c) {
     warp_min_last(best, bi);
     if (!(best <= 2147483647.0) || bi < 0) bi = k;
   }
-  if (E.isNano) {
-    if (lane == 0) E.memo[offset] = (unsigned short)bi;
-    __syncwarp();
-  }
+  if (E.isNano) memo_put(E, offset, bi);
   return bi;
 }
 
@@ -572,6 +587,7 @@ __device__ __forceinline__ void dither_prologue_regs(NqImage& I, const NqSlot& S
   E.exp15 = E.semi ? nqm::nq_exp(1.5) : 1.0;
   E.beta = I.gBeta;
   E.memo = S.memo;
+  E.mcache = nullptr;
   E.cells = reinterpret_cast<const uint4*>(S.cells);
   E.bits = S.bits; E.distinct = &I.distinctColors;
   E.rng.set_seed(I.seed);
@@ -948,9 +964,10 @@ __device__ uint32_t prelookup_commit(Env& E, uint32_t c, bool mine) {
   return sh.pal[qi];
 }
 
-__global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot* slots, const uint32_t* order) {
+__global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot* slots, const uint32_t* order, int cacheBytes) {
   __shared__ WarpShared sh;
   __shared__ DitherRing ring;
+  extern __shared__ unsigned short dynCache[];     // 16 384 entries when launched with cacheBytes, else nothing
   const int img = blockIdx.x;
   NqImage& I = imgs[img];
   const NqSlot& S = slots[img];
@@ -959,6 +976,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
   if (plen <= 0 || I.error || I.gSorted) return;
   DitherCtx D;
   const bool producer = threadIdx.x >= 32;
+  if (cacheBytes) for (int i = threadIdx.x; i < 16384; i += 64) dynCache[i] = 0;
   if (!producer) {
     dither_prologue(I, S, sh, D);
     if (lane == 0) { ring.fetched = 0; ring.looked = 0; ring.consumed = 0; ring.rngSeed = D.E.rng.seed; ring.draws = 0; }
@@ -1020,6 +1038,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
   }
 
   // =========================== consumer warp ===========================
+  if (cacheBytes) E.mcache = dynCache;             // the producer's lookups (pre-lookup blocks) go to global memory
   uint32_t* out = D.out;
   const int ditherMax = E.ditherMax;
   const float wk = lane < (unsigned)DM ? I.gWeights[lane] : 0.f;   // this lane's tap

@@ -308,6 +308,7 @@ __device__ void warp_find_nn_lab(const LabProbe& P, const LabView& V, int first,
   };
   auto pushA = [&](bool keep, int i) {
     const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (!m) return;                           // most blocks that survive their summary hold no survivor
     if (keep) sBufA[nA + __popc(m & ((1u << lane) - 1u))] = i;
     nA += __popc(m);
     __syncwarp();

@@ -231,6 +231,21 @@ def test_full_size_4k_properties(gpu_ctx, kind, K, alpha):
     assert err.mean() < 40
 
 
+def test_full_size_8192_properties(gpu_ctx):
+    """BASELINE.json configs[4] size (8192x8192, 268 MB per image): size-independent properties of the headline
+    quantizer (PnnLABQuantizer, 256 colours, dither on) -- the oracle would need minutes for one such image."""
+    W = H = 8192
+    img = make_image(W, H, "noisy", "opaque")
+    out, pal, plen, ha = gpu_ctx.convert_batch(1, img[None, :], W, H, 256, True, seeds=[11])
+    assert plen[0] == 256 and not ha[0]
+    assert np.isin(out[0], pal[0, :256]).all(), "every output pixel must be a palette colour (GilbertCurve.java:279)"
+    info = gpu_ctx.image_info(0)
+    assert info["merges"] == info["maxbins"] - 256 and info["rng_draws"] > W * H * 0.9
+    sub = slice(0, W * 64)   # the first 64 rows are enough for the error statistic
+    err = np.abs(((out[0][sub, None] >> np.array([16, 8, 0])) & 255).astype(np.int32) - ((img[sub, None] >> np.array([16, 8, 0])) & 255).astype(np.int32))
+    assert err.mean() < 40
+
+
 def test_error_codes(gpu_ctx):
     from nquant_android_b200.quantizer import NQuantError
     with pytest.raises(NQuantError) as e:   # pixelMap.size() is not tracked when getLab's calls depend on scan order
