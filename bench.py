@@ -30,7 +30,9 @@ KINDS = {"rgb": 0, "lab": 1}
 CLASSES = {"smooth": 0, "noisy": 1, "rand": 2}
 METRIC = "Mpixels/s 256-color PNN quantize+dither, 4K batch, 1/2/4/8 B200 vs JVM CPU"
 # algorithmic bytes per pixel (SURVEY.md 8d / DESIGN.md): stage -> bytes
-STAGE_BYTES = {"alpha_scan": 4, "histogram": 4, "find_nn_sweep": 0, "merge": 0, "dither_setup": 4, "dither": 8}
+STAGE_BYTES = {"alpha_scan": 4, "histogram": 4, "find_nn_sweep": 0, "merge": 0, "dither_setup": 0, "dither": 8}
+# dram__bytes_read.sum + dram__bytes_write.sum per pixel, from the ncu capture named in profiles/ (filled per round)
+NCU_DRAM_BYTES_PER_PIXEL = {}
 
 
 def parse():
@@ -231,15 +233,26 @@ def run_ours(a, rank, world, local_rank):
     # ---- end to end: pinned host buffers through nq_convert_batch
     e2e = None
     if not a.no_e2e:
-        hin = torch.empty(n * npix, dtype=torch.int32, pin_memory=True)
-        hout = torch.empty(n * npix, dtype=torch.int32, pin_memory=True)
-        hin.copy_(din)
+        # pinned host buffers for the whole batch (in + out); every local rank needs its own. If the host cannot hold
+        # them next to everything else, the end-to-end leg runs on a smaller batch and says so.
+        ne = n
+        try:
+            import psutil
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            avail = psutil.virtual_memory().available
+            while ne > 1 and 2 * ne * npix * 4 * local_world > 0.6 * avail:
+                ne //= 2
+        except Exception:
+            pass
+        hin = torch.empty(ne * npix, dtype=torch.int32, pin_memory=True)
+        hout = torch.empty(ne * npix, dtype=torch.int32, pin_memory=True)
+        hin.copy_(din[:ne * npix])
         torch.cuda.synchronize()
-        pal = np.zeros((n, 256), dtype=np.uint32)
-        plen = np.zeros(n, dtype=np.int32)
+        pal = np.zeros((ne, 256), dtype=np.uint32)
+        plen = np.zeros(ne, dtype=np.int32)
 
         def step_host():
-            ctx.convert_batch_ptr(kind, hin.data_ptr(), hout.data_ptr(), n, a.width, a.height, a.colors, a.dither, seeds=seeds,
+            ctx.convert_batch_ptr(kind, hin.data_ptr(), hout.data_ptr(), ne, a.width, a.height, a.colors, a.dither, seeds=seeds[:ne],
                                   device=False, palettes=pal, palette_lens=plen)
 
         step_host()   # allocates the staging buffers
@@ -254,10 +267,12 @@ def run_ours(a, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e_ms = float(t2.item())
-        same = bool(torch.equal(hout.cuda(), dout))
-        e2e = {"value": total_px / (e2e_ms / 1e3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": n * npix * 4,
-               "d2h_bytes_per_step": n * npix * 4 + n * 256 * 4 + n * 4, "ms_per_step": e2e_ms / a.steps,
-               "matches_device_path": same}
+        same = bool(torch.equal(hout.cuda(), dout[:ne * npix]))
+        e2e = {"value": world * ne * npix * a.steps / (e2e_ms / 1e3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": ne * npix * 4,
+               "d2h_bytes_per_step": ne * npix * 4 + ne * 256 * 4 + ne * 4, "ms_per_step": e2e_ms / a.steps,
+               "matches_device_path": same, "batch_images_per_gpu": ne}
+        if ne != n:
+            e2e["note"] = f"host memory holds pinned buffers for {ne} of the {n} images per GPU: end-to-end leg run on the smaller batch"
 
     if rank == 0:
         peaks = {}
@@ -268,20 +283,29 @@ def run_ours(a, rank, world, local_rank):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
         per_stage = {}
-        dom, dom_ms = None, -1.0
+        dom, dom_ms = None, -1.0          # dominant stage among those that move pixel bytes
+        top, top_ms = None, -1.0          # dominant stage overall
         for name, (sms, ln) in stages.items():
             bytes_total = STAGE_BYTES[name] * n * npix * a.steps
             gbs = bytes_total / (sms / 1e3) / 1e9 if sms > 0 else 0.0
             per_stage[name] = {"ms_per_step": sms / a.steps, "launches_per_step": ln / a.steps, "share": sms / ms if ms > 0 else 0,
                                "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
-            if sms > dom_ms:
+            if sms > top_ms:
+                top, top_ms = name, sms
+            if STAGE_BYTES[name] > 0 and sms > dom_ms:
                 dom, dom_ms = name, sms
         dom_launches = max(1, stages[dom][1])
         dom_bytes_per_launch = STAGE_BYTES[dom] * n * npix * a.steps / dom_launches
         achieved = dom_bytes_per_launch / (dom_ms / dom_launches / 1e3) / 1e9 if dom_ms > 0 else 0.0
+        # DRAM bytes per pixel of the stage's kernels from one `ncu --set full` capture (profiles/), scaled to this launch
+        tpp = NCU_DRAM_BYTES_PER_PIXEL.get((a.kind, dom))
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src,
-                    "note": "dominant stage by device time; serial dependency chain per image (latency bound, see DESIGN.md)",
+                    "traffic": (tpp * n * npix * a.steps / dom_launches) if tpp else None, "peak_source": peak_src,
+                    "note": "largest stage that moves pixel bytes; it is a distance-1 recurrence per image (dependent-issue latency bound, "
+                            "DESIGN.md 4.1/4.2), so the HBM fraction is structurally tiny. The pixel passes' fractions are under `stages`.",
+                    "dominant_by_time": {"stage": top, "share": top_ms / ms if ms > 0 else 0,
+                                         "note": "find_nn sweep and merge loop work on histogram bins (<= 65 536 per image), not pixels: "
+                                                 "0 algorithmic pixel bytes; issue/latency evidence in profiles/*_ncu_merge_sweep.md"},
                     "end_to_end_frac": (12.0 * total_px / (ms_max / 1e3) / 1e9) / (peak * world)}
         line = {"metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -1047,6 +1047,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
   const float divisor = (float)(1 + nqm::sqrt_((double)ditherMax));
   const bool denoise = plen > 2;
   const bool illusion0 = bn[0] > thresold;          // yDiff == 1: bn[(int)(4096.0) & 4095] (GC:251-252)
+  const bool rgbMemo = !E.lab && dither && E.isNano;
 
   // systolic state: lane k carries the sum of some pixel through tap k, and its running maximum
   float P0 = 0.f, P1 = 0.f, P2 = 0.f, P3 = 0.f, M = (float)(DM - 1);
@@ -1114,10 +1115,16 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
       uint32_t pc;
       if (blockPre) pc = pcPre;
       else {
-        const uint32_t xy = __shfl_sync(FULL, curXy, j);
-        const int x = xy & 0xFFFF, y = xy >> 16;
-        const int qi = quantize_pixel(E, x, y, x + y * width, pixel, __shfl_sync(FULL, curSal, j), shfl_d(curY, j),
-                                      c_argb(a_pix, r_pix, g_pix, b_pix));
+        const uint32_t c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
+        // PnnQuantizer with dither: the branch of GC:211-229 is nearestColorIndex(c2), and with the reduced memo key
+        // (PQ:271) it is nearly always a hit: answer it inline, without the call into the general path
+        int qi = -1;
+        if (rgbMemo) qi = memo_get(E, color_index(c2, E.semi, E.hasTrans));
+        if (qi < 0) {
+          const uint32_t xy = __shfl_sync(FULL, curXy, j);
+          const int x = xy & 0xFFFF, y = xy >> 16;
+          qi = quantize_pixel(E, x, y, x + y * width, pixel, __shfl_sync(FULL, curSal, j), shfl_d(curY, j), c2);
+        }
         pc = sh.pal[qi];
         const uint32_t res = (dither || plen <= 32) ? pc : (uint32_t)qi;   // GC:278-279
         if ((int)lane == j) myOut = res;

@@ -173,6 +173,18 @@ def test_reference_config0_512_rgb(gpu_ctx, oracle):
     assert np.array_equal(pal[0, :plen[0]], ref.palette) and np.array_equal(out[0], ref.out)
 
 
+def test_headline_class_512_lab(gpu_ctx, oracle):
+    """The bench workload's class and quantizer (noisy, PnnLABQuantizer, 256 colours, dither on) at the largest
+    size the oracle finishes in seconds: 26 778 bins, 58 016 rescans, every pruning layer of the merge loop and the
+    pre-lookup dither path at work. Palette and output bit-exact, RNG draws equal."""
+    W = H = 512
+    img = make_image(W, H, "noisy", "opaque")
+    ref = oracle.convert(1, img, W, H, 256, True, seed=0xC0FFEE, trace=False)
+    out, pal, plen, _ = gpu_ctx.convert_batch(1, img[None, :], W, H, 256, True, seeds=[0xC0FFEE])
+    assert np.array_equal(pal[0, :plen[0]], ref.palette) and np.array_equal(out[0], ref.out)
+    assert gpu_ctx.image_info(0)["rng_draws"] == ref.scalars["rng_draws"]
+
+
 def test_reference_config1_1080p_lab(gpu_ctx, oracle):
     """BASELINE.json configs[1]: PnnLABQuantizer 256 colours, dither on, 1920x1080 (smooth class so
     the oracle finishes in seconds)."""
