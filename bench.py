@@ -32,7 +32,11 @@ METRIC = "Mpixels/s 256-color PNN quantize+dither, 4K batch, 1/2/4/8 B200 vs JVM
 # algorithmic bytes per pixel (SURVEY.md 8d / DESIGN.md): stage -> bytes
 STAGE_BYTES = {"alpha_scan": 4, "histogram": 4, "find_nn_sweep": 0, "merge": 0, "dither_setup": 0, "dither": 8}
 # dram__bytes_read.sum + dram__bytes_write.sum per pixel, from the ncu capture named in profiles/ (filled per round)
-NCU_DRAM_BYTES_PER_PIXEL = {}
+NCU_DRAM_BYTES_PER_PIXEL = {
+    # profiles/r1_final_ncu_lab_8x1080p.md: k_dither_fifo read 236.1 MB + wrote 58.8 MB for 8 x 1920x1080 pixels
+    # (8 B/px algorithmic + visiting-order table, RGB->Lab table sectors, candidate lists)
+    ("lab", "dither"): (236.132352e6 + 58.803712e6) / (8 * 1920 * 1080),
+}
 
 
 def parse():

@@ -334,11 +334,18 @@ __device__ void warp_find_nn_lab(const LabProbe& P, const LabView& V, int first,
     n0 = none;
     if (nb < nblk) { n0 = V.bs[2 * nb]; n1 = V.bs[2 * nb + 1]; }
     unsigned bm = __ballot_sync(0xffffffffu, !lab_block_skip_v(P, s0, s1, err));
-    while (bm) {
-      const int b = __ffs(bm) - 1;
+    // records of the next live block are requested before the current one is tested
+    const float4 dead = make_float4(-1.f, 0.f, 0.f, 0.f);
+    int b = bm ? __ffs(bm) - 1 : -1;
+    int i = ((blk0 + b) << 5) + (int)lane;
+    float4 rec = (b >= 0 && i >= stop && i < n) ? V.q[i] : dead;
+    while (b >= 0) {
       bm &= bm - 1;
-      const int i = ((blk0 + b) << 5) + (int)lane;
-      pushA(i >= stop && i < n && lab_cheap_keep(P, V, i, err), i);
+      const int b2 = bm ? __ffs(bm) - 1 : -1;
+      const int i2 = ((blk0 + b2) << 5) + (int)lane;
+      const float4 rec2 = (b2 >= 0 && i2 >= stop && i2 < n) ? V.q[i2] : dead;
+      pushA(lab_cheap_keep_q(P, rec, err), i);
+      b = b2; i = i2; rec = rec2;
     }
   }
   if (nA) flushA(nA);
@@ -397,7 +404,7 @@ __global__ void __launch_bounds__(256) k_lab_blocks(const NqImage* imgs, const N
 // -------------------------------------------------------------------------------------------------
 // CIELAB: one warp per bin, streaming with block summaries (warp_find_nn_lab). Bins are dealt out
 // interleaved so that every warp gets a mix of long (small idx) and short candidate lists.
-__global__ void __launch_bounds__(256) k_find_nn_lab(NqImage* imgs, const NqSlot* slots, int nimg) {
+__global__ void __launch_bounds__(256, 3) k_find_nn_lab(NqImage* imgs, const NqSlot* slots, int nimg) {
   __shared__ int sBufA[8][64], sBufB[8][64];
   const unsigned lane = lane_id();
   const int w = threadIdx.x >> 5, wpb = blockDim.x >> 5;

@@ -17,6 +17,7 @@ struct NqImage {
   unsigned long long seed;
   // alpha scan (PQ:411-431)
   unsigned int semiCount;
+  unsigned int notOpaque;  // some pixel has alpha != 255
   int transIdx;            // m_transparentPixelIndex
   int hasSemi;             // hasSemiTransparency
   uint32_t transColor;     // m_transparentColor
