@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -197,7 +198,7 @@ namespace {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SlotLayout {
-  size_t hCnt, hSum, keyOff, sortA, sortB, warpHist, sal, bD, bF, bCnt, bErr, bNn, bTm, bMtm, hErr, hId, mergeLog, memo, cells, bits, total;
+  size_t hCnt, hSum, keyOff, sortA, sortB, warpHist, sal, bD, bF, bCnt, bErr, bNn, bTm, bMtm, heap, mergeLog, memo, cells, bits, total;
 };
 SlotLayout slot_layout(int kind, int npix, bool debug, bool needBits) {
   SlotLayout L;
@@ -216,8 +217,7 @@ SlotLayout slot_layout(int kind, int npix, bool debug, bool needBits) {
   L.bNn = take(NQ_NBINS * 4);
   L.bTm = take(NQ_NBINS * 4);
   L.bMtm = take(NQ_NBINS * 4);
-  L.hErr = take((NQ_NBINS + 1) * 4);
-  L.hId = take((NQ_NBINS + 1) * 4);
+  L.heap = take((NQ_NBINS + 2) * 8);
   L.mergeLog = take(debug ? (size_t)2 * NQ_NBINS * 4 : 0);
   L.memo = take(NQ_NBINS * 2);
   L.cells = take(lab ? (size_t)32768 * 32 : 0);
@@ -281,8 +281,7 @@ int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots, bool needBits
     S.bNn = reinterpret_cast<int*>(b + L.bNn);
     S.bTm = reinterpret_cast<int*>(b + L.bTm);
     S.bMtm = reinterpret_cast<int*>(b + L.bMtm);
-    S.hErr = reinterpret_cast<float*>(b + L.hErr);
-    S.hId = reinterpret_cast<int*>(b + L.hId);
+    S.heap = reinterpret_cast<uint2*>(b + L.heap);
     S.mergeLog = c->debug ? reinterpret_cast<int*>(b + L.mergeLog) : nullptr;
     S.memo = reinterpret_cast<unsigned short*>(b + L.memo);
     S.cells = lab ? b + L.cells : nullptr;

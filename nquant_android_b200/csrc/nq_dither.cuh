@@ -10,7 +10,6 @@
 // work that has no order: the four channels of the error-queue sum (lane & 3), the palette scan
 // (palette entry = lane + 32 t) and the three error-shaping channels.
 #pragma once
-#include <type_traits>
 #include "nq_types.h"
 #include "nq_color.h"
 #include "nq_hist.cuh"
@@ -1050,35 +1049,24 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
   const bool illusion0 = bn[0] > thresold;          // yDiff == 1: bn[(int)(4096.0) & 4095] (GC:251-252)
   const bool rgbMemo = !E.lab && dither && E.isNano;
 
-  long long cwait = 0;
-  const long long cstart = clock64();
-  // Opaque images with an opaque palette (alpha == 255 everywhere): the alpha channel of the recurrence is constant
-  // (sum 255, error 0), so it is compiled out.
-  const bool opaque3 = I.notOpaque == 0 && __all_sync(FULL, [&] { bool ok = true; for (int i = lane; i < plen; i += 32) ok = ok && (sh.pal[i] >> 24) == 255u; return ok; }());
-  auto run = [&](auto opaqTag) {
-  constexpr bool OPAQ = decltype(opaqTag)::value;
   // systolic state: lane k carries the sum of some pixel through tap k, and its running maximum
-  float P0 = 0.f, P1 = 0.f, P2 = 0.f, P3 = OPAQ ? 255.f : 0.f, M = (float)(DM - 1);
+  float P0 = 0.f, P1 = 0.f, P2 = 0.f, P3 = 0.f, M = (float)(DM - 1);
   float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;    // shaped error of the previous pixel (r, g, b, a)
 
   // one systolic step: inject `px` at lane 0, every lane adds e * w[k]
   auto advance = [&](uint32_t injectPx) {
-    float q0 = __shfl_up_sync(FULL, P0, 1), q1 = __shfl_up_sync(FULL, P1, 1), q2 = __shfl_up_sync(FULL, P2, 1);
+    float q0 = __shfl_up_sync(FULL, P0, 1), q1 = __shfl_up_sync(FULL, P1, 1), q2 = __shfl_up_sync(FULL, P2, 1), q3 = __shfl_up_sync(FULL, P3, 1);
     float qm = __shfl_up_sync(FULL, M, 1);
     if (lane == 0) {
-      q0 = (float)c_red(injectPx); q1 = (float)c_green(injectPx); q2 = (float)c_blue(injectPx);
-      qm = OPAQ ? 255.f : (float)(DM - 1);      // opaque: the alpha sums are 255 throughout and join maxErr here
+      q0 = (float)c_red(injectPx); q1 = (float)c_green(injectPx); q2 = (float)c_blue(injectPx); q3 = (float)c_alpha(injectPx);
+      qm = (float)(DM - 1);
     }
-    P0 = q0 + e0 * wk; P1 = q1 + e1 * wk; P2 = q2 + e2 * wk;
-    M = fmaxf(fmaxf(qm, P0), fmaxf(P1, P2));
-    if constexpr (!OPAQ) {
-      float q3 = __shfl_up_sync(FULL, P3, 1);
-      if (lane == 0) q3 = (float)c_alpha(injectPx);
-      P3 = q3 + e3 * wk;
-      M = fmaxf(M, P3);
-    }
+    P0 = q0 + e0 * wk; P1 = q1 + e1 * wk; P2 = q2 + e2 * wk; P3 = q3 + e3 * wk;
+    M = fmaxf(fmaxf(fmaxf(qm, P0), fmaxf(P1, P2)), P3);
   };
 
+  long long cwait = 0;
+  const long long cstart = clock64();
   ring_wait(&ring.fetched, 1);
   uint32_t nxtPx = ring.px[0][lane];
   // fill the pipeline: pixels 0 .. DM-2 enter with zero errors behind them
@@ -1107,9 +1095,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
     uint32_t myOut = preCol;
     for (int j = 0; j < cnt; ++j) {
       // ---- independent of the previous pixel's error: sum of this pixel through tap DM-2
-      const float b0 = __shfl_sync(FULL, P0, DM - 2), b1 = __shfl_sync(FULL, P1, DM - 2), b2 = __shfl_sync(FULL, P2, DM - 2);
-      float b3 = 255.f;
-      if constexpr (!OPAQ) b3 = __shfl_sync(FULL, P3, DM - 2);
+      const float b0 = __shfl_sync(FULL, P0, DM - 2), b1 = __shfl_sync(FULL, P1, DM - 2), b2 = __shfl_sync(FULL, P2, DM - 2), b3 = __shfl_sync(FULL, P3, DM - 2);
       const float bm = __shfl_sync(FULL, M, DM - 2);
       const uint32_t pixel = __shfl_sync(FULL, curPx, j);
       const uint32_t pcPre = __shfl_sync(FULL, preCol, j);
@@ -1118,19 +1104,18 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
       const uint32_t inject = jn < 32 ? injA : injB;
 
       // ---- last tap, clamp (GC:199-211)
-      const float a0 = b0 + e0 * wLast, a1 = b1 + e1 * wLast, a2 = b2 + e2 * wLast, a3 = OPAQ ? 255.f : b3 + e3 * wLast;
-      const float maxErr = OPAQ ? fmaxf(fmaxf(bm, a0), fmaxf(a1, a2)) : fmaxf(fmaxf(fmaxf(bm, a0), fmaxf(a1, a2)), a3);
-      // (int) Math.min(BYTE_MAX, Math.max(error.p[j], 0.0)): widening the float is exact, so the clamp can stay in float,
-      // and truncf keeps the integer value as a float (0..255): the error below is then one exact float subtraction
-      const float f0 = truncf(fminf(255.f, fmaxf(a0, 0.f))), f1 = truncf(fminf(255.f, fmaxf(a1, 0.f)));
-      const float f2 = truncf(fminf(255.f, fmaxf(a2, 0.f))), f3 = OPAQ ? 255.f : truncf(fminf(255.f, fmaxf(a3, 0.f)));
+      const float a0 = b0 + e0 * wLast, a1 = b1 + e1 * wLast, a2 = b2 + e2 * wLast, a3 = b3 + e3 * wLast;
+      const float maxErr = fmaxf(fmaxf(fmaxf(bm, a0), fmaxf(a1, a2)), a3);
+      // (int) Math.min(BYTE_MAX, Math.max(error.p[j], 0.0)): widening the float is exact, so the clamp can stay in float
+      const int r_pix = __float2int_rz(fminf(255.f, fmaxf(a0, 0.f))), g_pix = __float2int_rz(fminf(255.f, fmaxf(a1, 0.f)));
+      const int b_pix = __float2int_rz(fminf(255.f, fmaxf(a2, 0.f))), a_pix = __float2int_rz(fminf(255.f, fmaxf(a3, 0.f)));
       advance(inject);     // uses e0..e3 of the previous pixel; must precede their update below
 
       // ---- quantize (GC:211-229)
       uint32_t pc;
       if (blockPre) pc = pcPre;
       else {
-        const uint32_t c2 = c_argb((int)f3, (int)f0, (int)f1, (int)f2);
+        const uint32_t c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
         // PnnQuantizer with dither: the branch of GC:211-229 is nearestColorIndex(c2), and with the reduced memo key
         // (PQ:271) it is nearly always a hit: answer it inline, without the call into the general path
         int qi = -1;
@@ -1146,8 +1131,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
       }
 
       // ---- error of this pixel and its shaping (GC:236-264); yDiff == 1 in this mode
-      e0 = f0 - (float)c_red(pc); e1 = f1 - (float)c_green(pc); e2 = f2 - (float)c_blue(pc);   // exact: small integers
-      if constexpr (!OPAQ) e3 = f3 - (float)c_alpha(pc);
+      e0 = (float)(r_pix - c_red(pc)); e1 = (float)(g_pix - c_green(pc)); e2 = (float)(b_pix - c_blue(pc)); e3 = (float)(a_pix - c_alpha(pc));
       if (denoise) {
         const bool s0 = fabsf(e0) >= fDitherMax, s1 = fabsf(e1) >= fDitherMax, s2 = fabsf(e2) >= fDitherMax;
         if (s0 || s1 || s2) {
@@ -1183,8 +1167,6 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
     ring_signal(&ring.consumed, b + 1);
   }
 
-  };
-  if (opaque3) run(std::true_type{}); else run(std::false_type{});
   if (lane == 0) { I.statDither[0] = (unsigned long long)(clock64() - cstart); I.statDither[1] = (unsigned long long)cwait; }
   E.rng.seed = ring.rngSeed; E.draws = ring.draws;
   if (!dither && plen > 32) bluenoise_pass(I, D);

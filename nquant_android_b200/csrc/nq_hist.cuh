@@ -48,14 +48,13 @@ __global__ void __launch_bounds__(256) k_alpha_scan(NqImage* imgs, const NqSlot*
   const int img = blockIdx.y;
   const int n = imgs[img].npix;
   const uint32_t* in = slots[img].in;
-  unsigned semi = 0, nonop = 0;
+  unsigned semi = 0;
   int last = -1;
   const bool vec = ((uintptr_t)in & 15) == 0;
   const int n4 = vec ? (n >> 2) : 0;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += gridDim.x * blockDim.x) {
     uint4 v = ld_stream4(in + 4 * (size_t)q);
     uint32_t px[4] = {v.x, v.y, v.z, v.w};
-    nonop |= ~(v.x & v.y & v.z & v.w) >> 24;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       unsigned a = px[k] >> 24;
@@ -67,7 +66,6 @@ __global__ void __launch_bounds__(256) k_alpha_scan(NqImage* imgs, const NqSlot*
   }
   for (int i = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     unsigned a = in[i] >> 24;
-    nonop |= a ^ 255u;
     if (a < 0xE0) {
       if (a == 0) last = max(last, i);
       else if (a > 0xF) ++semi;
@@ -82,7 +80,6 @@ __global__ void __launch_bounds__(256) k_alpha_scan(NqImage* imgs, const NqSlot*
     if (semi) atomicAdd(&imgs[img].semiCount, semi);
     if (last >= 0) atomicMax(&imgs[img].transIdx, last);
   }
-  if (__any_sync(0xffffffffu, nonop != 0) && lane_id() == 0) imgs[img].notOpaque = 1u;
 }
 
 // ---- scalars that follow the scan (PQ:431-436, PQ:144) ------------------------------------------

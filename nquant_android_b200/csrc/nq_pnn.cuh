@@ -84,7 +84,11 @@ __device__ __forceinline__ double rgb_take(const RgbProbe& P, const RgbCand& c, 
 // gs (must be < err), gw (must be <= err) and f (the new err).
 // -------------------------------------------------------------------------------------------------
 // upper bound of sqrt(A^2 + B^2) as a float
-__device__ __forceinline__ float chroma_ub(float A, float B) { return sqrtf((A * A) + (B * B)) * 1.000001f; }
+__device__ __forceinline__ float chroma_ub(float A, float B) {
+  const float x = (A * A) + (B * B);
+  // x * rsqrt(x) with the hardware estimate (relative error < 2^-22) and a margin: an upper bound is all that is needed
+  return x > 1e-30f ? (x * __frsqrt_rn(x)) * 1.00001f : 1e-15f;
+}
 
 struct LabProbe {
   float n1, a1, L1, A1, B1, C1;   // C1: upper bound of the chroma sqrt(A1^2 + B1^2)
@@ -142,7 +146,7 @@ __device__ __forceinline__ bool lab_block_skip_v(const LabProbe& P, const float4
   const float rf = g_rtFac[min(255, (int)cb)];
   const float d2 = fmaxf(0.f, (((da * da) + (db * db)) * 0.9999f) - 1e-4f);
   const float t = dl * 0.57234f;                           // 1 / 1.7472 rounded down
-  const float q = (t * t) + (rf * d2) / ((sc * sc) * 1.00001f);
+  const float q = (t * t) + __fdividef(rf * d2, (sc * sc) * 1.00001f) * 0.99999f;
   const float lb = (P.ratioLo * nerr2) * q * 0.9999f;
   return lb > Uup;
 }
@@ -185,7 +189,7 @@ __device__ __forceinline__ bool lab_cheap_keep_q(const LabProbe& P, const float4
   const float rf = g_rtFac[min(255, (int)cb)];
   const float d2 = fmaxf(0.f, (((da * da) + (db * db)) * 0.9999f) - 1e-4f);
   const float tl = dl * 0.57234f;                                  // 1 / 1.7472 rounded down
-  const float q = (tl * tl) + (rf * d2) / ((sc * sc) * 1.00001f);
+  const float q = (tl * tl) + __fdividef(rf * d2, (sc * sc) * 1.00001f) * 0.99999f;
   const float lb = (P.ratioLo * nerr2) * q * 0.9999f;
   return !(lb > errUp);
 }
@@ -437,22 +441,32 @@ __global__ void __launch_bounds__(256, 3) k_find_nn_lab(NqImage* imgs, const NqS
 // to global memory: tm/mtm of the bin and mtm of its nn are loaded together.
 template <int HS>
 struct HeapView {
+  static_assert((HS & 1) == 0, "children l2, l2 + 1 must fall on the same side of the split");
   float* sErr; unsigned* sIdNn;       // shared part, slots [0, HS): err, id | nn << 16
-  float* gErr; int* gIdNn;            // global spill for the deepest level(s)
-  __device__ __forceinline__ float err(int l) const { return l < HS ? sErr[l] : gErr[l]; }
-  __device__ __forceinline__ unsigned idnn(int l) const { return l < HS ? sIdNn[l] : (unsigned)gIdNn[l]; }
+  uint2* gH;                          // global spill for the deepest levels: {err bits, id | nn << 16} per slot, so the
+                                      // two children of a node (slots 2l, 2l + 1) arrive with ONE 16-byte load
+  __device__ __forceinline__ float err(int l) const { return l < HS ? sErr[l] : __uint_as_float(gH[l].x); }
+  __device__ __forceinline__ unsigned idnn(int l) const { return l < HS ? sIdNn[l] : gH[l].y; }
   __device__ __forceinline__ int id(int l) const { return (int)(idnn(l) & 0xFFFFu); }
   __device__ __forceinline__ void set(int l, unsigned idnn_, float e) {
-    if (l < HS) { sErr[l] = e; sIdNn[l] = idnn_; } else { gErr[l] = e; gIdNn[l] = (int)idnn_; }
+    if (l < HS) { sErr[l] = e; sIdNn[l] = idnn_; } else gH[l] = make_uint2(__float_as_uint(e), idnn_);
   }
   // "push slot down" (PQ:228-236): sift (b1, e1) down from the root of a heap with heapN entries
   __device__ __forceinline__ void sift_down(unsigned idnn1, float e1, int heapN) {
     int l = 1, l2;
     for (; (l2 = l + l) <= heapN; l = l2) {
-      float ea = err(l2);
-      if (l2 < heapN) { float eb = err(l2 + 1); if (ea > eb) { ++l2; ea = eb; } }
+      float ea, eb = 0.f;
+      unsigned ia, ib = 0u;
+      if (l2 < HS) {
+        ea = sErr[l2]; ia = sIdNn[l2];
+        if (l2 < heapN) { eb = sErr[l2 + 1]; ib = sIdNn[l2 + 1]; }
+      } else {
+        const uint4 ch = *reinterpret_cast<const uint4*>(&gH[l2]);   // slot l2 + 1 exists in the allocation even past heapN
+        ea = __uint_as_float(ch.x); ia = ch.y; eb = __uint_as_float(ch.z); ib = ch.w;
+      }
+      if (l2 < heapN && ea > eb) { ++l2; ea = eb; ia = ib; }
       if (e1 <= ea) break;
-      set(l, idnn(l2), ea);
+      set(l, ia, ea);
     }
     set(l, idnn1, e1);
   }
@@ -550,7 +564,7 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
   const int maxbins = I.maxbins, extbins = I.extbins;
   int* live = liveBuf + (size_t)img * NQ_NBINS;
   int* posOf = posBuf + (size_t)img * NQ_NBINS;
-  HeapView<NQ_LAB_HEAP_SMEM> H{sErr, sId, S.hErr, S.hId};
+  HeapView<NQ_LAB_HEAP_SMEM> H{sErr, sId, S.heap};
 
   // ---- heap build: sequential pushes in bin order (PL:246-257), replayed by warp 0
   if (w == 0) {
@@ -962,7 +976,7 @@ __global__ void __launch_bounds__(NQ_RGB_THREADS, 4) k_merge_rgb(NqImage* imgs, 
   const int maxbins = I.maxbins, extbins = I.extbins;
   int* live = liveBuf + (size_t)img * NQ_NBINS;
   int* posOf = posBuf + (size_t)img * NQ_NBINS;
-  HeapView<NQ_RGB_HEAP_SMEM> H{sErr, sId, S.hErr, S.hId};
+  HeapView<NQ_RGB_HEAP_SMEM> H{sErr, sId, S.heap};
 
   // ---- heap build: sequential pushes in bin order (PQ:196-207), replayed by warp 0
   if (w == 0) {

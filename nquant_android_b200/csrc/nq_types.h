@@ -17,7 +17,6 @@ struct NqImage {
   unsigned long long seed;
   // alpha scan (PQ:411-431)
   unsigned int semiCount;
-  unsigned int notOpaque;  // some pixel has alpha != 255
   int transIdx;            // m_transparentPixelIndex
   int hasSemi;             // hasSemiTransparency
   uint32_t transColor;     // m_transparentColor
@@ -64,8 +63,8 @@ struct NqSlot {
   float* fAc; float* fC1; float* fC2; float* fC3;
   float* bCnt; float* bErr;
   int* bNn; int* bTm; int* bMtm;
-  // heap (values mirrored next to ids, see nq_pnn.cuh)
-  float* hErr; int* hId;           // [65537] global spill of the lower heap levels
+  // heap (see HeapView in nq_pnn.cuh)
+  uint2* heap;                     // [65538] global spill of the lower heap levels: {err bits, id | nn << 16}
   int* mergeLog;                   // optional [2*65536] (tb, nb) pairs for parity tests
   // dither
   unsigned short* memo;            // [65536] nearestMap for reduced keys (0xFFFF = absent)
