@@ -621,6 +621,7 @@ __global__ void __launch_bounds__(256) k_lab_fewcolors(NqImage* imgs, const NqSl
         }
     I.paletteLen = cnt;
     I.skipPnn = 1;
+    I.ratio = I.ratioMerge = .5;      // pnnquan returns before PL:219-241: `ratio` keeps its field default (PQ:25)
   }
 }
 
