@@ -123,6 +123,8 @@ typedef struct nq_image_info {
   unsigned long long dither_cycles[3];
 } nq_image_info;
 int nq_get_image_info(nq_ctx* ctx, int image, nq_image_info* out);
+/* sizeof(nq_image_info) as the library was built: lets a binding check its own mirror of the struct. */
+int nq_sizeof_image_info(void);
 
 /* When enabled (flag != 0) the next calls keep, per image, the compacted bins before merging, the
  * initial find_nn results and the merge sequence, retrievable below. Costs memory and a few copies. */

@@ -11,7 +11,7 @@ SYMBOLS = [
     "nq_device_count", "nq_create", "nq_destroy", "nq_last_error", "nq_convert", "nq_convert_batch",
     "nq_convert_batch_device", "nq_dither_with_palette", "nq_gilbert_order", "nq_get_image_info", "nq_set_debug",
     "nq_debug_get_bins", "nq_debug_get_merges", "nq_debug_get_saliencies", "nq_kernel_launches", "nq_debug_math",
-    "nq_synth_device", "nq_get_stage_times", "nq_set_stream", "nq_debug_ciede",
+    "nq_synth_device", "nq_get_stage_times", "nq_set_stream", "nq_debug_ciede", "nq_sizeof_image_info",
 ]
 
 NQ_KIND_PNN, NQ_KIND_PNNLAB = 0, 1
@@ -78,5 +78,7 @@ def load():
     L.nq_synth_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, u64]
     for s in SYMBOLS:
         getattr(L, s)
+    if L.nq_sizeof_image_info() != ctypes.sizeof(ImageInfo):
+        raise ImportError("nq_image_info: the ctypes mirror in _lib.py does not match include/nquant_b200.h")
     _lib = L
     return L

@@ -677,6 +677,8 @@ int nq_get_image_info(nq_ctx* c, int image, nq_image_info* o) {
   return NQ_OK;
 }
 
+int nq_sizeof_image_info(void) { return (int)sizeof(nq_image_info); }
+
 int nq_set_stream(nq_ctx* c, void* stream) {
   if (!c) return fail(NQ_ERR_ARG, "null context");
   c->stream = stream ? reinterpret_cast<cudaStream_t>(stream) : c->ownStream;

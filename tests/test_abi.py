@@ -35,6 +35,11 @@ def test_binding_lists_every_symbol():
     assert sorted(_lib.SYMBOLS) == header_functions()
 
 
+def test_image_info_mirror_matches(lib):
+    from nquant_android_b200 import _lib
+    assert lib.nq_sizeof_image_info() == ctypes.sizeof(_lib.ImageInfo)
+
+
 def test_header_cites_reference_lines():
     text = open(os.path.join(ROOT, "include", "nquant_b200.h")).read()
     for cite in ["PnnQuantizer.java:409", "PnnQuantizer.java:35", "PnnLABQuantizer.java:24", "PnnQuantizer.java:458",

@@ -19,7 +19,8 @@ def _cases(n, seed):
         kind = int(rng.integers(0, 2))
         cls = ["smooth", "noisy", "rand", "few"][int(rng.integers(0, 4))]
         alpha = ["opaque", "opaque", "transparent", "semi"][int(rng.integers(0, 4))]
-        w, h = int(rng.integers(1, 180)), int(rng.integers(1, 140))
+        scale = int(os.environ.get("NQ_FUZZ_SCALE", "1"))      # ad-hoc: larger images reach the reduced-key memo regime
+        w, h = int(rng.integers(1, 180)) * scale, int(rng.integers(1, 140)) * scale
         if cls == "rand":                      # 65 536 possible bins: keep the oracle's merge loop short
             w, h = min(w, 90), min(h, 70)
         k = ks[int(rng.integers(0, len(ks)))]

@@ -211,6 +211,20 @@ def test_batch_matches_single_and_device_matches_host(gpu_ctx):
         assert np.array_equal(dout.cpu().numpy().view(np.uint32), out)
 
 
+def test_large_mixed_batch_matches_single(gpu_ctx):
+    """40 different images in one call (more than the 32 sets of CIELAB sort scratch, several merge CTAs per SM,
+    every synthetic class and alpha mode side by side) must give each image the result it gets alone."""
+    W, H, K = 72, 56, 64
+    classes, alphas = ["noisy", "smooth", "rand", "few"], ["opaque", "transparent", "semi", "opaque"]
+    imgs = np.stack([make_image(W, H, classes[i % 4], alphas[(i // 4) % 4], seed=0x5EED0000 + i) for i in range(40)])
+    seeds = np.arange(40, dtype=np.uint64) * 977 + 5
+    for kind in (0, 1):
+        out, pal, plen, ha = gpu_ctx.convert_batch(kind, imgs, W, H, K, True, seeds=seeds)
+        for i in range(0, 40, 3):
+            o1, p1, l1, h1 = gpu_ctx.convert_batch(kind, imgs[i:i + 1], W, H, K, True, seeds=seeds[i:i + 1])
+            assert l1[0] == plen[i] and np.array_equal(p1[0], pal[i]) and np.array_equal(o1[0], out[i]) and h1[0] == ha[i], (kind, i)
+
+
 def test_device_synth_matches_numpy(gpu_ctx):
     import torch
     W, H = 70, 50
