@@ -890,11 +890,14 @@ struct DitherRing {
   int fetched, looked, consumed;
   unsigned long long rngSeed, draws;
 };
+// `ns`: how long to sleep between polls. The producer runs blocks ahead and idles most of the time, so it polls
+// rarely (its polling instructions would otherwise take a fifth of the SM's issue slots from the consumers).
+template <int NS = 40>
 __device__ __forceinline__ void ring_wait(const int* p, int v, long long* waited = nullptr) {
   const volatile int* vp = p;
   if (*vp < v) {
     const long long t0 = clock64();
-    while (*vp < v) __nanosleep(40);
+    while (*vp < v) __nanosleep(NS);
     if (waited) *waited += clock64() - t0;
   }
   __syncwarp();
@@ -1001,7 +1004,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
     long long pwait = 0;
     for (int b = 0; b < nblocks; ++b) {
       const int slot = b & (NQ_RING - 1);
-      ring_wait(&ring.consumed, b - (NQ_RING - 1), &pwait);
+      ring_wait<500>(&ring.consumed, b - (NQ_RING - 1), &pwait);
       const PixBlock cur = fetch_block(D, order, b << 5);
       const int cnt = min(32, npix - (b << 5));
       const bool mine = (int)lane < cnt;
@@ -1022,7 +1025,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
         }
         blockPre = __all_sync(FULL, ok);
         if (blockPre) {
-          ring_wait(&ring.consumed, lastSlow + 1);   // the consumer is done drawing for every earlier block
+          ring_wait<200>(&ring.consumed, lastSlow + 1);   // the consumer is done drawing for every earlier block
           E.rng.seed = ring.rngSeed; E.draws = ring.draws;
           preCol = prelookup_commit(E, c, mine);
           if (lane == 0) { ring.rngSeed = E.rng.seed; ring.draws = E.draws; }
