@@ -6,9 +6,11 @@
 // The dither is a strictly serial chain along the curve: every pixel needs the quantization error
 // of the previous one, the lookups share a first-seen memo when the key is the reduced 16-bit
 // colour (PQ:271-274, PL:332-335) and the LAB lookup consumes a java.util.Random stream in visiting
-// order (PL:467). So one warp owns one image and walks the curve; inside a step the warp splits the
-// work that has no order: the four channels of the error-queue sum (lane & 3), the palette scan
-// (palette entry = lane + 32 t) and the three error-shaping channels.
+// order (PL:467). One CTA per image: k_dither_fifo pairs a producer warp (pixel gather, and the palette
+// lookups whenever they do not depend on the running error) with a consumer warp that owns the error
+// recurrence; k_dither_sorted is the PriorityQueue mode. The cooperative per-pixel routines below
+// (nearest_* / closest_* / dither_pixel) split a single lookup across the 32 lanes and are what the
+// consumer falls back to when a lookup does read the diffused colour.
 #pragma once
 #include "nq_types.h"
 #include "nq_color.h"

@@ -8,8 +8,9 @@
 //    `continue` tests is always taken, with err := the first partial sum of the YUV loop that
 //    reaches err (the `break` falls through, PQ:97-112) -- err can grow. LAB: err := full cost,
 //    early exits use >= for the first tests and > later, and R_T may be negative (PL:57-108).
-//    We evaluate the err-independent partial sums of many candidates in parallel and resolve
-//    acceptance in list order with ballot rounds (one round per ACCEPTED candidate).
+//    Candidates are pruned only by tests the reference itself would fail them on, evaluated against an
+//    upper bound of the running err (block summaries, per-candidate bounds, exact prefixes), and the
+//    survivors are resolved in list order with ballot rounds (one round per ACCEPTED candidate).
 //  * the binary heap code, including its tie behaviour, is replayed verbatim by one thread; heap
 //    slots carry a copy of the bin's err (a bin's err only changes while it sits at heap[1]).
 //  * forward links only ever skip deleted bins, so "list order" == ascending index among live bins;
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(256, 3) k_find_nn_lab(NqImage* imgs, const NqS
 }
 
 // -------------------------------------------------------------------------------------------------
-// merge loop: one persistent CTA per image.
+// merge loops: one persistent 128-thread CTA per image, several images per SM (k_merge_lab, k_merge_rgb).
 // -------------------------------------------------------------------------------------------------
 
 // The heap of bin ids keyed by err (PQ:195-236). A slot also carries a copy of the bin's err (a bin's err only
