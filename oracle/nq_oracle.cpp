@@ -31,6 +31,11 @@
 #include <algorithm>
 #include <stdexcept>
 
+// study hook (tools/spec_dither_emul.cpp): sees every nearestMap key that is looked up; nothing by default
+#ifndef NQ_ORACLE_PROBE
+#define NQ_ORACLE_PROBE(key) ((void)0)
+#endif
+
 #include "../nquant_android_b200/csrc/nq_math.h"
 #include "../nquant_android_b200/csrc/nq_bluenoise_table.h"
 
@@ -927,6 +932,7 @@ class PnnQuantizer {
 
   virtual short nearestColorIndex(const std::vector<int32_t>& palette, int32_t c, int pos) {  // PQ:269-311
     const int32_t offset = weight > .015 ? c : getColorIndex(c, hasSemiTransparency, m_transparentPixelIndex >= 0);
+    NQ_ORACLE_PROBE(offset);
     auto got = nearestMap.find(offset);
     if (got != nearestMap.end()) return got->second;
 
@@ -1342,6 +1348,7 @@ class PnnLABQuantizer : public PnnQuantizer {
 
   short nearestColorIndex(const std::vector<int32_t>& palette, int32_t c, int pos) override {  // PL:329-404
     const int32_t offset = !isNano ? c : getColorIndex(c, hasSemiTransparency, m_transparentPixelIndex >= 0);
+    NQ_ORACLE_PROBE(offset);
     auto got = nearestMap.find(offset);
     if (got != nearestMap.end()) return got->second;
 
