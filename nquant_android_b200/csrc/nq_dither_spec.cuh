@@ -1,0 +1,565 @@
+// nq_dither_spec.cuh -- speculative segment-parallel Gilbert dither for the images
+// whose palette lookups do not read the error-diffused colour: PnnLABQuantizer, dither on, ArrayDeque queue,
+// no semi-transparency, more than 64 colours (GilbertCurve.ditherPixel replaces the colour by
+// BlueNoise.diffuse(pixel, palette[0], kappa) before the lookup, GC:137-141; see nq_dither.cuh).
+//
+// Reference: GilbertCurve.diffusePixel / ditherPixel (GC:125-280), PnnLABQuantizer.closestColorIndex /
+// nearestColorIndex (PL:329-474), java.util.Random (PL:22,467).
+//
+// The sequential chain carries three states (profiles/r1_spec_dither_study.md): the error queue Q, the number D
+// of java.util.Random draws, and the first-seen memo nearestMap. For these images D and the memo are decided by
+// per-pixel passes (stages 1-5 below) because 99.8 % of the lookups never see the running error; Q re-synchronises
+// within a few hundred pixels of a restart from an empty queue. Stage 6 runs one THREAD per segment of the curve
+// (warm-up from an empty queue, then the owned pixels); stage 7 validates the segments in curve order: the queue
+// a segment warmed up to must equal, bit for bit, the queue its predecessor ended with, the draws it made must
+// equal the prediction, and a memo entry created by one of its error-dependent lookups must not contradict an
+// earlier one. A segment that fails re-runs from its predecessor's exact state in the next round; an image
+// whose draw prediction or memo was contradicted is handed to the serial kernel (k_dither_fifo). The result is
+// therefore bit-identical to the sequential run by construction.
+//
+// Every stage body is a scalar NQ_HD function so that the very same code is compiled by g++ and checked
+// against the CPU oracle (tests/test_spec_dither_host.py); the kernels at the end of the file only index.
+#pragma once
+#include "nq_types.h"
+#include "nq_color.h"
+
+namespace nq {
+namespace spec {
+
+#define NQS_NOTES 12            // memo entries a segment may create through error-dependent lookups
+#define NQS_NOPOS 0x7fffffff
+#define NQS_NONE 0xFFFFFFFFu    // absent top-2 key
+
+// per-pixel flags (curve order)
+#define NQS_F_PRE 1u            // lookup does not read the diffused colour
+#define NQS_F_DRAW 2u           // the lookup is predicted to call Random.nextInt (PL:467)
+#define NQS_F_NEAR 4u           // resolved through nearestColorIndex's memo (PL:470-472): ck0 holds the memo key
+
+// Constants of one image: what GilbertCurve's constructor and the quantizer hold while dithering.
+struct SpecConst {
+  int plen, margin, thresold, DM, ditherMax, width, npix;
+  int isNano, hasTrans, salReplaced;
+  int seg, warm, nseg;
+  uint32_t transColor;
+  double gWeight, PR, PG, PB, ratio;
+  float beta;
+  unsigned long long seed0;              // java.util.Random state after setSeed
+  float w[NQ_MAXQ];                      // initWeights(DITHER_MAX)
+  uint32_t pal[NQ_MAXK];
+  Lab4 palLab[NQ_MAXK];                  // getLab(palette[i]) (PL:352)
+  double Tr[256], Tg[256], Tb[256];      // closestColorIndex cost of one channel difference (see nq_dither.cuh)
+};
+
+// Per-image work arrays (curve order, npix entries unless noted) and segment records.
+struct SpecSeg {
+  float qwarm[NQ_MAXQ][4];               // queue when the owned pixels begin (oldest box first)
+  float qout[NQ_MAXQ][4];                // queue after the last owned pixel
+  float qstart[NQ_MAXQ][4];              // exact start state (when exact != 0)
+  int exact, dirty, done;
+  int draws;                             // draws made by the owned pixels
+  int nnotes;                            // > NQS_NOTES: overflow
+  int noteKey[NQS_NOTES], notePos[NQS_NOTES], noteVal[NQS_NOTES];
+};
+struct SpecWork {
+  const uint32_t* order;                 // x | y << 16 per curve position
+  const uint32_t* in;                    // source pixels, row-major
+  uint32_t* out;
+  uint32_t* cpx;                         // pixel per curve position
+  uint32_t* ccol;                        // colour the pre-lookup asks for
+  uint32_t* ck0;                         // smallest top-2 key (floor(err) << 8 | index)
+  uint32_t* ck1;                         // second smallest
+  unsigned short* cq;                    // resolved palette index (or memo key while NQS_F_NEAR)
+  unsigned char* cflag;
+  uint32_t* cdraw;                       // [npix + 1] draws predicted before this pixel (exclusive prefix of NQS_F_DRAW)
+  int* firstPos;                         // [65536] first curve position whose pre-lookup needs memo key k
+  unsigned short* memo;                  // [65536] nearestMap for reduced keys (0xFFFF = absent)
+  int* slowPos;                          // [65536] entries created by error-dependent lookups of validated segments
+  unsigned short* slowVal;               // [65536]
+  const unsigned char* cells;            // candidate lists of k_build_cells, or nullptr
+  const double* lut;                     // gammaToLinear table
+  const signed char* bn;                 // TELL_BLUE_NOISE
+  SpecSeg* segs;
+  int* state;                            // [4]: firstOpen, anomaly, patch key + 1 (0 = none), patch position
+};
+
+// ---- java.util.Random: state after j more steps of the LCG ------------------------------------------------
+NQ_HD unsigned long long lcg_jump(unsigned long long seed, unsigned long long j) {
+  const unsigned long long MASK = (1ULL << 48) - 1;
+  unsigned long long a = 0x5DEECE66DULL, c = 0xBULL;
+  while (j) {
+    if (j & 1ULL) seed = (a * seed + c) & MASK;
+    c = ((a + 1ULL) * c) & MASK;
+    a = (a * a) & MASK;
+    j >>= 1;
+  }
+  return seed;
+}
+// value of Random.nextInt(32767) taken from state `s` (the state AFTER the step); rejected = the reference would draw again
+NQ_HD int next_int_from(unsigned long long s, bool* rejected) {
+  const int u = (int)(s >> 17), r = u % 32767;
+  *rejected = (int)((unsigned)(u - r) + 32766u) < 0;
+  return r;
+}
+
+NQ_HD Lab4 lab_at(uint32_t c, const double* lut) {
+#if defined(__CUDA_ARCH__)
+  return lab_of(c);                      // 2^24-entry table (nq_hist.cuh)
+#else
+  Lab4 l = rgb2lab(0xFF000000u | c, lut);
+  l.alpha = (float)(c >> 24);
+  return l;
+#endif
+}
+NQ_HD float tanh_f(double x) {            // (float) Math.tanh(x) (GC:255)
+#if defined(__CUDA_ARCH__)
+  float v;
+  if (tanh_fast(x, &v)) return v;        // nq_dither.cuh: same float whenever it answers
+#endif
+  return (float)nqm::nq_tanh(x);
+}
+NQ_HD float coeff(int i, int j) {         // PQ:26-30
+  constexpr float k[3][3] = {{0.299f, 0.587f, 0.114f}, {-0.14713f, -0.28886f, 0.436f}, {0.615f, -0.51499f, -0.10001f}};
+  return k[i][j];
+}
+
+// ---- tables --------------------------------------------------------------------------------------------------
+NQ_HD void fill_tables(SpecConst& C, const double* lut) {
+  for (int v = 0; v < 256; ++v) {
+    const double dv = (double)v;
+    double r = C.PR * (1 - C.ratio) * (dv * dv), g = C.PG * (1 - C.ratio) * (dv * dv), b = C.PB * (1 - C.ratio) * (dv * dv);
+    for (int i = 0; i < 3; ++i) {
+      double t0 = (double)(coeff(i, 0) * (float)v), t1 = (double)(coeff(i, 1) * (float)v), t2 = (double)(coeff(i, 2) * (float)v);
+      r += C.ratio * (t0 * t0); g += C.ratio * (t1 * t1); b += C.ratio * (t2 * t2);
+    }
+    C.Tr[v] = r; C.Tg[v] = g; C.Tb[v] = b;
+  }
+  for (int i = 0; i < C.plen; ++i) C.palLab[i] = lab_at(C.pal[i], lut);
+}
+
+// exact cost of palette entry c2 for colour c in the reference's operation order (PL:421-446), no semi-transparency
+NQ_HD double closest_err(const SpecConst& C, uint32_t c2, int cr, int cg, int cb) {
+  const int ir = c_red(c2) - cr, ig = c_green(c2) - cg, ib = c_blue(c2) - cb;
+  const double dr = (double)ir, dg = (double)ig, db = (double)ib;
+  double err = C.PR * (1 - C.ratio) * (dr * dr);
+  err += C.PG * (1 - C.ratio) * (dg * dg);
+  err += C.PB * (1 - C.ratio) * (db * db);
+  for (int i = 0; i < 3; ++i) {
+    double t0 = (double)(coeff(i, 0) * (float)ir);
+    err += C.ratio * (t0 * t0);
+    double t1 = (double)(coeff(i, 1) * (float)ig);
+    err += C.ratio * (t1 * t1);
+    double t2 = (double)(coeff(i, 2) * (float)ib);
+    err += C.ratio * (t2 * t2);
+  }
+  return err;
+}
+NQ_HD unsigned top2_key(const SpecConst& C, int k, int cr, int cg, int cb) {
+  const uint32_t c2 = C.pal[k];
+  const int ar = c_red(c2) - cr, ag = c_green(c2) - cg, ab = c_blue(c2) - cb;
+  const double a = C.Tr[ar < 0 ? -ar : ar] + C.Tg[ag < 0 ? -ag : ag] + C.Tb[ab < 0 ? -ab : ab];
+  int d = j2i(a);
+  const double fr = a - (double)d;
+  if (fr < 1e-6 || fr > 1.0 - 1e-6) d = j2i(closest_err(C, c2, cr, cg, cb));   // only floor(err) is compared (PL:448-456)
+  return ((unsigned)d << 8) | (unsigned)k;
+}
+// the two smallest (floor(err), index) pairs = closest[0..3] of PL:418-458
+NQ_HD void top2(const SpecConst& C, const unsigned char* cells, uint32_t c, unsigned* k0, unsigned* k1) {
+  const int cr = c_red(c), cg = c_green(c), cb = c_blue(c);
+  unsigned a0 = NQS_NONE, a1 = NQS_NONE;
+  int cnt = 255;
+  const unsigned char* cell = nullptr;
+  if (cells) {
+    cell = cells + 32 * (size_t)(((cr >> 3) << 10) | ((cg >> 3) << 5) | (cb >> 3));
+    cnt = cell[0];
+  }
+  if (cnt != 255) {
+    for (int j = 1; j <= cnt; ++j) {
+      const unsigned key = top2_key(C, cell[j], cr, cg, cb);
+      const unsigned t = key > a0 ? key : a0;
+      a0 = key < a0 ? key : a0;
+      a1 = a1 < t ? a1 : t;
+    }
+  } else {
+    for (int k = 0; k < C.plen; ++k) {
+      const unsigned key = top2_key(C, k, cr, cg, cb);
+      const unsigned t = key > a0 ? key : a0;
+      a0 = key < a0 ? key : a0;
+      a1 = a1 < t ? a1 : t;
+    }
+  }
+  *k0 = a0; *k1 = a1;
+}
+
+// PnnLABQuantizer.nearestColorIndex without its memo (PL:337-401), palettes of more than 32 colours, no semi-transparency
+NQ_HD int nearest_nomemo(const SpecConst& C, uint32_t c, const double* lut) {
+  int k = 0;
+  if (c_alpha(c) <= 0xF) c = C.transColor;
+  if (C.plen > 2 && C.hasTrans && c_alpha(c) > 0xF) k = 1;
+  const Lab4 l1 = lab_at(c, lut);
+  double best = 1e300;
+  int bi = -1;
+  for (int i = k; i < C.plen; ++i) {
+    const Lab4 l2 = C.palLab[i];
+    float dl = l2.L - l1.L;
+    double cur = (double)(dl < 0.f ? -dl : dl);
+    const double da = (double)(l2.A - l1.A), db = (double)(l2.B - l1.B);
+    cur += nqm::sqrt_((da * da) + (db * db));
+    if (cur <= best) { best = cur; bi = i; }            // strict > pruning: the last minimal index wins (PL:397-400)
+  }
+  if (!(best <= 2147483647.0) || bi < 0) bi = k;         // mindist starts at Integer.MAX_VALUE
+  return bi;
+}
+
+// GilbertCurve.normalDistribution (GC:114-123)
+NQ_HD float normal_dist(float x, float peak) {
+  const float mean = .5f, stdDev = .1f;
+  const double d = (double)(x - mean), sd = (double)stdDev;
+  const double exponent = -(d * d) / (2 * (sd * sd));
+  const double pdf = (1 / (sd * nqm::sqrt_(2 * 3.141592653589793))) * nqm::nq_exp(exponent);
+  const double maxPdf = 1 / (sd * nqm::sqrt_(2 * 3.141592653589793));
+  const double scaledPdf = (pdf / maxPdf) * (double)peak;
+  return (float)dmax(0.0, dmin((double)peak, scaledPdf));
+}
+NQ_HD double ydiff_pre(double ypix, uint32_t c, const double* lut) { return nqm::fabs_(color_y(c, lut) - ypix) * 100; }
+
+// ditherPixel (GC:125-185) with qPixels[bidx] == 0, evaluated without the diffused colour; false when the reference's
+// result would read it. Requires plen > 64 and 2 * (plen - margin) > 101 (GC:137 then holds for any colour).
+NQ_HD bool pre_colour(const SpecConst& C, const SpecWork& W, int x, int y, uint32_t pixel, float sal, double ypix, uint32_t* out) {
+  const int plen = C.plen, margin = C.margin;
+  const float beta = C.beta;
+  const uint32_t qcol = C.pal[0];
+  const float strength = 1 / 3.f;
+  const int acceptedDiff = plen - margin > 2 ? plen - margin : 2;
+  const float kappa = sal < .6f ? beta * .15f / sal : beta * .4f / sal;
+  uint32_t c2 = bn_diffuse(pixel, qcol, kappa, strength, x, y, W.bn);
+  const double gamma = (double)beta;                      // plen > 32
+  if (ydiff_pre(ypix, c2, W.lut) > (gamma * acceptedDiff)) return false;   // GC:149-172 reads r_pix..a_pix
+  if (C.DM < 16 && sal < .6f && ydiff_pre(ypix, c2, W.lut) > (double)(margin - 1)) return false;   // GC:175
+  if ((double)sal > .95) {
+    const float k2 = beta * fmaxf(.05f, .75f - plen / 128.f) * sal;
+    c2 = bn_diffuse(pixel, qcol, k2, strength, x, y, W.bn);
+  }
+  *out = c2;
+  return true;
+}
+
+// ditherPixel (GC:125-185) in full for plen > 64, qPixels[bidx] == 0: the colour that is looked up
+NQ_HD uint32_t slow_colour(const SpecConst& C, const SpecWork& W, int x, int y, uint32_t pixel, float sal, double ypix, uint32_t c2) {
+  const int plen = C.plen, margin = C.margin;
+  const double weight = C.gWeight;
+  const float beta = C.beta;
+  const uint32_t qcol = C.pal[0];
+  const int r_pix = c_red(c2), g_pix = c_green(c2), b_pix = c_blue(c2), a_pix = c_alpha(c2);
+  const float strength = 1 / 3.f;
+  const int acceptedDiff = plen - margin > 2 ? plen - margin : 2;
+  if (ydiff_pre(ypix, c2, W.lut) < (double)(2 * acceptedDiff)) {
+    const float kappa = sal < .6f ? beta * .15f / sal : beta * .4f / sal;
+    c2 = bn_diffuse(pixel, qcol, kappa, strength, x, y, W.bn);
+  }
+  const double gamma = (double)beta;
+  if (ydiff_pre(ypix, c2, W.lut) > (gamma * acceptedDiff)) {
+    if (margin > 6) {                                      // gamma > beta cannot hold for plen > 32
+      float kappa = sal < .4f ? beta * .4f * sal : beta * .4f / sal;
+      uint32_t c1 = c_argb(a_pix, r_pix, g_pix, b_pix);
+      if ((double)sal < .9)
+        kappa = beta * normal_dist(sal, 2.f);
+      else {
+        if (weight >= .0015 && (double)sal < .6) c1 = pixel;
+        if (weight >= .005 && (double)sal < .6)
+          kappa = beta * normal_dist(sal, weight < .0008 ? 2.5f : 1.75f);
+        else {                                             // plen >= 32
+          const double ub = 1 - plen / 320.0;
+          if ((double)sal > .15 && (double)sal < ub)
+            kappa = beta * (weight < .0025 ? .55f : .5f) / sal;   // !sortedByYDiff in this mode
+          else
+            kappa = beta * normal_dist(sal, weight < .0025 ? 1.82f : 2.f);
+        }
+      }
+      c2 = bn_diffuse(c1, qcol, kappa, strength, x, y, W.bn);
+    } else
+      c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
+  }
+  if (C.DM < 16 && sal < .6f && ydiff_pre(ypix, c2, W.lut) > (double)(margin - 1))
+    c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
+  if ((double)sal > .95) {
+    const float kappa = beta * fmaxf(.05f, .75f - plen / 128.f) * sal;
+    c2 = bn_diffuse(pixel, qcol, kappa, strength, x, y, W.bn);
+  }
+  return c2;
+}
+
+NQ_HD float saliency_of(const SpecConst& C, const SpecWork& W, uint32_t px) {     // PL:155-156, 503-506
+  uint32_t sp = px;
+  if (C.salReplaced && (sp >> 24) <= 0xF) sp = C.transColor;
+  const Lab4 l = lab_at(sp, W.lut);
+  const float saliencyBase = .1f;
+  return saliencyBase + (1 - saliencyBase) * l.L / 100.f * l.alpha / 255.f;
+}
+
+// closestColorIndex (PL:406-474) after the top-2 scan: which entry, and whether nearestColorIndex takes over
+NQ_HD int closest_pick(const SpecConst& C, uint32_t c, unsigned k0, unsigned k1, int r, bool* needNear) {
+  const int c0 = k0 == NQS_NONE ? 0 : (int)(k0 & 255u), d0 = k0 == NQS_NONE ? 0x7fffffff : (int)(k0 >> 8);
+  const int c1 = k1 == NQS_NONE ? c0 : (int)(k1 & 255u), d1 = k1 == NQS_NONE ? 0x7fffffff : (int)(k1 >> 8);
+  int idx = 1;
+  if (d0 == 0) idx = 0;
+  else {
+    const int sum = (int)((unsigned)d1 + (unsigned)d0);
+    if ((r % sum) <= d1) idx = 0;
+  }
+  const int ci = idx ? c1 : c0, ei = idx ? d1 : d0;
+  *needNear = ei >= C.plen || ci == 0 || c_alpha(C.pal[ci]) < c_alpha(c);        // PL:470-472
+  return ci;
+}
+
+// ---- stage 1: one pixel of the curve ------------------------------------------------------------------------
+NQ_HD void stage_pre(const SpecConst& C, const SpecWork& W, int n) {
+  const uint32_t xy = W.order[n];
+  const int x = (int)(xy & 0xFFFF), y = (int)(xy >> 16);
+  const uint32_t px = W.in[x + y * C.width];
+  W.cpx[n] = px;
+  const float sal = saliency_of(C, W, px);
+  const double ypix = color_y(px, W.lut);
+  uint32_t c = px;                                         // error-dependent lookups: predict the draw with the undiffused pixel
+  unsigned flag = 0;
+  if (!(C.plen >= 256 && sal > .99f) && pre_colour(C, W, x, y, px, sal, ypix, &c)) flag |= NQS_F_PRE;   // GC:214-215
+  else c = px;
+  unsigned k0 = NQS_NONE, k1 = NQS_NONE;
+  const bool viaClosest = c_alpha(c) > 0xF;                // PL:407-408
+  if (viaClosest) {
+    top2(C, W.cells, c, &k0, &k1);
+    if ((k0 >> 8) != 0u) flag |= NQS_F_DRAW;               // short-circuit: no draw when closest[2] == 0 (PL:467)
+  }
+  W.ccol[n] = c; W.ck0[n] = k0; W.ck1[n] = k1;
+  W.cflag[n] = (unsigned char)flag;
+}
+
+// ---- stage 3: the draw, the choice between the two candidates, first-seen positions of the memo keys -------
+// (stage 2 = exclusive prefix sum of NQS_F_DRAW into cdraw). Returns false when a nextInt would have rejected.
+NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firstPosOut /* key or -1 */) {
+  *firstPosOut = -1;
+  const unsigned flag = W.cflag[n];
+  if (!(flag & NQS_F_PRE)) return true;
+  const uint32_t c = W.ccol[n];
+  bool needNear = true;
+  int qi = 0;
+  bool ok = true;
+  if (c_alpha(c) > 0xF) {
+    int r = 0;
+    if (flag & NQS_F_DRAW) {
+      bool rej;
+      r = next_int_from(lcg_jump(C.seed0, (unsigned long long)W.cdraw[n] + 1ULL), &rej);
+      ok = !rej;
+    }
+    qi = closest_pick(C, c, W.ck0[n], W.ck1[n], r, &needNear);
+  }
+  if (needNear) {
+    if (C.isNano) {
+      const int key = color_index(c, false, C.hasTrans != 0);
+      W.ck0[n] = (uint32_t)key;                            // the top-2 keys are not needed any more
+      W.cflag[n] = (unsigned char)(flag | NQS_F_NEAR);
+      *firstPosOut = key;                                  // caller: firstPos[key] = min(firstPos[key], n)
+    } else
+      W.cq[n] = (unsigned short)nearest_nomemo(C, c, W.lut);   // full-colour key: the memo is a pure cache (PL:332)
+  } else
+    W.cq[n] = (unsigned short)qi;
+  return ok;
+}
+// ---- stage 4: one memo key ------------------------------------------------------------------------------------
+NQ_HD void stage_memo(const SpecConst& C, const SpecWork& W, int key) {
+  const int n = W.firstPos[key];
+  W.memo[key] = n == NQS_NOPOS ? (unsigned short)0xFFFF : (unsigned short)nearest_nomemo(C, W.ccol[n], W.lut);
+}
+// ---- stage 5 ------------------------------------------------------------------------------------------------------
+NQ_HD void stage_fill(const SpecWork& W, int n) {
+  if (W.cflag[n] & NQS_F_NEAR) W.cq[n] = W.memo[W.ck0[n]];
+}
+// ---- patch: an error-dependent lookup at curve position state[3] created memo entry state[2] - 1 BEFORE the first
+//      pre-lookup that needs it, with another value than stage 4 gave it (PL:402: the first colour of a bucket fixes
+//      it). stage_validate has already corrected memo/firstPos; every later pre-lookup of that key is redirected and
+//      its segment re-runs. One call per pixel.
+NQ_HD void stage_patch(const SpecConst& C, const SpecWork& W, int n) {
+  const int key = W.state[2] - 1, pos = W.state[3];
+  if (key < 0 || n <= pos) return;
+  if ((W.cflag[n] & NQS_F_NEAR) && (int)W.ck0[n] == key) {
+    W.cq[n] = W.memo[key];
+    W.segs[n / C.seg].dirty = 1;                           // benign race on the device: every writer stores 1
+  }
+}
+
+// ---- stage 6: one segment ---------------------------------------------------------------------------------------
+// An error-dependent lookup (GC:214-216 with the diffused colour c2): closestColorIndex with the draw this pixel
+// was predicted to make, nearestColorIndex through the memo. `owned` = the pixel belongs to the segment (notes kept).
+NQ_HD int slow_lookup(const SpecConst& C, const SpecWork& W, SpecSeg& S, int n, uint32_t c, bool owned, int* draws) {
+  bool needNear = true;
+  int qi = 0;
+  if (c_alpha(c) > 0xF) {
+    unsigned k0, k1;
+    top2(C, W.cells, c, &k0, &k1);
+    int r = 0;
+    if ((k0 >> 8) != 0u) {
+      bool rej;
+      r = next_int_from(lcg_jump(C.seed0, (unsigned long long)W.cdraw[n] + 1ULL), &rej);
+      if (rej) S.nnotes = NQS_NOTES + 1;                   // never seen; handled as an overflow = not validated
+      ++*draws;
+    }
+    qi = closest_pick(C, c, k0, k1, r, &needNear);
+  }
+  if (!needNear) return qi;
+  if (!C.isNano) return nearest_nomemo(C, c, W.lut);
+  const int key = color_index(c, false, C.hasTrans != 0);
+  if (owned) for (int i = 0; i < S.nnotes && i < NQS_NOTES; ++i) if (S.noteKey[i] == key) return S.noteVal[i];
+  if (W.slowPos[key] < n) return W.slowVal[key];           // created by an error-dependent lookup of a validated segment
+  if (W.firstPos[key] < n || (!owned && W.firstPos[key] != NQS_NOPOS)) return W.memo[key];
+  const int v = nearest_nomemo(C, c, W.lut);               // first colour of the bucket: this lookup fixes the entry (PL:402)
+  if (owned) {
+    if (S.nnotes < NQS_NOTES) { S.noteKey[S.nnotes] = key; S.notePos[S.nnotes] = n; S.noteVal[S.nnotes] = v; }
+    ++S.nnotes;
+  }
+  return v;
+}
+
+NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
+  SpecSeg& S = W.segs[s];
+  if (S.done || !S.dirty) return;
+  const int DM = C.DM, p0 = s * C.seg, p1 = (p0 + C.seg < C.npix) ? p0 + C.seg : C.npix;
+  float e[NQ_MAXQ][4];                                     // the queue, e[head] = oldest box
+  int head = 0;
+  int from = p0;
+  if (S.exact && p0 > 0) {
+    for (int k = 0; k < DM; ++k) for (int j = 0; j < 4; ++j) e[k][j] = S.qstart[k][j];
+  } else {
+    for (int k = 0; k < DM; ++k) for (int j = 0; j < 4; ++j) e[k][j] = 0.f;
+    if (!S.exact) from = p0 - C.warm > 0 ? p0 - C.warm : 0;
+  }
+  const float fDitherMax = (float)C.ditherMax, fDitherMax1 = (float)(C.ditherMax - 1);
+  const float divisor = (float)(1 + nqm::sqrt_((double)C.ditherMax));
+  const bool illusion0 = W.bn[0] > C.thresold;             // yDiff == 1 in this mode: bn[(int)4096.0 & 4095] (GC:251-252)
+  int draws = 0;
+  S.nnotes = 0;
+  for (int n = from; n < p1; ++n) {
+    if (n == p0) {
+      for (int k = 0; k < DM; ++k) { const int q = head + k < DM ? head + k : head + k - DM; for (int j = 0; j < 4; ++j) S.qwarm[k][j] = e[q][j]; }
+      draws = 0;
+    }
+    const bool owned = n >= p0;
+    const uint32_t px = W.cpx[n];
+    // ---- error.p = pixel + sum(queue[i].p * weights[i]), oldest box first (GC:190-204)
+    float a0 = (float)c_red(px), a1 = (float)c_green(px), a2 = (float)c_blue(px), a3 = (float)c_alpha(px);
+    float maxErr = (float)(DM - 1);
+    {
+      int q = head;
+      for (int k = 0; k < DM; ++k) {
+        const float wk = C.w[k];
+        a0 = a0 + e[q][0] * wk; if (a0 > maxErr) maxErr = a0;
+        a1 = a1 + e[q][1] * wk; if (a1 > maxErr) maxErr = a1;
+        a2 = a2 + e[q][2] * wk; if (a2 > maxErr) maxErr = a2;
+        a3 = a3 + e[q][3] * wk; if (a3 > maxErr) maxErr = a3;
+        if (++q == DM) q = 0;
+      }
+    }
+    const int r_pix = (int)fminf(255.f, fmaxf(a0, 0.f)), g_pix = (int)fminf(255.f, fmaxf(a1, 0.f));
+    const int b_pix = (int)fminf(255.f, fmaxf(a2, 0.f)), a_pix = (int)fminf(255.f, fmaxf(a3, 0.f));
+    const unsigned flag = W.cflag[n];
+    const uint32_t xy = W.order[n];
+    const int x = (int)(xy & 0xFFFF), y = (int)(xy >> 16), bidx = x + y * C.width;
+    // ---- quantize (GC:211-229)
+    int qi;
+    if (flag & NQS_F_PRE) {
+      qi = W.cq[n];
+      if (flag & NQS_F_DRAW) ++draws;
+    } else {
+      const uint32_t c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
+      const float sal = saliency_of(C, W, px);
+      uint32_t c = c2;
+      if (!(C.plen >= 256 && sal > .99f)) c = slow_colour(C, W, x, y, px, sal, color_y(px, W.lut), c2);
+      qi = slow_lookup(C, W, S, n, c, owned, &draws);
+    }
+    const uint32_t pc = C.pal[qi];
+    if (owned) W.out[bidx] = pc;                           // dither == true: the palette colour (GC:278-279)
+    // ---- error of this pixel and its shaping (GC:236-264)
+    float e0 = (float)(r_pix - c_red(pc)), e1 = (float)(g_pix - c_green(pc)), e2 = (float)(b_pix - c_blue(pc)), e3 = (float)(a_pix - c_alpha(pc));
+    const bool s0 = fabsf_(e0) >= fDitherMax, s1 = fabsf_(e1) >= fDitherMax, s2 = fabsf_(e2) >= fDitherMax;
+    if (s0 || s1 || s2) {
+      if (W.bn[bidx & 4095] > C.thresold) {
+        if (s0) e0 = tanh_f((double)(e0 / maxErr * 20.f)) * fDitherMax1;
+        if (s1) e1 = tanh_f((double)(e1 / maxErr * 20.f)) * fDitherMax1;
+        if (s2) e2 = tanh_f((double)(e2 / maxErr * 20.f)) * fDitherMax1;
+      } else if (illusion0) {
+        if (s0) e0 = (float)((double)(e0 / maxErr) * 1.0) * fDitherMax1;
+        if (s1) e1 = (float)((double)(e1 / maxErr) * 1.0) * fDitherMax1;
+        if (s2) e2 = (float)((double)(e2 / maxErr) * 1.0) * fDitherMax1;
+      } else {
+        if (s0) e0 /= divisor;
+        if (s1) e1 /= divisor;
+        if (s2) e2 /= divisor;
+      }
+    }
+    // ---- errorq.poll(); errorq.add(error) (GC:231, 276)
+    e[head][0] = e0; e[head][1] = e1; e[head][2] = e2; e[head][3] = e3;
+    if (++head == DM) head = 0;
+  }
+  if (p0 >= p1) { for (int k = 0; k < DM; ++k) for (int j = 0; j < 4; ++j) S.qwarm[k][j] = e[k][j]; }
+  for (int k = 0; k < DM; ++k) { const int q = head + k < DM ? head + k : head + k - DM; for (int j = 0; j < 4; ++j) S.qout[k][j] = e[q][j]; }
+  S.draws = draws;
+  S.dirty = 0;
+}
+
+// ---- stage 7: ordered validation of one image. Returns the number of segments still open. ------------------------
+NQ_HD bool same_queue(const float (*a)[4], const float (*b)[4], int DM) {
+  for (int k = 0; k < DM; ++k)
+    for (int j = 0; j < 4; ++j)
+      if (nqm::d2bits((double)a[k][j]) != nqm::d2bits((double)b[k][j])) return false;   // widening is exact and keeps the sign of zero
+  return true;
+}
+NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
+  int s = W.state[0];
+  if (W.state[1]) return 0;
+  for (; s < C.nseg; ++s) {
+    SpecSeg& S = W.segs[s];
+    const int p0 = s * C.seg, p1 = (p0 + C.seg < C.npix) ? p0 + C.seg : C.npix;
+    bool ok = S.nnotes <= NQS_NOTES;
+    if (ok && s > 0) ok = same_queue(S.exact ? S.qstart : S.qwarm, W.segs[s - 1].qout, C.DM);
+    if (ok) {
+      // the draws of the owned pixels against the prediction every later pre-lookup was computed with
+      const int predicted = (int)(W.cdraw[p1] - W.cdraw[p0]);   // cdraw has npix + 1 entries
+      if (S.draws != predicted) { W.state[1] = 1; return 0; }
+      for (int i = 0; i < S.nnotes; ++i) {
+        const int key = S.noteKey[i], pos = S.notePos[i], val = S.noteVal[i];
+        if (W.slowPos[key] < pos && W.slowVal[key] != val) { ok = false; break; }
+      }
+    }
+    if (!ok) {
+      if (S.exact && S.nnotes > NQS_NOTES) { W.state[1] = 1; return 0; }     // even the exact run overflows its notes
+      S.exact = 1; S.dirty = 1;
+      if (s > 0) for (int k = 0; k < C.DM; ++k) for (int j = 0; j < 4; ++j) S.qstart[k][j] = W.segs[s - 1].qout[k][j];
+      break;
+    }
+    {
+      // an entry first created by an error-dependent lookup which the pre-lookups after it resolved differently:
+      // correct the memo, ask for stage_patch, and re-run this segment (its own later pixels read the entry too)
+      bool patched = false;
+      for (int i = 0; i < S.nnotes; ++i) {
+        const int key = S.noteKey[i], pos = S.notePos[i], val = S.noteVal[i];
+        if (W.slowPos[key] != NQS_NOPOS && W.slowPos[key] < pos) continue;      // agrees with an earlier entry (checked above)
+        if (W.firstPos[key] != NQS_NOPOS && W.firstPos[key] > pos && W.memo[key] != (unsigned short)val) {
+          W.memo[key] = (unsigned short)val; W.firstPos[key] = pos;
+          W.state[2] = key + 1; W.state[3] = pos;
+          S.dirty = 1;
+          patched = true;
+          break;
+        }
+      }
+      if (patched) break;
+    }
+    for (int i = 0; i < S.nnotes; ++i) {
+      const int key = S.noteKey[i], pos = S.notePos[i], val = S.noteVal[i];
+      if (W.slowPos[key] == NQS_NOPOS) { W.slowPos[key] = pos; W.slowVal[key] = (unsigned short)val; }
+    }
+    S.done = 1;
+  }
+  W.state[0] = s;
+  return C.nseg - s;
+}
+
+}  // namespace spec
+}  // namespace nq

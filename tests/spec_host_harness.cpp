@@ -1,0 +1,181 @@
+// spec_host_harness.cpp -- TEST INFRASTRUCTURE. Compiles the stage bodies of
+// nquant_android_b200/csrc/nq_dither_spec.cuh (scalar host/device functions) with g++ and runs the whole
+// speculative segment-parallel dither on the CPU, image constants taken from the oracle, result compared
+// with the oracle's sequential GilbertCurve (GC:187-280). The CUDA kernels wrap the same functions, so this
+// checks their arithmetic and the validation logic without a GPU (tests/test_spec_dither_host.py).
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <cstdio>
+#include <vector>
+#include <deque>
+#include <unordered_map>
+#include <array>
+#include <string>
+#include <algorithm>
+#include <stdexcept>
+#define private public
+#define protected public
+#define class struct
+#include "../oracle/nq_oracle.cpp"
+#undef private
+#undef protected
+#undef class
+struct uint2 { unsigned x, y; };   // CUDA vector type named by nq_types.h
+#include "../nquant_android_b200/csrc/nq_dither_spec.cuh"
+
+namespace {
+
+struct HarnessOut {
+  long long eligible = 0, exact = 0, rounds = 0, anomaly = 0, nseg = 0, segRuns = 0, slowPixels = 0, notes = 0, mismatches = 0, rejected = 0, patches = 0;
+};
+struct HarnessCfg { int seg = 4096, warm = 1024, useCells = 1; HarnessOut out; };
+HarnessCfg* g_h = nullptr;
+
+// host copy of k_build_cells (nq_dither.cuh): candidate lists per 5-5-5 RGB cell
+void build_cells(const nq::spec::SpecConst& C, std::vector<unsigned char>& cells) {
+  cells.assign((size_t)32768 * 32, 0);
+  for (int cell = 0; cell < 32768; ++cell) {
+    const int r0 = (cell >> 10) << 3, g0 = ((cell >> 5) & 31) << 3, b0 = (cell & 31) << 3;
+    int h0 = 0x7fffffff, h1 = 0x7fffffff;
+    for (int k = 0; k < C.plen; ++k) {
+      const uint32_t pc = C.pal[k];
+      const int pr = nq::c_red(pc), pg = nq::c_green(pc), pb = nq::c_blue(pc);
+      const double hi = C.Tr[std::max(std::abs(pr - r0), std::abs(pr - r0 - 7))] + C.Tg[std::max(std::abs(pg - g0), std::abs(pg - g0 - 7))] +
+                        C.Tb[std::max(std::abs(pb - b0), std::abs(pb - b0 - 7))];
+      const int d = nq::j2i(hi * (1.0 + 1e-12) + 1e-9);
+      if (d < h0) { h1 = h0; h0 = d; } else if (d < h1) h1 = d;
+    }
+    unsigned char* o = &cells[(size_t)cell * 32];
+    int cnt = 0;
+    for (int k = 0; k < C.plen; ++k) {
+      const uint32_t pc = C.pal[k];
+      const int pr = nq::c_red(pc), pg = nq::c_green(pc), pb = nq::c_blue(pc);
+      const double lo = C.Tr[std::max(0, std::max(r0 - pr, pr - r0 - 7))] + C.Tg[std::max(0, std::max(g0 - pg, pg - g0 - 7))] +
+                        C.Tb[std::max(0, std::max(b0 - pb, pb - b0 - 7))];
+      const int d = nq::j2i(lo * (1.0 - 1e-12) - 1e-9);
+      if (d <= h1) { ++cnt; if (cnt <= 31) o[cnt] = (unsigned char)k; }
+    }
+    o[0] = cnt > 31 ? 255 : (unsigned char)cnt;
+  }
+}
+
+void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std::vector<int32_t>& palette, int width, int height,
+              bool dither, double weightSigned, int nMaxColors, const std::vector<int32_t>& reference) {
+  using namespace nq::spec;
+  HarnessCfg& H = *g_h;
+  HarnessOut& R = H.out;
+  const int npix = width * height;
+  std::vector<int32_t> scratch(npix, 0);
+  PnnLABQuantizer::LabDitherable dummy(q);
+  GilbertCurve gc(width, height, cPixels, palette, scratch, dummy, q.hasSaliencies ? &q.saliencies : nullptr, weightSigned, dither);
+  const int plen = (int)palette.size();
+  // same eligibility rule as the device (k_spec_setup)
+  const int acceptedDiff = std::max(2, plen - gc.margin);
+  const bool eligible = dither && q.hasSaliencies && !gc.sortedByYDiff && !gc.hasAlpha && plen > 64 && 2 * acceptedDiff > 101;
+  R.eligible = eligible;
+  if (!eligible) return;
+
+  static SpecConst C;
+  memset(&C, 0, sizeof(C));
+  C.plen = plen; C.margin = gc.margin; C.thresold = gc.thresold; C.DM = gc.DITHER_MAX; C.ditherMax = gc.ditherMax;
+  C.width = width; C.npix = npix;
+  C.isNano = q.isNano; C.hasTrans = q.m_transparentPixelIndex >= 0; C.salReplaced = nMaxColors < 128 && nMaxColors > 2;
+  C.seg = H.seg; C.warm = H.warm; C.nseg = (npix + H.seg - 1) / H.seg;
+  C.transColor = (uint32_t)q.m_transparentColor;
+  C.gWeight = gc.weight; C.PR = q.PR; C.PG = q.PG; C.PB = q.PB; C.ratio = q.ratio;
+  C.beta = gc.beta;
+  C.seed0 = (q.rngSeed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1);
+  gc.initWeights(gc.DITHER_MAX);
+  for (int k = 0; k < C.DM; ++k) C.w[k] = gc.weights[k];
+  for (int i = 0; i < plen; ++i) C.pal[i] = (uint32_t)palette[i];
+  std::vector<double> lut(256);
+  for (int v = 0; v < 256; ++v) lut[v] = nq::gamma_to_linear(v);
+  fill_tables(C, lut.data());
+
+  OrderOnly oo;
+  oo.width = width;
+  if (width >= height) oo.gen(0, 0, width, 0, 0, height); else oo.gen(0, 0, 0, height, width, 0);
+  std::vector<uint32_t> order(npix);
+  for (int n = 0; n < npix; ++n) order[n] = (oo.out[n] % width) | ((oo.out[n] / width) << 16);
+
+  std::vector<uint32_t> in(npix), out(npix, 0), cpx(npix), ccol(npix), ck0(npix), ck1(npix), cdraw(npix + 1);
+  for (int i = 0; i < npix; ++i) in[i] = (uint32_t)cPixels[i];
+  std::vector<unsigned short> cq(npix), memo(65536, 0xFFFF), slowVal(65536, 0);
+  std::vector<unsigned char> cflag(npix), cells;
+  std::vector<int> firstPos(65536, NQS_NOPOS), slowPos(65536, NQS_NOPOS), state(4, 0);
+  std::vector<SpecSeg> segs(C.nseg);
+  memset(segs.data(), 0, sizeof(SpecSeg) * segs.size());
+  for (auto& s : segs) s.dirty = 1;
+  segs[0].exact = 1;
+  if (H.useCells) build_cells(C, cells);
+  static const signed char bn[4096] = NQ_BLUE_NOISE_INIT;
+
+  SpecWork W;
+  W.order = order.data(); W.in = in.data(); W.out = out.data(); W.cpx = cpx.data(); W.ccol = ccol.data(); W.ck0 = ck0.data(); W.ck1 = ck1.data();
+  W.cq = cq.data(); W.cflag = cflag.data(); W.cdraw = cdraw.data(); W.firstPos = firstPos.data(); W.memo = memo.data();
+  W.slowPos = slowPos.data(); W.slowVal = slowVal.data(); W.cells = H.useCells ? cells.data() : nullptr; W.lut = lut.data(); W.bn = bn;
+  W.segs = segs.data(); W.state = state.data();
+
+  for (int n = 0; n < npix; ++n) stage_pre(C, W, n);                                     // stage 1
+  { uint32_t d = 0; for (int n = 0; n < npix; ++n) { cdraw[n] = d; d += (cflag[n] & NQS_F_DRAW) ? 1u : 0u; } cdraw[npix] = d; }   // stage 2
+  for (int n = 0; n < npix; ++n) {                                                       // stage 3
+    int key;
+    if (!stage_resolve(C, W, n, &key)) { ++R.rejected; state[1] = 1; }
+    if (key >= 0 && n < firstPos[key]) firstPos[key] = n;
+    if (!(cflag[n] & NQS_F_PRE)) ++R.slowPixels;
+  }
+  for (int key = 0; key < 65536; ++key) stage_memo(C, W, key);                           // stage 4
+  for (int n = 0; n < npix; ++n) stage_fill(W, n);                                       // stage 5
+  R.nseg = C.nseg;
+  int open = C.nseg;
+  while (open > 0 && !state[1] && R.rounds < 100000) {
+    ++R.rounds;
+    for (int s = 0; s < C.nseg; ++s) { if (!segs[s].done && segs[s].dirty) ++R.segRuns; stage_run(C, W, s); }   // stage 6
+    open = stage_validate(C, W);                                                         // stage 7
+    if (state[2]) { ++R.patches; for (int n = 0; n < npix; ++n) stage_patch(C, W, n); state[2] = 0; }
+  }
+  R.anomaly = state[1];
+  for (auto& s : segs) R.notes += std::min(s.nnotes, NQS_NOTES);
+  if (!state[1]) {
+    for (int i = 0; i < npix; ++i) R.mismatches += out[i] != (uint32_t)reference[i];
+    R.exact = R.mismatches == 0;
+  }
+}
+
+struct HostLab : PnnLABQuantizer {
+  using PnnLABQuantizer::PnnLABQuantizer;
+  int nMax = 0;
+  std::vector<int32_t> ditherImage(const std::vector<int32_t>& cPixels, std::vector<int32_t>& palette, int width, int height, bool dither) override {
+    const double w0 = weight;
+    std::vector<int32_t> ref = PnnLABQuantizer::ditherImage(cPixels, palette, width, height, dither);
+    weight = w0;
+    const double ws = hasSemiTransparency ? -weight : weight;
+    run_spec(*this, cPixels, palette, width, height, dither, ws, nMax, ref);
+    return ref;
+  }
+};
+
+}  // namespace
+
+extern "C" int nqs_spec_host(const uint32_t* argb, int w, int h, int nmax, int dither, uint64_t seed, int seg, int warm, int useCells,
+                             long long* out /* 11 values */) {
+  HarnessCfg cfg;
+  cfg.seg = seg; cfg.warm = warm; cfg.useCells = useCells;
+  g_h = &cfg;
+  M.mode = 0;
+  try {
+    HostLab q(argb, w, h);
+    q.rngSeed = seed; q.nMax = nmax;
+    q.convert(nmax, dither != 0);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "spec host harness: %s\n", e.what());
+    g_h = nullptr;
+    return -1;
+  }
+  const HarnessOut& R = cfg.out;
+  long long v[11] = {R.eligible, R.exact, R.rounds, R.anomaly, R.nseg, R.segRuns, R.slowPixels, R.notes, R.mismatches, R.rejected, R.patches};
+  memcpy(out, v, sizeof(v));
+  g_h = nullptr;
+  return 0;
+}

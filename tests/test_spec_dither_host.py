@@ -1,0 +1,61 @@
+"""The stage bodies of csrc/nq_dither_spec.cuh (speculative segment-parallel Gilbert dither) are scalar
+host/device functions: compiled here with g++ and run as a whole pipeline on the CPU, they must reproduce
+the oracle's sequential GilbertCurve bit for bit (tests/spec_host_harness.cpp). No GPU involved; the CUDA
+kernels wrap the same functions and get their own parity tests under -m gpu."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from nquant_android_b200.synth import make_image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "build", "libnq_spec_host.so")
+SRC = os.path.join(ROOT, "tests", "spec_host_harness.cpp")
+DEPS = [SRC, os.path.join(ROOT, "oracle", "nq_oracle.cpp"), os.path.join(ROOT, "nquant_android_b200", "csrc", "nq_dither_spec.cuh"),
+        os.path.join(ROOT, "nquant_android_b200", "csrc", "nq_color.h"), os.path.join(ROOT, "nquant_android_b200", "csrc", "nq_math.h")]
+KEYS = ["eligible", "exact", "rounds", "anomaly", "nseg", "segRuns", "slowPixels", "notes", "mismatches", "rejected", "patches"]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in DEPS):
+        fma = ["-mfma"] if " fma " in open("/proc/cpuinfo").read() else []
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w"] + fma +
+                              ["-o", SO, SRC])
+    L = ctypes.CDLL(SO)
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    L.nqs_spec_host.argtypes = [vp, ci, ci, ci, ci, ctypes.c_uint64, ci, ci, ci, vp]
+    return L
+
+
+def run(L, w, h, nmax, cls, alpha, seg, warm, cells=1, seed=0xC0FFEE, img_seed=0x5EED0000):
+    img = np.ascontiguousarray(make_image(w, h, cls, alpha, seed=img_seed))
+    out = np.zeros(11, np.int64)
+    assert L.nqs_spec_host(img.ctypes.data, w, h, nmax, 1, seed, seg, warm, cells, out.ctypes.data) == 0
+    return dict(zip(KEYS, [int(v) for v in out]))
+
+
+@pytest.mark.parametrize("w,h,nmax,cls,alpha,seg,warm,cells", [
+    (256, 256, 256, "noisy", "opaque", 4096, 1024, 1),      # headline class; error-dependent lookups at the bright corner
+    (256, 256, 256, "noisy", "opaque", 4096, 1024, 0),      # same without the candidate lists
+    (256, 192, 256, "rand", "opaque", 2048, 512, 1),
+    (320, 180, 128, "noisy", "opaque", 2048, 512, 1),
+    (256, 256, 256, "noisy", "transparent", 4096, 1024, 1),  # a transparent colour: palette[0], k = 1 start of the scans
+    (173, 211, 200, "noisy", "opaque", 1000, 300, 1),        # ragged sizes, warm-up too short for some segments: re-runs
+])
+def test_spec_pipeline_matches_sequential_oracle(lib, w, h, nmax, cls, alpha, seg, warm, cells):
+    r = run(lib, w, h, nmax, cls, alpha, seg, warm, cells)
+    assert r["eligible"] == 1
+    assert r["anomaly"] == 0 and r["rejected"] == 0
+    assert r["mismatches"] == 0 and r["exact"] == 1, r
+    assert r["rounds"] >= 1 and r["segRuns"] >= r["nseg"]
+
+
+def test_spec_declines_what_it_does_not_cover(lib):
+    # smooth class -> PriorityQueue mode (GC:87-94); 16 colours -> lookups read the diffused colour
+    assert run(lib, 128, 128, 256, "smooth", "opaque", 2048, 512)["eligible"] == 0
+    assert run(lib, 128, 128, 16, "noisy", "opaque", 2048, 512)["eligible"] == 0
