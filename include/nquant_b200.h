@@ -126,6 +126,15 @@ int nq_get_image_info(nq_ctx* ctx, int image, nq_image_info* out);
 /* sizeof(nq_image_info) as the library was built: lets a binding check its own mirror of the struct. */
 int nq_sizeof_image_info(void);
 
+/* Speculative segment-parallel error diffusion (csrc/nq_dither_spec.cuh) for PnnLABQuantizer images with more than 64
+ * colours, dither on, no transparency: GilbertCurve.dither (GilbertCurve.java:367-373) is cut into `segment`-pixel
+ * pieces of the curve that start from an empty error queue `warmup` pixels early and are validated, in curve order,
+ * against the exact state of their predecessor (bit-identical results by construction; images it cannot finish go
+ * through the serial kernel). Off by default (or NQ_SPEC_DITHER=1 in the environment at nq_create).
+ * nq_get_spec_stats: images completed by this path and validation rounds since the context was created. */
+int nq_set_spec_dither(nq_ctx* ctx, int on, int segment, int warmup);
+int nq_get_spec_stats(nq_ctx* ctx, unsigned long long* images, unsigned long long* rounds);
+
 /* When enabled (flag != 0) the next calls keep, per image, the compacted bins before merging, the
  * initial find_nn results and the merge sequence, retrievable below. Costs memory and a few copies. */
 int nq_set_debug(nq_ctx* ctx, int flag);

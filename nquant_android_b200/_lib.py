@@ -12,6 +12,7 @@ SYMBOLS = [
     "nq_convert_batch_device", "nq_dither_with_palette", "nq_gilbert_order", "nq_get_image_info", "nq_set_debug",
     "nq_debug_get_bins", "nq_debug_get_merges", "nq_debug_get_saliencies", "nq_kernel_launches", "nq_debug_math",
     "nq_synth_device", "nq_get_stage_times", "nq_set_stream", "nq_debug_ciede", "nq_sizeof_image_info",
+    "nq_set_spec_dither", "nq_get_spec_stats",
 ]
 
 NQ_KIND_PNN, NQ_KIND_PNNLAB = 0, 1
@@ -76,6 +77,8 @@ def load():
     L.nq_debug_ciede.argtypes = [vp, vp, vp, vp, vp, ci]
     L.nq_get_stage_times.argtypes = [vp, vp, vp, ci]
     L.nq_synth_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, u64]
+    L.nq_set_spec_dither.argtypes = [vp, ci, ci, ci]
+    L.nq_get_spec_stats.argtypes = [vp, vp, vp]
     for s in SYMBOLS:
         getattr(L, s)
     if L.nq_sizeof_image_info() != ctypes.sizeof(ImageInfo):

@@ -20,6 +20,7 @@
 #include "nq_hist.cuh"
 #include "nq_pnn.cuh"
 #include "nq_dither.cuh"
+#include "nq_dither_spec.cuh"
 
 #define NQ_NSTAGES 6   // scan, histogram, find_nn sweep, merge, dither setup + saliency, dither
 
@@ -188,6 +189,16 @@ struct nq_ctx {
   cudaEvent_t ev[NQ_NSTAGES + 1] = {};
   double stageMs[NQ_NSTAGES] = {};
   unsigned long long stageLaunches[NQ_NSTAGES] = {};
+  // speculative segment-parallel dither (nq_dither_spec.cuh); off unless nq_set_spec_dither / NQ_SPEC_DITHER=1
+  bool specDither = false;
+  int specSeg = 8192, specWarm = 1024;
+  nq::spec::SpecImage* dSpec = nullptr;
+  int specCap = 0;                 // images dSpec holds
+  unsigned char* specBuf = nullptr;
+  size_t specBufBytes = 0;
+  int* dSpecInts = nullptr;        // [0..1] round counters, [2..] eligibility per image
+  int specIntsCap = 0;
+  unsigned long long specImages = 0, specRounds = 0, specFallbacks = 0;
   // results of the last batch
   std::vector<NqImage> lastImgs;
   std::vector<DebugImage> dbg;
@@ -315,6 +326,95 @@ int pixel_grid_x(const nq_ctx* c, int npix, int nimg) {
   return std::max(1, std::min(want, cap));
 }
 
+// Speculative segment-parallel dither for the images that qualify (decided on the device, k_spec_setup). Images it
+// completes get NqImage::specDone and are skipped by k_dither_fifo; every other image is untouched.
+int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
+  using namespace nq::spec;
+  cudaStream_t st = c->stream;
+  const int seg = c->specSeg, warm = c->specWarm;
+  const int nseg = (npix + seg - 1) / seg;
+  if (npix < 4 * seg) return NQ_OK;
+  if (c->specCap < n) {
+    if (c->dSpec) cudaFree(c->dSpec);
+    c->dSpec = nullptr; c->specCap = 0;
+    CU(cudaMalloc(&c->dSpec, sizeof(SpecImage) * (size_t)n));
+    c->specCap = n;
+  }
+  if (c->specIntsCap < n + 2) {
+    if (c->dSpecInts) cudaFree(c->dSpecInts);
+    c->dSpecInts = nullptr; c->specIntsCap = 0;
+    CU(cudaMalloc(&c->dSpecInts, sizeof(int) * (size_t)(n + 2)));
+    c->specIntsCap = n + 2;
+  }
+  // work arrays of one wave slot
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  const size_t oCpx = take((size_t)npix * 4), oCol = take((size_t)npix * 4), oK0 = take((size_t)npix * 4), oK1 = take((size_t)npix * 4);
+  const size_t oDraw = take(((size_t)npix + 1) * 4), oQ = take((size_t)npix * 2), oFlag = take((size_t)npix);
+  const size_t oFirst = take(65536 * 4), oSlowPos = take(65536 * 4), oMemo = take(65536 * 2), oSlowVal = take(65536 * 2);
+  const size_t oSegs = take(sizeof(SpecSeg) * (size_t)nseg), oState = take(64);
+  const size_t perSlot = o;
+  size_t freeB = 0, totalB = 0;
+  CU(cudaMemGetInfo(&freeB, &totalB));
+  const size_t budget = (size_t)((double)(freeB + c->specBufBytes) * 0.8);
+  const int wave = (int)std::min<size_t>((size_t)n, budget / perSlot);
+  if (wave < 1) return NQ_OK;                       // no room: the serial kernel does the work
+  if (c->specBufBytes < perSlot * (size_t)wave) {
+    if (c->specBuf) cudaFree(c->specBuf);
+    c->specBuf = nullptr; c->specBufBytes = 0;
+    CU(cudaMalloc(&c->specBuf, perSlot * (size_t)wave));
+    c->specBufBytes = perSlot * (size_t)wave;
+  }
+  std::vector<SpecImage> h(n);
+  memset(h.data(), 0, sizeof(SpecImage) * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    unsigned char* b = c->specBuf + perSlot * (size_t)(i % wave);
+    SpecWork& W = h[i].W;
+    W.cpx = reinterpret_cast<uint32_t*>(b + oCpx); W.ccol = reinterpret_cast<uint32_t*>(b + oCol);
+    W.ck0 = reinterpret_cast<uint32_t*>(b + oK0); W.ck1 = reinterpret_cast<uint32_t*>(b + oK1);
+    W.cdraw = reinterpret_cast<uint32_t*>(b + oDraw); W.cq = reinterpret_cast<unsigned short*>(b + oQ); W.cflag = b + oFlag;
+    W.firstPos = reinterpret_cast<int*>(b + oFirst); W.slowPos = reinterpret_cast<int*>(b + oSlowPos);
+    W.memo = reinterpret_cast<unsigned short*>(b + oMemo); W.slowVal = reinterpret_cast<unsigned short*>(b + oSlowVal);
+    W.segs = reinterpret_cast<SpecSeg*>(b + oSegs); W.state = reinterpret_cast<int*>(b + oState);
+  }
+  CU(cudaMemcpyAsync(c->dSpec, h.data(), sizeof(SpecImage) * (size_t)n, cudaMemcpyHostToDevice, st));
+  k_spec_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, c->dSpec, dOrder, n, seg, warm, c->dSpecInts + 2); ++c->launches;
+  std::vector<int> elig(n);
+  CU(cudaMemcpyAsync(elig.data(), c->dSpecInts + 2, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));                    // also keeps `h` alive until the copy is done
+  const int roundCap = nseg / 4 + 16;
+  for (int base = 0; base < n; base += wave) {
+    const int m = std::min(wave, n - base);
+    int any = 0;
+    for (int i = 0; i < m; ++i) any += elig[base + i];
+    if (!any) continue;
+    SpecImage* sp = c->dSpec + base;
+    const int gx = pixel_grid_x(c, npix, m);
+    const dim3 pg(gx, m), kg(8, m);
+    k_spec_init<<<kg, 256, 0, st>>>(sp); ++c->launches;
+    k_spec_pre<<<pg, 256, 0, st>>>(sp); ++c->launches;
+    k_spec_scan<<<m, 1024, 0, st>>>(sp); ++c->launches;
+    k_spec_resolve<<<pg, 256, 0, st>>>(sp); ++c->launches;
+    k_spec_memo<<<kg, 256, 0, st>>>(sp); ++c->launches;
+    k_spec_fill<<<pg, 256, 0, st>>>(sp); ++c->launches;
+    for (int round = 0; round < roundCap; ++round) {
+      CU(cudaMemsetAsync(c->dSpecInts, 0, 2 * sizeof(int), st));
+      k_spec_run<<<dim3((nseg + 63) / 64, m), 64, 0, st>>>(sp); ++c->launches;
+      k_spec_validate<<<(m + 63) / 64, 64, 0, st>>>(sp, m, c->dSpecInts); ++c->launches;
+      int counters[2] = {0, 0};
+      CU(cudaMemcpyAsync(counters, c->dSpecInts, sizeof(counters), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      ++c->specRounds;
+      if (counters[1]) { k_spec_patch<<<pg, 256, 0, st>>>(sp); ++c->launches; }
+      if (!counters[0]) break;
+    }
+    k_spec_finish<<<(m + 63) / 64, 64, 0, st>>>(c->dImgs + base, sp, m); ++c->launches;
+    c->specImages += (unsigned long long)any;
+  }
+  CU(cudaGetLastError());
+  return NQ_OK;
+}
+
 // Runs convert() for images [0, n) already resident on the device. palIn != nullptr replaces the
 // palette before dithering (stage hook).
 int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, int w, int h, int nmax, int dither,
@@ -435,6 +535,10 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
   if (kind == NQ_KIND_LAB && c->debug) { nq::k_saliency<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches; }
   if (kind == NQ_KIND_LAB) { nq::k_build_cells<<<dim3(std::max(1, std::min(128, c->smCount * 8 / n)), n), 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches; }
   mark(5);
+  if (c->specDither && kind == NQ_KIND_LAB && dither) {
+    rc = run_spec_dither(c, n, npix, dOrder);
+    if (rc) return rc;
+  }
   // each kernel returns at once for images of the other queue mode (decided on the device)
   {  // images whose lookups stay on the serial chain (PnnQuantizer; dither == false) get a shared-memory memo cache
     const int cacheBytes = (kind == NQ_KIND_RGB || !dither) ? 32768 : 0;
@@ -547,6 +651,7 @@ nq_ctx* nq_create(int device) {
   if (cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking) == cudaSuccess) c->stream = c->ownStream;
   else { fail(NQ_ERR_CUDA, "cudaStreamCreate failed"); delete c; return nullptr; }
   for (int k = 0; k <= NQ_NSTAGES; ++k) cudaEventCreate(&c->ev[k]);
+  if (const char* e = getenv("NQ_SPEC_DITHER")) c->specDither = atoi(e) != 0;
   signed char* dBn = nullptr;
   bool ok = cudaMalloc(&dBn, 4096) == cudaSuccess && cudaMemcpy(dBn, kBlueNoise, 4096, cudaMemcpyHostToDevice) == cudaSuccess;
   if (ok) {
@@ -595,6 +700,9 @@ void nq_destroy(nq_ctx* c) {
   if (c->ws) cudaFree(c->ws);
   if (c->dIn) cudaFree(c->dIn);
   if (c->dOut) cudaFree(c->dOut);
+  if (c->dSpec) cudaFree(c->dSpec);
+  if (c->specBuf) cudaFree(c->specBuf);
+  if (c->dSpecInts) cudaFree(c->dSpecInts);
   for (int k = 0; k <= NQ_NSTAGES; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
   if (c->ownStream) cudaStreamDestroy(c->ownStream);
   delete c;
@@ -682,6 +790,20 @@ int nq_sizeof_image_info(void) { return (int)sizeof(nq_image_info); }
 int nq_set_stream(nq_ctx* c, void* stream) {
   if (!c) return fail(NQ_ERR_ARG, "null context");
   c->stream = stream ? reinterpret_cast<cudaStream_t>(stream) : c->ownStream;
+  return NQ_OK;
+}
+
+int nq_set_spec_dither(nq_ctx* c, int on, int segment, int warmup) {
+  if (!c) return fail(NQ_ERR_ARG, "null context");
+  if (on && (segment < 64 || warmup < 0 || warmup > (1 << 24))) return fail(NQ_ERR_ARG, "segment must be >= 64 pixels and warm-up >= 0");
+  c->specDither = on != 0;
+  if (on) { c->specSeg = segment; c->specWarm = warmup; }
+  return NQ_OK;
+}
+int nq_get_spec_stats(nq_ctx* c, unsigned long long* images, unsigned long long* rounds) {
+  if (!c) return fail(NQ_ERR_ARG, "null context");
+  if (images) *images = c->specImages;
+  if (rounds) *rounds = c->specRounds;
   return NQ_OK;
 }
 

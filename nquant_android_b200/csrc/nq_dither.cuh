@@ -978,7 +978,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
   const NqSlot& S = slots[img];
   const unsigned lane = lane_id();
   const int plen = I.paletteLen;
-  if (plen <= 0 || I.error || I.gSorted) return;
+  if (plen <= 0 || I.error || I.gSorted || I.specDone) return;
   DitherCtx D;
   const bool producer = threadIdx.x >= 32;
   if (cacheBytes) for (int i = threadIdx.x; i < 16384; i += 64) dynCache[i] = 0;

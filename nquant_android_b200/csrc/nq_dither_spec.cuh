@@ -79,7 +79,7 @@ struct SpecWork {
   const double* lut;                     // gammaToLinear table
   const signed char* bn;                 // TELL_BLUE_NOISE
   SpecSeg* segs;
-  int* state;                            // [4]: firstOpen, anomaly, patch key + 1 (0 = none), patch position
+  int* state;                            // [8]: firstOpen, anomaly, patch key + 1 (0 = none), patch position, failed validations
 };
 
 // ---- java.util.Random: state after j more steps of the LCG ------------------------------------------------
@@ -530,6 +530,8 @@ NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
     }
     if (!ok) {
       if (S.exact && S.nnotes > NQS_NOTES) { W.state[1] = 1; return 0; }     // even the exact run overflows its notes
+      // every failure costs a round in which one segment runs alone: past a quarter of the segments the serial kernel is cheaper
+      if (++W.state[4] > (C.nseg >> 2) + 4) { W.state[1] = 1; return 0; }
       S.exact = 1; S.dirty = 1;
       if (s > 0) for (int k = 0; k < C.DM; ++k) for (int j = 0; j < 4; ++j) S.qstart[k][j] = W.segs[s - 1].qout[k][j];
       break;
@@ -560,6 +562,135 @@ NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
   W.state[0] = s;
   return C.nseg - s;
 }
+
+#if defined(__CUDACC__)
+// =====================================================================================================================
+// Kernels: indexing only, every body is one of the stage functions above. One SpecImage per image of the batch;
+// the work arrays of image i live in wave slot i % wave (nq_api.cu), waves run one after the other.
+// =====================================================================================================================
+struct SpecImage {
+  SpecConst C;
+  SpecWork W;
+  int eligible;
+};
+#define NQS_ACTIVE(P) ((P).eligible && !(P).W.state[1])
+
+// GilbertCurve / quantizer constants of every image, and which images this path takes (one thread per image)
+__global__ void k_spec_setup(const NqImage* imgs, const NqSlot* slots, SpecImage* sp, const uint32_t* order, int nimg, int seg, int warm, int* eligOut) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nimg) return;
+  const NqImage& I = imgs[i];
+  SpecImage& P = sp[i];
+  SpecConst& C = P.C;
+  const int plen = I.paletteLen;
+  const int acceptedDiff = max(2, plen - I.gMargin);
+  // PnnLABQuantizer, dither on, saliency map, ArrayDeque queue, opaque image (a transparent pixel leaves a constant alpha
+  // error in the queue for ever: alpha is never shaped, GC:248), ditherPixel lookups independent of the diffused colour
+  P.eligible = I.kind == NQ_KIND_LAB && I.dither && I.gUseSal && !I.gSorted && !I.gHasAlpha && !I.hasSemi && I.transIdx < 0 && !I.error &&
+               plen > 64 && 2 * acceptedDiff > 101 && I.gDitherMaxQ > 9 && I.nmax > 2 && slots[i].cells != nullptr && I.npix >= 4 * seg;
+  eligOut[i] = P.eligible;
+  if (!P.eligible) return;
+  C.plen = plen; C.margin = I.gMargin; C.thresold = I.gThresold; C.DM = I.gDitherMaxQ; C.ditherMax = I.gDitherMax;
+  C.width = I.width; C.npix = I.npix;
+  C.isNano = I.isNano; C.hasTrans = I.transIdx >= 0; C.salReplaced = I.nmax < 128 && I.nmax > 2;
+  C.seg = seg; C.warm = warm; C.nseg = (I.npix + seg - 1) / seg;
+  C.transColor = I.transColor;
+  C.gWeight = I.gWeight; C.PR = I.PR; C.PG = I.PG; C.PB = I.PB; C.ratio = I.ratioMerge;
+  C.beta = I.gBeta;
+  JRandom r; r.set_seed(I.seed);
+  C.seed0 = r.seed;
+  for (int k = 0; k < NQ_MAXQ; ++k) C.w[k] = k < C.DM ? I.gWeights[k] : 0.f;
+  for (int k = 0; k < plen; ++k) C.pal[k] = I.palette[k];
+  P.W.order = order; P.W.in = slots[i].in; P.W.out = slots[i].out; P.W.cells = slots[i].cells;
+  P.W.lut = g_gammaLut; P.W.bn = g_blueNoise;
+  fill_tables(C, g_gammaLut);
+}
+// memo tables, segment records, state (grid: x strides, y = image)
+__global__ void __launch_bounds__(256) k_spec_init(SpecImage* sp) {
+  SpecImage& P = sp[blockIdx.y];
+  if (!P.eligible) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  for (int k = t; k < 65536; k += nt) { P.W.firstPos[k] = NQS_NOPOS; P.W.slowPos[k] = NQS_NOPOS; P.W.memo[k] = 0xFFFF; P.W.slowVal[k] = 0; }
+  for (int s = t; s < P.C.nseg; s += nt) { SpecSeg& S = P.W.segs[s]; S.exact = s == 0; S.dirty = 1; S.done = 0; S.draws = 0; S.nnotes = 0; }
+  if (t < 8) P.W.state[t] = 0;
+}
+__global__ void __launch_bounds__(256) k_spec_pre(SpecImage* sp) {
+  const SpecImage& P = sp[blockIdx.y];
+  if (!P.eligible) return;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_pre(P.C, P.W, n);
+}
+// stage 2: exclusive prefix sum of the predicted draws, one CTA of 1024 threads per image, 8 pixels per thread and tile
+__global__ void __launch_bounds__(1024) k_spec_scan(SpecImage* sp) {
+  __shared__ int sWarp[33];
+  const SpecImage& P = sp[blockIdx.x];
+  if (!P.eligible) return;
+  const int npix = P.C.npix;
+  unsigned carry = 0;
+  for (int base = 0; base < npix; base += 8192) {
+    const int n0 = base + (int)threadIdx.x * 8;
+    unsigned bits = 0;
+    for (int k = 0; k < 8; ++k) if (n0 + k < npix && (P.W.cflag[n0 + k] & NQS_F_DRAW)) bits |= 1u << k;
+    int total;
+    const int excl = block_excl_scan_1024(__popc(bits), &total, sWarp);
+    unsigned d = carry + (unsigned)excl;
+    for (int k = 0; k < 8; ++k) if (n0 + k < npix) { P.W.cdraw[n0 + k] = d; d += (bits >> k) & 1u; }
+    carry += (unsigned)total;
+  }
+  if (threadIdx.x == 0) P.W.cdraw[npix] = carry;
+}
+__global__ void __launch_bounds__(256) k_spec_resolve(SpecImage* sp) {
+  const SpecImage& P = sp[blockIdx.y];
+  if (!P.eligible) return;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) {
+    int key;
+    if (!stage_resolve(P.C, P.W, n, &key)) P.W.state[1] = 1;      // a nextInt that draws twice (2 in 2^31): leave the image to the serial kernel
+    if (key >= 0) atomicMin(&P.W.firstPos[key], n);
+  }
+}
+__global__ void __launch_bounds__(256) k_spec_memo(SpecImage* sp) {
+  const SpecImage& P = sp[blockIdx.y];
+  if (!NQS_ACTIVE(P)) return;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 65536; k += gridDim.x * blockDim.x) stage_memo(P.C, P.W, k);
+}
+__global__ void __launch_bounds__(256) k_spec_fill(SpecImage* sp) {
+  const SpecImage& P = sp[blockIdx.y];
+  if (!NQS_ACTIVE(P)) return;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_fill(P.W, n);
+}
+// stage 6: one thread per segment
+__global__ void __launch_bounds__(64) k_spec_run(SpecImage* sp) {
+  const SpecImage& P = sp[blockIdx.y];
+  if (!NQS_ACTIVE(P)) return;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < P.C.nseg) stage_run(P.C, P.W, s);
+}
+// stage 7: one thread per image; counters[0] += images with open segments, counters[1] += patch requests
+__global__ void k_spec_validate(SpecImage* sp, int nimg, int* counters) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nimg) return;
+  const SpecImage& P = sp[i];
+  if (!NQS_ACTIVE(P)) return;
+  P.W.state[2] = 0;
+  const int open = stage_validate(P.C, P.W);
+  if (open > 0 && !P.W.state[1]) atomicAdd(&counters[0], 1);
+  if (P.W.state[2]) atomicAdd(&counters[1], 1);
+}
+__global__ void __launch_bounds__(256) k_spec_patch(SpecImage* sp) {
+  const SpecImage& P = sp[blockIdx.y];
+  if (!NQS_ACTIVE(P) || !P.W.state[2]) return;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_patch(P.C, P.W, n);
+}
+// images that were completed here are skipped by k_dither_fifo; the others (not eligible, contradicted, round cap) are not
+__global__ void k_spec_finish(NqImage* imgs, SpecImage* sp, int nimg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nimg) return;
+  const SpecImage& P = sp[i];
+  if (NQS_ACTIVE(P) && P.W.state[0] == P.C.nseg) {
+    imgs[i].specDone = 1;
+    imgs[i].rngDraws = P.W.cdraw[P.C.npix];
+  }
+}
+#endif  // __CUDACC__
 
 }  // namespace spec
 }  // namespace nq

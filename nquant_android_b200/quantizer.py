@@ -92,6 +92,16 @@ class Context:
         """Run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None restores our own."""
         self._check(self._L.nq_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
 
+    def set_spec_dither(self, on, segment=8192, warmup=1024):
+        """Speculative segment-parallel error diffusion for the images that qualify (include/nquant_b200.h); results are
+        bit-identical either way."""
+        self._check(self._L.nq_set_spec_dither(self._h, int(bool(on)), int(segment), int(warmup)))
+
+    def spec_stats(self):
+        images, rounds = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        self._check(self._L.nq_get_spec_stats(self._h, ctypes.byref(images), ctypes.byref(rounds)))
+        return {"images": images.value, "rounds": rounds.value}
+
     # -- introspection ------------------------------------------------------------------------------
     def set_debug(self, flag):
         self._check(self._L.nq_set_debug(self._h, int(bool(flag))))

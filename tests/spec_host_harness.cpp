@@ -7,6 +7,7 @@
 #include <cstring>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include <deque>
 #include <unordered_map>
@@ -72,7 +73,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   const int plen = (int)palette.size();
   // same eligibility rule as the device (k_spec_setup)
   const int acceptedDiff = std::max(2, plen - gc.margin);
-  const bool eligible = dither && q.hasSaliencies && !gc.sortedByYDiff && !gc.hasAlpha && plen > 64 && 2 * acceptedDiff > 101;
+  const bool eligible = dither && q.hasSaliencies && !gc.sortedByYDiff && !gc.hasAlpha && plen > 64 && 2 * acceptedDiff > 101 && gc.DITHER_MAX > 9 && q.m_transparentPixelIndex < 0;
   R.eligible = eligible;
   if (!eligible) return;
 
@@ -103,7 +104,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   for (int i = 0; i < npix; ++i) in[i] = (uint32_t)cPixels[i];
   std::vector<unsigned short> cq(npix), memo(65536, 0xFFFF), slowVal(65536, 0);
   std::vector<unsigned char> cflag(npix), cells;
-  std::vector<int> firstPos(65536, NQS_NOPOS), slowPos(65536, NQS_NOPOS), state(4, 0);
+  std::vector<int> firstPos(65536, NQS_NOPOS), slowPos(65536, NQS_NOPOS), state(8, 0);
   std::vector<SpecSeg> segs(C.nseg);
   memset(segs.data(), 0, sizeof(SpecSeg) * segs.size());
   for (auto& s : segs) s.dirty = 1;
@@ -133,6 +134,14 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
     ++R.rounds;
     for (int s = 0; s < C.nseg; ++s) { if (!segs[s].done && segs[s].dirty) ++R.segRuns; stage_run(C, W, s); }   // stage 6
     open = stage_validate(C, W);                                                         // stage 7
+    if (getenv("NQ_SPEC_DEBUG") && open > 0 && !state[1]) {
+      const int s = state[0];
+      int diff = 0;
+      if (s > 0) for (int k = 0; k < C.DM; ++k) for (int j = 0; j < 4; ++j) diff += segs[s].qwarm[k][j] != segs[s - 1].qout[k][j];
+      fprintf(stderr, "round %lld: stopped at segment %d (exact %d, notes %d, %d queue floats differ from the predecessor's)\n", R.rounds, s, segs[s].exact, segs[s].nnotes, diff);
+      if (s > 0 && R.rounds < 3) for (int k = 0; k < C.DM; ++k) fprintf(stderr, "  box %2d warm (%g %g %g %g) prev (%g %g %g %g)\n", k, segs[s].qwarm[k][0], segs[s].qwarm[k][1], segs[s].qwarm[k][2], segs[s].qwarm[k][3],
+          segs[s - 1].qout[k][0], segs[s - 1].qout[k][1], segs[s - 1].qout[k][2], segs[s - 1].qout[k][3]);
+    }
     if (state[2]) { ++R.patches; for (int n = 0; n < npix; ++n) stage_patch(C, W, n); state[2] = 0; }
   }
   R.anomaly = state[1];
