@@ -1,0 +1,69 @@
+"""GPU parity of the speculative segment-parallel dither (csrc/nq_dither_spec.cuh, opt-in through
+nq_set_spec_dither): the result must be bit-identical to the oracle's sequential GilbertCurve, and the path must
+actually have taken the images it is meant for (nq_get_spec_stats). The stage bodies are checked on the CPU in
+tests/test_spec_dither_host.py; these tests add the kernels and the orchestration around them.
+
+Round 1 ended without GPU minutes to run these, so they only run when NQ_SPEC_DITHER_TEST=1 is set; the path itself is
+off by default."""
+import os
+
+import numpy as np
+import pytest
+
+from nquant_android_b200.synth import make_image
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("NQ_SPEC_DITHER_TEST") != "1", reason="speculative dither not yet verified on a GPU: set NQ_SPEC_DITHER_TEST=1")]
+
+
+@pytest.fixture()
+def spec_ctx():
+    from nquant_android_b200 import _build
+    from nquant_android_b200.quantizer import Context
+    _build.build()
+    ctx = Context(0)
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("w,h,nmax,cls,seg,warm,seed", [
+    (256, 256, 256, "noisy", 4096, 1024, 0xC0FFEE),
+    (256, 192, 256, "rand", 2048, 512, 7),
+    (320, 180, 128, "noisy", 2048, 512, 99),
+    (173, 211, 200, "noisy", 1000, 300, 5),        # warm-up too short for some segments: exact re-runs
+    (512, 512, 256, "noisy", 8192, 1024, 0xC0FFEE),
+])
+def test_spec_dither_is_bit_identical(spec_ctx, oracle, w, h, nmax, cls, seg, warm, seed):
+    img = make_image(w, h, cls, "opaque")
+    ref = oracle.convert(1, img, w, h, nmax, True, seed=seed, trace=False)
+    spec_ctx.set_spec_dither(True, seg, warm)
+    out, pal, plen, _ = spec_ctx.convert_batch(1, img[None, :], w, h, nmax, True, seeds=[seed])
+    assert np.array_equal(pal[0, :plen[0]], ref.palette)
+    assert np.array_equal(out[0], ref.out)
+    assert spec_ctx.image_info(0)["rng_draws"] == ref.scalars["rng_draws"]
+    assert spec_ctx.spec_stats()["images"] == 1, "the speculative path did not take (or finish) the image"
+
+
+def test_spec_dither_batch_and_mixed_eligibility(spec_ctx, oracle):
+    w, h = 256, 256
+    imgs = np.stack([make_image(w, h, "noisy", "opaque", seed=0x5EED0000 + i) for i in range(3)] +
+                    [make_image(w, h, "smooth", "opaque"), make_image(w, h, "rand", "transparent")])
+    seeds = [11, 12, 13, 14, 15]
+    spec_ctx.set_spec_dither(True, 4096, 1024)
+    out, pal, plen, _ = spec_ctx.convert_batch(1, imgs, w, h, 256, True, seeds=seeds)
+    for i in range(len(imgs)):
+        ref = oracle.convert(1, imgs[i], w, h, 256, True, seed=seeds[i], trace=False)
+        assert np.array_equal(pal[i, :plen[i]], ref.palette), i
+        assert np.array_equal(out[i], ref.out), i
+    assert spec_ctx.spec_stats()["images"] == 3       # the PriorityQueue-mode image and the transparent one are declined
+
+
+def test_spec_dither_leaves_other_quantizers_alone(spec_ctx, oracle):
+    w, h = 192, 160
+    img = make_image(w, h, "noisy", "opaque")
+    spec_ctx.set_spec_dither(True, 2048, 512)
+    for kind, nmax, dither in ((0, 256, True), (1, 16, True), (1, 256, False)):
+        ref = oracle.convert(kind, img, w, h, nmax, dither, seed=3, trace=False)
+        out, pal, plen, _ = spec_ctx.convert_batch(kind, img[None, :], w, h, nmax, dither, seeds=[3])
+        assert np.array_equal(out[0], ref.out), (kind, nmax, dither)
+    assert spec_ctx.spec_stats()["images"] == 0
