@@ -383,6 +383,19 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
   CU(cudaMemcpyAsync(elig.data(), c->dSpecInts + 2, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));                    // also keeps `h` alive until the copy is done
   const int roundCap = nseg / 4 + 16;
+  // NQ_SPEC_TIMING=1: device time of every launch of this path on stderr (synchronises after each; diagnosis only)
+  const bool timing = getenv("NQ_SPEC_TIMING") != nullptr;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  if (timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, st); }
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaEventRecord(t1, st);
+    cudaEventSynchronize(t1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    fprintf(stderr, "[nq spec] %-14s %9.3f ms\n", what, ms);
+    cudaEventRecord(t0, st);
+  };
   for (int base = 0; base < n; base += wave) {
     const int m = std::min(wave, n - base);
     int any = 0;
@@ -391,26 +404,29 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
     SpecImage* sp = c->dSpec + base;
     const int gx = pixel_grid_x(c, npix, m);
     const dim3 pg(gx, m), kg(8, m);
-    k_spec_init<<<kg, 256, 0, st>>>(sp); ++c->launches;
-    k_spec_pre<<<pg, 256, 0, st>>>(sp); ++c->launches;
-    k_spec_scan<<<m, 1024, 0, st>>>(sp); ++c->launches;
-    k_spec_resolve<<<pg, 256, 0, st>>>(sp); ++c->launches;
-    k_spec_memo<<<kg, 256, 0, st>>>(sp); ++c->launches;
-    k_spec_fill<<<pg, 256, 0, st>>>(sp); ++c->launches;
+    k_spec_init<<<kg, 256, 0, st>>>(sp); ++c->launches; lap("init");
+    k_spec_pre<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("pre");
+    k_spec_scan<<<m, 1024, 0, st>>>(sp); ++c->launches; lap("scan");
+    k_spec_resolve<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("resolve");
+    k_spec_memo<<<kg, 256, 0, st>>>(sp); ++c->launches; lap("memo");
+    k_spec_fill<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("fill");
     for (int round = 0; round < roundCap; ++round) {
       CU(cudaMemsetAsync(c->dSpecInts, 0, 2 * sizeof(int), st));
-      k_spec_run<<<dim3((nseg + 63) / 64, m), 64, 0, st>>>(sp); ++c->launches;
-      k_spec_validate<<<(m + 63) / 64, 64, 0, st>>>(sp, m, c->dSpecInts); ++c->launches;
+      k_spec_run<<<dim3((nseg + 63) / 64, m), 64, 0, st>>>(sp); ++c->launches; lap("run");
+      k_spec_compare<<<dim3((nseg + 63) / 64, m), 64, 0, st>>>(sp); ++c->launches; lap("compare");
+      k_spec_validate<<<(m + 63) / 64, 64, 0, st>>>(sp, m, c->dSpecInts); ++c->launches; lap("validate");
       int counters[2] = {0, 0};
       CU(cudaMemcpyAsync(counters, c->dSpecInts, sizeof(counters), cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
       ++c->specRounds;
-      if (counters[1]) { k_spec_patch<<<pg, 256, 0, st>>>(sp); ++c->launches; }
+      if (timing) fprintf(stderr, "[nq spec] round %d: %d image(s) open, %d patch(es)\n", round, counters[0], counters[1]);
+      if (counters[1]) { k_spec_patch<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("patch"); }
       if (!counters[0]) break;
     }
     k_spec_finish<<<(m + 63) / 64, 64, 0, st>>>(c->dImgs + base, sp, m); ++c->launches;
     c->specImages += (unsigned long long)any;
   }
+  if (timing) { cudaEventDestroy(t0); cudaEventDestroy(t1); }
   CU(cudaGetLastError());
   return NQ_OK;
 }

@@ -27,6 +27,7 @@ namespace nq {
 namespace spec {
 
 #define NQS_NOTES 12            // memo entries a segment may create through error-dependent lookups
+#define NQS_READS 24            // memo entries of the pre-lookups its error-dependent lookups may read
 #define NQS_NOPOS 0x7fffffff
 #define NQS_NONE 0xFFFFFFFFu    // absent top-2 key
 
@@ -56,9 +57,12 @@ struct SpecSeg {
   float qout[NQ_MAXQ][4];                // queue after the last owned pixel
   float qstart[NQ_MAXQ][4];              // exact start state (when exact != 0)
   int exact, dirty, done;
+  int qok;                               // stage 6b: start queue == predecessor's final queue, bit for bit
   int draws;                             // draws made by the owned pixels
   int nnotes;                            // > NQS_NOTES: overflow
   int noteKey[NQS_NOTES], notePos[NQS_NOTES], noteVal[NQS_NOTES];
+  int nreads;                            // > NQS_READS: overflow (treated as "may have read any key")
+  int readKey[NQS_READS];
 };
 struct SpecWork {
   const uint32_t* order;                 // x | y << 16 per curve position
@@ -409,7 +413,13 @@ NQ_HD int slow_lookup(const SpecConst& C, const SpecWork& W, SpecSeg& S, int n, 
   const int key = color_index(c, false, C.hasTrans != 0);
   if (owned) for (int i = 0; i < S.nnotes && i < NQS_NOTES; ++i) if (S.noteKey[i] == key) return S.noteVal[i];
   if (W.slowPos[key] < n) return W.slowVal[key];           // created by an error-dependent lookup of a validated segment
-  if (W.firstPos[key] < n || (!owned && W.firstPos[key] != NQS_NOPOS)) return W.memo[key];
+  if (W.firstPos[key] < n || (!owned && W.firstPos[key] != NQS_NOPOS)) {
+    if (owned) {                                           // remembered: a later patch of this key invalidates the segment
+      if (S.nreads < NQS_READS) S.readKey[S.nreads] = key;
+      ++S.nreads;
+    }
+    return W.memo[key];
+  }
   const int v = nearest_nomemo(C, c, W.lut);               // first colour of the bucket: this lookup fixes the entry (PL:402)
   if (owned) {
     if (S.nnotes < NQS_NOTES) { S.noteKey[S.nnotes] = key; S.notePos[S.nnotes] = n; S.noteVal[S.nnotes] = v; }
@@ -436,6 +446,7 @@ NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
   const bool illusion0 = W.bn[0] > C.thresold;             // yDiff == 1 in this mode: bn[(int)4096.0 & 4095] (GC:251-252)
   int draws = 0;
   S.nnotes = 0;
+  S.nreads = 0;
   for (int n = from; n < p1; ++n) {
     if (n == p0) {
       for (int k = 0; k < DM; ++k) { const int q = head + k < DM ? head + k : head + k - DM; for (int j = 0; j < 4; ++j) S.qwarm[k][j] = e[q][j]; }
@@ -511,6 +522,12 @@ NQ_HD bool same_queue(const float (*a)[4], const float (*b)[4], int DM) {
       if (nqm::d2bits((double)a[k][j]) != nqm::d2bits((double)b[k][j])) return false;   // widening is exact and keeps the sign of zero
   return true;
 }
+// stage 6b, one call per segment (parallel): the comparison stage 7 needs, so that its sequential walk reads one flag
+NQ_HD void stage_compare(const SpecConst& C, const SpecWork& W, int s) {
+  SpecSeg& S = W.segs[s];
+  if (S.done) return;
+  S.qok = s == 0 || same_queue(S.exact ? S.qstart : S.qwarm, W.segs[s - 1].qout, C.DM);
+}
 NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
   int s = W.state[0];
   if (W.state[1]) return 0;
@@ -518,7 +535,7 @@ NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
     SpecSeg& S = W.segs[s];
     const int p0 = s * C.seg, p1 = (p0 + C.seg < C.npix) ? p0 + C.seg : C.npix;
     bool ok = S.nnotes <= NQS_NOTES;
-    if (ok && s > 0) ok = same_queue(S.exact ? S.qstart : S.qwarm, W.segs[s - 1].qout, C.DM);
+    if (ok && s > 0) ok = S.qok != 0;
     if (ok) {
       // the draws of the owned pixels against the prediction every later pre-lookup was computed with
       const int predicted = (int)(W.cdraw[p1] - W.cdraw[p0]);   // cdraw has npix + 1 entries
@@ -547,6 +564,12 @@ NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
           W.memo[key] = (unsigned short)val; W.firstPos[key] = pos;
           W.state[2] = key + 1; W.state[3] = pos;
           S.dirty = 1;
+          for (int t = s + 1; t < C.nseg; ++t) {           // later segments whose error-dependent lookups read the old entry
+            SpecSeg& T = W.segs[t];
+            bool hit = T.nreads > NQS_READS;
+            for (int r = 0; !hit && r < T.nreads; ++r) hit = T.readKey[r] == key;
+            if (hit) T.dirty = 1;
+          }
           patched = true;
           break;
         }
@@ -611,7 +634,7 @@ __global__ void __launch_bounds__(256) k_spec_init(SpecImage* sp) {
   if (!P.eligible) return;
   const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   for (int k = t; k < 65536; k += nt) { P.W.firstPos[k] = NQS_NOPOS; P.W.slowPos[k] = NQS_NOPOS; P.W.memo[k] = 0xFFFF; P.W.slowVal[k] = 0; }
-  for (int s = t; s < P.C.nseg; s += nt) { SpecSeg& S = P.W.segs[s]; S.exact = s == 0; S.dirty = 1; S.done = 0; S.draws = 0; S.nnotes = 0; }
+  for (int s = t; s < P.C.nseg; s += nt) { SpecSeg& S = P.W.segs[s]; S.exact = s == 0; S.dirty = 1; S.done = 0; S.draws = 0; S.nnotes = 0; S.nreads = 0; }
   if (t < 8) P.W.state[t] = 0;
 }
 __global__ void __launch_bounds__(256) k_spec_pre(SpecImage* sp) {
@@ -663,6 +686,12 @@ __global__ void __launch_bounds__(64) k_spec_run(SpecImage* sp) {
   if (!NQS_ACTIVE(P)) return;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < P.C.nseg) stage_run(P.C, P.W, s);
+}
+__global__ void __launch_bounds__(64) k_spec_compare(SpecImage* sp) {
+  const SpecImage& P = sp[blockIdx.y];
+  if (!NQS_ACTIVE(P)) return;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < P.C.nseg) stage_compare(P.C, P.W, s);
 }
 // stage 7: one thread per image; counters[0] += images with open segments, counters[1] += patch requests
 __global__ void k_spec_validate(SpecImage* sp, int nimg, int* counters) {

@@ -19,7 +19,7 @@ def main():
     batch = a[4] if len(a) > 4 else 1
     imgs = np.stack([make_image(w, h, "noisy", "opaque", seed=0x5EED0000 + i) for i in range(batch)])
     seeds = [0xC0FFEE + i for i in range(batch)]
-    ref = pyoracle.convert(1, imgs[0], w, h, 256, True, seed=seeds[0], trace=False) if w * h <= 1 << 21 else None
+    ref = pyoracle.convert(1, imgs[0], w, h, 256, True, seed=seeds[0], trace=False) if (w * h <= 1 << 21 and not os.environ.get("NQ_PROBE_NOORACLE")) else None
     ctx = Context(0)
     for spec in (1, 0, 1):
         ctx.set_spec_dither(bool(spec), seg, warm)
@@ -32,7 +32,8 @@ def main():
         if spec == 1:
             keep = out.copy()
         else:
-            print("spec output == serial output:", bool(np.array_equal(out, keep)), flush=True)
+            print("spec output == serial output:", bool(np.array_equal(out, keep)),
+                  "differing pixels per image:", [int((out[i] != keep[i]).sum()) for i in range(batch)], flush=True)
     ms = ctx.stage_times(reset=True) if hasattr(ctx, "stage_times") else None
     print("stage ms:", ms)
 
