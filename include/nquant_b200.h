@@ -131,9 +131,10 @@ int nq_sizeof_image_info(void);
  * pieces of the curve that start from an empty error queue `warmup` pixels early and are validated, in curve order,
  * against the exact state of their predecessor (bit-identical results by construction; images it cannot finish go
  * through the serial kernel). Off by default (or NQ_SPEC_DITHER=1 in the environment at nq_create).
- * nq_get_spec_stats: images completed by this path and validation rounds since the context was created. */
+ * nq_get_spec_stats: images completed by this path, validation rounds, and qualifying images it handed back to the
+ * serial kernel, since the context was created. */
 int nq_set_spec_dither(nq_ctx* ctx, int on, int segment, int warmup);
-int nq_get_spec_stats(nq_ctx* ctx, unsigned long long* images, unsigned long long* rounds);
+int nq_get_spec_stats(nq_ctx* ctx, unsigned long long* images, unsigned long long* rounds, unsigned long long* fallbacks);
 
 /* When enabled (flag != 0) the next calls keep, per image, the compacted bins before merging, the
  * initial find_nn results and the merge sequence, retrievable below. Costs memory and a few copies. */

@@ -78,7 +78,7 @@ def load():
     L.nq_get_stage_times.argtypes = [vp, vp, vp, ci]
     L.nq_synth_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, u64]
     L.nq_set_spec_dither.argtypes = [vp, ci, ci, ci]
-    L.nq_get_spec_stats.argtypes = [vp, vp, vp]
+    L.nq_get_spec_stats.argtypes = [vp, vp, vp, vp]
     for s in SYMBOLS:
         getattr(L, s)
     if L.nq_sizeof_image_info() != ctypes.sizeof(ImageInfo):

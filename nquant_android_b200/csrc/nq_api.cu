@@ -196,7 +196,7 @@ struct nq_ctx {
   int specCap = 0;                 // images dSpec holds
   unsigned char* specBuf = nullptr;
   size_t specBufBytes = 0;
-  int* dSpecInts = nullptr;        // [0..1] round counters, [2..] eligibility per image
+  int* dSpecInts = nullptr;        // [0..3] round counters, [4..] eligibility per image
   int specIntsCap = 0;
   unsigned long long specImages = 0, specRounds = 0, specFallbacks = 0;
   // results of the last batch
@@ -340,11 +340,11 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
     CU(cudaMalloc(&c->dSpec, sizeof(SpecImage) * (size_t)n));
     c->specCap = n;
   }
-  if (c->specIntsCap < n + 2) {
+  if (c->specIntsCap < n + 4) {
     if (c->dSpecInts) cudaFree(c->dSpecInts);
     c->dSpecInts = nullptr; c->specIntsCap = 0;
-    CU(cudaMalloc(&c->dSpecInts, sizeof(int) * (size_t)(n + 2)));
-    c->specIntsCap = n + 2;
+    CU(cudaMalloc(&c->dSpecInts, sizeof(int) * (size_t)(n + 4)));
+    c->specIntsCap = n + 4;
   }
   // work arrays of one wave slot
   size_t o = 0;
@@ -378,11 +378,11 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
     W.segs = reinterpret_cast<SpecSeg*>(b + oSegs); W.state = reinterpret_cast<int*>(b + oState);
   }
   CU(cudaMemcpyAsync(c->dSpec, h.data(), sizeof(SpecImage) * (size_t)n, cudaMemcpyHostToDevice, st));
-  k_spec_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, c->dSpec, dOrder, n, seg, warm, c->dSpecInts + 2); ++c->launches;
+  k_spec_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, c->dSpec, dOrder, n, seg, warm, c->dSpecInts + 4); ++c->launches;
   std::vector<int> elig(n);
-  CU(cudaMemcpyAsync(elig.data(), c->dSpecInts + 2, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(elig.data(), c->dSpecInts + 4, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));                    // also keeps `h` alive until the copy is done
-  const int roundCap = nseg / 4 + 16;
+  const int roundCap = nseg / 4 + 96;
   // NQ_SPEC_TIMING=1: device time of every launch of this path on stderr (synchronises after each; diagnosis only)
   const bool timing = getenv("NQ_SPEC_TIMING") != nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -406,25 +406,37 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
     const dim3 pg(gx, m), kg(8, m);
     k_spec_init<<<kg, 256, 0, st>>>(sp); ++c->launches; lap("init");
     k_spec_pre<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("pre");
-    k_spec_scan<<<m, 1024, 0, st>>>(sp); ++c->launches; lap("scan");
+    k_spec_scan<<<m, 1024, 0, st>>>(sp, 0); ++c->launches; lap("scan");
     k_spec_resolve<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("resolve");
     k_spec_memo<<<kg, 256, 0, st>>>(sp); ++c->launches; lap("memo");
     k_spec_fill<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("fill");
     for (int round = 0; round < roundCap; ++round) {
-      CU(cudaMemsetAsync(c->dSpecInts, 0, 2 * sizeof(int), st));
+      CU(cudaMemsetAsync(c->dSpecInts, 0, 4 * sizeof(int), st));
       k_spec_run<<<dim3((nseg + 63) / 64, m), 64, 0, st>>>(sp); ++c->launches; lap("run");
       k_spec_compare<<<dim3((nseg + 63) / 64, m), 64, 0, st>>>(sp); ++c->launches; lap("compare");
       k_spec_validate<<<(m + 63) / 64, 64, 0, st>>>(sp, m, c->dSpecInts); ++c->launches; lap("validate");
-      int counters[2] = {0, 0};
+      int counters[4] = {0, 0, 0, 0};
       CU(cudaMemcpyAsync(counters, c->dSpecInts, sizeof(counters), cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
       ++c->specRounds;
-      if (timing) fprintf(stderr, "[nq spec] round %d: %d image(s) open, %d patch(es)\n", round, counters[0], counters[1]);
+      if (timing) fprintf(stderr, "[nq spec] round %d: %d image(s) open, %d patch(es), %d re-resolve(s)\n", round, counters[0], counters[1], counters[2]);
       if (counters[1]) { k_spec_patch<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("patch"); }
+      if (counters[2]) {   // a draw misprediction: prefix sum again, then stages 3-5 behind it, for the images that asked
+        k_spec_scan<<<m, 1024, 0, st>>>(sp, 1); ++c->launches;
+        k_spec_redo_a<<<kg, 256, 0, st>>>(sp); ++c->launches;
+        k_spec_redo_b<<<pg, 256, 0, st>>>(sp); ++c->launches;
+        k_spec_redo_c<<<kg, 256, 0, st>>>(sp); ++c->launches;
+        k_spec_redo_d<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("re-resolve");
+      }
       if (!counters[0]) break;
     }
-    k_spec_finish<<<(m + 63) / 64, 64, 0, st>>>(c->dImgs + base, sp, m); ++c->launches;
-    c->specImages += (unsigned long long)any;
+    CU(cudaMemsetAsync(c->dSpecInts + 3, 0, sizeof(int), st));
+    k_spec_finish<<<(m + 63) / 64, 64, 0, st>>>(c->dImgs + base, sp, m, c->dSpecInts + 3); ++c->launches;
+    int done = 0;
+    CU(cudaMemcpyAsync(&done, c->dSpecInts + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    c->specImages += (unsigned long long)done;                 // completed here; the rest goes through k_dither_fifo
+    c->specFallbacks += (unsigned long long)(any - done);
   }
   if (timing) { cudaEventDestroy(t0); cudaEventDestroy(t1); }
   CU(cudaGetLastError());
@@ -816,10 +828,11 @@ int nq_set_spec_dither(nq_ctx* c, int on, int segment, int warmup) {
   if (on) { c->specSeg = segment; c->specWarm = warmup; }
   return NQ_OK;
 }
-int nq_get_spec_stats(nq_ctx* c, unsigned long long* images, unsigned long long* rounds) {
+int nq_get_spec_stats(nq_ctx* c, unsigned long long* images, unsigned long long* rounds, unsigned long long* fallbacks) {
   if (!c) return fail(NQ_ERR_ARG, "null context");
   if (images) *images = c->specImages;
   if (rounds) *rounds = c->specRounds;
+  if (fallbacks) *fallbacks = c->specFallbacks;
   return NQ_OK;
 }
 

@@ -34,7 +34,7 @@ namespace spec {
 // per-pixel flags (curve order)
 #define NQS_F_PRE 1u            // lookup does not read the diffused colour
 #define NQS_F_DRAW 2u           // the lookup is predicted to call Random.nextInt (PL:467)
-#define NQS_F_NEAR 4u           // resolved through nearestColorIndex's memo (PL:470-472): ck0 holds the memo key
+#define NQS_F_NEAR 4u           // resolved through nearestColorIndex's memo (PL:470-472), key = memo_key(ccol)
 
 // Constants of one image: what GilbertCurve's constructor and the quantizer hold while dithering.
 struct SpecConst {
@@ -59,6 +59,7 @@ struct SpecSeg {
   int exact, dirty, done;
   int qok;                               // stage 6b: start queue == predecessor's final queue, bit for bit
   int draws;                             // draws made by the owned pixels
+  int mispos;                            // first owned error-dependent lookup whose draw differs from its prediction, or -1
   int nnotes;                            // > NQS_NOTES: overflow
   int noteKey[NQS_NOTES], notePos[NQS_NOTES], noteVal[NQS_NOTES];
   int nreads;                            // > NQS_READS: overflow (treated as "may have read any key")
@@ -83,7 +84,8 @@ struct SpecWork {
   const double* lut;                     // gammaToLinear table
   const signed char* bn;                 // TELL_BLUE_NOISE
   SpecSeg* segs;
-  int* state;                            // [8]: firstOpen, anomaly, patch key + 1 (0 = none), patch position, failed validations
+  int* state;                            // [8]: firstOpen, anomaly, patch key + 1 (0 = none), patch position, failed validations,
+                                         //      re-resolve position + 1 (0 = none), re-resolves so far
 };
 
 // ---- java.util.Random: state after j more steps of the LCG ------------------------------------------------
@@ -339,9 +341,11 @@ NQ_HD void stage_pre(const SpecConst& C, const SpecWork& W, int n) {
 
 // ---- stage 3: the draw, the choice between the two candidates, first-seen positions of the memo keys -------
 // (stage 2 = exclusive prefix sum of NQS_F_DRAW into cdraw). Returns false when a nextInt would have rejected.
+NQ_HD int memo_key(const SpecConst& C, uint32_t c) { return color_index(c, false, C.hasTrans != 0); }   // PL:332
 NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firstPosOut /* key or -1 */) {
   *firstPosOut = -1;
-  const unsigned flag = W.cflag[n];
+  const unsigned flag = W.cflag[n] & ~NQS_F_NEAR;          // (a re-resolve after a draw misprediction starts over)
+  W.cflag[n] = (unsigned char)flag;
   if (!(flag & NQS_F_PRE)) return true;
   const uint32_t c = W.ccol[n];
   bool needNear = true;
@@ -358,10 +362,8 @@ NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firs
   }
   if (needNear) {
     if (C.isNano) {
-      const int key = color_index(c, false, C.hasTrans != 0);
-      W.ck0[n] = (uint32_t)key;                            // the top-2 keys are not needed any more
       W.cflag[n] = (unsigned char)(flag | NQS_F_NEAR);
-      *firstPosOut = key;                                  // caller: firstPos[key] = min(firstPos[key], n)
+      *firstPosOut = memo_key(C, c);                       // caller: firstPos[key] = min(firstPos[key], n)
     } else
       W.cq[n] = (unsigned short)nearest_nomemo(C, c, W.lut);   // full-colour key: the memo is a pure cache (PL:332)
   } else
@@ -369,13 +371,20 @@ NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firs
   return ok;
 }
 // ---- stage 4: one memo key ------------------------------------------------------------------------------------
-NQ_HD void stage_memo(const SpecConst& C, const SpecWork& W, int key) {
+// `after`: only entries first seen behind that curve position (-1 = all); the others are settled
+NQ_HD void stage_memo(const SpecConst& C, const SpecWork& W, int key, int after) {
   const int n = W.firstPos[key];
+  if (n != NQS_NOPOS && n <= after) return;
   W.memo[key] = n == NQS_NOPOS ? (unsigned short)0xFFFF : (unsigned short)nearest_nomemo(C, W.ccol[n], W.lut);
 }
 // ---- stage 5 ------------------------------------------------------------------------------------------------------
-NQ_HD void stage_fill(const SpecWork& W, int n) {
-  if (W.cflag[n] & NQS_F_NEAR) W.cq[n] = W.memo[W.ck0[n]];
+NQ_HD void stage_fill(const SpecConst& C, const SpecWork& W, int n) {
+  if (W.cflag[n] & NQS_F_NEAR) W.cq[n] = W.memo[memo_key(C, W.ccol[n])];
+}
+// ---- re-resolve after a draw misprediction at curve position `from` = state[5] - 1 (stage_validate has corrected the
+//      pixel's flag): stage 2 again, then per memo key this reset, then stages 3-5 for the pixels behind `from`
+NQ_HD void stage_rekey(const SpecWork& W, int key, int from) {
+  if (W.firstPos[key] != NQS_NOPOS && W.firstPos[key] > from) { W.firstPos[key] = NQS_NOPOS; W.memo[key] = 0xFFFF; }
 }
 // ---- patch: an error-dependent lookup at curve position state[3] created memo entry state[2] - 1 BEFORE the first
 //      pre-lookup that needs it, with another value than stage 4 gave it (PL:402: the first colour of a bucket fixes
@@ -384,7 +393,7 @@ NQ_HD void stage_fill(const SpecWork& W, int n) {
 NQ_HD void stage_patch(const SpecConst& C, const SpecWork& W, int n) {
   const int key = W.state[2] - 1, pos = W.state[3];
   if (key < 0 || n <= pos) return;
-  if ((W.cflag[n] & NQS_F_NEAR) && (int)W.ck0[n] == key) {
+  if ((W.cflag[n] & NQS_F_NEAR) && memo_key(C, W.ccol[n]) == key) {
     W.cq[n] = W.memo[key];
     W.segs[n / C.seg].dirty = 1;                           // benign race on the device: every writer stores 1
   }
@@ -393,7 +402,8 @@ NQ_HD void stage_patch(const SpecConst& C, const SpecWork& W, int n) {
 // ---- stage 6: one segment ---------------------------------------------------------------------------------------
 // An error-dependent lookup (GC:214-216 with the diffused colour c2): closestColorIndex with the draw this pixel
 // was predicted to make, nearestColorIndex through the memo. `owned` = the pixel belongs to the segment (notes kept).
-NQ_HD int slow_lookup(const SpecConst& C, const SpecWork& W, SpecSeg& S, int n, uint32_t c, bool owned, int* draws) {
+NQ_HD int slow_lookup(const SpecConst& C, const SpecWork& W, SpecSeg& S, int n, uint32_t c, bool owned, int* draws, bool* drew) {
+  *drew = false;
   bool needNear = true;
   int qi = 0;
   if (c_alpha(c) > 0xF) {
@@ -405,6 +415,7 @@ NQ_HD int slow_lookup(const SpecConst& C, const SpecWork& W, SpecSeg& S, int n, 
       r = next_int_from(lcg_jump(C.seed0, (unsigned long long)W.cdraw[n] + 1ULL), &rej);
       if (rej) S.nnotes = NQS_NOTES + 1;                   // never seen; handled as an overflow = not validated
       ++*draws;
+      *drew = true;
     }
     qi = closest_pick(C, c, k0, k1, r, &needNear);
   }
@@ -447,6 +458,7 @@ NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
   int draws = 0;
   S.nnotes = 0;
   S.nreads = 0;
+  S.mispos = -1;
   for (int n = from; n < p1; ++n) {
     if (n == p0) {
       for (int k = 0; k < DM; ++k) { const int q = head + k < DM ? head + k : head + k - DM; for (int j = 0; j < 4; ++j) S.qwarm[k][j] = e[q][j]; }
@@ -483,7 +495,9 @@ NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
       const float sal = saliency_of(C, W, px);
       uint32_t c = c2;
       if (!(C.plen >= 256 && sal > .99f)) c = slow_colour(C, W, x, y, px, sal, color_y(px, W.lut), c2);
-      qi = slow_lookup(C, W, S, n, c, owned, &draws);
+      bool drew;
+      qi = slow_lookup(C, W, S, n, c, owned, &draws, &drew);
+      if (owned && S.mispos < 0 && drew != ((flag & NQS_F_DRAW) != 0)) S.mispos = n;   // every later draw index is off by one
     }
     const uint32_t pc = C.pal[qi];
     if (owned) W.out[bidx] = pc;                           // dither == true: the palette colour (GC:278-279)
@@ -536,10 +550,21 @@ NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
     const int p0 = s * C.seg, p1 = (p0 + C.seg < C.npix) ? p0 + C.seg : C.npix;
     bool ok = S.nnotes <= NQS_NOTES;
     if (ok && s > 0) ok = S.qok != 0;
+    if (ok && S.mispos >= 0) {
+      // An error-dependent lookup drew (or did not draw) against its prediction (PL:467: closest[2] == 0 for the diffused
+      // colour but not for the pixel, or the reverse). Up to that pixel the segment is exact; behind it every draw index
+      // moves by one. Correct the pixel's flag, ask for a re-resolve of everything behind it (stage_rekey and stages
+      // 2-5), and run this segment and all later ones again.
+      W.cflag[S.mispos] = (unsigned char)(W.cflag[S.mispos] ^ NQS_F_DRAW);
+      W.state[5] = S.mispos + 1;
+      for (int t = s; t < C.nseg; ++t) W.segs[t].dirty = 1;
+      if (++W.state[6] > 64) { W.state[1] = 1; return 0; }
+      break;
+    }
     if (ok) {
       // the draws of the owned pixels against the prediction every later pre-lookup was computed with
       const int predicted = (int)(W.cdraw[p1] - W.cdraw[p0]);   // cdraw has npix + 1 entries
-      if (S.draws != predicted) { W.state[1] = 1; return 0; }
+      if (S.draws != predicted) { W.state[1] = 1; return 0; }      // cannot happen without a mispos; kept as a guard
       for (int i = 0; i < S.nnotes; ++i) {
         const int key = S.noteKey[i], pos = S.notePos[i], val = S.noteVal[i];
         if (W.slowPos[key] < pos && W.slowVal[key] != val) { ok = false; break; }
@@ -634,7 +659,7 @@ __global__ void __launch_bounds__(256) k_spec_init(SpecImage* sp) {
   if (!P.eligible) return;
   const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   for (int k = t; k < 65536; k += nt) { P.W.firstPos[k] = NQS_NOPOS; P.W.slowPos[k] = NQS_NOPOS; P.W.memo[k] = 0xFFFF; P.W.slowVal[k] = 0; }
-  for (int s = t; s < P.C.nseg; s += nt) { SpecSeg& S = P.W.segs[s]; S.exact = s == 0; S.dirty = 1; S.done = 0; S.draws = 0; S.nnotes = 0; S.nreads = 0; }
+  for (int s = t; s < P.C.nseg; s += nt) { SpecSeg& S = P.W.segs[s]; S.exact = s == 0; S.dirty = 1; S.done = 0; S.draws = 0; S.nnotes = 0; S.nreads = 0; S.mispos = -1; }
   if (t < 8) P.W.state[t] = 0;
 }
 __global__ void __launch_bounds__(256) k_spec_pre(SpecImage* sp) {
@@ -643,10 +668,10 @@ __global__ void __launch_bounds__(256) k_spec_pre(SpecImage* sp) {
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_pre(P.C, P.W, n);
 }
 // stage 2: exclusive prefix sum of the predicted draws, one CTA of 1024 threads per image, 8 pixels per thread and tile
-__global__ void __launch_bounds__(1024) k_spec_scan(SpecImage* sp) {
+__global__ void __launch_bounds__(1024) k_spec_scan(SpecImage* sp, int redo) {
   __shared__ int sWarp[33];
   const SpecImage& P = sp[blockIdx.x];
-  if (!P.eligible) return;
+  if (!P.eligible || (redo && (!P.W.state[5] || P.W.state[1]))) return;
   const int npix = P.C.npix;
   unsigned carry = 0;
   for (int base = 0; base < npix; base += 8192) {
@@ -670,15 +695,44 @@ __global__ void __launch_bounds__(256) k_spec_resolve(SpecImage* sp) {
     if (key >= 0) atomicMin(&P.W.firstPos[key], n);
   }
 }
+// re-resolve behind a draw misprediction (images with state[5] != 0): a = reset keys, b = stages 3, c = stage 4, d = stage 5
+__global__ void __launch_bounds__(256) k_spec_redo_a(SpecImage* sp) {
+  const SpecImage& P = sp[blockIdx.y];
+  if (!NQS_ACTIVE(P) || !P.W.state[5]) return;
+  const int from = P.W.state[5] - 1;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 65536; k += gridDim.x * blockDim.x) stage_rekey(P.W, k, from);
+}
+__global__ void __launch_bounds__(256) k_spec_redo_b(SpecImage* sp) {
+  const SpecImage& P = sp[blockIdx.y];
+  if (!NQS_ACTIVE(P) || !P.W.state[5]) return;
+  const int from = P.W.state[5] - 1;
+  for (int n = from + 1 + blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) {
+    int key;
+    if (!stage_resolve(P.C, P.W, n, &key)) P.W.state[1] = 1;
+    if (key >= 0) atomicMin(&P.W.firstPos[key], n);
+  }
+}
+__global__ void __launch_bounds__(256) k_spec_redo_c(SpecImage* sp) {
+  const SpecImage& P = sp[blockIdx.y];
+  if (!NQS_ACTIVE(P) || !P.W.state[5]) return;
+  const int from = P.W.state[5] - 1;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 65536; k += gridDim.x * blockDim.x) stage_memo(P.C, P.W, k, from);
+}
+__global__ void __launch_bounds__(256) k_spec_redo_d(SpecImage* sp) {
+  const SpecImage& P = sp[blockIdx.y];
+  if (!NQS_ACTIVE(P) || !P.W.state[5]) return;
+  const int from = P.W.state[5] - 1;
+  for (int n = from + 1 + blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_fill(P.C, P.W, n);
+}
 __global__ void __launch_bounds__(256) k_spec_memo(SpecImage* sp) {
   const SpecImage& P = sp[blockIdx.y];
   if (!NQS_ACTIVE(P)) return;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 65536; k += gridDim.x * blockDim.x) stage_memo(P.C, P.W, k);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 65536; k += gridDim.x * blockDim.x) stage_memo(P.C, P.W, k, -1);
 }
 __global__ void __launch_bounds__(256) k_spec_fill(SpecImage* sp) {
   const SpecImage& P = sp[blockIdx.y];
   if (!NQS_ACTIVE(P)) return;
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_fill(P.W, n);
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_fill(P.C, P.W, n);
 }
 // stage 6: one thread per segment
 __global__ void __launch_bounds__(64) k_spec_run(SpecImage* sp) {
@@ -693,16 +747,18 @@ __global__ void __launch_bounds__(64) k_spec_compare(SpecImage* sp) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < P.C.nseg) stage_compare(P.C, P.W, s);
 }
-// stage 7: one thread per image; counters[0] += images with open segments, counters[1] += patch requests
+// stage 7: one thread per image; counters[0] += images with open segments, [1] += patch requests, [2] += re-resolve requests
 __global__ void k_spec_validate(SpecImage* sp, int nimg, int* counters) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nimg) return;
   const SpecImage& P = sp[i];
   if (!NQS_ACTIVE(P)) return;
   P.W.state[2] = 0;
+  P.W.state[5] = 0;
   const int open = stage_validate(P.C, P.W);
   if (open > 0 && !P.W.state[1]) atomicAdd(&counters[0], 1);
   if (P.W.state[2]) atomicAdd(&counters[1], 1);
+  if (P.W.state[5] && !P.W.state[1]) atomicAdd(&counters[2], 1);
 }
 __global__ void __launch_bounds__(256) k_spec_patch(SpecImage* sp) {
   const SpecImage& P = sp[blockIdx.y];
@@ -710,13 +766,14 @@ __global__ void __launch_bounds__(256) k_spec_patch(SpecImage* sp) {
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_patch(P.C, P.W, n);
 }
 // images that were completed here are skipped by k_dither_fifo; the others (not eligible, contradicted, round cap) are not
-__global__ void k_spec_finish(NqImage* imgs, SpecImage* sp, int nimg) {
+__global__ void k_spec_finish(NqImage* imgs, SpecImage* sp, int nimg, int* doneCount) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nimg) return;
   const SpecImage& P = sp[i];
   if (NQS_ACTIVE(P) && P.W.state[0] == P.C.nseg) {
     imgs[i].specDone = 1;
     imgs[i].rngDraws = P.W.cdraw[P.C.npix];
+    atomicAdd(doneCount, 1);
   }
 }
 #endif  // __CUDACC__

@@ -98,9 +98,9 @@ class Context:
         self._check(self._L.nq_set_spec_dither(self._h, int(bool(on)), int(segment), int(warmup)))
 
     def spec_stats(self):
-        images, rounds = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
-        self._check(self._L.nq_get_spec_stats(self._h, ctypes.byref(images), ctypes.byref(rounds)))
-        return {"images": images.value, "rounds": rounds.value}
+        images, rounds, fallbacks = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        self._check(self._L.nq_get_spec_stats(self._h, ctypes.byref(images), ctypes.byref(rounds), ctypes.byref(fallbacks)))
+        return {"images": images.value, "rounds": rounds.value, "fallbacks": fallbacks.value}
 
     # -- introspection ------------------------------------------------------------------------------
     def set_debug(self, flag):

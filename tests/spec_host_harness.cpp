@@ -28,7 +28,7 @@ struct uint2 { unsigned x, y; };   // CUDA vector type named by nq_types.h
 namespace {
 
 struct HarnessOut {
-  long long eligible = 0, exact = 0, rounds = 0, anomaly = 0, nseg = 0, segRuns = 0, slowPixels = 0, notes = 0, mismatches = 0, rejected = 0, patches = 0;
+  long long eligible = 0, exact = 0, rounds = 0, anomaly = 0, nseg = 0, segRuns = 0, slowPixels = 0, notes = 0, mismatches = 0, rejected = 0, patches = 0, redos = 0;
 };
 struct HarnessCfg { int seg = 4096, warm = 1024, useCells = 1; HarnessOut out; };
 HarnessCfg* g_h = nullptr;
@@ -126,8 +126,8 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
     if (key >= 0 && n < firstPos[key]) firstPos[key] = n;
     if (!(cflag[n] & NQS_F_PRE)) ++R.slowPixels;
   }
-  for (int key = 0; key < 65536; ++key) stage_memo(C, W, key);                           // stage 4
-  for (int n = 0; n < npix; ++n) stage_fill(W, n);                                       // stage 5
+  for (int key = 0; key < 65536; ++key) stage_memo(C, W, key, -1);                       // stage 4
+  for (int n = 0; n < npix; ++n) stage_fill(C, W, n);                                    // stage 5
   R.nseg = C.nseg;
   int open = C.nseg;
   while (open > 0 && !state[1] && R.rounds < 100000) {
@@ -142,6 +142,20 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
       fprintf(stderr, "round %lld: stopped at segment %d (exact %d, notes %d, %d queue floats differ from the predecessor's)\n", R.rounds, s, segs[s].exact, segs[s].nnotes, diff);
       if (s > 0 && R.rounds < 3) for (int k = 0; k < C.DM; ++k) fprintf(stderr, "  box %2d warm (%g %g %g %g) prev (%g %g %g %g)\n", k, segs[s].qwarm[k][0], segs[s].qwarm[k][1], segs[s].qwarm[k][2], segs[s].qwarm[k][3],
           segs[s - 1].qout[k][0], segs[s - 1].qout[k][1], segs[s - 1].qout[k][2], segs[s - 1].qout[k][3]);
+    }
+    if (state[5] && !state[1]) {                                                         // draw misprediction: re-resolve behind it
+      ++R.redos;
+      const int from = state[5] - 1;
+      { uint32_t d = 0; for (int n = 0; n < npix; ++n) { cdraw[n] = d; d += (cflag[n] & NQS_F_DRAW) ? 1u : 0u; } cdraw[npix] = d; }
+      for (int key = 0; key < 65536; ++key) stage_rekey(W, key, from);
+      for (int n = from + 1; n < npix; ++n) {
+        int key;
+        if (!stage_resolve(C, W, n, &key)) { ++R.rejected; state[1] = 1; }
+        if (key >= 0 && n < firstPos[key]) firstPos[key] = n;
+      }
+      for (int key = 0; key < 65536; ++key) stage_memo(C, W, key, from);
+      for (int n = from + 1; n < npix; ++n) stage_fill(C, W, n);
+      state[5] = 0;
     }
     if (state[2]) { ++R.patches; for (int n = 0; n < npix; ++n) stage_patch(C, W, n); state[2] = 0; }
   }
@@ -169,7 +183,7 @@ struct HostLab : PnnLABQuantizer {
 }  // namespace
 
 extern "C" int nqs_spec_host(const uint32_t* argb, int w, int h, int nmax, int dither, uint64_t seed, int seg, int warm, int useCells,
-                             long long* out /* 11 values */) {
+                             long long* out /* 12 values */) {
   HarnessCfg cfg;
   cfg.seg = seg; cfg.warm = warm; cfg.useCells = useCells;
   g_h = &cfg;
@@ -184,7 +198,7 @@ extern "C" int nqs_spec_host(const uint32_t* argb, int w, int h, int nmax, int d
     return -1;
   }
   const HarnessOut& R = cfg.out;
-  long long v[11] = {R.eligible, R.exact, R.rounds, R.anomaly, R.nseg, R.segRuns, R.slowPixels, R.notes, R.mismatches, R.rejected, R.patches};
+  long long v[12] = {R.eligible, R.exact, R.rounds, R.anomaly, R.nseg, R.segRuns, R.slowPixels, R.notes, R.mismatches, R.rejected, R.patches, R.redos};
   memcpy(out, v, sizeof(v));
   g_h = nullptr;
   return 0;

@@ -16,7 +16,7 @@ SO = os.path.join(ROOT, "build", "libnq_spec_host.so")
 SRC = os.path.join(ROOT, "tests", "spec_host_harness.cpp")
 DEPS = [SRC, os.path.join(ROOT, "oracle", "nq_oracle.cpp"), os.path.join(ROOT, "nquant_android_b200", "csrc", "nq_dither_spec.cuh"),
         os.path.join(ROOT, "nquant_android_b200", "csrc", "nq_color.h"), os.path.join(ROOT, "nquant_android_b200", "csrc", "nq_math.h")]
-KEYS = ["eligible", "exact", "rounds", "anomaly", "nseg", "segRuns", "slowPixels", "notes", "mismatches", "rejected", "patches"]
+KEYS = ["eligible", "exact", "rounds", "anomaly", "nseg", "segRuns", "slowPixels", "notes", "mismatches", "rejected", "patches", "redos"]
 
 
 @pytest.fixture(scope="module")
@@ -34,7 +34,7 @@ def lib():
 
 def run(L, w, h, nmax, cls, alpha, seg, warm, cells=1, seed=0xC0FFEE, img_seed=0x5EED0000):
     img = np.ascontiguousarray(make_image(w, h, cls, alpha, seed=img_seed))
-    out = np.zeros(11, np.int64)
+    out = np.zeros(12, np.int64)
     assert L.nqs_spec_host(img.ctypes.data, w, h, nmax, 1, seed, seg, warm, cells, out.ctypes.data) == 0
     return dict(zip(KEYS, [int(v) for v in out]))
 
