@@ -352,7 +352,7 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
   const size_t oCpx = take((size_t)npix * 4), oCol = take((size_t)npix * 4), oK0 = take((size_t)npix * 4), oK1 = take((size_t)npix * 4);
   const size_t oDraw = take(((size_t)npix + 1) * 4), oQ = take((size_t)npix * 2), oFlag = take((size_t)npix);
   const size_t oFirst = take(65536 * 4), oSlowPos = take(65536 * 4), oMemo = take(65536 * 2), oSlowVal = take(65536 * 2);
-  const size_t oSegs = take(sizeof(SpecSeg) * (size_t)nseg), oState = take(64);
+  const size_t oSegs = take(sizeof(SpecSeg) * (size_t)nseg), oState = take(64), oRec = take(sizeof(SpecRec) * (size_t)nseg * (size_t)seg);
   const size_t perSlot = o;
   size_t freeB = 0, totalB = 0;
   CU(cudaMemGetInfo(&freeB, &totalB));
@@ -375,7 +375,7 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
     W.cdraw = reinterpret_cast<uint32_t*>(b + oDraw); W.cq = reinterpret_cast<unsigned short*>(b + oQ); W.cflag = b + oFlag;
     W.firstPos = reinterpret_cast<int*>(b + oFirst); W.slowPos = reinterpret_cast<int*>(b + oSlowPos);
     W.memo = reinterpret_cast<unsigned short*>(b + oMemo); W.slowVal = reinterpret_cast<unsigned short*>(b + oSlowVal);
-    W.segs = reinterpret_cast<SpecSeg*>(b + oSegs); W.state = reinterpret_cast<int*>(b + oState);
+    W.segs = reinterpret_cast<SpecSeg*>(b + oSegs); W.state = reinterpret_cast<int*>(b + oState); W.rec = reinterpret_cast<SpecRec*>(b + oRec);
   }
   CU(cudaMemcpyAsync(c->dSpec, h.data(), sizeof(SpecImage) * (size_t)n, cudaMemcpyHostToDevice, st));
   k_spec_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, c->dSpec, dOrder, n, seg, warm, c->dSpecInts + 4); ++c->launches;
@@ -410,6 +410,7 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
     k_spec_resolve<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("resolve");
     k_spec_memo<<<kg, 256, 0, st>>>(sp); ++c->launches; lap("memo");
     k_spec_fill<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("fill");
+    k_spec_pack<<<pg, 256, 0, st>>>(sp, 0); ++c->launches; lap("pack");
     for (int round = 0; round < roundCap; ++round) {
       CU(cudaMemsetAsync(c->dSpecInts, 0, 4 * sizeof(int), st));
       k_spec_run<<<dim3((nseg + 63) / 64, m), 64, 0, st>>>(sp); ++c->launches; lap("run");
@@ -428,6 +429,7 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
         k_spec_redo_c<<<kg, 256, 0, st>>>(sp); ++c->launches;
         k_spec_redo_d<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("re-resolve");
       }
+      if (counters[1] || counters[2]) { k_spec_pack<<<pg, 256, 0, st>>>(sp, 1); ++c->launches; lap("pack"); }
       if (!counters[0]) break;
     }
     CU(cudaMemsetAsync(c->dSpecInts + 3, 0, sizeof(int), st));

@@ -65,6 +65,15 @@ struct SpecSeg {
   int nreads;                            // > NQS_READS: overflow (treated as "may have read any key")
   int readKey[NQS_READS];
 };
+// What stage 6 reads per pixel, packed by stage 5b and stored SEGMENT-INTERLEAVED: record of curve position n lives at
+// (n % seg) * nseg + n / seg, so the threads of a warp (consecutive segments, same offset inside the segment) read
+// consecutive 16-byte records.
+struct alignas(16) SpecRec {
+  uint32_t px;                           // source pixel
+  uint32_t bidx;                         // x + y * width
+  uint32_t qf;                           // palette index | flags << 16 | (TELL_BLUE_NOISE[bidx & 4095] > thresold) << 24
+  uint32_t pad;
+};
 struct SpecWork {
   const uint32_t* order;                 // x | y << 16 per curve position
   const uint32_t* in;                    // source pixels, row-major
@@ -75,6 +84,7 @@ struct SpecWork {
   uint32_t* ck1;                         // second smallest
   unsigned short* cq;                    // resolved palette index (or memo key while NQS_F_NEAR)
   unsigned char* cflag;
+  SpecRec* rec;                          // [nseg * seg] packed view for stage 6 (stage_pack)
   uint32_t* cdraw;                       // [npix + 1] draws predicted before this pixel (exclusive prefix of NQS_F_DRAW)
   int* firstPos;                         // [65536] first curve position whose pre-lookup needs memo key k
   unsigned short* memo;                  // [65536] nearestMap for reduced keys (0xFFFF = absent)
@@ -381,6 +391,18 @@ NQ_HD void stage_memo(const SpecConst& C, const SpecWork& W, int key, int after)
 NQ_HD void stage_fill(const SpecConst& C, const SpecWork& W, int n) {
   if (W.cflag[n] & NQS_F_NEAR) W.cq[n] = W.memo[memo_key(C, W.ccol[n])];
 }
+// ---- stage 5b: the packed record of one pixel (again after a patch or a re-resolve) -------------------------------
+NQ_HD size_t rec_index(const SpecConst& C, int n) { return (size_t)(n % C.seg) * (size_t)C.nseg + (size_t)(n / C.seg); }
+NQ_HD void stage_pack(const SpecConst& C, const SpecWork& W, int n) {
+  const uint32_t xy = W.order[n];
+  const int bidx = (int)(xy & 0xFFFF) + (int)(xy >> 16) * C.width;
+  SpecRec r;
+  r.px = W.cpx[n];
+  r.bidx = (uint32_t)bidx;
+  r.qf = (uint32_t)W.cq[n] | ((uint32_t)W.cflag[n] << 16) | (W.bn[bidx & 4095] > C.thresold ? 1u << 24 : 0u);
+  r.pad = 0;
+  W.rec[rec_index(C, n)] = r;
+}
 // ---- re-resolve after a draw misprediction at curve position `from` = state[5] - 1 (stage_validate has corrected the
 //      pixel's flag): stage 2 again, then per memo key this reset, then stages 3-5 for the pixels behind `from`
 NQ_HD void stage_rekey(const SpecWork& W, int key, int from) {
@@ -459,13 +481,16 @@ NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
   S.nnotes = 0;
   S.nreads = 0;
   S.mispos = -1;
+  SpecRec nxt = W.rec[rec_index(C, from < p1 ? from : 0)];
   for (int n = from; n < p1; ++n) {
     if (n == p0) {
       for (int k = 0; k < DM; ++k) { const int q = head + k < DM ? head + k : head + k - DM; for (int j = 0; j < 4; ++j) S.qwarm[k][j] = e[q][j]; }
       draws = 0;
     }
     const bool owned = n >= p0;
-    const uint32_t px = W.cpx[n];
+    const SpecRec rc = nxt;
+    if (n + 1 < p1) nxt = W.rec[rec_index(C, n + 1)];         // one pixel ahead of its use
+    const uint32_t px = rc.px;
     // ---- error.p = pixel + sum(queue[i].p * weights[i]), oldest box first (GC:190-204)
     float a0 = (float)c_red(px), a1 = (float)c_green(px), a2 = (float)c_blue(px), a3 = (float)c_alpha(px);
     float maxErr = (float)(DM - 1);
@@ -482,15 +507,15 @@ NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
     }
     const int r_pix = (int)fminf(255.f, fmaxf(a0, 0.f)), g_pix = (int)fminf(255.f, fmaxf(a1, 0.f));
     const int b_pix = (int)fminf(255.f, fmaxf(a2, 0.f)), a_pix = (int)fminf(255.f, fmaxf(a3, 0.f));
-    const unsigned flag = W.cflag[n];
-    const uint32_t xy = W.order[n];
-    const int x = (int)(xy & 0xFFFF), y = (int)(xy >> 16), bidx = x + y * C.width;
+    const unsigned flag = (rc.qf >> 16) & 0xFFu;
+    const int bidx = (int)rc.bidx;
     // ---- quantize (GC:211-229)
     int qi;
     if (flag & NQS_F_PRE) {
-      qi = W.cq[n];
+      qi = (int)(rc.qf & 0xFFFFu);
       if (flag & NQS_F_DRAW) ++draws;
     } else {
+      const int x = bidx % C.width, y = bidx / C.width;
       const uint32_t c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
       const float sal = saliency_of(C, W, px);
       uint32_t c = c2;
@@ -505,7 +530,7 @@ NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
     float e0 = (float)(r_pix - c_red(pc)), e1 = (float)(g_pix - c_green(pc)), e2 = (float)(b_pix - c_blue(pc)), e3 = (float)(a_pix - c_alpha(pc));
     const bool s0 = fabsf_(e0) >= fDitherMax, s1 = fabsf_(e1) >= fDitherMax, s2 = fabsf_(e2) >= fDitherMax;
     if (s0 || s1 || s2) {
-      if (W.bn[bidx & 4095] > C.thresold) {
+      if ((rc.qf >> 24) & 1u) {                              // diffuse = TELL_BLUE_NOISE[bidx & 4095] > thresold (GC:250)
         if (s0) e0 = tanh_f((double)(e0 / maxErr * 20.f)) * fDitherMax1;
         if (s1) e1 = tanh_f((double)(e1 / maxErr * 20.f)) * fDitherMax1;
         if (s2) e2 = tanh_f((double)(e2 / maxErr * 20.f)) * fDitherMax1;
@@ -733,6 +758,12 @@ __global__ void __launch_bounds__(256) k_spec_fill(SpecImage* sp) {
   const SpecImage& P = sp[blockIdx.y];
   if (!NQS_ACTIVE(P)) return;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_fill(P.C, P.W, n);
+}
+// stage 5b; `only` = 0: every active image, 1: images with a pending patch or re-resolve
+__global__ void __launch_bounds__(256) k_spec_pack(SpecImage* sp, int only) {
+  const SpecImage& P = sp[blockIdx.y];
+  if (!NQS_ACTIVE(P) || (only && !P.W.state[2] && !P.W.state[5])) return;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_pack(P.C, P.W, n);
 }
 // stage 6: one thread per segment
 __global__ void __launch_bounds__(64) k_spec_run(SpecImage* sp) {

@@ -105,6 +105,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   std::vector<unsigned short> cq(npix), memo(65536, 0xFFFF), slowVal(65536, 0);
   std::vector<unsigned char> cflag(npix), cells;
   std::vector<int> firstPos(65536, NQS_NOPOS), slowPos(65536, NQS_NOPOS), state(8, 0);
+  std::vector<SpecRec> rec((size_t)C.nseg * C.seg);
   std::vector<SpecSeg> segs(C.nseg);
   memset(segs.data(), 0, sizeof(SpecSeg) * segs.size());
   for (auto& s : segs) s.dirty = 1;
@@ -116,7 +117,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   W.order = order.data(); W.in = in.data(); W.out = out.data(); W.cpx = cpx.data(); W.ccol = ccol.data(); W.ck0 = ck0.data(); W.ck1 = ck1.data();
   W.cq = cq.data(); W.cflag = cflag.data(); W.cdraw = cdraw.data(); W.firstPos = firstPos.data(); W.memo = memo.data();
   W.slowPos = slowPos.data(); W.slowVal = slowVal.data(); W.cells = H.useCells ? cells.data() : nullptr; W.lut = lut.data(); W.bn = bn;
-  W.segs = segs.data(); W.state = state.data();
+  W.segs = segs.data(); W.state = state.data(); W.rec = rec.data();
 
   for (int n = 0; n < npix; ++n) stage_pre(C, W, n);                                     // stage 1
   { uint32_t d = 0; for (int n = 0; n < npix; ++n) { cdraw[n] = d; d += (cflag[n] & NQS_F_DRAW) ? 1u : 0u; } cdraw[npix] = d; }   // stage 2
@@ -128,6 +129,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   }
   for (int key = 0; key < 65536; ++key) stage_memo(C, W, key, -1);                       // stage 4
   for (int n = 0; n < npix; ++n) stage_fill(C, W, n);                                    // stage 5
+  for (int n = 0; n < npix; ++n) stage_pack(C, W, n);                                    // stage 5b
   R.nseg = C.nseg;
   int open = C.nseg;
   while (open > 0 && !state[1] && R.rounds < 100000) {
@@ -143,6 +145,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
       if (s > 0 && R.rounds < 3) for (int k = 0; k < C.DM; ++k) fprintf(stderr, "  box %2d warm (%g %g %g %g) prev (%g %g %g %g)\n", k, segs[s].qwarm[k][0], segs[s].qwarm[k][1], segs[s].qwarm[k][2], segs[s].qwarm[k][3],
           segs[s - 1].qout[k][0], segs[s - 1].qout[k][1], segs[s - 1].qout[k][2], segs[s - 1].qout[k][3]);
     }
+    const bool repack = state[2] || state[5];
     if (state[5] && !state[1]) {                                                         // draw misprediction: re-resolve behind it
       ++R.redos;
       const int from = state[5] - 1;
@@ -158,6 +161,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
       state[5] = 0;
     }
     if (state[2]) { ++R.patches; for (int n = 0; n < npix; ++n) stage_patch(C, W, n); state[2] = 0; }
+    if (repack) for (int n = 0; n < npix; ++n) stage_pack(C, W, n);
   }
   R.anomaly = state[1];
   for (auto& s : segs) R.notes += std::min(s.nnotes, NQS_NOTES);
