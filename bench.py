@@ -53,6 +53,11 @@ def parse():
     ap.add_argument("--colors", type=int, default=256)
     ap.add_argument("--dither", type=int, default=1)
     ap.add_argument("--cls", default="noisy", choices=list(CLASSES))
+    ap.add_argument("--spec-dither", type=int, default=int(os.environ.get("NQ_SPEC_DITHER", "0")),
+                    help="1: speculative segment-parallel dither for the images that qualify (DESIGN.md 7.1; bit-identical results). "
+                         "Off by default until its GPU tests have run on a B200")
+    ap.add_argument("--spec-segment", type=int, default=8192)
+    ap.add_argument("--spec-warmup", type=int, default=1024)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-workers", type=int, default=0, help="reference arm: worker processes (0 = all cores)")
@@ -194,6 +199,7 @@ def run_ours(a, rank, world, local_rank):
     ctx = Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
+    ctx.set_spec_dither(bool(a.spec_dither), a.spec_segment, a.spec_warmup)
     kind, cls = KINDS[a.kind], CLASSES[a.cls]
     npix = a.width * a.height
     n = a.batch
@@ -316,7 +322,9 @@ def run_ours(a, rank, world, local_rank):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(a), "global_batch_images": world * n, "pixels_per_step": world * n * npix,
                            "parallelism": f"one image shard per GPU x{world}, no collective",
-                           "l2": "inputs larger than L2 (batch x 33 MB per image)"},
+                           "l2": "inputs larger than L2 (batch x 33 MB per image)",
+                           "dither_path": ("speculative segments %d/%d (%s)" % (a.spec_segment, a.spec_warmup, ctx.spec_stats())) if a.spec_dither
+                                          else "serial chain per image"},
                 "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "stages": per_stage}
         if e2e:
             line["e2e"] = e2e
