@@ -461,17 +461,23 @@ NQ_HD int slow_lookup(const SpecConst& C, const SpecWork& W, SpecSeg& S, int n, 
   return v;
 }
 
-NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
+// DM is a template constant (DITHER_MAX is 16 or 25 for the images this path takes, GC:96) so that the queue and the
+// weights are fully unrolled: a shift register of DM boxes in registers, e[0] = oldest, no indexed local memory.
+template <int DM>
+NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s) {
   SpecSeg& S = W.segs[s];
   if (S.done || !S.dirty) return;
-  const int DM = C.DM, p0 = s * C.seg, p1 = (p0 + C.seg < C.npix) ? p0 + C.seg : C.npix;
-  float e[NQ_MAXQ][4];                                     // the queue, e[head] = oldest box
-  int head = 0;
+  const int p0 = s * C.seg, p1 = (p0 + C.seg < C.npix) ? p0 + C.seg : C.npix;
+  float e[DM][4], w[DM];                                   // the queue (e[0] = oldest box) and initWeights(DITHER_MAX)
   int from = p0;
+#pragma unroll
+  for (int k = 0; k < DM; ++k) w[k] = C.w[k];
   if (S.exact && p0 > 0) {
-    for (int k = 0; k < DM; ++k) for (int j = 0; j < 4; ++j) e[k][j] = S.qstart[k][j];
+#pragma unroll
+    for (int k = 0; k < DM; ++k) { e[k][0] = S.qstart[k][0]; e[k][1] = S.qstart[k][1]; e[k][2] = S.qstart[k][2]; e[k][3] = S.qstart[k][3]; }
   } else {
-    for (int k = 0; k < DM; ++k) for (int j = 0; j < 4; ++j) e[k][j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < DM; ++k) { e[k][0] = 0.f; e[k][1] = 0.f; e[k][2] = 0.f; e[k][3] = 0.f; }
     if (!S.exact) from = p0 - C.warm > 0 ? p0 - C.warm : 0;
   }
   const float fDitherMax = (float)C.ditherMax, fDitherMax1 = (float)(C.ditherMax - 1);
@@ -484,7 +490,8 @@ NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
   SpecRec nxt = W.rec[rec_index(C, from < p1 ? from : 0)];
   for (int n = from; n < p1; ++n) {
     if (n == p0) {
-      for (int k = 0; k < DM; ++k) { const int q = head + k < DM ? head + k : head + k - DM; for (int j = 0; j < 4; ++j) S.qwarm[k][j] = e[q][j]; }
+#pragma unroll
+      for (int k = 0; k < DM; ++k) { S.qwarm[k][0] = e[k][0]; S.qwarm[k][1] = e[k][1]; S.qwarm[k][2] = e[k][2]; S.qwarm[k][3] = e[k][3]; }
       draws = 0;
     }
     const bool owned = n >= p0;
@@ -494,16 +501,12 @@ NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
     // ---- error.p = pixel + sum(queue[i].p * weights[i]), oldest box first (GC:190-204)
     float a0 = (float)c_red(px), a1 = (float)c_green(px), a2 = (float)c_blue(px), a3 = (float)c_alpha(px);
     float maxErr = (float)(DM - 1);
-    {
-      int q = head;
-      for (int k = 0; k < DM; ++k) {
-        const float wk = C.w[k];
-        a0 = a0 + e[q][0] * wk; if (a0 > maxErr) maxErr = a0;
-        a1 = a1 + e[q][1] * wk; if (a1 > maxErr) maxErr = a1;
-        a2 = a2 + e[q][2] * wk; if (a2 > maxErr) maxErr = a2;
-        a3 = a3 + e[q][3] * wk; if (a3 > maxErr) maxErr = a3;
-        if (++q == DM) q = 0;
-      }
+#pragma unroll
+    for (int k = 0; k < DM; ++k) {
+      a0 = a0 + e[k][0] * w[k]; if (a0 > maxErr) maxErr = a0;
+      a1 = a1 + e[k][1] * w[k]; if (a1 > maxErr) maxErr = a1;
+      a2 = a2 + e[k][2] * w[k]; if (a2 > maxErr) maxErr = a2;
+      a3 = a3 + e[k][3] * w[k]; if (a3 > maxErr) maxErr = a3;
     }
     const int r_pix = (int)fminf(255.f, fmaxf(a0, 0.f)), g_pix = (int)fminf(255.f, fmaxf(a1, 0.f));
     const int b_pix = (int)fminf(255.f, fmaxf(a2, 0.f)), a_pix = (int)fminf(255.f, fmaxf(a3, 0.f));
@@ -545,13 +548,23 @@ NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
       }
     }
     // ---- errorq.poll(); errorq.add(error) (GC:231, 276)
-    e[head][0] = e0; e[head][1] = e1; e[head][2] = e2; e[head][3] = e3;
-    if (++head == DM) head = 0;
+#pragma unroll
+    for (int k = 0; k + 1 < DM; ++k) { e[k][0] = e[k + 1][0]; e[k][1] = e[k + 1][1]; e[k][2] = e[k + 1][2]; e[k][3] = e[k + 1][3]; }
+    e[DM - 1][0] = e0; e[DM - 1][1] = e1; e[DM - 1][2] = e2; e[DM - 1][3] = e3;
   }
-  if (p0 >= p1) { for (int k = 0; k < DM; ++k) for (int j = 0; j < 4; ++j) S.qwarm[k][j] = e[k][j]; }
-  for (int k = 0; k < DM; ++k) { const int q = head + k < DM ? head + k : head + k - DM; for (int j = 0; j < 4; ++j) S.qout[k][j] = e[q][j]; }
+  if (p0 >= p1) {
+#pragma unroll
+    for (int k = 0; k < DM; ++k) { S.qwarm[k][0] = e[k][0]; S.qwarm[k][1] = e[k][1]; S.qwarm[k][2] = e[k][2]; S.qwarm[k][3] = e[k][3]; }
+  }
+#pragma unroll
+  for (int k = 0; k < DM; ++k) { S.qout[k][0] = e[k][0]; S.qout[k][1] = e[k][1]; S.qout[k][2] = e[k][2]; S.qout[k][3] = e[k][3]; }
   S.draws = draws;
   S.dirty = 0;
+}
+NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
+  if (C.DM == 25) stage_run_t<25>(C, W, s);
+  else if (C.DM == 16) stage_run_t<16>(C, W, s);
+  // DITHER_MAX == 9 is not taken by this path (k_spec_setup)
 }
 
 // ---- stage 7: ordered validation of one image. Returns the number of segments still open. ------------------------
