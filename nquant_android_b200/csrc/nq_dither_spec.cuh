@@ -26,14 +26,18 @@
 namespace nq {
 namespace spec {
 
-#define NQS_NOTES 12            // memo entries a segment may create through error-dependent lookups
-#define NQS_READS 24            // memo entries of the pre-lookups its error-dependent lookups may read
+#define NQS_NOTES 48            // memo entries a segment may create through error-dependent lookups
+#define NQS_READS 64            // memo entries of the pre-lookups its error-dependent lookups may read
 #define NQS_NOPOS 0x7fffffff
 #define NQS_NONE 0xFFFFFFFFu    // absent top-2 key
 
 // per-pixel flags (curve order)
 #define NQS_F_PRE 1u            // lookup does not read the diffused colour
 #define NQS_F_DRAW 2u           // the lookup is predicted to call Random.nextInt (PL:467)
+#define NQS_F_RISK 8u           // error-dependent lookup predicted NOT to draw: the pixel is (nearly) a palette colour, any diffused
+                                // error makes it draw (PL:467) and every later draw index moves
+#define NQS_MAXRISK 16          // more such pixels than this: the image is left to the serial kernel before any segment runs
+#define NQS_MAXREDO 24          // draw mispredictions corrected per image before giving up
 #define NQS_F_NEAR 4u           // resolved through nearestColorIndex's memo (PL:470-472), key = memo_key(ccol)
 
 // Constants of one image: what GilbertCurve's constructor and the quantizer hold while dithering.
@@ -94,8 +98,8 @@ struct SpecWork {
   const double* lut;                     // gammaToLinear table
   const signed char* bn;                 // TELL_BLUE_NOISE
   SpecSeg* segs;
-  int* state;                            // [8]: firstOpen, anomaly, patch key + 1 (0 = none), patch position, failed validations,
-                                         //      re-resolve position + 1 (0 = none), re-resolves so far
+  int* state;                            // [16]: firstOpen, anomaly, patch key + 1 (0 = none), patch position, failed validations,
+                                         //      re-resolve position + 1 (0 = none), re-resolves so far, pixels flagged NQS_F_RISK, error-dependent lookups
 };
 
 // ---- java.util.Random: state after j more steps of the LCG ------------------------------------------------
@@ -344,6 +348,7 @@ NQ_HD void stage_pre(const SpecConst& C, const SpecWork& W, int n) {
   if (viaClosest) {
     top2(C, W.cells, c, &k0, &k1);
     if ((k0 >> 8) != 0u) flag |= NQS_F_DRAW;               // short-circuit: no draw when closest[2] == 0 (PL:467)
+    else if (!(flag & NQS_F_PRE)) flag |= NQS_F_RISK;
   }
   W.ccol[n] = c; W.ck0[n] = k0; W.ck1[n] = k1;
   W.cflag[n] = (unsigned char)flag;
@@ -379,6 +384,11 @@ NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firs
   } else
     W.cq[n] = (unsigned short)qi;
   return ok;
+}
+// ---- gate after stage 3 (state[7] = pixels flagged NQS_F_RISK): too many likely mispredictions, do not start
+NQ_HD void stage_gate(const SpecConst& C, const SpecWork& W) {
+  if (W.state[7] > NQS_MAXRISK) W.state[1] = 1;
+  if (W.state[8] > (C.npix >> 6)) W.state[1] = 1;           // state[8] = error-dependent lookups: past 1.5 % one thread per segment stops paying
 }
 // ---- stage 4: one memo key ------------------------------------------------------------------------------------
 // `after`: only entries first seen behind that curve position (-1 = all); the others are settled
@@ -596,7 +606,7 @@ NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
       W.cflag[S.mispos] = (unsigned char)(W.cflag[S.mispos] ^ NQS_F_DRAW);
       W.state[5] = S.mispos + 1;
       for (int t = s; t < C.nseg; ++t) W.segs[t].dirty = 1;
-      if (++W.state[6] > 64) { W.state[1] = 1; return 0; }
+      if (++W.state[6] > NQS_MAXREDO) { W.state[1] = 1; return 0; }
       break;
     }
     if (ok) {
@@ -698,7 +708,7 @@ __global__ void __launch_bounds__(256) k_spec_init(SpecImage* sp) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   for (int k = t; k < 65536; k += nt) { P.W.firstPos[k] = NQS_NOPOS; P.W.slowPos[k] = NQS_NOPOS; P.W.memo[k] = 0xFFFF; P.W.slowVal[k] = 0; }
   for (int s = t; s < P.C.nseg; s += nt) { SpecSeg& S = P.W.segs[s]; S.exact = s == 0; S.dirty = 1; S.done = 0; S.draws = 0; S.nnotes = 0; S.nreads = 0; S.mispos = -1; }
-  if (t < 8) P.W.state[t] = 0;
+  if (t < 16) P.W.state[t] = 0;
 }
 __global__ void __launch_bounds__(256) k_spec_pre(SpecImage* sp) {
   const SpecImage& P = sp[blockIdx.y];
@@ -729,6 +739,8 @@ __global__ void __launch_bounds__(256) k_spec_resolve(SpecImage* sp) {
   if (!P.eligible) return;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) {
     int key;
+    if (P.W.cflag[n] & NQS_F_RISK) atomicAdd(&P.W.state[7], 1);
+    if (!(P.W.cflag[n] & NQS_F_PRE)) atomicAdd(&P.W.state[8], 1);
     if (!stage_resolve(P.C, P.W, n, &key)) P.W.state[1] = 1;      // a nextInt that draws twice (2 in 2^31): leave the image to the serial kernel
     if (key >= 0) atomicMin(&P.W.firstPos[key], n);
   }
@@ -765,6 +777,7 @@ __global__ void __launch_bounds__(256) k_spec_redo_d(SpecImage* sp) {
 __global__ void __launch_bounds__(256) k_spec_memo(SpecImage* sp) {
   const SpecImage& P = sp[blockIdx.y];
   if (!NQS_ACTIVE(P)) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) stage_gate(P.C, P.W);   // seen by every later launch (NQS_ACTIVE)
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 65536; k += gridDim.x * blockDim.x) stage_memo(P.C, P.W, k, -1);
 }
 __global__ void __launch_bounds__(256) k_spec_fill(SpecImage* sp) {

@@ -104,7 +104,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   for (int i = 0; i < npix; ++i) in[i] = (uint32_t)cPixels[i];
   std::vector<unsigned short> cq(npix), memo(65536, 0xFFFF), slowVal(65536, 0);
   std::vector<unsigned char> cflag(npix), cells;
-  std::vector<int> firstPos(65536, NQS_NOPOS), slowPos(65536, NQS_NOPOS), state(8, 0);
+  std::vector<int> firstPos(65536, NQS_NOPOS), slowPos(65536, NQS_NOPOS), state(16, 0);
   std::vector<SpecRec> rec((size_t)C.nseg * C.seg);
   std::vector<SpecSeg> segs(C.nseg);
   memset(segs.data(), 0, sizeof(SpecSeg) * segs.size());
@@ -126,7 +126,10 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
     if (!stage_resolve(C, W, n, &key)) { ++R.rejected; state[1] = 1; }
     if (key >= 0 && n < firstPos[key]) firstPos[key] = n;
     if (!(cflag[n] & NQS_F_PRE)) ++R.slowPixels;
+    if (cflag[n] & NQS_F_RISK) ++state[7];
+    if (!(cflag[n] & NQS_F_PRE)) ++state[8];
   }
+  stage_gate(C, W);
   for (int key = 0; key < 65536; ++key) stage_memo(C, W, key, -1);                       // stage 4
   for (int n = 0; n < npix; ++n) stage_fill(C, W, n);                                    // stage 5
   for (int n = 0; n < npix; ++n) stage_pack(C, W, n);                                    // stage 5b
