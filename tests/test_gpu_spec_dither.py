@@ -32,6 +32,7 @@ def spec_ctx():
     (320, 180, 128, "noisy", 2048, 512, 99),
     (173, 211, 200, "noisy", 1000, 300, 5),        # warm-up too short for some segments: exact re-runs
     (512, 512, 256, "noisy", 8192, 1024, 0xC0FFEE),
+    (256, 192, 256, "rand", 2048, 512, 0xC0FFEE),    # a memo entry created by an error-dependent lookup is patched in (1 patch on the CPU harness)
 ])
 def test_spec_dither_is_bit_identical(spec_ctx, oracle, w, h, nmax, cls, seg, warm, seed):
     img = make_image(w, h, cls, "opaque")
@@ -42,6 +43,20 @@ def test_spec_dither_is_bit_identical(spec_ctx, oracle, w, h, nmax, cls, seg, wa
     assert np.array_equal(out[0], ref.out)
     assert spec_ctx.image_info(0)["rng_draws"] == ref.scalars["rng_draws"]
     assert spec_ctx.spec_stats()["images"] == 1, "the speculative path did not take (or finish) the image"
+
+
+def test_spec_dither_corrects_draw_mispredictions(spec_ctx, oracle):
+    """Image 13 of the 1080p probe batch: five error-dependent lookups draw against their prediction (CPU harness: 5 re-resolves,
+    6 rounds); the path must finish it itself, bit-identical."""
+    w, h, i = 1920, 1080, 13
+    img = make_image(w, h, "noisy", "opaque", seed=0x5EED0000 + i)
+    ref = oracle.convert(1, img, w, h, 256, True, seed=0xC0FFEE + i, trace=False)
+    spec_ctx.set_spec_dither(True, 8192, 1024)
+    out, pal, plen, _ = spec_ctx.convert_batch(1, img[None, :], w, h, 256, True, seeds=[0xC0FFEE + i])
+    assert np.array_equal(out[0], ref.out)
+    assert spec_ctx.image_info(0)["rng_draws"] == ref.scalars["rng_draws"]
+    st = spec_ctx.spec_stats()
+    assert st["images"] == 1 and st["fallbacks"] == 0 and st["rounds"] >= 2, st
 
 
 def test_spec_dither_batch_and_mixed_eligibility(spec_ctx, oracle):
