@@ -497,7 +497,11 @@ NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s) {
   S.nnotes = 0;
   S.nreads = 0;
   S.mispos = -1;
-  SpecRec nxt = W.rec[rec_index(C, from < p1 ? from : 0)];
+  // position of the NEXT record to fetch in the segment-interleaved layout, advanced without a division per pixel
+  const int segLen = C.seg, nsegs = C.nseg;
+  int rrow = (from < p1 ? from : 0) % segLen, rcol = (from < p1 ? from : 0) / segLen;
+  const SpecRec* const recs = W.rec;
+  SpecRec nxt = recs[(size_t)rrow * (size_t)nsegs + (size_t)rcol];
   for (int n = from; n < p1; ++n) {
     if (n == p0) {
 #pragma unroll
@@ -506,7 +510,10 @@ NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s) {
     }
     const bool owned = n >= p0;
     const SpecRec rc = nxt;
-    if (n + 1 < p1) nxt = W.rec[rec_index(C, n + 1)];         // one pixel ahead of its use
+    if (n + 1 < p1) {                                         // one pixel ahead of its use
+      if (++rrow == segLen) { rrow = 0; ++rcol; }
+      nxt = recs[(size_t)rrow * (size_t)nsegs + (size_t)rcol];
+    }
     const uint32_t px = rc.px;
     // ---- error.p = pixel + sum(queue[i].p * weights[i]), oldest box first (GC:190-204)
     float a0 = (float)c_red(px), a1 = (float)c_green(px), a2 = (float)c_blue(px), a3 = (float)c_alpha(px);
