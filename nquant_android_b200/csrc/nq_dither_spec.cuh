@@ -471,7 +471,7 @@ NQ_HD int slow_lookup(const SpecConst& C, const SpecWork& W, SpecSeg& S, int n, 
   return v;
 }
 
-// DM is a template constant (DITHER_MAX is 16 or 25 for the images this path takes, GC:96) so that the queue and the
+// DM is a template constant (DITHER_MAX is 9, 16 or 25, GC:96) so that the queue and the
 // weights are fully unrolled: a shift register of DM boxes in registers, e[0] = oldest, no indexed local memory.
 template <int DM>
 NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s) {
@@ -581,7 +581,7 @@ NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s) {
 NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
   if (C.DM == 25) stage_run_t<25>(C, W, s);
   else if (C.DM == 16) stage_run_t<16>(C, W, s);
-  // DITHER_MAX == 9 is not taken by this path (k_spec_setup)
+  else if (C.DM == 9) stage_run_t<9>(C, W, s);
 }
 
 // ---- stage 7: ordered validation of one image. Returns the number of segments still open. ------------------------
@@ -690,7 +690,7 @@ __global__ void k_spec_setup(const NqImage* imgs, const NqSlot* slots, SpecImage
   // PnnLABQuantizer, dither on, saliency map, ArrayDeque queue, opaque image (a transparent pixel leaves a constant alpha
   // error in the queue for ever: alpha is never shaped, GC:248), ditherPixel lookups independent of the diffused colour
   P.eligible = I.kind == NQ_KIND_LAB && I.dither && I.gUseSal && !I.gSorted && !I.gHasAlpha && !I.hasSemi && I.transIdx < 0 && !I.error &&
-               plen > 64 && 2 * acceptedDiff > 101 && I.gDitherMaxQ > 9 && I.nmax > 2 && slots[i].cells != nullptr && I.npix >= 4 * seg;
+               plen > 64 && 2 * acceptedDiff > 101 && I.nmax > 2 && slots[i].cells != nullptr && I.npix >= 4 * seg;
   eligOut[i] = P.eligible;
   if (!P.eligible) return;
   C.plen = plen; C.margin = I.gMargin; C.thresold = I.gThresold; C.DM = I.gDitherMaxQ; C.ditherMax = I.gDitherMax;

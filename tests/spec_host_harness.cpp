@@ -73,7 +73,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   const int plen = (int)palette.size();
   // same eligibility rule as the device (k_spec_setup)
   const int acceptedDiff = std::max(2, plen - gc.margin);
-  const bool eligible = dither && q.hasSaliencies && !gc.sortedByYDiff && !gc.hasAlpha && plen > 64 && 2 * acceptedDiff > 101 && gc.DITHER_MAX > 9 && q.m_transparentPixelIndex < 0;
+  const bool eligible = dither && q.hasSaliencies && !gc.sortedByYDiff && !gc.hasAlpha && plen > 64 && 2 * acceptedDiff > 101 && q.m_transparentPixelIndex < 0;
   R.eligible = eligible;
   if (!eligible) return;
 

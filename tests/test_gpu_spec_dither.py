@@ -32,6 +32,7 @@ def spec_ctx():
     (320, 180, 128, "noisy", 2048, 512, 99),
     (173, 211, 200, "noisy", 1000, 300, 5),        # warm-up too short for some segments: exact re-runs
     (512, 512, 256, "noisy", 8192, 1024, 0xC0FFEE),
+    (256, 256, 128, "smooth", 4096, 1024, 3),         # DITHER_MAX 9
     (256, 192, 256, "rand", 2048, 512, 0xC0FFEE),    # a memo entry created by an error-dependent lookup is patched in (1 patch on the CPU harness)
 ])
 def test_spec_dither_is_bit_identical(spec_ctx, oracle, w, h, nmax, cls, seg, warm, seed):

@@ -45,6 +45,7 @@ def run(L, w, h, nmax, cls, alpha, seg, warm, cells=1, seed=0xC0FFEE, img_seed=0
     (256, 192, 256, "rand", "opaque", 2048, 512, 1),
     (320, 180, 128, "noisy", "opaque", 2048, 512, 1),
     (173, 211, 200, "noisy", "opaque", 1000, 300, 1),        # ragged sizes, warm-up too short for some segments: re-runs
+    (256, 256, 128, "smooth", "opaque", 4096, 1024, 1),      # DITHER_MAX 9 (weight >= .015), ArrayDeque because of <= 128 colours
 ])
 def test_spec_pipeline_matches_sequential_oracle(lib, w, h, nmax, cls, alpha, seg, warm, cells):
     r = run(lib, w, h, nmax, cls, alpha, seg, warm, cells)
