@@ -13,9 +13,13 @@
 // (warm-up from an empty queue, then the owned pixels); stage 7 validates the segments in curve order: the queue
 // a segment warmed up to must equal, bit for bit, the queue its predecessor ended with, the draws it made must
 // equal the prediction, and a memo entry created by one of its error-dependent lookups must not contradict an
-// earlier one. A segment that fails re-runs from its predecessor's exact state in the next round; an image
-// whose draw prediction or memo was contradicted is handed to the serial kernel (k_dither_fifo). The result is
-// therefore bit-identical to the sequential run by construction.
+// earlier one. A segment that fails re-runs from its predecessor's exact state in the next round. A memo entry that
+// an error-dependent lookup created before the first pre-lookup of its key is patched into the later pixels
+// (stage_patch); a draw that goes against its prediction moves every later draw index, so the pixel's flag is
+// corrected and stages 2-5 are redone behind it (stage_rekey, k_spec_redo_*). Images that would thrash (stage_gate)
+// or exhaust a cap are left to the serial kernel (k_dither_fifo) -- one such image costs the batch the whole serial
+// chain, so the gates sit before any segment runs. The result is bit-identical to the sequential run by
+// construction: a segment is only accepted from an exact input state.
 //
 // Every stage body is a scalar NQ_HD function so that the very same code is compiled by g++ and checked
 // against the CPU oracle (tests/test_spec_dither_host.py); the kernels at the end of the file only index.
