@@ -409,8 +409,7 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
     k_spec_scan<<<m, 1024, 0, st>>>(sp, 0); ++c->launches; lap("scan");
     k_spec_resolve<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("resolve");
     k_spec_memo<<<kg, 256, 0, st>>>(sp); ++c->launches; lap("memo");
-    k_spec_fill<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("fill");
-    k_spec_pack<<<pg, 256, 0, st>>>(sp, 0); ++c->launches; lap("pack");
+    k_spec_fill<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("fill+pack");
     for (int round = 0; round < roundCap; ++round) {
       CU(cudaMemsetAsync(c->dSpecInts, 0, 4 * sizeof(int), st));
       k_spec_run<<<dim3((nseg + 63) / 64, m), 64, 0, st>>>(sp); ++c->launches; lap("run");

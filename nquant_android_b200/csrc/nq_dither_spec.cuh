@@ -794,9 +794,9 @@ __global__ void __launch_bounds__(256) k_spec_memo(SpecImage* sp) {
 __global__ void __launch_bounds__(256) k_spec_fill(SpecImage* sp) {
   const SpecImage& P = sp[blockIdx.y];
   if (!NQS_ACTIVE(P)) return;
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_fill(P.C, P.W, n);
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) { stage_fill(P.C, P.W, n); stage_pack(P.C, P.W, n); }   // stages 5 and 5b
 }
-// stage 5b; `only` = 0: every active image, 1: images with a pending patch or re-resolve
+// stage 5b alone; `only` = 0: every active image, 1: images with a pending patch or re-resolve
 __global__ void __launch_bounds__(256) k_spec_pack(SpecImage* sp, int only) {
   const SpecImage& P = sp[blockIdx.y];
   if (!NQS_ACTIVE(P) || (only && !P.W.state[2] && !P.W.state[5])) return;
