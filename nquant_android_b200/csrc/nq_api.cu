@@ -356,7 +356,8 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
   const size_t perSlot = o;
   size_t freeB = 0, totalB = 0;
   CU(cudaMemGetInfo(&freeB, &totalB));
-  const size_t budget = (size_t)((double)(freeB + c->specBufBytes) * 0.8);
+  // a wave only has to fill the machine (one thread per segment: ~100 4K images); keep the rest of the memory for the caller
+  const size_t budget = std::min<size_t>((size_t)((double)(freeB + c->specBufBytes) * 0.5), (size_t)32 << 30);
   const int wave = (int)std::min<size_t>((size_t)n, budget / perSlot);
   if (wave < 1) return NQ_OK;                       // no room: the serial kernel does the work
   if (c->specBufBytes < perSlot * (size_t)wave) {
