@@ -328,11 +328,45 @@ int pixel_grid_x(const nq_ctx* c, int npix, int nimg) {
 
 // Speculative segment-parallel dither for the images that qualify (decided on the device, k_spec_setup). Images it
 // completes get NqImage::specDone and are skipped by k_dither_fifo; every other image is untouched.
+// launches and small copies of the wave / round loop (spec_drive in nq_dither_spec.cuh) on the context's stream
+struct SpecCudaBackend {
+  nq_ctx* c;
+  cudaStream_t st;
+  bool timing = false;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  cudaError_t err = cudaSuccess;
+  template <class... P, class... A>
+  void launch(void (*kernel)(P...), dim3 grid, int block, A... args) {
+    kernel<<<grid, block, 0, st>>>(args...);
+    ++c->launches;
+  }
+  void keep(cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; }
+  void zero_ints(int* p, int n) { keep(cudaMemsetAsync(p, 0, sizeof(int) * (size_t)n, st)); }
+  void read_ints(int* host, const int* dev, int n) {
+    keep(cudaMemcpyAsync(host, dev, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    keep(cudaStreamSynchronize(st));
+  }
+  // NQ_SPEC_TIMING=1: device time of every launch of this path on stderr (synchronises after each; diagnosis only)
+  void begin() { if (timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, st); } }
+  void end() { if (timing) { cudaEventDestroy(t0); cudaEventDestroy(t1); } }
+  void lap(const char* what) {
+    if (!timing) return;
+    cudaEventRecord(t1, st);
+    cudaEventSynchronize(t1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, t0, t1);
+    fprintf(stderr, "[nq spec] %-14s %9.3f ms\n", what, ms);
+    cudaEventRecord(t0, st);
+  }
+  void note(int round, const int* counters) {
+    if (timing) fprintf(stderr, "[nq spec] round %d: %d image(s) open, %d patch(es), %d re-resolve(s)\n", round, counters[0], counters[1], counters[2]);
+  }
+};
+
 int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
   using namespace nq::spec;
   cudaStream_t st = c->stream;
   const int seg = c->specSeg, warm = c->specWarm;
-  const int nseg = (npix + seg - 1) / seg;
   if (npix < 4 * seg) return NQ_OK;
   if (c->specCap < n) {
     if (c->dSpec) cudaFree(c->dSpec);
@@ -346,101 +380,35 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
     CU(cudaMalloc(&c->dSpecInts, sizeof(int) * (size_t)(n + 4)));
     c->specIntsCap = n + 4;
   }
-  // work arrays of one wave slot
-  size_t o = 0;
-  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-  const size_t oCpx = take((size_t)npix * 4), oCol = take((size_t)npix * 4), oK0 = take((size_t)npix * 4), oK1 = take((size_t)npix * 4);
-  const size_t oDraw = take(((size_t)npix + 1) * 4), oQ = take((size_t)npix * 2), oFlag = take((size_t)npix);
-  const size_t oFirst = take(65536 * 4), oSlowPos = take(65536 * 4), oMemo = take(65536 * 2), oSlowVal = take(65536 * 2);
-  const size_t oSegs = take(sizeof(SpecSeg) * (size_t)nseg), oState = take(64), oRec = take(sizeof(SpecRec) * (size_t)nseg * (size_t)seg);
-  const size_t perSlot = o;
+  const SpecLayout L = spec_layout(npix, seg);
   size_t freeB = 0, totalB = 0;
   CU(cudaMemGetInfo(&freeB, &totalB));
   // a wave only has to fill the machine (one thread per segment: ~100 4K images); keep the rest of the memory for the caller
   const size_t budget = std::min<size_t>((size_t)((double)(freeB + c->specBufBytes) * 0.5), (size_t)32 << 30);
-  const int wave = (int)std::min<size_t>((size_t)n, budget / perSlot);
+  const int wave = (int)std::min<size_t>((size_t)n, budget / L.perSlot);
   if (wave < 1) return NQ_OK;                       // no room: the serial kernel does the work
-  if (c->specBufBytes < perSlot * (size_t)wave) {
+  if (c->specBufBytes < L.perSlot * (size_t)wave) {
     if (c->specBuf) cudaFree(c->specBuf);
     c->specBuf = nullptr; c->specBufBytes = 0;
-    CU(cudaMalloc(&c->specBuf, perSlot * (size_t)wave));
-    c->specBufBytes = perSlot * (size_t)wave;
+    CU(cudaMalloc(&c->specBuf, L.perSlot * (size_t)wave));
+    c->specBufBytes = L.perSlot * (size_t)wave;
   }
   std::vector<SpecImage> h(n);
   memset(h.data(), 0, sizeof(SpecImage) * (size_t)n);
-  for (int i = 0; i < n; ++i) {
-    unsigned char* b = c->specBuf + perSlot * (size_t)(i % wave);
-    SpecWork& W = h[i].W;
-    W.cpx = reinterpret_cast<uint32_t*>(b + oCpx); W.ccol = reinterpret_cast<uint32_t*>(b + oCol);
-    W.ck0 = reinterpret_cast<uint32_t*>(b + oK0); W.ck1 = reinterpret_cast<uint32_t*>(b + oK1);
-    W.cdraw = reinterpret_cast<uint32_t*>(b + oDraw); W.cq = reinterpret_cast<unsigned short*>(b + oQ); W.cflag = b + oFlag;
-    W.firstPos = reinterpret_cast<int*>(b + oFirst); W.slowPos = reinterpret_cast<int*>(b + oSlowPos);
-    W.memo = reinterpret_cast<unsigned short*>(b + oMemo); W.slowVal = reinterpret_cast<unsigned short*>(b + oSlowVal);
-    W.segs = reinterpret_cast<SpecSeg*>(b + oSegs); W.state = reinterpret_cast<int*>(b + oState); W.rec = reinterpret_cast<SpecRec*>(b + oRec);
-  }
+  spec_bind(h.data(), n, c->specBuf, L, wave);
   CU(cudaMemcpyAsync(c->dSpec, h.data(), sizeof(SpecImage) * (size_t)n, cudaMemcpyHostToDevice, st));
   k_spec_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, c->dSpec, dOrder, n, seg, warm, c->dSpecInts + 4); ++c->launches;
   std::vector<int> elig(n);
   CU(cudaMemcpyAsync(elig.data(), c->dSpecInts + 4, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));                    // also keeps `h` alive until the copy is done
-  const int roundCap = nseg / 4 + 96;
-  // NQ_SPEC_TIMING=1: device time of every launch of this path on stderr (synchronises after each; diagnosis only)
-  const bool timing = getenv("NQ_SPEC_TIMING") != nullptr;
-  cudaEvent_t t0 = nullptr, t1 = nullptr;
-  if (timing) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventRecord(t0, st); }
-  auto lap = [&](const char* what) {
-    if (!timing) return;
-    cudaEventRecord(t1, st);
-    cudaEventSynchronize(t1);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, t0, t1);
-    fprintf(stderr, "[nq spec] %-14s %9.3f ms\n", what, ms);
-    cudaEventRecord(t0, st);
-  };
-  for (int base = 0; base < n; base += wave) {
-    const int m = std::min(wave, n - base);
-    int any = 0;
-    for (int i = 0; i < m; ++i) any += elig[base + i];
-    if (!any) continue;
-    SpecImage* sp = c->dSpec + base;
-    const int gx = pixel_grid_x(c, npix, m);
-    const dim3 pg(gx, m), kg(8, m);
-    k_spec_init<<<kg, 256, 0, st>>>(sp); ++c->launches; lap("init");
-    k_spec_pre<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("pre");
-    k_spec_scan<<<m, 1024, 0, st>>>(sp, 0); ++c->launches; lap("scan");
-    k_spec_resolve<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("resolve");
-    k_spec_memo<<<kg, 256, 0, st>>>(sp); ++c->launches; lap("memo");
-    k_spec_fill<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("fill+pack");
-    for (int round = 0; round < roundCap; ++round) {
-      CU(cudaMemsetAsync(c->dSpecInts, 0, 4 * sizeof(int), st));
-      k_spec_run<<<dim3((nseg + 63) / 64, m), 64, 0, st>>>(sp); ++c->launches; lap("run");
-      k_spec_compare<<<dim3((nseg + 63) / 64, m), 64, 0, st>>>(sp); ++c->launches; lap("compare");
-      k_spec_validate<<<(m + 63) / 64, 64, 0, st>>>(sp, m, c->dSpecInts); ++c->launches; lap("validate");
-      int counters[4] = {0, 0, 0, 0};
-      CU(cudaMemcpyAsync(counters, c->dSpecInts, sizeof(counters), cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      ++c->specRounds;
-      if (timing) fprintf(stderr, "[nq spec] round %d: %d image(s) open, %d patch(es), %d re-resolve(s)\n", round, counters[0], counters[1], counters[2]);
-      if (counters[1]) { k_spec_patch<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("patch"); }
-      if (counters[2]) {   // a draw misprediction: prefix sum again, then stages 3-5 behind it, for the images that asked
-        k_spec_scan<<<m, 1024, 0, st>>>(sp, 1); ++c->launches;
-        k_spec_redo_a<<<kg, 256, 0, st>>>(sp); ++c->launches;
-        k_spec_redo_b<<<pg, 256, 0, st>>>(sp); ++c->launches;
-        k_spec_redo_c<<<kg, 256, 0, st>>>(sp); ++c->launches;
-        k_spec_redo_d<<<pg, 256, 0, st>>>(sp); ++c->launches; lap("re-resolve");
-      }
-      if (counters[1] || counters[2]) { k_spec_pack<<<pg, 256, 0, st>>>(sp, 1); ++c->launches; lap("pack"); }
-      if (!counters[0]) break;
-    }
-    CU(cudaMemsetAsync(c->dSpecInts + 3, 0, sizeof(int), st));
-    k_spec_finish<<<(m + 63) / 64, 64, 0, st>>>(c->dImgs + base, sp, m, c->dSpecInts + 3); ++c->launches;
-    int done = 0;
-    CU(cudaMemcpyAsync(&done, c->dSpecInts + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    c->specImages += (unsigned long long)done;                 // completed here; the rest goes through k_dither_fifo
-    c->specFallbacks += (unsigned long long)(any - done);
-  }
-  if (timing) { cudaEventDestroy(t0); cudaEventDestroy(t1); }
+  SpecCudaBackend be{c, st};
+  be.timing = getenv("NQ_SPEC_TIMING") != nullptr;
+  be.begin();
+  SpecStats stats;
+  spec_drive(be, c->dImgs, c->dSpec, elig.data(), n, npix, seg, wave, c->dSpecInts, c->smCount, &stats);
+  be.end();
+  c->specImages += stats.done; c->specRounds += stats.rounds; c->specFallbacks += stats.handedBack;
+  CU(be.err);
   CU(cudaGetLastError());
   return NQ_OK;
 }

@@ -670,7 +670,7 @@ NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
   return C.nseg - s;
 }
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(NQS_EMULATE)   // NQS_EMULATE: tests/spec_host_harness.cpp runs the kernels thread by thread on the CPU
 // =====================================================================================================================
 // Kernels: indexing only, every body is one of the stage functions above. One SpecImage per image of the batch;
 // the work arrays of image i live in wave slot i % wave (nq_api.cu), waves run one after the other.
@@ -690,7 +690,7 @@ __global__ void k_spec_setup(const NqImage* imgs, const NqSlot* slots, SpecImage
   SpecImage& P = sp[i];
   SpecConst& C = P.C;
   const int plen = I.paletteLen;
-  const int acceptedDiff = max(2, plen - I.gMargin);
+  const int acceptedDiff = plen - I.gMargin > 2 ? plen - I.gMargin : 2;
   // PnnLABQuantizer, dither on, saliency map, ArrayDeque queue, opaque image (a transparent pixel leaves a constant alpha
   // error in the queue for ever: alpha is never shaped, GC:248), ditherPixel lookups independent of the diffused colour
   P.eligible = I.kind == NQ_KIND_LAB && I.dither && I.gUseSal && !I.gSorted && !I.gHasAlpha && !I.hasSemi && I.transIdx < 0 && !I.error &&
@@ -727,6 +727,15 @@ __global__ void __launch_bounds__(256) k_spec_pre(SpecImage* sp) {
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_pre(P.C, P.W, n);
 }
 // stage 2: exclusive prefix sum of the predicted draws, one CTA of 1024 threads per image, 8 pixels per thread and tile
+#if defined(NQS_EMULATE)
+__global__ void k_spec_scan(SpecImage* sp, int redo) {         // the block scan needs real warps: sequential stand-in
+  const SpecImage& P = sp[blockIdx.x];
+  if (threadIdx.x || !P.eligible || (redo && (!P.W.state[5] || P.W.state[1]))) return;
+  unsigned d = 0;
+  for (int n = 0; n < P.C.npix; ++n) { P.W.cdraw[n] = d; d += (P.W.cflag[n] & NQS_F_DRAW) ? 1u : 0u; }
+  P.W.cdraw[P.C.npix] = d;
+}
+#else
 __global__ void __launch_bounds__(1024) k_spec_scan(SpecImage* sp, int redo) {
   __shared__ int sWarp[33];
   const SpecImage& P = sp[blockIdx.x];
@@ -745,6 +754,7 @@ __global__ void __launch_bounds__(1024) k_spec_scan(SpecImage* sp, int redo) {
   }
   if (threadIdx.x == 0) P.W.cdraw[npix] = carry;
 }
+#endif
 __global__ void __launch_bounds__(256) k_spec_resolve(SpecImage* sp) {
   const SpecImage& P = sp[blockIdx.y];
   if (!P.eligible) return;
@@ -844,7 +854,91 @@ __global__ void k_spec_finish(NqImage* imgs, SpecImage* sp, int nimg, int* doneC
     atomicAdd(doneCount, 1);
   }
 }
-#endif  // __CUDACC__
+
+// ---- host side: layout of one wave slot, binding of the work arrays, and the wave / round loop -------------------------
+struct SpecLayout {
+  size_t cpx, ccol, ck0, ck1, cdraw, cq, cflag, firstPos, slowPos, memo, slowVal, segs, state, rec, perSlot;
+  int nseg;
+};
+inline SpecLayout spec_layout(int npix, int seg) {
+  SpecLayout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = (o + bytes + 255) / 256 * 256; return r; };
+  L.nseg = (npix + seg - 1) / seg;
+  L.cpx = take((size_t)npix * 4); L.ccol = take((size_t)npix * 4); L.ck0 = take((size_t)npix * 4); L.ck1 = take((size_t)npix * 4);
+  L.cdraw = take(((size_t)npix + 1) * 4); L.cq = take((size_t)npix * 2); L.cflag = take((size_t)npix);
+  L.firstPos = take(65536 * 4); L.slowPos = take(65536 * 4); L.memo = take(65536 * 2); L.slowVal = take(65536 * 2);
+  L.segs = take(sizeof(SpecSeg) * (size_t)L.nseg); L.state = take(64); L.rec = take(sizeof(SpecRec) * (size_t)L.nseg * (size_t)seg);
+  L.perSlot = o;
+  return L;
+}
+// work arrays of image i = wave slot i % wave of `buf` (host copy of the SpecImage array, uploaded before k_spec_setup)
+inline void spec_bind(SpecImage* h, int n, unsigned char* buf, const SpecLayout& L, int wave) {
+  for (int i = 0; i < n; ++i) {
+    unsigned char* b = buf + L.perSlot * (size_t)(i % wave);
+    SpecWork& W = h[i].W;
+    W.cpx = reinterpret_cast<uint32_t*>(b + L.cpx); W.ccol = reinterpret_cast<uint32_t*>(b + L.ccol);
+    W.ck0 = reinterpret_cast<uint32_t*>(b + L.ck0); W.ck1 = reinterpret_cast<uint32_t*>(b + L.ck1);
+    W.cdraw = reinterpret_cast<uint32_t*>(b + L.cdraw); W.cq = reinterpret_cast<unsigned short*>(b + L.cq); W.cflag = b + L.cflag;
+    W.firstPos = reinterpret_cast<int*>(b + L.firstPos); W.slowPos = reinterpret_cast<int*>(b + L.slowPos);
+    W.memo = reinterpret_cast<unsigned short*>(b + L.memo); W.slowVal = reinterpret_cast<unsigned short*>(b + L.slowVal);
+    W.segs = reinterpret_cast<SpecSeg*>(b + L.segs); W.state = reinterpret_cast<int*>(b + L.state); W.rec = reinterpret_cast<SpecRec*>(b + L.rec);
+  }
+}
+struct SpecStats { unsigned long long done = 0, rounds = 0, handedBack = 0, patches = 0, redos = 0; };
+// The wave / round loop. `be` launches kernels and moves a few ints: launch(kernel, grid, block, args...), zero_ints(ptr, n),
+// read_ints(host, dev, n) (synchronises), lap(name). dInts: 4 counters. elig: host copy of k_spec_setup's verdicts.
+template <class Backend>
+void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const int* elig, int n, int npix, int seg, int wave, int* dInts,
+                int smCount, SpecStats* st) {
+  const int nseg = (npix + seg - 1) / seg;
+  const int roundCap = nseg / 4 + 96;
+  for (int base = 0; base < n; base += wave) {
+    const int m = wave < n - base ? wave : n - base;
+    int any = 0;
+    for (int i = 0; i < m; ++i) any += elig[base + i];
+    if (!any) continue;
+    SpecImage* sp = dSpec + base;
+    int gx = (npix + 256 * 8 - 1) / (256 * 8);
+    const int cap = (smCount * 8) / m > 1 ? (smCount * 8) / m : 1;
+    if (gx > cap) gx = cap;
+    const dim3 pg(gx, m), kg(8, m), sg((nseg + 63) / 64, m);
+    be.launch(k_spec_init, kg, 256, sp); be.lap("init");
+    be.launch(k_spec_pre, pg, 256, sp); be.lap("pre");
+    be.launch(k_spec_scan, dim3(m), 1024, sp, 0); be.lap("scan");
+    be.launch(k_spec_resolve, pg, 256, sp); be.lap("resolve");
+    be.launch(k_spec_memo, kg, 256, sp); be.lap("memo");
+    be.launch(k_spec_fill, pg, 256, sp); be.lap("fill+pack");
+    for (int round = 0; round < roundCap; ++round) {
+      be.zero_ints(dInts, 4);
+      be.launch(k_spec_run, sg, 64, sp); be.lap("run");
+      be.launch(k_spec_compare, sg, 64, sp); be.lap("compare");
+      be.launch(k_spec_validate, dim3((m + 63) / 64), 64, sp, m, dInts); be.lap("validate");
+      int counters[4] = {0, 0, 0, 0};
+      be.read_ints(counters, dInts, 4);
+      ++st->rounds;
+      st->patches += (unsigned long long)counters[1]; st->redos += (unsigned long long)counters[2];
+      be.note(round, counters);
+      if (counters[1]) { be.launch(k_spec_patch, pg, 256, sp); be.lap("patch"); }
+      if (counters[2]) {   // a draw misprediction: prefix sum again, then stages 3-5 behind it, for the images that asked
+        be.launch(k_spec_scan, dim3(m), 1024, sp, 1);
+        be.launch(k_spec_redo_a, kg, 256, sp);
+        be.launch(k_spec_redo_b, pg, 256, sp);
+        be.launch(k_spec_redo_c, kg, 256, sp);
+        be.launch(k_spec_redo_d, pg, 256, sp); be.lap("re-resolve");
+      }
+      if (counters[1] || counters[2]) { be.launch(k_spec_pack, pg, 256, sp, 1); be.lap("pack"); }
+      if (!counters[0]) break;
+    }
+    be.zero_ints(dInts + 3, 1);
+    be.launch(k_spec_finish, dim3((m + 63) / 64), 64, dImgs + base, sp, m, dInts + 3);
+    int done = 0;
+    be.read_ints(&done, dInts + 3, 1);
+    st->done += (unsigned long long)done;                      // completed here; the rest goes through k_dither_fifo
+    st->handedBack += (unsigned long long)(any - done);
+  }
+}
+#endif  // __CUDACC__ || NQS_EMULATE
 
 }  // namespace spec
 }  // namespace nq

@@ -23,6 +23,15 @@
 #undef protected
 #undef class
 struct uint2 { unsigned x, y; };   // CUDA vector type named by nq_types.h
+// ---- the kernels of nq_dither_spec.cuh, run thread by thread on the CPU (NQS_EMULATE) -------------------------------------
+#define NQS_EMULATE 1
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+static thread_local dim3 blockIdx, threadIdx, blockDim, gridDim;
+#define __global__ static
+#define __launch_bounds__(x)
+static inline int atomicMin(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+namespace nq { static double g_gammaLut[256]; static signed char g_blueNoise[4096]; }   // device globals of nq_hist.cuh
 #include "../nquant_android_b200/csrc/nq_dither_spec.cuh"
 
 namespace {
@@ -32,6 +41,15 @@ struct HarnessOut {
 };
 struct HarnessCfg { int seg = 4096, warm = 1024, useCells = 1; HarnessOut out; };
 HarnessCfg* g_h = nullptr;
+
+// one image of a batch for the kernel-level emulation (nqs_spec_batch_*)
+struct Collected {
+  NqImage I;
+  std::vector<uint32_t> in, ref;
+  std::vector<unsigned char> cells;
+};
+std::vector<Collected> g_batch;
+bool g_collect = false;
 
 // host copy of k_build_cells (nq_dither.cuh): candidate lists per 5-5-5 RGB cell
 void build_cells(const nq::spec::SpecConst& C, std::vector<unsigned char>& cells) {
@@ -111,6 +129,24 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   for (auto& s : segs) s.dirty = 1;
   segs[0].exact = 1;
   if (H.useCells) build_cells(C, cells);
+  if (g_collect) {   // what k_dither_setup leaves in NqImage for this image (the fields k_spec_setup reads)
+    Collected B;
+    memset(&B.I, 0, sizeof(B.I));
+    NqImage& I = B.I;
+    I.kind = NQ_KIND_LAB; I.width = width; I.height = height; I.npix = npix; I.nmax = nMaxColors; I.dither = 1;
+    I.seed = q.rngSeed; I.transIdx = q.m_transparentPixelIndex; I.hasSemi = q.hasSemiTransparency; I.transColor = (uint32_t)q.m_transparentColor;
+    I.isNano = q.isNano; I.PR = q.PR; I.PG = q.PG; I.PB = q.PB; I.PA = q.PA; I.ratioMerge = q.ratio;
+    I.paletteLen = plen;
+    for (int i = 0; i < plen; ++i) I.palette[i] = (uint32_t)palette[i];
+    I.gMargin = gc.margin; I.gThresold = gc.thresold; I.gDitherMaxQ = gc.DITHER_MAX; I.gDitherMax = gc.ditherMax;
+    I.gSorted = gc.sortedByYDiff; I.gHasAlpha = gc.hasAlpha; I.gUseSal = q.hasSaliencies; I.gBeta = gc.beta; I.gWeight = gc.weight;
+    for (int k = 0; k < C.DM; ++k) I.gWeights[k] = gc.weights[k];
+    B.in.resize(npix); B.ref.resize(npix);
+    for (int i = 0; i < npix; ++i) { B.in[i] = (uint32_t)cPixels[i]; B.ref[i] = (uint32_t)reference[i]; }
+    build_cells(C, B.cells);
+    g_batch.push_back(std::move(B));
+    return;
+  }
   static const signed char bn[4096] = NQ_BLUE_NOISE_INIT;
 
   SpecWork W;
@@ -208,5 +244,91 @@ extern "C" int nqs_spec_host(const uint32_t* argb, int w, int h, int nmax, int d
   long long v[12] = {R.eligible, R.exact, R.rounds, R.anomaly, R.nseg, R.segRuns, R.slowPixels, R.notes, R.mismatches, R.rejected, R.patches, R.redos};
   memcpy(out, v, sizeof(v));
   g_h = nullptr;
+  return 0;
+}
+
+// ---- kernel-level emulation of a batch: k_spec_setup, spec_bind, spec_drive with the kernels run thread by thread -------
+namespace {
+struct EmuBackend {
+  long long launches = 0;
+  template <class... P, class... A>
+  void launch(void (*kernel)(P...), dim3 grid, int block, A... args) {
+    gridDim = grid; blockDim = dim3((unsigned)block);
+    for (unsigned y = 0; y < grid.y; ++y)
+      for (unsigned x = 0; x < grid.x; ++x) {
+        blockIdx = dim3(x, y);
+        for (unsigned t = 0; t < (unsigned)block; ++t) { threadIdx = dim3(t); kernel(args...); }
+      }
+    ++launches;
+  }
+  void zero_ints(int* p, int n) { memset(p, 0, sizeof(int) * (size_t)n); }
+  void read_ints(int* host, const int* dev, int n) { memcpy(host, dev, sizeof(int) * (size_t)n); }
+  void lap(const char*) {}
+  void note(int, const int*) {}
+};
+}  // namespace
+
+extern "C" void nqs_spec_batch_begin() { g_batch.clear(); }
+extern "C" int nqs_spec_batch_add(const uint32_t* argb, int w, int h, int nmax, uint64_t seed, int seg, int warm) {
+  HarnessCfg cfg;
+  cfg.seg = seg; cfg.warm = warm; cfg.useCells = 1;
+  g_h = &cfg; g_collect = true;
+  M.mode = 0;
+  int rc = 0;
+  try {
+    HostLab q(argb, w, h);
+    q.rngSeed = seed; q.nMax = nmax;
+    q.convert(nmax, true);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "spec host harness: %s\n", e.what());
+    rc = -1;
+  }
+  g_h = nullptr; g_collect = false;
+  return rc;
+}
+// out: images, eligible, completed, handed back, rounds, patches, re-resolves, images with wrong pixels, launches
+extern "C" int nqs_spec_batch_run(int seg, int warm, int wave, long long* out /* 9 values */) {
+  using namespace nq::spec;
+  const int n = (int)g_batch.size();
+  if (!n) return -1;
+  const int npix = g_batch[0].I.npix, width = g_batch[0].I.width, height = g_batch[0].I.height;
+  for (int v = 0; v < 256; ++v) nq::g_gammaLut[v] = nq::gamma_to_linear(v);
+  static const signed char bn[4096] = NQ_BLUE_NOISE_INIT;
+  memcpy(nq::g_blueNoise, bn, 4096);
+  OrderOnly oo;
+  oo.width = width;
+  if (width >= height) oo.gen(0, 0, width, 0, 0, height); else oo.gen(0, 0, 0, height, width, 0);
+  std::vector<uint32_t> order(npix);
+  for (int i = 0; i < npix; ++i) order[i] = (oo.out[i] % width) | ((oo.out[i] / width) << 16);
+  std::vector<NqImage> imgs(n);
+  std::vector<NqSlot> slots(n);
+  std::vector<std::vector<uint32_t>> outs(n, std::vector<uint32_t>(npix, 0));
+  for (int i = 0; i < n; ++i) {
+    imgs[i] = g_batch[i].I;
+    memset(&slots[i], 0, sizeof(NqSlot));
+    slots[i].in = g_batch[i].in.data(); slots[i].out = outs[i].data(); slots[i].cells = g_batch[i].cells.data();
+  }
+  const SpecLayout L = spec_layout(npix, seg);
+  if (wave < 1 || wave > n) wave = n;
+  std::vector<unsigned char> buf(L.perSlot * (size_t)wave);
+  std::vector<SpecImage> sp(n);
+  memset(sp.data(), 0, sizeof(SpecImage) * (size_t)n);
+  spec_bind(sp.data(), n, buf.data(), L, wave);
+  std::vector<int> ints(n + 4, 0);
+  EmuBackend be;
+  be.launch(k_spec_setup, dim3((n + 63) / 64), 64, (const NqImage*)imgs.data(), (const NqSlot*)slots.data(), sp.data(), (const uint32_t*)order.data(), n, seg, warm, ints.data() + 4);
+  SpecStats st;
+  spec_drive(be, imgs.data(), sp.data(), ints.data() + 4, n, npix, seg, wave, ints.data(), 148, &st);
+  long long eligible = 0, wrong = 0;
+  for (int i = 0; i < n; ++i) {
+    eligible += ints[4 + i];
+    if (imgs[i].specDone) {
+      long long bad = 0;
+      for (int k = 0; k < npix; ++k) bad += outs[i][k] != g_batch[i].ref[k];
+      wrong += bad != 0;
+    }
+  }
+  long long v[9] = {n, eligible, (long long)st.done, (long long)st.handedBack, (long long)st.rounds, (long long)st.patches, (long long)st.redos, wrong, be.launches};
+  memcpy(out, v, sizeof(v));
   return 0;
 }

@@ -29,6 +29,8 @@ def lib():
     L = ctypes.CDLL(SO)
     vp, ci = ctypes.c_void_p, ctypes.c_int
     L.nqs_spec_host.argtypes = [vp, ci, ci, ci, ci, ctypes.c_uint64, ci, ci, ci, vp]
+    L.nqs_spec_batch_add.argtypes = [vp, ci, ci, ci, ctypes.c_uint64, ci, ci]
+    L.nqs_spec_batch_run.argtypes = [ci, ci, ci, vp]
     return L
 
 
@@ -61,3 +63,21 @@ def test_spec_declines_what_it_does_not_cover(lib):
     assert run(lib, 128, 128, 16, "noisy", "opaque", 2048, 512)["eligible"] == 0
     # a transparent pixel leaves a constant alpha error in the queue for ever (alpha is never shaped, GC:248): no re-synchronisation
     assert run(lib, 256, 256, 256, "rand", "transparent", 4096, 1024)["eligible"] == 0
+
+
+def test_kernels_and_wave_loop_emulated_on_a_batch(lib):
+    """The CUDA kernels themselves (k_spec_*), run thread by thread with emulated blockIdx/threadIdx, driven by the same
+    spec_drive() wave / round loop nq_api.cu uses: five images through wave slots of two (slot reuse across waves), one of
+    them needing memo patches. Every image must be completed here and match the sequential oracle."""
+    w, h, seg, warm = 256, 192, 2048, 512
+    items = [("rand", 0x5EED0000, 0xC0FFEE), ("noisy", 0x5EED0001, 1), ("noisy", 0x5EED0002, 2), ("rand", 0x5EED0003, 3), ("noisy", 0x5EED0004, 4)]
+    lib.nqs_spec_batch_begin()
+    for cls, iseed, rseed in items:
+        img = np.ascontiguousarray(make_image(w, h, cls, "opaque", seed=iseed))
+        assert lib.nqs_spec_batch_add(img.ctypes.data, w, h, 256, rseed, seg, warm) == 0
+    out = np.zeros(9, np.int64)
+    assert lib.nqs_spec_batch_run(seg, warm, 2, out.ctypes.data) == 0
+    r = dict(zip(["images", "eligible", "completed", "handed_back", "rounds", "patches", "redos", "wrong", "launches"], [int(v) for v in out]))
+    assert r["images"] == 5 and r["eligible"] == 5 and r["completed"] == 5 and r["handed_back"] == 0, r
+    assert r["wrong"] == 0, r
+    assert r["patches"] >= 1 and r["rounds"] >= 4, r       # three waves, at least one extra round for the patches
