@@ -364,9 +364,17 @@ struct EmuRgb : PnnQuantizer {
     const double w0 = weight;
     std::vector<int32_t> ref = PnnQuantizer::ditherImage(cPixels, palette, width, height, dither);
     weight = w0;
-    if (!dither && palette.size() > 32) return ref;   // second pass not emulated
     RgbDitherable ditherable(*this, dither);
     if (hasSemiTransparency) weight *= -1;
+    if (!dither && palette.size() > 32) {
+      // dither == false: only the Gilbert pass is emulated (the BlueNoise second pass, BN:207-222, is a raster pass of
+      // its own); its sequential result = one GilbertCurve run with fresh maps
+      std::vector<int32_t> ref1(cPixels.size(), 0);
+      { GilbertCurve gc(width, height, cPixels, palette, ref1, ditherable, nullptr, weight, dither); gc.run(); }
+      closestMap.clear(); nearestMap.clear();
+      emulate(*this, nullptr, 0, width, height, cPixels, palette, ditherable, nullptr, weight, dither, ref1);
+      return ref;
+    }
     emulate(*this, nullptr, 0, width, height, cPixels, palette, ditherable, nullptr, weight, dither, ref);
     return ref;
   }

@@ -32,6 +32,8 @@ CASES = [
     ("PnnQuantizer", 0, 16, True, "noisy", "opaque"),
     ("PnnQuantizer", 0, 2, True, "noisy", "opaque"),
     ("PnnLABQuantizer", 1, 256, True, "noisy", "transparent"),
+    ("PnnQuantizer", 0, 256, False, "noisy", "opaque"),
+    ("PnnQuantizer", 0, 64, False, "noisy", "opaque"),
 ]
 
 
