@@ -57,6 +57,7 @@ struct SpecConst {
   uint32_t pal[NQ_MAXK];
   Lab4 palLab[NQ_MAXK];                  // getLab(palette[i]) (PL:352)
   double Tr[256], Tg[256], Tb[256];      // closestColorIndex cost of one channel difference (see nq_dither.cuh)
+  unsigned long long jmpA[40], jmpC[40]; // java.util.Random: state after 2^i more steps = jmpA[i] * state + jmpC[i] (mod 2^48)
 };
 
 // Per-image work arrays (curve order, npix entries unless noted) and segment records.
@@ -107,15 +108,19 @@ struct SpecWork {
 };
 
 // ---- java.util.Random: state after j more steps of the LCG ------------------------------------------------
-NQ_HD unsigned long long lcg_jump(unsigned long long seed, unsigned long long j) {
+NQ_HD void lcg_tables(unsigned long long* A, unsigned long long* Cc, int n) {
   const unsigned long long MASK = (1ULL << 48) - 1;
   unsigned long long a = 0x5DEECE66DULL, c = 0xBULL;
-  while (j) {
-    if (j & 1ULL) seed = (a * seed + c) & MASK;
+  for (int i = 0; i < n; ++i) {
+    A[i] = a; Cc[i] = c;
     c = ((a + 1ULL) * c) & MASK;
     a = (a * a) & MASK;
-    j >>= 1;
   }
+}
+NQ_HD unsigned long long lcg_jump(const unsigned long long* A, const unsigned long long* Cc, unsigned long long seed, unsigned long long j) {
+  const unsigned long long MASK = (1ULL << 48) - 1;
+  for (int i = 0; j; ++i, j >>= 1)
+    if (j & 1ULL) seed = (A[i] * seed + Cc[i]) & MASK;
   return seed;
 }
 // value of Random.nextInt(32767) taken from state `s` (the state AFTER the step); rejected = the reference would draw again
@@ -158,6 +163,7 @@ NQ_HD void fill_tables(SpecConst& C, const double* lut) {
     C.Tr[v] = r; C.Tg[v] = g; C.Tb[v] = b;
   }
   for (int i = 0; i < C.plen; ++i) C.palLab[i] = lab_at(C.pal[i], lut);
+  lcg_tables(C.jmpA, C.jmpC, 40);
 }
 
 // exact cost of palette entry c2 for colour c in the reference's operation order (PL:421-446), no semi-transparency
@@ -374,7 +380,7 @@ NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firs
     int r = 0;
     if (flag & NQS_F_DRAW) {
       bool rej;
-      r = next_int_from(lcg_jump(C.seed0, (unsigned long long)W.cdraw[n] + 1ULL), &rej);
+      r = next_int_from(lcg_jump(C.jmpA, C.jmpC, C.seed0, (unsigned long long)W.cdraw[n] + 1ULL), &rej);
       ok = !rej;
     }
     qi = closest_pick(C, c, W.ck0[n], W.ck1[n], r, &needNear);
@@ -448,7 +454,7 @@ NQ_HD int slow_lookup(const SpecConst& C, const SpecWork& W, SpecSeg& S, int n, 
     int r = 0;
     if ((k0 >> 8) != 0u) {
       bool rej;
-      r = next_int_from(lcg_jump(C.seed0, (unsigned long long)W.cdraw[n] + 1ULL), &rej);
+      r = next_int_from(lcg_jump(C.jmpA, C.jmpC, C.seed0, (unsigned long long)W.cdraw[n] + 1ULL), &rej);
       if (rej) S.nnotes = NQS_NOTES + 1;                   // never seen; handled as an overflow = not validated
       ++*draws;
       *drew = true;
