@@ -67,6 +67,7 @@ struct SpecSeg {
   float qstart[NQ_MAXQ][4];              // exact start state (when exact != 0)
   int exact, dirty, done;
   int qok;                               // stage 6b: start queue == predecessor's final queue, bit for bit
+  int warmMul;                           // warm-up length in units of SpecConst::warm (grows when the warm-up proved too short)
   int draws;                             // draws made by the owned pixels
   int mispos;                            // first owned error-dependent lookup whose draw differs from its prediction, or -1
   int nnotes;                            // > NQS_NOTES: overflow
@@ -498,7 +499,7 @@ NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s) {
   } else {
 #pragma unroll
     for (int k = 0; k < DM; ++k) { e[k][0] = 0.f; e[k][1] = 0.f; e[k][2] = 0.f; e[k][3] = 0.f; }
-    if (!S.exact) from = p0 - C.warm > 0 ? p0 - C.warm : 0;
+    if (!S.exact) { const long long w = (long long)C.warm * (long long)S.warmMul; from = (long long)p0 - w > 0 ? (int)((long long)p0 - w) : 0; }
   }
   const float fDitherMax = (float)C.ditherMax, fDitherMax1 = (float)(C.ditherMax - 1);
   const float divisor = (float)(1 + nqm::sqrt_((double)C.ditherMax));
@@ -606,6 +607,9 @@ NQ_HD void stage_compare(const SpecConst& C, const SpecWork& W, int s) {
   SpecSeg& S = W.segs[s];
   if (S.done) return;
   S.qok = s == 0 || same_queue(S.exact ? S.qstart : S.qwarm, W.segs[s - 1].qout, C.DM);
+  // A speculative segment whose warm-up did not reach its predecessor's state: do not wait for the ordered walk to get
+  // here, try again at once with a four times longer warm-up (all such segments in parallel). The walk still decides.
+  if (!S.qok && !S.exact && !S.dirty && S.warmMul < 64) { S.warmMul *= 4; S.dirty = 1; }
 }
 NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
   int s = W.state[0];
@@ -724,7 +728,7 @@ __global__ void __launch_bounds__(256) k_spec_init(SpecImage* sp) {
   if (!P.eligible) return;
   const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   for (int k = t; k < 65536; k += nt) { P.W.firstPos[k] = NQS_NOPOS; P.W.slowPos[k] = NQS_NOPOS; P.W.memo[k] = 0xFFFF; P.W.slowVal[k] = 0; }
-  for (int s = t; s < P.C.nseg; s += nt) { SpecSeg& S = P.W.segs[s]; S.exact = s == 0; S.dirty = 1; S.done = 0; S.draws = 0; S.nnotes = 0; S.nreads = 0; S.mispos = -1; }
+  for (int s = t; s < P.C.nseg; s += nt) { SpecSeg& S = P.W.segs[s]; S.exact = s == 0; S.dirty = 1; S.done = 0; S.draws = 0; S.nnotes = 0; S.nreads = 0; S.mispos = -1; S.warmMul = 1; }
   if (t < 16) P.W.state[t] = 0;
 }
 __global__ void __launch_bounds__(256) k_spec_pre(SpecImage* sp) {

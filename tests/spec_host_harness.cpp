@@ -126,7 +126,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   std::vector<SpecRec> rec((size_t)C.nseg * C.seg);
   std::vector<SpecSeg> segs(C.nseg);
   memset(segs.data(), 0, sizeof(SpecSeg) * segs.size());
-  for (auto& s : segs) s.dirty = 1;
+  for (auto& s : segs) { s.dirty = 1; s.warmMul = 1; s.mispos = -1; }
   segs[0].exact = 1;
   if (H.useCells) build_cells(C, cells);
   if (g_collect) {   // what k_dither_setup leaves in NqImage for this image (the fields k_spec_setup reads)
