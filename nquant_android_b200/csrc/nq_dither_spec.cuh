@@ -359,7 +359,21 @@ NQ_HD void stage_pre(const SpecConst& C, const SpecWork& W, int n) {
   if (viaClosest) {
     top2(C, W.cells, c, &k0, &k1);
     if ((k0 >> 8) != 0u) flag |= NQS_F_DRAW;               // short-circuit: no draw when closest[2] == 0 (PL:467)
-    else if (!(flag & NQS_F_PRE)) flag |= NQS_F_RISK;
+    else if (!(flag & NQS_F_PRE)) {
+      // The pixel itself costs 0 (it is a palette colour): the reference draws unless the DIFFUSED colour is that colour
+      // too, i.e. unless the errors around it are zero. Guess from the previous pixel of the curve: if that one is not a
+      // zero-cost colour either, its error is not zero and this lookup will draw; in a flat run of palette colours it
+      // will not. Only a prediction -- stage 7 corrects what it gets wrong.
+      bool flat = n == 0;
+      if (n > 0) {
+        const uint32_t pxy = W.order[n - 1];
+        const uint32_t ppx = W.in[(int)(pxy & 0xFFFF) + (int)(pxy >> 16) * C.width];
+        unsigned p0 = NQS_NONE, p1 = NQS_NONE;
+        if (c_alpha(ppx) > 0xF) top2(C, W.cells, ppx, &p0, &p1);
+        flat = (p0 >> 8) == 0u;
+      }
+      if (flat) flag |= NQS_F_RISK; else flag |= NQS_F_DRAW;
+    }
   }
   W.ccol[n] = c; W.ck0[n] = k0; W.ck1[n] = k1;
   W.cflag[n] = (unsigned char)flag;
@@ -399,7 +413,7 @@ NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firs
 // ---- gate after stage 3 (state[7] = pixels flagged NQS_F_RISK): too many likely mispredictions, do not start
 NQ_HD void stage_gate(const SpecConst& C, const SpecWork& W) {
   if (W.state[7] > NQS_MAXRISK) W.state[1] = 1;
-  if (W.state[8] > (C.npix >> 6)) W.state[1] = 1;           // state[8] = error-dependent lookups: past 1.5 % one thread per segment stops paying
+  if (W.state[8] > (C.npix >> 8)) W.state[1] = 1;           // state[8] = error-dependent lookups: past 0.4 % their draws are mispredicted too often
 }
 // ---- stage 4: one memo key ------------------------------------------------------------------------------------
 // `after`: only entries first seen behind that curve position (-1 = all); the others are settled

@@ -203,6 +203,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
     if (repack) for (int n = 0; n < npix; ++n) stage_pack(C, W, n);
   }
   R.anomaly = state[1];
+  if (getenv("NQ_SPEC_DEBUG")) fprintf(stderr, "risk pixels %d, error-dependent lookups %d of %d\n", state[7], state[8], npix);
   for (auto& s : segs) R.notes += std::min(s.nnotes, NQS_NOTES);
   if (!state[1]) {
     for (int i = 0; i < npix; ++i) R.mismatches += out[i] != (uint32_t)reference[i];
