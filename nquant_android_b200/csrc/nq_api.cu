@@ -401,6 +401,8 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
   std::vector<int> elig(n);
   CU(cudaMemcpyAsync(elig.data(), c->dSpecInts + 4, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));                    // also keeps `h` alive until the copy is done
+  // k_dither_fifo's time is one serial chain as soon as it has a single image to do: if it has one anyway, nothing is gained here
+  for (int i = 0; i < n; ++i) if (elig[i] == 2) return NQ_OK;
   SpecCudaBackend be{c, st};
   be.timing = getenv("NQ_SPEC_TIMING") != nullptr;
   be.begin();

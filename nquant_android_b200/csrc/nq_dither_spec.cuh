@@ -719,7 +719,8 @@ __global__ void k_spec_setup(const NqImage* imgs, const NqSlot* slots, SpecImage
   // error in the queue for ever: alpha is never shaped, GC:248), ditherPixel lookups independent of the diffused colour
   P.eligible = I.kind == NQ_KIND_LAB && I.dither && I.gUseSal && !I.gSorted && !I.gHasAlpha && !I.hasSemi && I.transIdx < 0 && !I.error &&
                plen > 64 && 2 * acceptedDiff > 101 && I.nmax > 2 && slots[i].cells != nullptr && I.npix >= 4 * seg;
-  eligOut[i] = P.eligible;
+  // 1 = taken; 2 = not taken and k_dither_fifo will run its serial chain for it anyway; 0 = another kernel's image
+  eligOut[i] = P.eligible ? 1 : ((plen > 0 && !I.error && !I.gSorted) ? 2 : 0);
   if (!P.eligible) return;
   C.plen = plen; C.margin = I.gMargin; C.thresold = I.gThresold; C.DM = I.gDitherMaxQ; C.ditherMax = I.gDitherMax;
   C.width = I.width; C.npix = I.npix;
@@ -849,18 +850,21 @@ __global__ void __launch_bounds__(64) k_spec_compare(SpecImage* sp) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < P.C.nseg) stage_compare(P.C, P.W, s);
 }
-// stage 7: one thread per image; counters[0] += images with open segments, [1] += patch requests, [2] += re-resolve requests
+// stage 7: one thread per image; counters[0] += images with open segments, [1] += patch requests, [2] += re-resolve requests,
+// [3] += images left to the serial kernel
 __global__ void k_spec_validate(SpecImage* sp, int nimg, int* counters) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nimg) return;
   const SpecImage& P = sp[i];
-  if (!NQS_ACTIVE(P)) return;
+  if (!P.eligible) return;
+  if (P.W.state[1]) { atomicAdd(&counters[3], 1); return; }    // left to the serial kernel
   P.W.state[2] = 0;
   P.W.state[5] = 0;
   const int open = stage_validate(P.C, P.W);
   if (open > 0 && !P.W.state[1]) atomicAdd(&counters[0], 1);
   if (P.W.state[2]) atomicAdd(&counters[1], 1);
   if (P.W.state[5] && !P.W.state[1]) atomicAdd(&counters[2], 1);
+  if (P.W.state[1]) atomicAdd(&counters[3], 1);
 }
 __global__ void __launch_bounds__(256) k_spec_patch(SpecImage* sp) {
   const SpecImage& P = sp[blockIdx.y];
@@ -909,7 +913,7 @@ inline void spec_bind(SpecImage* h, int n, unsigned char* buf, const SpecLayout&
     W.segs = reinterpret_cast<SpecSeg*>(b + L.segs); W.state = reinterpret_cast<int*>(b + L.state); W.rec = reinterpret_cast<SpecRec*>(b + L.rec);
   }
 }
-struct SpecStats { unsigned long long done = 0, rounds = 0, handedBack = 0, patches = 0, redos = 0; };
+struct SpecStats { unsigned long long done = 0, rounds = 0, handedBack = 0, patches = 0, redos = 0; bool abandoned = false; };
 // The wave / round loop. `be` launches kernels and moves a few ints: launch(kernel, grid, block, args...), zero_ints(ptr, n),
 // read_ints(host, dev, n) (synchronises), lap(name). dInts: 4 counters. elig: host copy of k_spec_setup's verdicts.
 template <class Backend>
@@ -920,8 +924,9 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const int* elig, 
   for (int base = 0; base < n; base += wave) {
     const int m = wave < n - base ? wave : n - base;
     int any = 0;
-    for (int i = 0; i < m; ++i) any += elig[base + i];
+    for (int i = 0; i < m; ++i) any += elig[base + i] == 1;
     if (!any) continue;
+    if (st->abandoned) { st->handedBack += (unsigned long long)any; continue; }
     SpecImage* sp = dSpec + base;
     int gx = (npix + 256 * 8 - 1) / (256 * 8);
     const int cap = (smCount * 8) / m > 1 ? (smCount * 8) / m : 1;
@@ -952,6 +957,9 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const int* elig, 
         be.launch(k_spec_redo_d, pg, 256, sp); be.lap("re-resolve");
       }
       if (counters[1] || counters[2]) { be.launch(k_spec_pack, pg, 256, sp, 1); be.lap("pack"); }
+      // One image on k_dither_fifo costs the batch that kernel's whole serial chain, whatever else was done here: once an
+      // image has been left to it, finishing the others speculatively only adds time.
+      if (counters[3]) { st->abandoned = true; break; }
       if (!counters[0]) break;
     }
     be.zero_ints(dInts + 3, 1);

@@ -322,7 +322,7 @@ extern "C" int nqs_spec_batch_run(int seg, int warm, int wave, long long* out /*
   spec_drive(be, imgs.data(), sp.data(), ints.data() + 4, n, npix, seg, wave, ints.data(), 148, &st);
   long long eligible = 0, wrong = 0;
   for (int i = 0; i < n; ++i) {
-    eligible += ints[4 + i];
+    eligible += ints[4 + i] == 1;
     if (imgs[i].specDone) {
       long long bad = 0;
       for (int k = 0; k < npix; ++k) bad += outs[i][k] != g_batch[i].ref[k];

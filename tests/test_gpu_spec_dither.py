@@ -63,15 +63,22 @@ def test_spec_dither_corrects_draw_mispredictions(spec_ctx, oracle):
 def test_spec_dither_batch_and_mixed_eligibility(spec_ctx, oracle):
     w, h = 256, 256
     imgs = np.stack([make_image(w, h, "noisy", "opaque", seed=0x5EED0000 + i) for i in range(3)] +
-                    [make_image(w, h, "smooth", "opaque"), make_image(w, h, "rand", "transparent")])
-    seeds = [11, 12, 13, 14, 15]
+                    [make_image(w, h, "smooth", "opaque")])
+    seeds = [11, 12, 13, 14]
     spec_ctx.set_spec_dither(True, 4096, 1024)
     out, pal, plen, _ = spec_ctx.convert_batch(1, imgs, w, h, 256, True, seeds=seeds)
     for i in range(len(imgs)):
         ref = oracle.convert(1, imgs[i], w, h, 256, True, seed=seeds[i], trace=False)
         assert np.array_equal(pal[i, :plen[i]], ref.palette), i
         assert np.array_equal(out[i], ref.out), i
-    assert spec_ctx.spec_stats()["images"] == 3       # the PriorityQueue-mode image and the transparent one are declined
+    assert spec_ctx.spec_stats()["images"] == 3       # the PriorityQueue-mode image belongs to k_dither_sorted
+    # with an image that k_dither_fifo has to do anyway (a transparent pixel), the path stands aside for the whole batch
+    imgs2 = np.stack([imgs[0], make_image(w, h, "rand", "transparent")])
+    out2, pal2, plen2, _ = spec_ctx.convert_batch(1, imgs2, w, h, 256, True, seeds=[11, 15])
+    for i, sd in enumerate([11, 15]):
+        ref = oracle.convert(1, imgs2[i], w, h, 256, True, seed=sd, trace=False)
+        assert np.array_equal(out2[i], ref.out), i
+    assert spec_ctx.spec_stats()["images"] == 3
 
 
 def test_spec_dither_leaves_other_quantizers_alone(spec_ctx, oracle):
