@@ -130,7 +130,8 @@ int nq_sizeof_image_info(void);
  * colours, dither on, no transparency: GilbertCurve.dither (GilbertCurve.java:367-373) is cut into `segment`-pixel
  * pieces of the curve that start from an empty error queue `warmup` pixels early and are validated, in curve order,
  * against the exact state of their predecessor (bit-identical results by construction; images it cannot finish go
- * through the serial kernel). Off by default (or NQ_SPEC_DITHER=1 in the environment at nq_create).
+ * through the serial kernel). segment == 0 picks the length from the size of the job (8192, shorter for small batches).
+ * Off by default (or NQ_SPEC_DITHER=1 in the environment at nq_create).
  * nq_get_spec_stats: images completed by this path, validation rounds, and qualifying images it handed back to the
  * serial kernel, since the context was created. */
 int nq_set_spec_dither(nq_ctx* ctx, int on, int segment, int warmup);

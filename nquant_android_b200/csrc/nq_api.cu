@@ -366,7 +366,13 @@ struct SpecCudaBackend {
 int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
   using namespace nq::spec;
   cudaStream_t st = c->stream;
-  const int seg = c->specSeg, warm = c->specWarm;
+  int seg = c->specSeg;
+  const int warm = c->specWarm;
+  if (seg == 0) {   // automatic: 8192-pixel segments when that gives the machine enough threads, shorter ones for small jobs
+    const long long total = (long long)n * (long long)npix;
+    seg = total / 8192 >= 16384 ? 8192 : (int)std::max<long long>(2048, (total / 16384 + 255) / 256 * 256);
+    if (seg > 8192) seg = 8192;
+  }
   if (npix < 4 * seg) return NQ_OK;
   if (c->specCap < n) {
     if (c->dSpec) cudaFree(c->dSpec);
@@ -795,7 +801,7 @@ int nq_set_stream(nq_ctx* c, void* stream) {
 
 int nq_set_spec_dither(nq_ctx* c, int on, int segment, int warmup) {
   if (!c) return fail(NQ_ERR_ARG, "null context");
-  if (on && (segment < 64 || warmup < 0 || warmup > (1 << 24))) return fail(NQ_ERR_ARG, "segment must be >= 64 pixels and warm-up >= 0");
+  if (on && ((segment != 0 && segment < 64) || warmup < 0 || warmup > (1 << 24))) return fail(NQ_ERR_ARG, "segment must be 0 (automatic) or >= 64 pixels, warm-up >= 0");
   c->specDither = on != 0;
   if (on) { c->specSeg = segment; c->specWarm = warmup; }
   return NQ_OK;
