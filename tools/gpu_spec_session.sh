@@ -5,9 +5,9 @@
 # 4. ncu launch list and one full capture of k_spec_run (only after the plain runs exited 0).
 set -u
 mkdir -p gpurun_out
-export NQ_SPEC_DITHER_TEST=1
+
 timeout 600 python -m pytest tests/test_gpu_spec_dither.py -x -q > gpurun_out/spec_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/spec_pytest.log
-unset NQ_SPEC_DITHER_TEST
+
 NQ_PROBE_NOORACLE=1 NQ_SPEC_TIMING=1 timeout 120 python tools/spec_gpu_probe.py 3840 2160 8192 1024 64 > gpurun_out/spec_probe_4k64.log 2>&1; echo "exit $?" >> gpurun_out/spec_probe_4k64.log
 timeout 300 python bench.py --no-cpu > gpurun_out/bench_serial.log 2>&1; echo "exit $?" >> gpurun_out/bench_serial.log
 timeout 300 python bench.py --no-cpu --spec-dither 1 > gpurun_out/bench_spec.log 2>&1; rc=$?; echo "exit $rc" >> gpurun_out/bench_spec.log
