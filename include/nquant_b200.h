@@ -47,10 +47,18 @@ int nq_device_count(void);
 nq_ctx* nq_create(int device);
 void nq_destroy(nq_ctx* ctx);
 
-/* Run this context's copies and kernels on a caller-owned CUDA stream (a cudaStream_t passed as
- * void*; NULL restores the context's own stream), so a host framework can order and time them with
- * its own events. */
+/* Order this context's work with a caller-owned CUDA stream (a cudaStream_t passed as void*): a call starts after
+ * everything already enqueued on that stream and the stream continues only after the call's last kernel and copy, so a
+ * host framework can feed and time the library with its own kernels and events. NULL is CUDA's legacy default stream
+ * (stream handle 0, e.g. torch.cuda.default_stream().cuda_stream). Internally a call fans out over the context's own
+ * streams (chunks of the batch: copies, histogram / merge loop and dither overlap). nq_reset_stream goes back to the
+ * context's private non-blocking stream (the state after nq_create). */
 int nq_set_stream(nq_ctx* ctx, void* cuda_stream);
+int nq_reset_stream(nq_ctx* ctx);
+
+/* Images per chunk of a batch call (0 = automatic). A batch is cut into chunks that move through the stages as a
+ * pipeline: host->device copy, scan/histogram/find_nn/merge, dither, device->host copy each run on their own stream. */
+int nq_set_chunk_images(nq_ctx* ctx, int images);
 
 /* Thread-local message of the last failing call. */
 const char* nq_last_error(void);
@@ -130,8 +138,9 @@ int nq_sizeof_image_info(void);
  * colours, dither on, no transparency: GilbertCurve.dither (GilbertCurve.java:367-373) is cut into `segment`-pixel
  * pieces of the curve that start from an empty error queue `warmup` pixels early and are validated, in curve order,
  * against the exact state of their predecessor (bit-identical results by construction; images it cannot finish go
- * through the serial kernel). segment == 0 picks the length from the size of the job (8192, shorter for small batches).
- * Off by default (or NQ_SPEC_DITHER=1 in the environment at nq_create).
+ * through the serial kernel, which runs next to it for the images that do not qualify). segment == 0 picks the length
+ * from the size of the job (8192, shorter for small batches). ON by default (NQ_SPEC_DITHER=0 in the environment at
+ * nq_create, or on == 0 here, leaves every image to the serial kernels).
  * nq_get_spec_stats: images completed by this path, validation rounds, and qualifying images it handed back to the
  * serial kernel, since the context was created. */
 int nq_set_spec_dither(nq_ctx* ctx, int on, int segment, int warmup);
@@ -150,10 +159,14 @@ int nq_debug_get_saliencies(nq_ctx* ctx, int image, float* out);
 
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 unsigned long long nq_kernel_launches(nq_ctx* ctx);
-/* Device time per stage, measured with CUDA events on the context's stream and accumulated over the
- * calls since the last reset. ms[6] / launches[6]: 0 alpha scan, 1 histogram (+compaction), 2 initial
+/* Device time per stage, measured with CUDA events on the streams the stages run on and accumulated over the
+ * chunks and calls since the last reset (chunks overlap: the sum can exceed the wall time of the call). ms[6] / launches[6]: 0 alpha scan, 1 histogram (+compaction), 2 initial
  * find_nn sweep, 3 merge loop, 4 dither setup + saliency, 5 dither (Gilbert pass + blue-noise pass). */
 int nq_get_stage_times(nq_ctx* ctx, double* ms, unsigned long long* launches, int reset);
+/* Device time of single kernels, each bracketed by its own pair of CUDA events on the stream it is launched on
+ * (bench.py's roofline line): ms[4] / launches[4]: 0 k_spec_run (stage 6 of the speculative dither, one entry per launch),
+ * 1 k_dither_fifo, 2 k_dither_sorted, 3 k_merge_lab / k_merge_rgb. Accumulated since the last reset. */
+int nq_get_kernel_times(nq_ctx* ctx, double* ms, unsigned long long* launches, int reset);
 /* Device-side math probe (tests): evaluates the shared nq_math.h kernels ON THE GPU.
  * fn: 0 pow(x,y) 1 exp 2 tanh 3 cbrt 4 atan2(x,y) 5 sin 6 cos. n elements, host buffers. */
 int nq_debug_math(nq_ctx* ctx, int fn, const double* x, const double* y, double* out, int n);

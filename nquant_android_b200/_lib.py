@@ -12,7 +12,7 @@ SYMBOLS = [
     "nq_convert_batch_device", "nq_dither_with_palette", "nq_gilbert_order", "nq_get_image_info", "nq_set_debug",
     "nq_debug_get_bins", "nq_debug_get_merges", "nq_debug_get_saliencies", "nq_kernel_launches", "nq_debug_math",
     "nq_synth_device", "nq_get_stage_times", "nq_set_stream", "nq_debug_ciede", "nq_sizeof_image_info",
-    "nq_set_spec_dither", "nq_get_spec_stats",
+    "nq_set_spec_dither", "nq_get_spec_stats", "nq_reset_stream", "nq_set_chunk_images", "nq_get_kernel_times",
 ]
 
 NQ_KIND_PNN, NQ_KIND_PNNLAB = 0, 1
@@ -74,6 +74,9 @@ def load():
     L.nq_kernel_launches.restype = ctypes.c_ulonglong
     L.nq_debug_math.argtypes = [vp, ci, vp, vp, vp, ci]
     L.nq_set_stream.argtypes = [vp, vp]
+    L.nq_reset_stream.argtypes = [vp]
+    L.nq_set_chunk_images.argtypes = [vp, ci]
+    L.nq_get_kernel_times.argtypes = [vp, vp, vp, ci]
     L.nq_debug_ciede.argtypes = [vp, vp, vp, vp, vp, ci]
     L.nq_get_stage_times.argtypes = [vp, vp, vp, ci]
     L.nq_synth_device.argtypes = [vp, vp, ci, ci, ci, ci, ci, u64]

@@ -11,6 +11,7 @@
 #include <utility>
 #include <algorithm>
 #include <mutex>
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/nquant_b200.h"
 #include "nq_types.h"
@@ -23,6 +24,7 @@
 #include "nq_dither_spec.cuh"
 
 #define NQ_NSTAGES 6   // scan, histogram, find_nn sweep, merge, dither setup + saliency, dither
+#define NQ_NKERNELS 4  // kernels timed on their own (nq_get_kernel_times): 0 k_spec_run, 1 k_dither_fifo, 2 k_dither_sorted, 3 k_merge_*
 
 namespace {
 
@@ -162,15 +164,25 @@ struct DebugImage {
 
 }  // namespace
 
+#define NQ_FRONT_STREAMS 2   // histogram / find_nn / merge of consecutive chunks alternate between these
+
 struct nq_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // where the caller's order and timing live (nq_set_stream)
   cudaStream_t ownStream = nullptr;
+  // internal streams of a call (convert_group): front = scan .. merge of a chunk, dith = dither of the chunks in order,
+  // aux = the serial dither kernels next to the speculative rounds, copyOut = device -> host of finished chunks
+  cudaStream_t sFront[NQ_FRONT_STREAMS] = {}, sDith = nullptr, sAux = nullptr, sOut = nullptr;
+  std::vector<cudaEvent_t> evPool;    // grows on demand, reused by every call
+  size_t evUsed = 0;
   int smCount = 148;
   unsigned long long launches = 0;
   bool debug = false;
-  // Gilbert orders by (w,h)
+  int chunkImages = 0;                // images per chunk (0 = automatic)
+  // Gilbert orders by (w,h), least recently used first in orderLru
   std::map<std::pair<int, int>, uint32_t*> orders;
+  std::vector<std::pair<int, int>> orderLru;
+  size_t orderBytes = 0;
   // workspace
   unsigned char* ws = nullptr;
   size_t wsBytes = 0;
@@ -178,26 +190,35 @@ struct nq_ctx {
   NqSlot* dSlots = nullptr;
   int* dLive = nullptr;
   int* dPos = nullptr;
-  int wsSlots = 0, wsNpix = 0, wsKind = -1, sortPool = 0;
+  unsigned char* zeroPlane = nullptr;   // hCnt + hSum of every slot, contiguous: one memset per chunk
+  unsigned char* memoPlane = nullptr;   // memo of every slot, contiguous
+  unsigned char* sortPool = nullptr;    // NQ_FRONT_STREAMS x sortSets sets of CIELAB sort scratch
+  size_t zeroSlotBytes = 0, memoSlotBytes = 0, sortSetBytes = 0, sortABytes = 0;
+  int wsSlots = 0, wsNpix = 0, wsKind = -1, sortSets = 0;
   bool wsDebug = false, wsBits = false;
   std::vector<NqSlot> hSlots;
   // staging for host-buffer calls
   uint32_t* dIn = nullptr;
   uint32_t* dOut = nullptr;
   size_t stageBytes = 0;
-  // per-stage device timing (CUDA events on the context's stream)
-  cudaEvent_t ev[NQ_NSTAGES + 1] = {};
+  // per-stage device timing (CUDA events on the internal streams, summed over the chunks of a call)
   double stageMs[NQ_NSTAGES] = {};
   unsigned long long stageLaunches[NQ_NSTAGES] = {};
-  // speculative segment-parallel dither (nq_dither_spec.cuh); off unless nq_set_spec_dither / NQ_SPEC_DITHER=1
-  bool specDither = false;
-  int specSeg = 8192, specWarm = 1024;
+  // named kernels timed on their own (bench.py's roofline line): 0 = k_spec_run
+  double kernelMs[NQ_NKERNELS] = {};
+  unsigned long long kernelLaunches[NQ_NKERNELS] = {};
+  // speculative segment-parallel dither (nq_dither_spec.cuh); on unless nq_set_spec_dither(0) / NQ_SPEC_DITHER=0
+  bool specDither = true;
+  int specSeg = 0, specWarm = 1024;
+  int specSlotsMax = 0;            // cap on the pool of work-array slots (0 = none; NQ_SPEC_SLOTS, tests force slot reuse with it)
   nq::spec::SpecImage* dSpec = nullptr;
   int specCap = 0;                 // images dSpec holds
   unsigned char* specBuf = nullptr;
   size_t specBufBytes = 0;
-  int* dSpecInts = nullptr;        // [0..3] round counters, [4..] eligibility per image
-  int specIntsCap = 0;
+  nq::spec::SpecWork* dSpecPool = nullptr;
+  int* dSpecInts = nullptr;
+  int specPoolCap = 0;
+  float* dTanh = nullptr;          // (float) tanh(e / 255 * 20), e = -255 .. 255 (nq_dither_spec.cuh shape_tanh)
   unsigned long long specImages = 0, specRounds = 0, specFallbacks = 0;
   // results of the last batch
   std::vector<NqImage> lastImgs;
@@ -209,17 +230,14 @@ namespace {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SlotLayout {
-  size_t hCnt, hSum, keyOff, sortA, sortB, warpHist, sal, bD, bF, bCnt, bErr, bNn, bTm, bMtm, heap, mergeLog, memo, cells, bits, total;
+  size_t keyOff, sal, bD, bF, bCnt, bErr, bNn, bTm, bMtm, heap, mergeLog, cells, bits, total;
 };
 SlotLayout slot_layout(int kind, int npix, bool debug, bool needBits) {
   SlotLayout L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
-  L.hCnt = take(NQ_NBINS * 4);
-  L.hSum = take((size_t)4 * NQ_NBINS * 8);
   L.keyOff = take((NQ_NBINS + 1) * 4);
   const bool lab = kind == NQ_KIND_LAB;
-  L.sortA = L.sortB = L.warpHist = 0;                 // these live in the sort pool (see ensure_workspace)
   L.sal = take(lab && debug ? (size_t)npix * 4 : 0);  // the dither kernel derives saliency itself; kept for parity tests
   L.bD = take((size_t)4 * NQ_NBINS * 8);
   L.bF = take((size_t)4 * NQ_NBINS * 4);
@@ -230,7 +248,6 @@ SlotLayout slot_layout(int kind, int npix, bool debug, bool needBits) {
   L.bMtm = take(NQ_NBINS * 4);
   L.heap = take((NQ_NBINS + 2) * 8);
   L.mergeLog = take(debug ? (size_t)2 * NQ_NBINS * 4 : 0);
-  L.memo = take(NQ_NBINS * 2);
   L.cells = take(lab ? (size_t)32768 * 32 : 0);
   L.bits = take(needBits ? ((size_t)1 << 29) : 0);      // one bit per ARGB value
   L.total = o;
@@ -239,28 +256,30 @@ SlotLayout slot_layout(int kind, int npix, bool debug, bool needBits) {
 
 // Sort scratch of the strict-order CIELAB histogram (2 x npix words + run counters per image) is only
 // needed while an image's histogram is being built, so a small pool of sets is cycled through the
-// batch instead of giving every image its own.
+// batch instead of giving every image its own. Every front stream owns NQ_SORT_POOL of them.
 #define NQ_SORT_POOL 32
 
 int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots, bool needBits) {
   SlotLayout L = slot_layout(kind, npix, c->debug, needBits);
   const bool lab = kind == NQ_KIND_LAB;
   const size_t nruns = ((size_t)npix + NQ_RUN - 1) / NQ_RUN;
-  const size_t sortSet = lab ? align_up((size_t)npix * 4, 256) * 2 + align_up(nruns * 256 * 4, 256) : 0;
+  const size_t sortA = align_up((size_t)npix * 4, 256);
+  const size_t sortSet = lab ? sortA * 2 + align_up(nruns * 256 * 4, 256) : 0;
+  const size_t zeroSlot = (size_t)NQ_NBINS * 4 + (size_t)4 * NQ_NBINS * 8, memoSlot = (size_t)NQ_NBINS * 2;
   size_t freeB = 0, totalB = 0;
   CU(cudaMemGetInfo(&freeB, &totalB));
   const size_t budget = (size_t)((double)(freeB + c->wsBytes) * 0.85);
-  const size_t perImage = L.total + sizeof(NqImage) + sizeof(NqSlot) + 2 * NQ_NBINS * 4 + 1024;
+  const size_t perImage = L.total + zeroSlot + memoSlot + sizeof(NqImage) + sizeof(NqSlot) + 2 * NQ_NBINS * 4 + 1024;
   int pool = std::min(wantSlots, NQ_SORT_POOL);
-  while (pool > 1 && pool * sortSet + perImage > budget) pool /= 2;
-  if (pool * sortSet + perImage > budget) return fail(NQ_ERR_NOMEM, "not enough device memory for one image workspace");
-  const int maxSlots = (int)std::min<size_t>((budget - pool * sortSet) / perImage, 8192);
+  while (pool > 1 && NQ_FRONT_STREAMS * pool * sortSet + perImage > budget) pool /= 2;
+  if (NQ_FRONT_STREAMS * pool * sortSet + perImage > budget) return fail(NQ_ERR_NOMEM, "not enough device memory for one image workspace");
+  const int maxSlots = (int)std::min<size_t>((budget - NQ_FRONT_STREAMS * pool * sortSet) / perImage, 8192);
   const int slots = std::min(wantSlots, maxSlots);
   if (c->ws && c->wsKind == kind && c->wsNpix == npix && c->wsSlots >= slots && c->wsDebug == c->debug && c->wsBits == needBits) return NQ_OK;
-  if (c->ws) { cudaFree(c->ws); c->ws = nullptr; c->wsBytes = 0; }
+  if (c->ws) { CU(cudaDeviceSynchronize()); cudaFree(c->ws); c->ws = nullptr; c->wsBytes = 0; c->wsSlots = 0; }
   const size_t imgsB = align_up(sizeof(NqImage) * slots, 256), slotsB = align_up(sizeof(NqSlot) * slots, 256);
   const size_t liveB = align_up((size_t)slots * NQ_NBINS * 4, 256);
-  const size_t total = imgsB + slotsB + 2 * liveB + L.total * slots + sortSet * pool;
+  const size_t total = imgsB + slotsB + 2 * liveB + (zeroSlot + memoSlot + L.total) * slots + sortSet * pool * NQ_FRONT_STREAMS;
   CU(cudaMalloc(&c->ws, total));
   c->wsBytes = total;
   unsigned char* p = c->ws;
@@ -268,20 +287,17 @@ int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots, bool needBits
   c->dSlots = reinterpret_cast<NqSlot*>(p); p += slotsB;
   c->dLive = reinterpret_cast<int*>(p); p += liveB;
   c->dPos = reinterpret_cast<int*>(p); p += liveB;
-  unsigned char* poolBase = p; p += sortSet * pool;
+  c->zeroPlane = p; p += zeroSlot * slots;
+  c->memoPlane = p; p += memoSlot * slots;
+  c->sortPool = p; p += sortSet * pool * NQ_FRONT_STREAMS;
+  c->zeroSlotBytes = zeroSlot; c->memoSlotBytes = memoSlot; c->sortSetBytes = sortSet; c->sortABytes = sortA;
   c->hSlots.assign(slots, NqSlot{});
   for (int s = 0; s < slots; ++s) {
     unsigned char* b = p + L.total * s;
     NqSlot& S = c->hSlots[s];
-    S.hCnt = reinterpret_cast<unsigned int*>(b + L.hCnt);
-    S.hSum = reinterpret_cast<unsigned long long*>(b + L.hSum);
+    S.hCnt = reinterpret_cast<unsigned int*>(c->zeroPlane + zeroSlot * s);
+    S.hSum = reinterpret_cast<unsigned long long*>(c->zeroPlane + zeroSlot * s + (size_t)NQ_NBINS * 4);
     S.keyOff = reinterpret_cast<unsigned int*>(b + L.keyOff);
-    if (lab) {
-      unsigned char* sp = poolBase + sortSet * (s % pool);
-      S.sortA = reinterpret_cast<uint32_t*>(sp);
-      S.sortB = reinterpret_cast<uint32_t*>(sp + align_up((size_t)npix * 4, 256));
-      S.warpHist = reinterpret_cast<unsigned int*>(sp + 2 * align_up((size_t)npix * 4, 256));
-    }
     S.sal = (lab && c->debug) ? reinterpret_cast<float*>(b + L.sal) : nullptr;
     double* bd = reinterpret_cast<double*>(b + L.bD);
     S.bAc = bd; S.bC1 = bd + NQ_NBINS; S.bC2 = bd + 2 * NQ_NBINS; S.bC3 = bd + 3 * NQ_NBINS;
@@ -294,28 +310,49 @@ int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots, bool needBits
     S.bMtm = reinterpret_cast<int*>(b + L.bMtm);
     S.heap = reinterpret_cast<uint2*>(b + L.heap);
     S.mergeLog = c->debug ? reinterpret_cast<int*>(b + L.mergeLog) : nullptr;
-    S.memo = reinterpret_cast<unsigned short*>(b + L.memo);
+    S.memo = reinterpret_cast<unsigned short*>(c->memoPlane + memoSlot * s);
     S.cells = lab ? b + L.cells : nullptr;
     S.bits = needBits ? reinterpret_cast<unsigned int*>(b + L.bits) : nullptr;
     S.idx = nullptr;
   }
-  c->wsSlots = slots; c->wsNpix = npix; c->wsKind = kind; c->sortPool = pool; c->wsDebug = c->debug; c->wsBits = needBits;
+  c->wsSlots = slots; c->wsNpix = npix; c->wsKind = kind; c->sortSets = pool; c->wsDebug = c->debug; c->wsBits = needBits;
   return NQ_OK;
 }
 
+// The visiting order of a (w, h) image is a table of 4 bytes per pixel, built by a host walk the first time the size is
+// seen. The cache is bounded (entries and bytes): a long-lived context that serves many sizes evicts the least recently used.
+#define NQ_ORDER_MAX_ENTRIES 8
+#define NQ_ORDER_MAX_BYTES ((size_t)2 << 30)
 int ensure_order(nq_ctx* c, int w, int h, const uint32_t** out) {
   auto key = std::make_pair(w, h);
   auto it = c->orders.find(key);
-  if (it != c->orders.end()) { *out = it->second; return NQ_OK; }
+  if (it != c->orders.end()) {
+    auto pos = std::find(c->orderLru.begin(), c->orderLru.end(), key);
+    if (pos != c->orderLru.end()) { c->orderLru.erase(pos); c->orderLru.push_back(key); }
+    *out = it->second;
+    return NQ_OK;
+  }
   if (w > 65535 || h > 65535) return fail(NQ_ERR_ARG, "image side exceeds 65535");
+  const size_t bytes = (size_t)w * h * 4;
+  while (!c->orderLru.empty() && (c->orderLru.size() >= NQ_ORDER_MAX_ENTRIES || c->orderBytes + bytes > NQ_ORDER_MAX_BYTES)) {
+    const auto old = c->orderLru.front();
+    c->orderLru.erase(c->orderLru.begin());
+    CU(cudaDeviceSynchronize());                    // nothing in flight may still read the table
+    cudaFree(c->orders[old]);
+    c->orderBytes -= (size_t)old.first * old.second * 4;
+    c->orders.erase(old);
+  }
   std::vector<uint32_t> host;
   host.reserve((size_t)w * h);
   gilbert_walk(w, h, [&](int x, int y) { host.push_back((uint32_t)x | ((uint32_t)y << 16)); });
   if (host.size() != (size_t)w * h) return fail(NQ_ERR_ARG, "gilbert walk size mismatch");
   uint32_t* d = nullptr;
-  CU(cudaMalloc(&d, host.size() * 4));
-  CU(cudaMemcpy(d, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&d, bytes));
+  cudaError_t e = cudaMemcpy(d, host.data(), bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d); return fail(NQ_ERR_CUDA, std::string("cudaMemcpy(order): ") + cudaGetErrorString(e)); }
   c->orders[key] = d;
+  c->orderLru.push_back(key);
+  c->orderBytes += bytes;
   *out = d;
   return NQ_OK;
 }
@@ -326,11 +363,36 @@ int pixel_grid_x(const nq_ctx* c, int npix, int nimg) {
   return std::max(1, std::min(want, cap));
 }
 
-// Speculative segment-parallel dither for the images that qualify (decided on the device, k_spec_setup). Images it
-// completes get NqImage::specDone and are skipped by k_dither_fifo; every other image is untouched.
-// launches and small copies of the wave / round loop (spec_drive in nq_dither_spec.cuh) on the context's stream
+cudaEvent_t take_event(nq_ctx* c) {
+  if (c->evUsed == c->evPool.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    c->evPool.push_back(e);
+  }
+  return c->evPool[c->evUsed++];
+}
+
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
+// One chunk of a call: images [base, base + n) of the group, with the events that bracket its stages.
+struct Chunk {
+  int base = 0, n = 0;
+  cudaStream_t front = nullptr;
+  int frontIdx = 0;
+  cudaEvent_t ev[5] = {};          // on `front`: start, after scan, after histogram, after the find_nn sweep, after the merge loop
+  cudaEvent_t evD[3] = {};         // on the dither stream: start, after setup, end
+  cudaEvent_t evK[2 * NQ_NKERNELS] = {};   // pairs around the kernels timed on their own (0 when not recorded)
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evRuns;   // around every k_spec_run launch
+  unsigned long long launches[NQ_NSTAGES] = {};
+};
+
+// launches and small copies of the admission / round loop (spec_drive in nq_dither_spec.cuh) on the dither stream
 struct SpecCudaBackend {
   nq_ctx* c;
+  Chunk* ch;
   cudaStream_t st;
   bool timing = false;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -340,8 +402,18 @@ struct SpecCudaBackend {
     kernel<<<grid, block, 0, st>>>(args...);
     ++c->launches;
   }
+  // stage 6 (k_spec_run): bracketed by its own events, for nq_get_kernel_times
+  template <class... P, class... A>
+  void launch_run(void (*kernel)(P...), dim3 grid, int block, A... args) {
+    cudaEvent_t a = take_event(c), b = take_event(c);
+    cudaEventRecord(a, st);
+    kernel<<<grid, block, 0, st>>>(args...);
+    cudaEventRecord(b, st);
+    ch->evRuns.emplace_back(a, b);
+    ++c->launches;
+  }
   void keep(cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; }
-  void zero_ints(int* p, int n) { keep(cudaMemsetAsync(p, 0, sizeof(int) * (size_t)n, st)); }
+  void write_ints(int* dev, const int* host, int n) { keep(cudaMemcpyAsync(dev, host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st)); }
   void read_ints(int* host, const int* dev, int n) {
     keep(cudaMemcpyAsync(host, dev, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
     keep(cudaStreamSynchronize(st));
@@ -358,62 +430,83 @@ struct SpecCudaBackend {
     fprintf(stderr, "[nq spec] %-14s %9.3f ms\n", what, ms);
     cudaEventRecord(t0, st);
   }
-  void note(int round, const int* counters) {
-    if (timing) fprintf(stderr, "[nq spec] round %d: %d image(s) open, %d patch(es), %d re-resolve(s)\n", round, counters[0], counters[1], counters[2]);
+  void note(int round, int active, int open, int patches, int redos) {
+    if (timing) fprintf(stderr, "[nq spec] round %d: %d image(s) in the pool, %d open, %d patch(es), %d re-resolve(s)\n", round, active, open, patches, redos);
   }
 };
 
-int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
+// Speculative segment-parallel dither of the chunk's images that qualify, on stream `st`, in two steps so that the
+// serial kernels of the other images can be enqueued in between. spec_prepare: the pool of work-array slots and
+// k_spec_setup, which decides on the device which images are taken (NqImage::specDone = 2, elig[i] = 1) -- synchronises.
+// spec_rounds: the admission / round loop; images it completes get specDone = 1, images it took but could not finish 3
+// (listed in `handed`).
+struct SpecPlan { int seg = 0, nslots = 0, any = 0; };
+int spec_prepare(nq_ctx* c, Chunk& ch, cudaStream_t st, int npix, const uint32_t* dOrder, std::vector<int>& elig, SpecPlan* plan) {
   using namespace nq::spec;
-  cudaStream_t st = c->stream;
+  const int n = ch.n;
+  elig.assign(n, 0);
+  *plan = SpecPlan{};
   int seg = c->specSeg;
   const int warm = c->specWarm;
   if (seg == 0) {   // automatic: 8192-pixel segments when that gives the machine enough threads, shorter ones for small jobs
     const long long total = (long long)n * (long long)npix;
-    seg = total / 8192 >= 16384 ? 8192 : (int)std::max<long long>(2048, (total / 16384 + 255) / 256 * 256);
+    seg = total / 8192 >= 32768 ? 8192 : (int)std::max<long long>(2048, (total / 32768 + 255) / 256 * 256);
     if (seg > 8192) seg = 8192;
   }
   if (npix < 4 * seg) return NQ_OK;
-  if (c->specCap < n) {
-    if (c->dSpec) cudaFree(c->dSpec);
+  const int nTotal = c->wsSlots;
+  if (c->specCap < nTotal) {
+    if (c->dSpec) { CU(cudaDeviceSynchronize()); cudaFree(c->dSpec); }
     c->dSpec = nullptr; c->specCap = 0;
-    CU(cudaMalloc(&c->dSpec, sizeof(SpecImage) * (size_t)n));
-    c->specCap = n;
-  }
-  if (c->specIntsCap < n + 4) {
-    if (c->dSpecInts) cudaFree(c->dSpecInts);
-    c->dSpecInts = nullptr; c->specIntsCap = 0;
-    CU(cudaMalloc(&c->dSpecInts, sizeof(int) * (size_t)(n + 4)));
-    c->specIntsCap = n + 4;
+    CU(cudaMalloc(&c->dSpec, sizeof(SpecImage) * (size_t)nTotal));
+    c->specCap = nTotal;
   }
   const SpecLayout L = spec_layout(npix, seg);
   size_t freeB = 0, totalB = 0;
   CU(cudaMemGetInfo(&freeB, &totalB));
-  // a wave only has to fill the machine (one thread per segment: ~100 4K images); keep the rest of the memory for the caller
-  const size_t budget = std::min<size_t>((size_t)((double)(freeB + c->specBufBytes) * 0.5), (size_t)32 << 30);
-  const int wave = (int)std::min<size_t>((size_t)n, budget / L.perSlot);
-  if (wave < 1) return NQ_OK;                       // no room: the serial kernel does the work
-  if (c->specBufBytes < L.perSlot * (size_t)wave) {
-    if (c->specBuf) cudaFree(c->specBuf);
+  // the pool only has to fill the machine (one thread per segment: ~150 4K images); the rest of the memory stays the caller's
+  const size_t budget = std::min<size_t>((size_t)((double)(freeB + c->specBufBytes) * 0.5), (size_t)48 << 30);
+  const long long wantThreads = (long long)c->smCount * 1024;                       // segments in flight that fill the SMs twice over
+  int nslots = (int)std::min<long long>(n, std::max<long long>(8, (wantThreads + L.nseg - 1) / L.nseg));
+  nslots = (int)std::min<size_t>((size_t)nslots, budget / L.perSlot);
+  if (c->specSlotsMax > 0) nslots = std::min(nslots, c->specSlotsMax);
+  if (nslots < 1) return NQ_OK;                     // no room: the serial kernel does the work
+  if (c->specBufBytes < L.perSlot * (size_t)nslots) {
+    if (c->specBuf) { CU(cudaDeviceSynchronize()); cudaFree(c->specBuf); }
     c->specBuf = nullptr; c->specBufBytes = 0;
-    CU(cudaMalloc(&c->specBuf, L.perSlot * (size_t)wave));
-    c->specBufBytes = L.perSlot * (size_t)wave;
+    CU(cudaMalloc(&c->specBuf, L.perSlot * (size_t)nslots));
+    c->specBufBytes = L.perSlot * (size_t)nslots;
   }
-  std::vector<SpecImage> h(n);
-  memset(h.data(), 0, sizeof(SpecImage) * (size_t)n);
-  spec_bind(h.data(), n, c->specBuf, L, wave);
-  CU(cudaMemcpyAsync(c->dSpec, h.data(), sizeof(SpecImage) * (size_t)n, cudaMemcpyHostToDevice, st));
-  k_spec_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, c->dSpec, dOrder, n, seg, warm, c->dSpecInts + 4); ++c->launches;
-  std::vector<int> elig(n);
-  CU(cudaMemcpyAsync(elig.data(), c->dSpecInts + 4, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));                    // also keeps `h` alive until the copy is done
-  // k_dither_fifo's time is one serial chain as soon as it has a single image to do: if it has one anyway, nothing is gained here
-  for (int i = 0; i < n; ++i) if (elig[i] == 2) return NQ_OK;
-  SpecCudaBackend be{c, st};
+  if (c->specPoolCap < nslots) {
+    if (c->dSpecPool) { CU(cudaDeviceSynchronize()); cudaFree(c->dSpecPool); cudaFree(c->dSpecInts); }
+    c->dSpecPool = nullptr; c->dSpecInts = nullptr; c->specPoolCap = 0;
+    CU(cudaMalloc(&c->dSpecPool, sizeof(SpecWork) * (size_t)nslots));
+    CU(cudaMalloc(&c->dSpecInts, sizeof(int) * (size_t)(4 * nslots + 4)));
+    c->specPoolCap = nslots;
+  }
+  std::vector<SpecWork> pool(nslots);
+  spec_bind_pool(pool.data(), nslots, c->specBuf, L);
+  CU(cudaMemcpyAsync(c->dSpecPool, pool.data(), sizeof(SpecWork) * (size_t)nslots, cudaMemcpyHostToDevice, st));
+  int* dElig = reinterpret_cast<int*>(c->specBuf);      // scratch: the pool's work arrays are not in use yet
+  k_spec_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs + ch.base, c->dSlots + ch.base, c->dSpec + ch.base, dOrder, n, seg, warm, dElig); ++c->launches;
+  CU(cudaMemcpyAsync(elig.data(), dElig, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));                    // also keeps `pool` alive until the copy is done
+  for (int i = 0; i < n; ++i) plan->any += (elig[i] & 255) == 1;
+  plan->seg = seg; plan->nslots = nslots;
+  return NQ_OK;
+}
+int spec_rounds(nq_ctx* c, Chunk& ch, cudaStream_t st, int npix, const SpecPlan& plan, const std::vector<int>& elig, std::vector<int>& handed) {
+  using namespace nq::spec;
+  handed.clear();
+  if (!plan.any) return NQ_OK;
+  SpecCudaBackend be{c, &ch, st};
   be.timing = getenv("NQ_SPEC_TIMING") != nullptr;
   be.begin();
   SpecStats stats;
-  spec_drive(be, c->dImgs, c->dSpec, elig.data(), n, npix, seg, wave, c->dSpecInts, c->smCount, &stats);
+  handed.assign(plan.any, 0);
+  spec_drive(be, c->dImgs + ch.base, c->dSpec + ch.base, c->dSpecPool, elig.data(), ch.n, npix, plan.seg, plan.nslots, c->dSpecInts, c->dTanh,
+             c->smCount, &stats, handed.data());
+  handed.resize((size_t)stats.handedBack);
   be.end();
   c->specImages += stats.done; c->specRounds += stats.rounds; c->specFallbacks += stats.handedBack;
   CU(be.err);
@@ -421,58 +514,69 @@ int run_spec_dither(nq_ctx* c, int n, int npix, const uint32_t* dOrder) {
   return NQ_OK;
 }
 
-// Runs convert() for images [0, n) already resident on the device. palIn != nullptr replaces the
-// palette before dithering (stage hook).
-int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, int w, int h, int nmax, int dither,
-              const uint64_t* seeds, const uint32_t* dPalIn, int palInLen) {
-  const int npix = w * h;
-  const uint32_t* dOrder = nullptr;
-  int rc = ensure_order(c, w, h, &dOrder);
-  if (rc) return rc;
-  cudaStream_t st = c->stream;
+struct GroupArgs {
+  int kind, w, h, nmax, dither;
+  const uint64_t* seeds;
+  const uint32_t* dPalIn;
+  int palInLen;
+  const uint32_t* hIn;     // host pixels (nullptr: dIn is the caller's device buffer and already holds them)
+  uint32_t* hOut;
+};
+
+// scan .. merge loop of one chunk, enqueued on its front stream (no host synchronisation unless the context is in debug mode)
+int enqueue_front(nq_ctx* c, Chunk& ch, const GroupArgs& A, const uint32_t* dIn, uint32_t* dOut) {
+  NvtxRange nv("nq front (scan, histogram, find_nn, merge)");
+  const int n = ch.n, npix = A.w * A.h, kind = A.kind, nmax = A.nmax;
+  cudaStream_t st = ch.front;
+  NqImage* dI = c->dImgs + ch.base;
+  NqSlot* dS = c->dSlots + ch.base;
+  if (A.hIn) CU(cudaMemcpyAsync(const_cast<uint32_t*>(dIn) + (size_t)ch.base * npix, A.hIn + (size_t)ch.base * npix, (size_t)n * npix * 4, cudaMemcpyHostToDevice, st));
   std::vector<NqImage> hImgs(n);
   for (int i = 0; i < n; ++i) {
     NqImage& I = hImgs[i];
     memset(&I, 0, sizeof(I));
-    I.kind = kind; I.width = w; I.height = h; I.npix = npix; I.nmax = nmax; I.dither = dither;
-    I.seed = seeds ? seeds[i] : 0ULL;
+    I.kind = kind; I.width = A.w; I.height = A.h; I.npix = npix; I.nmax = nmax; I.dither = A.dither;
+    I.seed = A.seeds ? A.seeds[ch.base + i] : 0ULL;
     I.transIdx = -1;
-    c->hSlots[i].in = dIn + (size_t)i * npix;
-    c->hSlots[i].out = dOut + (size_t)i * npix;
+    NqSlot& S = c->hSlots[ch.base + i];
+    S.in = dIn + (size_t)(ch.base + i) * npix;
+    S.out = dOut + (size_t)(ch.base + i) * npix;
+    if (kind == NQ_KIND_LAB) {   // sort scratch: the sets of this chunk's front stream, cycled through the chunk
+      unsigned char* sp = c->sortPool + c->sortSetBytes * ((size_t)ch.frontIdx * c->sortSets + (size_t)(i % c->sortSets));
+      S.sortA = reinterpret_cast<uint32_t*>(sp);
+      S.sortB = reinterpret_cast<uint32_t*>(sp + c->sortABytes);
+      S.warpHist = reinterpret_cast<unsigned int*>(sp + 2 * c->sortABytes);
+    }
   }
-  CU(cudaMemcpyAsync(c->dImgs, hImgs.data(), sizeof(NqImage) * n, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(c->dSlots, c->hSlots.data(), sizeof(NqSlot) * n, cudaMemcpyHostToDevice, st));
-  for (int i = 0; i < n; ++i) {
-    const NqSlot& S = c->hSlots[i];
-    CU(cudaMemsetAsync(S.hCnt, 0, NQ_NBINS * 4, st));
-    CU(cudaMemsetAsync(S.hSum, 0, (size_t)4 * NQ_NBINS * 8, st));
-    CU(cudaMemsetAsync(S.memo, 0xFF, NQ_NBINS * 2, st));
-    if (S.bits) CU(cudaMemsetAsync(S.bits, 0, (size_t)1 << 29, st));
-  }
+  CU(cudaMemcpyAsync(dI, hImgs.data(), sizeof(NqImage) * n, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(dS, c->hSlots.data() + ch.base, sizeof(NqSlot) * n, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(c->zeroPlane + c->zeroSlotBytes * ch.base, 0, c->zeroSlotBytes * n, st));
+  CU(cudaMemsetAsync(c->memoPlane + c->memoSlotBytes * ch.base, 0xFF, c->memoSlotBytes * n, st));
+  for (int i = 0; i < n; ++i) if (c->hSlots[ch.base + i].bits) CU(cudaMemsetAsync(c->hSlots[ch.base + i].bits, 0, (size_t)1 << 29, st));
   const int gx = pixel_grid_x(c, npix, n);
   const dim3 pg(gx, n);
   unsigned long long l0 = c->launches;
-  auto mark = [&](int k) { cudaEventRecord(c->ev[k], st); if (k > 0) { c->stageLaunches[k - 1] += c->launches - l0; l0 = c->launches; } };
+  auto mark = [&](int k) { cudaEventRecord(ch.ev[k], st); if (k > 0) { ch.launches[k - 1] += c->launches - l0; l0 = c->launches; } };
   mark(0);
-  nq::k_alpha_scan<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
-  nq::k_setup_scan<<<(n + 127) / 128, 128, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
+  nq::k_alpha_scan<<<pg, 256, 0, st>>>(dI, dS); ++c->launches;
+  nq::k_setup_scan<<<(n + 127) / 128, 128, 0, st>>>(dI, dS, n); ++c->launches;
   mark(1);
   if (nmax > 2) {
     if (kind == NQ_KIND_RGB) {
       {  // contiguous tiles per CTA; enough CTAs to fill the machine twice over
-        const int ntiles = ((w + NQ_HTW - 1) / NQ_HTW) * ((h + NQ_HTW - 1) / NQ_HTW);
+        const int ntiles = ((A.w + NQ_HTW - 1) / NQ_HTW) * ((A.h + NQ_HTW - 1) / NQ_HTW);
         const dim3 hg(std::max(1, std::min(ntiles, std::max(1, c->smCount * 8 / n))), n);
-        nq::k_hist_rgb<<<hg, 256, sizeof(nq::HistTable), st>>>(c->dImgs, c->dSlots); ++c->launches;
+        nq::k_hist_rgb<<<hg, 256, sizeof(nq::HistTable), st>>>(dI, dS); ++c->launches;
       }
-      nq::k_finalize_rgb<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_finalize_rgb<<<n, 1024, 0, st>>>(dI, dS); ++c->launches;
     } else {
       const int nruns = (npix + NQ_RUN - 1) / NQ_RUN;
-      nq::k_lab_count<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
-      nq::k_lab_scan_keys<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
-      for (int g0 = 0; g0 < n; g0 += c->sortPool) {   // images of one group own distinct sort scratch sets
-        const int gn = std::min(c->sortPool, n - g0);
-        NqImage* gi = c->dImgs + g0;
-        NqSlot* gs = c->dSlots + g0;
+      nq::k_lab_count<<<pg, 256, 0, st>>>(dI, dS); ++c->launches;
+      nq::k_lab_scan_keys<<<n, 1024, 0, st>>>(dI, dS); ++c->launches;
+      for (int g0 = 0; g0 < n; g0 += c->sortSets) {   // images of one group own distinct sort scratch sets
+        const int gn = std::min(c->sortSets, n - g0);
+        NqImage* gi = dI + g0;
+        NqSlot* gs = dS + g0;
         const dim3 rg(std::max(1, std::min((nruns + 7) / 8, std::max(1, c->smCount * 8 / gn))), gn);
         nq::k_radix_count<0><<<rg, 256, 0, st>>>(gi, gs); ++c->launches;
         nq::k_radix_offsets<<<gn, 256, 0, st>>>(gi, gs); ++c->launches;
@@ -483,27 +587,26 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
         const dim3 bg(std::max(1, c->smCount * 8 / gn), gn);
         nq::k_lab_bin_sum<<<bg, 256, 0, st>>>(gi, gs); ++c->launches;
       }
-      nq::k_finalize_lab<<<n, 1024, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
-      nq::k_lab_fewcolors<<<n, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
+      nq::k_finalize_lab<<<n, 1024, 0, st>>>(dI, dS); ++c->launches;
+      nq::k_lab_fewcolors<<<n, 256, 0, st>>>(dI, dS); ++c->launches;
     }
     mark(2);
     if (kind == NQ_KIND_RGB) {
-      nq::k_rgb_blocks<<<dim3(2, n), 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
-      nq::k_find_nn_all<<<c->smCount * 8, 256, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
-    }
-    else {
-      nq::k_lab_blocks<<<dim3(2, n), 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches;
-      nq::k_find_nn_lab<<<c->smCount * 8, 256, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
+      nq::k_rgb_blocks<<<dim3(2, n), 256, 0, st>>>(dI, dS); ++c->launches;
+      nq::k_find_nn_all<<<c->smCount * 8, 256, 0, st>>>(dI, dS, n); ++c->launches;
+    } else {
+      nq::k_lab_blocks<<<dim3(2, n), 256, 0, st>>>(dI, dS); ++c->launches;
+      nq::k_find_nn_lab<<<c->smCount * 8, 256, 0, st>>>(dI, dS, n); ++c->launches;
     }
     mark(3);
     if (c->debug) {
       CU(cudaStreamSynchronize(st));
       std::vector<NqImage> tmp(n);
-      CU(cudaMemcpy(tmp.data(), c->dImgs, sizeof(NqImage) * n, cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(tmp.data(), dI, sizeof(NqImage) * n, cudaMemcpyDeviceToHost));
       for (int i = 0; i < n; ++i) {
-        DebugImage& D = c->dbg[i];
+        DebugImage& D = c->dbg[ch.base + i];
         const int mb = tmp[i].maxbins;
-        const NqSlot& S = c->hSlots[i];
+        const NqSlot& S = c->hSlots[ch.base + i];
         D.bins5.assign((size_t)mb * 5, 0.0);
         D.initErr.assign(mb, 0.f); D.initNn.assign(mb, 0);
         if (mb <= 0) continue;
@@ -526,51 +629,76 @@ int run_chunk(nq_ctx* c, int kind, const uint32_t* dIn, uint32_t* dOut, int n, i
         CU(cudaMemcpy(D.initNn.data(), S.bNn, (size_t)mb * 4, cudaMemcpyDeviceToHost));
       }
     }
+    int* live = c->dLive + (size_t)ch.base * NQ_NBINS;
+    int* pos = c->dPos + (size_t)ch.base * NQ_NBINS;
     if (kind == NQ_KIND_RGB) {
-      nq::k_merge_rgb<<<n, NQ_RGB_THREADS, (size_t)NQ_RGB_HEAP_SMEM * 8, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
+      nq::k_merge_rgb<<<n, NQ_RGB_THREADS, (size_t)NQ_RGB_HEAP_SMEM * 8, st>>>(dI, dS, live, pos, c->debug ? 1 : 0); ++c->launches;
     } else {
-      nq::k_merge_lab<<<n, NQ_LAB_THREADS, (size_t)NQ_LAB_HEAP_SMEM * 8, st>>>(c->dImgs, c->dSlots, c->dLive, c->dPos, c->debug ? 1 : 0); ++c->launches;
+      nq::k_merge_lab<<<n, NQ_LAB_THREADS, (size_t)NQ_LAB_HEAP_SMEM * 8, st>>>(dI, dS, live, pos, c->debug ? 1 : 0); ++c->launches;
     }
   } else { mark(2); mark(3); }
   mark(4);
-  nq::k_dither_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
-  if (dPalIn) {
-    for (int i = 0; i < n; ++i) { k_set_palette<<<1, 256, 0, st>>>(c->dImgs, i, dPalIn, palInLen); ++c->launches; }
-    nq::k_dither_setup<<<(n + 63) / 64, 64, 0, st>>>(c->dImgs, c->dSlots, n); ++c->launches;
+  CU(cudaGetLastError());
+  return NQ_OK;
+}
+
+// dither of one chunk on the dither stream (after its front). The speculative path's rounds synchronise with the host;
+// the serial kernels of the images it does not take run next to it on the aux stream.
+int run_dither(nq_ctx* c, Chunk& ch, const GroupArgs& A, const uint32_t* dOrder) {
+  NvtxRange nv("nq dither (setup, Gilbert pass, BlueNoise pass)");
+  const int n = ch.n, npix = A.w * A.h, kind = A.kind;
+  cudaStream_t st = c->sDith, ax = c->sAux;
+  NqImage* dI = c->dImgs + ch.base;
+  NqSlot* dS = c->dSlots + ch.base;
+  unsigned long long l0 = c->launches;
+  CU(cudaStreamWaitEvent(st, ch.ev[4], 0));
+  CU(cudaEventRecord(ch.evD[0], st));
+  nq::k_dither_setup<<<(n + 63) / 64, 64, 0, st>>>(dI, dS, n); ++c->launches;
+  if (A.dPalIn) {
+    for (int i = 0; i < n; ++i) { k_set_palette<<<1, 256, 0, st>>>(dI, i, A.dPalIn, A.palInLen); ++c->launches; }
+    nq::k_dither_setup<<<(n + 63) / 64, 64, 0, st>>>(dI, dS, n); ++c->launches;
   }
-  if (kind == NQ_KIND_LAB && c->debug) { nq::k_saliency<<<pg, 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches; }
-  if (kind == NQ_KIND_LAB) { nq::k_build_cells<<<dim3(std::max(1, std::min(128, c->smCount * 8 / n)), n), 256, 0, st>>>(c->dImgs, c->dSlots); ++c->launches; }
-  mark(5);
-  if (c->specDither && kind == NQ_KIND_LAB && dither) {
-    rc = run_spec_dither(c, n, npix, dOrder);
+  const dim3 pg(pixel_grid_x(c, npix, n), n);
+  if (kind == NQ_KIND_LAB && c->debug) { nq::k_saliency<<<pg, 256, 0, st>>>(dI, dS); ++c->launches; }
+  if (kind == NQ_KIND_LAB) { nq::k_build_cells<<<dim3(std::max(1, std::min(128, c->smCount * 8 / n)), n), 256, 0, st>>>(dI, dS); ++c->launches; }
+  CU(cudaEventRecord(ch.evD[1], st));
+  ch.launches[4] += c->launches - l0; l0 = c->launches;
+  std::vector<int> elig, handed;
+  const bool spec = c->specDither && kind == NQ_KIND_LAB && A.dither;
+  SpecPlan plan;
+  if (spec) {
+    int rc = spec_prepare(c, ch, st, npix, dOrder, elig, &plan);
     if (rc) return rc;
   }
-  // each kernel returns at once for images of the other queue mode (decided on the device)
-  {  // images whose lookups stay on the serial chain (PnnQuantizer; dither == false) get a shared-memory memo cache
-    const int cacheBytes = (kind == NQ_KIND_RGB || !dither) ? 32768 : 0;
-    nq::k_dither_fifo<<<n, 64, cacheBytes, st>>>(c->dImgs, c->dSlots, dOrder, cacheBytes); ++c->launches;
-  }
-  nq::k_dither_sorted<<<n, 32, 0, st>>>(c->dImgs, c->dSlots, dOrder); ++c->launches;
-  mark(6);
-  CU(cudaGetLastError());
-  c->lastImgs.resize(n);
-  CU(cudaMemcpyAsync(c->lastImgs.data(), c->dImgs, sizeof(NqImage) * n, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  for (int k = 0; k < NQ_NSTAGES; ++k) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1]) == cudaSuccess) c->stageMs[k] += ms;
-  }
-  if (c->debug) {
-    for (int i = 0; i < n; ++i) {
-      DebugImage& D = c->dbg[i];
-      const NqImage& I = c->lastImgs[i];
-      const int merges = (nmax > 2 && I.extbins > 0) ? I.extbins : 0;
-      D.merges.assign((size_t)merges * 2, 0);
-      if (merges && c->hSlots[i].mergeLog) CU(cudaMemcpy(D.merges.data(), c->hSlots[i].mergeLog, (size_t)merges * 8, cudaMemcpyDeviceToHost));
-      D.sal.clear();
-      if (I.gUseSal && c->hSlots[i].sal) { D.sal.resize(npix); CU(cudaMemcpy(D.sal.data(), c->hSlots[i].sal, (size_t)npix * 4, cudaMemcpyDeviceToHost)); }
+  // Everything the speculative path did not take (specDone == 0) goes through the serial kernels on the aux stream, next
+  // to the speculative rounds; both kernels return at once for images of the other queue mode (decided on the device).
+  const int cacheBytes = (kind == NQ_KIND_RGB || !A.dither) ? 32768 : 0;   // shared-memory memo cache when lookups stay on the chain
+  cudaEvent_t evFork = take_event(c), evJoin = take_event(c);
+  CU(cudaEventRecord(evFork, st));
+  CU(cudaStreamWaitEvent(ax, evFork, 0));
+  ch.evK[2] = take_event(c); ch.evK[3] = take_event(c);
+  cudaEventRecord(ch.evK[2], ax);
+  nq::k_dither_fifo<<<n, 64, cacheBytes, ax>>>(dI, dS, dOrder, cacheBytes, 0); ++c->launches;
+  cudaEventRecord(ch.evK[3], ax);
+  ch.evK[4] = take_event(c); ch.evK[5] = take_event(c);
+  cudaEventRecord(ch.evK[4], ax);
+  nq::k_dither_sorted<<<n, 32, 0, ax>>>(dI, dS, dOrder); ++c->launches;
+  cudaEventRecord(ch.evK[5], ax);
+  if (spec) {
+    int rc = spec_rounds(c, ch, st, npix, plan, elig, handed);
+    if (rc) return rc;
+    if (!handed.empty()) {   // qualifying images the rounds gave up on (specDone == 3): the serial kernel after all
+      cudaEvent_t evBack = take_event(c);
+      CU(cudaEventRecord(evBack, st));
+      CU(cudaStreamWaitEvent(ax, evBack, 0));
+      nq::k_dither_fifo<<<n, 64, cacheBytes, ax>>>(dI, dS, dOrder, cacheBytes, 3); ++c->launches;
     }
   }
+  CU(cudaEventRecord(evJoin, ax));
+  CU(cudaStreamWaitEvent(st, evJoin, 0));
+  CU(cudaEventRecord(ch.evD[2], st));
+  ch.launches[5] += c->launches - l0;
+  CU(cudaGetLastError());
   return NQ_OK;
 }
 
@@ -596,8 +724,92 @@ int collect_results(nq_ctx* c, int base, int n, uint32_t* palettes, int* plens, 
   return NQ_OK;
 }
 
+// convert() for images [0, n) of a group that fits the workspace: the group is cut into chunks that flow through
+// front streams (scan .. merge), the dither stream and the copy-out stream, so that one chunk's merge loop, the previous
+// chunk's dither and the host copies of both overlap. dIn / dOut are device buffers holding (or receiving, A.hIn) the pixels.
+int convert_group(nq_ctx* c, const GroupArgs& A, int n, const uint32_t* dIn, uint32_t* dOut, int dbgBase) {
+  const int npix = A.w * A.h;
+  const uint32_t* dOrder = nullptr;
+  int rc = ensure_order(c, A.w, A.h, &dOrder);
+  if (rc) return rc;
+  int per = c->chunkImages;
+  if (per <= 0) {
+    // automatic: whole batches up to 640 images in one piece (the merge loop wants >= 4 images per SM in flight); larger
+    // ones, and host-buffer calls (whose copies should overlap the kernels), in equal pieces of at most 512 / 256 images
+    const int cap = A.hIn ? 256 : 512;
+    per = (n <= 640 && !A.hIn) ? n : (n + ((n + cap - 1) / cap) - 1) / ((n + cap - 1) / cap);
+    if (A.hIn && n <= 8) per = n;
+  }
+  if (c->debug) per = n;
+  per = std::max(1, std::min(per, n));
+  const int nch = (n + per - 1) / per;
+  c->evUsed = 0;
+  std::vector<Chunk> chunks(nch);
+  cudaEvent_t evStart = take_event(c), evOut = take_event(c), evEnd = take_event(c);
+  CU(cudaEventRecord(evStart, c->stream));
+  for (int k = 0; k < NQ_FRONT_STREAMS; ++k) CU(cudaStreamWaitEvent(c->sFront[k], evStart, 0));
+  CU(cudaStreamWaitEvent(c->sDith, evStart, 0));
+  CU(cudaStreamWaitEvent(c->sOut, evStart, 0));
+  for (int k = 0; k < nch; ++k) {
+    Chunk& ch = chunks[k];
+    ch.base = k * per; ch.n = std::min(per, n - ch.base);
+    ch.frontIdx = k % NQ_FRONT_STREAMS; ch.front = c->sFront[ch.frontIdx];
+    for (auto& e : ch.ev) e = take_event(c);
+    for (auto& e : ch.evD) e = take_event(c);
+  }
+  if (c->debug) for (int i = 0; i < n; ++i) c->dbg[dbgBase + i] = DebugImage{};
+  GroupArgs G = A;
+  // fronts are enqueued one chunk ahead of the dither that consumes them (the speculative rounds block this thread)
+  rc = enqueue_front(c, chunks[0], G, dIn, dOut);
+  if (rc) return rc;
+  for (int k = 0; k < nch; ++k) {
+    if (k + 1 < nch) { rc = enqueue_front(c, chunks[k + 1], G, dIn, dOut); if (rc) return rc; }
+    rc = run_dither(c, chunks[k], G, dOrder);
+    if (rc) return rc;
+    if (A.hOut) {   // device -> host of the finished chunk on its own stream
+      CU(cudaStreamWaitEvent(c->sOut, chunks[k].evD[2], 0));
+      CU(cudaMemcpyAsync(A.hOut + (size_t)chunks[k].base * npix, dOut + (size_t)chunks[k].base * npix, (size_t)chunks[k].n * npix * 4, cudaMemcpyDeviceToHost, c->sOut));
+    }
+  }
+  CU(cudaEventRecord(evOut, c->sOut));
+  CU(cudaStreamWaitEvent(c->sDith, evOut, 0));
+  c->lastImgs.resize(n);
+  CU(cudaMemcpyAsync(c->lastImgs.data(), c->dImgs, sizeof(NqImage) * n, cudaMemcpyDeviceToHost, c->sDith));
+  CU(cudaEventRecord(evEnd, c->sDith));
+  CU(cudaStreamWaitEvent(c->stream, evEnd, 0));     // the caller's stream is ordered behind the whole call
+  CU(cudaStreamSynchronize(c->sDith));
+  for (int k = 0; k < NQ_FRONT_STREAMS; ++k) CU(cudaStreamSynchronize(c->sFront[k]));
+  CU(cudaStreamSynchronize(c->sAux));
+  for (Chunk& ch : chunks) {
+    float ms = 0.f;
+    for (int k = 0; k < 4; ++k) if (cudaEventElapsedTime(&ms, ch.ev[k], ch.ev[k + 1]) == cudaSuccess) c->stageMs[k] += ms;
+    for (int k = 0; k < 2; ++k) if (cudaEventElapsedTime(&ms, ch.evD[k], ch.evD[k + 1]) == cudaSuccess) c->stageMs[4 + k] += ms;
+    for (int k = 0; k < NQ_NSTAGES; ++k) c->stageLaunches[k] += ch.launches[k];
+    for (auto& pr : ch.evRuns) if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { c->kernelMs[0] += ms; ++c->kernelLaunches[0]; }
+    for (int k = 1; k < NQ_NKERNELS; ++k)
+      if (ch.evK[2 * k] && cudaEventElapsedTime(&ms, ch.evK[2 * k], ch.evK[2 * k + 1]) == cudaSuccess) { c->kernelMs[k] += ms; ++c->kernelLaunches[k]; }
+    if (cudaEventElapsedTime(&ms, ch.ev[3], ch.ev[4]) == cudaSuccess) { c->kernelMs[3] += ms; ++c->kernelLaunches[3]; }
+  }
+  cudaGetLastError();
+  if (c->debug) {
+    for (int i = 0; i < n; ++i) {
+      DebugImage& D = c->dbg[dbgBase + i];
+      const NqImage& I = c->lastImgs[i];
+      const int merges = (A.nmax > 2 && I.extbins > 0) ? I.extbins : 0;
+      D.merges.assign((size_t)merges * 2, 0);
+      if (merges && c->hSlots[i].mergeLog) CU(cudaMemcpy(D.merges.data(), c->hSlots[i].mergeLog, (size_t)merges * 8, cudaMemcpyDeviceToHost));
+      D.sal.clear();
+      if (I.gUseSal && c->hSlots[i].sal) { D.sal.resize(npix); CU(cudaMemcpy(D.sal.data(), c->hSlots[i].sal, (size_t)npix * 4, cudaMemcpyDeviceToHost)); }
+    }
+  }
+  return NQ_OK;
+}
+
+// dIn / dOut: device buffers for the whole batch. hIn / hOut (optional): host buffers the batch is read from / written to
+// chunk by chunk, overlapped with the kernels.
 int convert_device(nq_ctx* c, int kind, const uint32_t* dIn, int n, int w, int h, int nmax, int dither, const uint64_t* seeds,
-                   uint32_t* dOut, uint32_t* palettes, int* plens, int* hasAlpha, const uint32_t* dPalIn, int palInLen) {
+                   uint32_t* dOut, uint32_t* palettes, int* plens, int* hasAlpha, const uint32_t* dPalIn, int palInLen,
+                   const uint32_t* hIn = nullptr, uint32_t* hOut = nullptr) {
   CU(cudaSetDevice(c->device));
   const int npix = w * h;
   // the BlueNoise second pass of PnnLABQuantizer weighs by pixelMap.size() (PL:511-513): track it only then
@@ -610,8 +822,9 @@ int convert_device(nq_ctx* c, int kind, const uint32_t* dIn, int n, int w, int h
   all.reserve(n);
   for (int base = 0; base < n; base += c->wsSlots) {
     const int m = std::min(c->wsSlots, n - base);
-    rc = run_chunk(c, kind, dIn + (size_t)base * npix, dOut + (size_t)base * npix, m, w, h, nmax, dither,
-                   seeds ? seeds + base : nullptr, dPalIn, palInLen);
+    GroupArgs A{kind, w, h, nmax, dither, seeds ? seeds + base : nullptr, dPalIn, palInLen,
+                hIn ? hIn + (size_t)base * npix : nullptr, hOut ? hOut + (size_t)base * npix : nullptr};
+    rc = convert_group(c, A, m, dIn + (size_t)base * npix, dOut + (size_t)base * npix, base);
     if (rc) return rc;
     collect_results(c, base, m, palettes, plens, hasAlpha, &firstErr);
     all.insert(all.end(), c->lastImgs.begin(), c->lastImgs.end());
@@ -625,15 +838,62 @@ int convert_device(nq_ctx* c, int kind, const uint32_t* dIn, int n, int w, int h
 
 int ensure_stage(nq_ctx* c, size_t bytes) {
   if (c->stageBytes >= bytes) return NQ_OK;
+  CU(cudaDeviceSynchronize());
   if (c->dIn) cudaFree(c->dIn);
   if (c->dOut) cudaFree(c->dOut);
   c->dIn = c->dOut = nullptr; c->stageBytes = 0;
   CU(cudaMalloc(&c->dIn, bytes));
-  CU(cudaMalloc(&c->dOut, bytes));
+  cudaError_t e = cudaMalloc(&c->dOut, bytes);
+  if (e != cudaSuccess) { cudaFree(c->dIn); c->dIn = nullptr; return fail(NQ_ERR_NOMEM, std::string("cudaMalloc(staging): ") + cudaGetErrorString(e)); }
   c->stageBytes = bytes;
   return NQ_OK;
 }
 
+}  // namespace
+
+namespace {
+void destroy_ctx(nq_ctx* c, bool dropLut) {
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (dropLut) {
+    std::lock_guard<std::mutex> lk(g_lutMutex);
+    auto it = g_lut.find(c->device);
+    if (it != g_lut.end() && it->second.refs > 0 && --it->second.refs == 0) { cudaFree(it->second.ptr); g_lut.erase(it); }
+  }
+  for (auto& kv : c->orders) cudaFree(kv.second);
+  if (c->ws) cudaFree(c->ws);
+  if (c->dIn) cudaFree(c->dIn);
+  if (c->dOut) cudaFree(c->dOut);
+  if (c->dSpec) cudaFree(c->dSpec);
+  if (c->specBuf) cudaFree(c->specBuf);
+  if (c->dSpecPool) cudaFree(c->dSpecPool);
+  if (c->dSpecInts) cudaFree(c->dSpecInts);
+  if (c->dTanh) cudaFree(c->dTanh);
+  for (cudaEvent_t e : c->evPool) if (e) cudaEventDestroy(e);
+  for (int k = 0; k < NQ_FRONT_STREAMS; ++k) if (c->sFront[k]) cudaStreamDestroy(c->sFront[k]);
+  if (c->sDith) cudaStreamDestroy(c->sDith);
+  if (c->sAux) cudaStreamDestroy(c->sAux);
+  if (c->sOut) cudaStreamDestroy(c->sOut);
+  if (c->ownStream) cudaStreamDestroy(c->ownStream);
+  delete c;
+}
+// temporary device buffers of the probe / hook entry points: freed on every exit
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+__global__ void k_spec_tables(float* tanhTab, float* w3) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 511) tanhTab[t] = nq::spec::tanh_f((double)((float)(t - 255) / 255.f * 20.f));
+  if (t < 3) {   // initWeights(9 | 16 | 25), padded to NQ_MAXQ + 3 floats per row (GC:336-354)
+    const int DM = t == 0 ? 9 : (t == 1 ? 16 : 25);
+    float w[NQ_MAXQ];
+    nq::init_weights(w, DM);
+    for (int k = 0; k < NQ_MAXQ + 3; ++k) w3[t * (NQ_MAXQ + 3) + k] = k < DM ? w[k] : 0.f;
+  }
+}
 }  // namespace
 
 extern "C" {
@@ -654,18 +914,29 @@ nq_ctx* nq_create(int device) {
   c->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->smCount = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking) == cudaSuccess) c->stream = c->ownStream;
-  else { fail(NQ_ERR_CUDA, "cudaStreamCreate failed"); delete c; return nullptr; }
-  for (int k = 0; k <= NQ_NSTAGES; ++k) cudaEventCreate(&c->ev[k]);
+  bool ok = cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int k = 0; ok && k < NQ_FRONT_STREAMS; ++k) ok = cudaStreamCreateWithFlags(&c->sFront[k], cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&c->sDith, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&c->sAux, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&c->sOut, cudaStreamNonBlocking) == cudaSuccess;
+  if (!ok) { fail(NQ_ERR_CUDA, "cudaStreamCreate failed"); destroy_ctx(c, false); return nullptr; }
+  c->stream = c->ownStream;
   if (const char* e = getenv("NQ_SPEC_DITHER")) c->specDither = atoi(e) != 0;
-  signed char* dBn = nullptr;
-  bool ok = cudaMalloc(&dBn, 4096) == cudaSuccess && cudaMemcpy(dBn, kBlueNoise, 4096, cudaMemcpyHostToDevice) == cudaSuccess;
-  if (ok) {
-    nq::k_init_tables<<<4, 256, 0, c->stream>>>(dBn); ++c->launches;
-    nq::k_init_rtfac<<<1, 256, 0, c->stream>>>(); ++c->launches;
-    ok = cudaStreamSynchronize(c->stream) == cudaSuccess;
+  if (const char* e = getenv("NQ_CHUNK")) c->chunkImages = atoi(e);
+  if (const char* e = getenv("NQ_SPEC_SLOTS")) c->specSlotsMax = atoi(e);
+  bool haveLut = false;
+  {
+    DevBuf dBn, dW;
+    ok = dBn.alloc(4096) == cudaSuccess && cudaMemcpy(dBn.p, kBlueNoise, 4096, cudaMemcpyHostToDevice) == cudaSuccess &&
+         dW.alloc(sizeof(float) * 3 * (NQ_MAXQ + 3)) == cudaSuccess && cudaMalloc(&c->dTanh, sizeof(float) * 512) == cudaSuccess;
+    if (ok) {
+      nq::k_init_tables<<<4, 256, 0, c->stream>>>(dBn.as<signed char>()); ++c->launches;
+      nq::k_init_rtfac<<<1, 256, 0, c->stream>>>(); ++c->launches;
+      k_spec_tables<<<2, 256, 0, c->stream>>>(c->dTanh, dW.as<float>()); ++c->launches;
+      ok = cudaMemcpyToSymbolAsync(nq::spec::c_specW, dW.p, sizeof(float) * 3 * (NQ_MAXQ + 3), 0, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess &&
+           cudaStreamSynchronize(c->stream) == cudaSuccess;
+    }
   }
-  if (dBn) cudaFree(dBn);
   if (ok) {
     std::lock_guard<std::mutex> lk(g_lutMutex);
     LabLutEntry& e = g_lut[device];
@@ -679,7 +950,7 @@ nq_ctx* nq_create(int device) {
       }
       if (!ok && e.ptr) { cudaFree(e.ptr); e.ptr = nullptr; }
     }
-    if (ok) ++e.refs;
+    if (ok) { ++e.refs; haveLut = true; }
   }
   if (ok) ok = cudaFuncSetAttribute(nq::k_merge_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_RGB_HEAP_SMEM * 8) == cudaSuccess;
   if (ok) ok = cudaFuncSetAttribute(nq::k_hist_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nq::HistTable)) == cudaSuccess;
@@ -687,8 +958,7 @@ nq_ctx* nq_create(int device) {
   if (ok) ok = cudaFuncSetAttribute(nq::k_merge_lab, cudaFuncAttributeMaxDynamicSharedMemorySize, NQ_LAB_HEAP_SMEM * 8) == cudaSuccess;
   if (!ok) {
     fail(NQ_ERR_CUDA, std::string("context initialisation failed: ") + cudaGetErrorString(cudaGetLastError()));
-    cudaStreamDestroy(c->ownStream);
-    delete c;
+    destroy_ctx(c, haveLut);          // drops the table reference taken above, the streams and every allocation
     return nullptr;
   }
   return c;
@@ -696,28 +966,14 @@ nq_ctx* nq_create(int device) {
 
 void nq_destroy(nq_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
-  {
-    std::lock_guard<std::mutex> lk(g_lutMutex);
-    auto it = g_lut.find(c->device);
-    if (it != g_lut.end() && it->second.refs > 0 && --it->second.refs == 0) { cudaFree(it->second.ptr); g_lut.erase(it); }
-  }
-  for (auto& kv : c->orders) cudaFree(kv.second);
-  if (c->ws) cudaFree(c->ws);
-  if (c->dIn) cudaFree(c->dIn);
-  if (c->dOut) cudaFree(c->dOut);
-  if (c->dSpec) cudaFree(c->dSpec);
-  if (c->specBuf) cudaFree(c->specBuf);
-  if (c->dSpecInts) cudaFree(c->dSpecInts);
-  for (int k = 0; k <= NQ_NSTAGES; ++k) if (c->ev[k]) cudaEventDestroy(c->ev[k]);
-  if (c->ownStream) cudaStreamDestroy(c->ownStream);
-  delete c;
+  destroy_ctx(c, true);
 }
 
 int nq_convert_batch_device(nq_ctx* c, int kind, const uint32_t* d_in, int n, int w, int h, int nmax, int dither,
                             const uint64_t* seeds, uint32_t* d_out, uint32_t* palettes, int* plens, int* hasAlpha) {
   int rc = check_args(c, kind, d_in, n, w, h, nmax, d_out);
   if (rc) return rc;
+  NvtxRange nv("nq_convert_batch_device");
   return convert_device(c, kind, d_in, n, w, h, nmax, dither, seeds, d_out, palettes, plens, hasAlpha, nullptr, 0);
 }
 
@@ -725,14 +981,14 @@ int nq_convert_batch(nq_ctx* c, int kind, const uint32_t* in, int n, int w, int 
                      uint32_t* out, uint32_t* palettes, int* plens, int* hasAlpha) {
   int rc = check_args(c, kind, in, n, w, h, nmax, out);
   if (rc) return rc;
+  NvtxRange nv("nq_convert_batch");
   CU(cudaSetDevice(c->device));
   const size_t bytes = (size_t)n * w * h * 4;
   rc = ensure_stage(c, bytes);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(c->dIn, in, bytes, cudaMemcpyHostToDevice, c->stream));
-  rc = convert_device(c, kind, c->dIn, n, w, h, nmax, dither, seeds, c->dOut, palettes, plens, hasAlpha, nullptr, 0);
+  // host -> device, kernels and device -> host are interleaved chunk by chunk inside convert_device
+  rc = convert_device(c, kind, c->dIn, n, w, h, nmax, dither, seeds, c->dOut, palettes, plens, hasAlpha, nullptr, 0, in, out);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(out, c->dOut, bytes, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return NQ_OK;
 }
@@ -751,14 +1007,11 @@ int nq_dither_with_palette(nq_ctx* c, int kind, const uint32_t* in, int w, int h
   const size_t bytes = (size_t)w * h * 4;
   rc = ensure_stage(c, bytes);
   if (rc) return rc;
-  uint32_t* dPal = nullptr;
-  CU(cudaMalloc(&dPal, NQ_MAXK * 4));
-  CU(cudaMemcpy(dPal, palette, (size_t)plen * 4, cudaMemcpyHostToDevice));
-  CU(cudaMemcpyAsync(c->dIn, in, bytes, cudaMemcpyHostToDevice, c->stream));
-  rc = convert_device(c, kind, c->dIn, 1, w, h, nmax, dither, &seed, c->dOut, nullptr, nullptr, nullptr, dPal, plen);
-  cudaFree(dPal);
+  DevBuf dPal;
+  CU(dPal.alloc(NQ_MAXK * 4));
+  CU(cudaMemcpy(dPal.p, palette, (size_t)plen * 4, cudaMemcpyHostToDevice));
+  rc = convert_device(c, kind, c->dIn, 1, w, h, nmax, dither, &seed, c->dOut, nullptr, nullptr, nullptr, dPal.as<uint32_t>(), plen, in, out);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(out, c->dOut, bytes, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return NQ_OK;
 }
@@ -795,7 +1048,18 @@ int nq_sizeof_image_info(void) { return (int)sizeof(nq_image_info); }
 
 int nq_set_stream(nq_ctx* c, void* stream) {
   if (!c) return fail(NQ_ERR_ARG, "null context");
-  c->stream = stream ? reinterpret_cast<cudaStream_t>(stream) : c->ownStream;
+  // a NULL handle is CUDA's legacy default stream (what torch.cuda.default_stream().cuda_stream is), not "our own"
+  c->stream = stream ? reinterpret_cast<cudaStream_t>(stream) : cudaStreamLegacy;
+  return NQ_OK;
+}
+int nq_reset_stream(nq_ctx* c) {
+  if (!c) return fail(NQ_ERR_ARG, "null context");
+  c->stream = c->ownStream;
+  return NQ_OK;
+}
+int nq_set_chunk_images(nq_ctx* c, int images) {
+  if (!c || images < 0) return fail(NQ_ERR_ARG, "bad arguments");
+  c->chunkImages = images;
   return NQ_OK;
 }
 
@@ -853,43 +1117,49 @@ int nq_get_stage_times(nq_ctx* c, double* ms, unsigned long long* launches, int 
   }
   return NQ_OK;
 }
+int nq_get_kernel_times(nq_ctx* c, double* ms, unsigned long long* launches, int reset) {
+  if (!c) return fail(NQ_ERR_ARG, "null context");
+  for (int k = 0; k < NQ_NKERNELS; ++k) {
+    if (ms) ms[k] = c->kernelMs[k];
+    if (launches) launches[k] = c->kernelLaunches[k];
+    if (reset) { c->kernelMs[k] = 0; c->kernelLaunches[k] = 0; }
+  }
+  return NQ_OK;
+}
 
 int nq_debug_math(nq_ctx* c, int fn, const double* x, const double* y, double* out, int n) {
   if (!c || !x || !out || n <= 0) return fail(NQ_ERR_ARG, "bad arguments");
   CU(cudaSetDevice(c->device));
-  double *dx = nullptr, *dy = nullptr, *dout = nullptr;
-  CU(cudaMalloc(&dx, (size_t)n * 8));
-  CU(cudaMalloc(&dy, (size_t)n * 8));
-  CU(cudaMalloc(&dout, (size_t)n * 8));
-  CU(cudaMemcpy(dx, x, (size_t)n * 8, cudaMemcpyHostToDevice));
-  if (y) CU(cudaMemcpy(dy, y, (size_t)n * 8, cudaMemcpyHostToDevice));
-  else CU(cudaMemset(dy, 0, (size_t)n * 8));
-  k_math_probe<<<(n + 127) / 128, 128, 0, c->stream>>>(fn, dx, dy, dout, n); ++c->launches;
-  CU(cudaStreamSynchronize(c->stream));
-  CU(cudaMemcpy(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost));
-  cudaFree(dx); cudaFree(dy); cudaFree(dout);
+  DevBuf dx, dy, dout;
+  CU(dx.alloc((size_t)n * 8));
+  CU(dy.alloc((size_t)n * 8));
+  CU(dout.alloc((size_t)n * 8));
+  CU(cudaMemcpy(dx.p, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+  if (y) CU(cudaMemcpy(dy.p, y, (size_t)n * 8, cudaMemcpyHostToDevice));
+  else CU(cudaMemset(dy.p, 0, (size_t)n * 8));
+  k_math_probe<<<(n + 127) / 128, 128, 0, c->ownStream>>>(fn, dx.as<double>(), dy.as<double>(), dout.as<double>(), n); ++c->launches;
+  CU(cudaStreamSynchronize(c->ownStream));
+  CU(cudaMemcpy(out, dout.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
   return NQ_OK;
 }
 
 int nq_debug_ciede(nq_ctx* c, const float* lab1, const float* lab2, float* out, int* nExact, int n) {
   if (!c || !lab1 || !lab2 || !out || n <= 0) return fail(NQ_ERR_ARG, "bad arguments");
   CU(cudaSetDevice(c->device));
-  float *d1 = nullptr, *d2 = nullptr, *dout = nullptr;
-  int* dcnt = nullptr;
-  CU(cudaMalloc(&d1, (size_t)n * 12));
-  CU(cudaMalloc(&d2, (size_t)n * 12));
-  CU(cudaMalloc(&dout, (size_t)n * 16));
-  CU(cudaMalloc(&dcnt, 4));
-  CU(cudaMemcpy(d1, lab1, (size_t)n * 12, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(d2, lab2, (size_t)n * 12, cudaMemcpyHostToDevice));
-  CU(cudaMemset(dcnt, 0, 4));
-  k_ciede_probe<<<(n + 127) / 128, 128, 0, c->stream>>>(d1, d2, dout, dcnt, n); ++c->launches;
-  CU(cudaStreamSynchronize(c->stream));
-  CU(cudaMemcpy(out, dout, (size_t)n * 16, cudaMemcpyDeviceToHost));
+  DevBuf d1, d2, dout, dcnt;
+  CU(d1.alloc((size_t)n * 12));
+  CU(d2.alloc((size_t)n * 12));
+  CU(dout.alloc((size_t)n * 16));
+  CU(dcnt.alloc(4));
+  CU(cudaMemcpy(d1.p, lab1, (size_t)n * 12, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(d2.p, lab2, (size_t)n * 12, cudaMemcpyHostToDevice));
+  CU(cudaMemset(dcnt.p, 0, 4));
+  k_ciede_probe<<<(n + 127) / 128, 128, 0, c->ownStream>>>(d1.as<float>(), d2.as<float>(), dout.as<float>(), dcnt.as<int>(), n); ++c->launches;
+  CU(cudaStreamSynchronize(c->ownStream));
+  CU(cudaMemcpy(out, dout.p, (size_t)n * 16, cudaMemcpyDeviceToHost));
   int cnt = 0;
-  CU(cudaMemcpy(&cnt, dcnt, 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(&cnt, dcnt.p, 4, cudaMemcpyDeviceToHost));
   if (nExact) *nExact = cnt;
-  cudaFree(d1); cudaFree(d2); cudaFree(dout); cudaFree(dcnt);
   return NQ_OK;
 }
 

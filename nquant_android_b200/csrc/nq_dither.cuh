@@ -969,7 +969,8 @@ __device__ uint32_t prelookup_commit(Env& E, uint32_t c, bool mine) {
   return sh.pal[qi];
 }
 
-__global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot* slots, const uint32_t* order, int cacheBytes) {
+// `want`: which images this launch takes by NqImage::specDone: 0 = not the speculative path's, 3 = handed back by it
+__global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot* slots, const uint32_t* order, int cacheBytes, int want) {
   __shared__ WarpShared sh;
   __shared__ DitherRing ring;
   extern __shared__ unsigned short dynCache[];     // 16 384 entries when launched with cacheBytes, else nothing
@@ -978,7 +979,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
   const NqSlot& S = slots[img];
   const unsigned lane = lane_id();
   const int plen = I.paletteLen;
-  if (plen <= 0 || I.error || I.gSorted || I.specDone) return;
+  if (plen <= 0 || I.error || I.gSorted || I.specDone != want) return;
   DitherCtx D;
   const bool producer = threadIdx.x >= 32;
   if (cacheBytes) for (int i = threadIdx.x; i < 16384; i += 64) dynCache[i] = 0;

@@ -48,6 +48,7 @@ namespace spec {
 struct SpecConst {
   int plen, margin, thresold, DM, ditherMax, width, npix;
   int isNano, hasTrans, salReplaced;
+  int opaque;                            // every pixel and every palette entry has alpha 255: stage 6 drops the alpha channel
   int seg, warm, nseg;
   uint32_t transColor;
   double gWeight, PR, PG, PB, ratio;
@@ -103,6 +104,7 @@ struct SpecWork {
   const unsigned char* cells;            // candidate lists of k_build_cells, or nullptr
   const double* lut;                     // gammaToLinear table
   const signed char* bn;                 // TELL_BLUE_NOISE
+  unsigned* chunkSum;                    // [npix / NQS_CHUNK + 1] draws predicted in front of each block of NQS_CHUNK pixels (stage 2)
   SpecSeg* segs;
   int* state;                            // [16]: firstOpen, anomaly, patch key + 1 (0 = none), patch position, failed validations,
                                          //      re-resolve position + 1 (0 = none), re-resolves so far, pixels flagged NQS_F_RISK, error-dependent lookups
@@ -496,117 +498,228 @@ NQ_HD int slow_lookup(const SpecConst& C, const SpecWork& W, SpecSeg& S, int n, 
   return v;
 }
 
-// DM is a template constant (DITHER_MAX is 9, 16 or 25, GC:96) so that the queue and the
-// weights are fully unrolled: a shift register of DM boxes in registers, e[0] = oldest, no indexed local memory.
-template <int DM>
-NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s) {
+// ---- stage 6 proper -----------------------------------------------------------------------------------------------------
+// DM is a template constant (DITHER_MAX is 9, 16 or 25, GC:96): the queue lives in registers as a window of DM + NQS_U boxes
+// that slides one box per pixel and is moved back every NQS_U pixels, the weights are compile-time-indexed operands (constant
+// bank on the device), and for images whose pixels all have alpha 255 (OPAQUE) the alpha channel is dropped: its error is
+// always 0 (a_pix = (int) min(255, 255 + 0) and every palette alpha is 255) and all its partial sums are exactly 255.0f, so
+// it only contributes "maxErr >= 255" (GC:192-201), which is how maxErr is seeded below.
+#define NQS_U 4                 // pixels per group: one slide of the register window per NQS_U pixels
+
+#if defined(__CUDACC__)
+__constant__ float c_specW[3][NQ_MAXQ + 3];   // initWeights(9 | 16 | 25), written once per context (k_spec_tables + cudaMemcpyToSymbol)
+#endif
+#if defined(__CUDA_ARCH__)
+#define NQS_W(C, DMI, k) c_specW[DMI][k]
+NQ_HD float max3f(float a, float b, float c) { float d; asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+#define NQS_NOINLINE __noinline__
+#else
+#define NQS_W(C, DMI, k) (C).w[k]
+NQ_HD float max3f(float a, float b, float c) { const float m = a > b ? a : b; return m > c ? m : c; }
+#define NQS_NOINLINE
+#endif
+
+// (float) Math.tanh(e / maxErr * 20) (GC:255). e is an integer in [-255, 255] and maxErr is exactly 255 nearly always, so
+// the value comes from a 511-entry table of exactly this expression (tab, nullptr = compute); otherwise it is evaluated.
+#if defined(__CUDA_ARCH__)
+__device__ NQS_NOINLINE float shape_tanh_eval(float e, float maxErr) { return tanh_f((double)(e / maxErr * 20.f)); }
+#else
+inline float shape_tanh_eval(float e, float maxErr) { return tanh_f((double)(e / maxErr * 20.f)); }
+#endif
+NQ_HD float shape_tanh(float e, float maxErr, const float* tab) {
+  if (tab && maxErr == 255.f) return tab[(int)e + 255];
+  return shape_tanh_eval(e, maxErr);
+}
+
+struct RunEnv {                 // what the pixel step needs besides the queue: loop-invariant
+  const SpecConst* C;
+  const SpecWork* W;
+  SpecSeg* S;
+  const uint32_t* pal;          // C->pal (shared memory copy on the device)
+  const float* tanhTab;         // shape_tanh
+  float fDitherMax, fDitherMax1, divisor;
+  bool illusion0;
+  int draws;
+};
+
+// the quantization of an error-dependent lookup (GC:211-229 with the diffused colour), kept out of the hot loop
+NQ_HD int run_slow_pixel_body(RunEnv& X, int n, uint32_t px, int bidx, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned) {
+  const SpecConst& C = *X.C;
+  const SpecWork& W = *X.W;
+  const int x = bidx % C.width, y = bidx / C.width;
+  const uint32_t c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
+  const float sal = saliency_of(C, W, px);
+  uint32_t c = c2;
+  if (!(C.plen >= 256 && sal > .99f)) c = slow_colour(C, W, x, y, px, sal, color_y(px, W.lut), c2);
+  bool drew;
+  const int qi = slow_lookup(C, W, *X.S, n, c, owned, &X.draws, &drew);
+  if (owned && X.S->mispos < 0 && drew != ((flag & NQS_F_DRAW) != 0)) X.S->mispos = n;   // every later draw index is off by one
+  return qi;
+}
+#if defined(__CUDA_ARCH__)
+__device__ NQS_NOINLINE int run_slow_pixel(RunEnv& X, int n, uint32_t px, int bidx, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned) {
+  return run_slow_pixel_body(X, n, px, bidx, flag, a_pix, r_pix, g_pix, b_pix, owned);
+}
+#else
+inline int run_slow_pixel(RunEnv& X, int n, uint32_t px, int bidx, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned) {
+  return run_slow_pixel_body(X, n, px, bidx, flag, a_pix, r_pix, g_pix, b_pix, owned);
+}
+#endif
+
+// One pixel at window offset u: the queue is e[u .. u + DM - 1] (oldest first), the new box goes to e[u + DM].
+template <int DM, int DMI, int NCH, int u, bool OWNED>
+NQ_HD void run_pixel(RunEnv& X, float (&e)[DM + NQS_U][NCH], const SpecRec& rc, int n) {
+  const SpecConst& C = *X.C; (void)C;
+  const uint32_t px = rc.px;
+  // ---- error.p = pixel + sum(queue[i].p * weights[i]), oldest box first (GC:190-204)
+  float a0 = (float)c_red(px), a1 = (float)c_green(px), a2 = (float)c_blue(px), a3 = (float)c_alpha(px);
+  float maxErr = NCH == 3 ? 255.f : (float)(DM - 1);
+#pragma unroll
+  for (int k = 0; k < DM; ++k) {
+    const float wk = NQS_W(C, DMI, k);
+    a0 = a0 + e[u + k][0] * wk;
+    a1 = a1 + e[u + k][1] * wk;
+    a2 = a2 + e[u + k][2] * wk;
+    maxErr = max3f(maxErr, a0, a1);
+    if (NCH == 4) { a3 = a3 + e[u + k][NCH - 1] * wk; maxErr = max3f(maxErr, a2, a3); }
+    else maxErr = fmaxf(maxErr, a2);
+  }
+  const int r_pix = (int)fminf(255.f, fmaxf(a0, 0.f)), g_pix = (int)fminf(255.f, fmaxf(a1, 0.f));
+  const int b_pix = (int)fminf(255.f, fmaxf(a2, 0.f)), a_pix = NCH == 4 ? (int)fminf(255.f, fmaxf(a3, 0.f)) : 255;
+  const unsigned flag = (rc.qf >> 16) & 0xFFu;
+  // ---- quantize (GC:211-229)
+  int qi;
+  if (flag & NQS_F_PRE) {
+    qi = (int)(rc.qf & 0xFFFFu);
+    X.draws += (flag & NQS_F_DRAW) ? 1 : 0;
+  } else
+    qi = run_slow_pixel(X, n, px, (int)rc.bidx, flag, a_pix, r_pix, g_pix, b_pix, OWNED);
+  const uint32_t pc = X.pal[qi];
+  if (OWNED) X.W->out[rc.bidx] = pc;                       // dither == true: the palette colour (GC:278-279)
+  // ---- error of this pixel and its shaping (GC:236-264)
+  float e0 = (float)(r_pix - c_red(pc)), e1 = (float)(g_pix - c_green(pc)), e2 = (float)(b_pix - c_blue(pc));
+  const bool s0 = fabsf_(e0) >= X.fDitherMax, s1 = fabsf_(e1) >= X.fDitherMax, s2 = fabsf_(e2) >= X.fDitherMax;
+  if (s0 || s1 || s2) {
+    if ((rc.qf >> 24) & 1u) {                              // diffuse = TELL_BLUE_NOISE[bidx & 4095] > thresold (GC:250)
+      if (s0) e0 = shape_tanh(e0, maxErr, X.tanhTab) * X.fDitherMax1;
+      if (s1) e1 = shape_tanh(e1, maxErr, X.tanhTab) * X.fDitherMax1;
+      if (s2) e2 = shape_tanh(e2, maxErr, X.tanhTab) * X.fDitherMax1;
+    } else if (X.illusion0) {
+      if (s0) e0 = (float)((double)(e0 / maxErr) * 1.0) * X.fDitherMax1;
+      if (s1) e1 = (float)((double)(e1 / maxErr) * 1.0) * X.fDitherMax1;
+      if (s2) e2 = (float)((double)(e2 / maxErr) * 1.0) * X.fDitherMax1;
+    } else {
+      if (s0) e0 /= X.divisor;
+      if (s1) e1 /= X.divisor;
+      if (s2) e2 /= X.divisor;
+    }
+  }
+  // ---- errorq.poll(); errorq.add(error) (GC:231, 276): the window slides
+  e[u + DM][0] = e0; e[u + DM][1] = e1; e[u + DM][2] = e2;
+  if (NCH == 4) e[u + DM][NCH - 1] = (float)(a_pix - c_alpha(pc));
+}
+template <int DM, int NCH, int BY>
+NQ_HD void run_slide(float (&e)[DM + NQS_U][NCH]) {
+#pragma unroll
+  for (int k = 0; k < DM; ++k)
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) e[k][j] = e[k + BY][j];
+}
+NQ_HD SpecRec run_fetch(const SpecRec* recs, int segLen, int nsegs, int n) {
+  return recs[(size_t)(n % segLen) * (size_t)nsegs + (size_t)(n / segLen)];
+}
+// pixels [n0, n1) from the queue in e[0 .. DM - 1]; groups of NQS_U with the records of the next group in flight
+template <int DM, int DMI, int NCH, bool OWNED>
+NQ_HD void run_span(RunEnv& X, float (&e)[DM + NQS_U][NCH], int n0, int n1) {
+  const SpecConst& C = *X.C;
+  const SpecRec* const recs = X.W->rec;
+  const int segLen = C.seg, nsegs = C.nseg;
+  int n = n0;
+  if (n + NQS_U <= n1) {
+    // record (row, col) of pixel n in the segment-interleaved layout, advanced without a division per pixel
+    int row = n % segLen, col = n / segLen;
+    SpecRec cur[NQS_U], nxt[NQS_U];
+#pragma unroll
+    for (int u = 0; u < NQS_U; ++u) {
+      cur[u] = recs[(size_t)row * (size_t)nsegs + (size_t)col];
+      if (++row == segLen) { row = 0; ++col; }
+    }
+    for (; n + NQS_U <= n1; n += NQS_U) {
+      const bool more = n + 2 * NQS_U <= n1;
+      if (more) {
+#pragma unroll
+        for (int u = 0; u < NQS_U; ++u) {
+          nxt[u] = recs[(size_t)row * (size_t)nsegs + (size_t)col];
+          if (++row == segLen) { row = 0; ++col; }
+        }
+      }
+      run_pixel<DM, DMI, NCH, 0, OWNED>(X, e, cur[0], n);
+      run_pixel<DM, DMI, NCH, 1, OWNED>(X, e, cur[1], n + 1);
+      run_pixel<DM, DMI, NCH, 2, OWNED>(X, e, cur[2], n + 2);
+      run_pixel<DM, DMI, NCH, 3, OWNED>(X, e, cur[3], n + 3);
+      run_slide<DM, NCH, NQS_U>(e);
+      if (more) {
+#pragma unroll
+        for (int u = 0; u < NQS_U; ++u) cur[u] = nxt[u];
+      }
+    }
+  }
+  for (; n < n1; ++n) {                                     // fewer than NQS_U pixels left
+    const SpecRec rc = run_fetch(recs, segLen, nsegs, n);
+    run_pixel<DM, DMI, NCH, 0, OWNED>(X, e, rc, n);
+    run_slide<DM, NCH, 1>(e);
+  }
+}
+static_assert(NQS_U == 4, "run_span spells out the NQS_U pixel steps");
+
+template <int DM, int DMI, int NCH>
+NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s, const uint32_t* pal, const float* tanhTab) {
   SpecSeg& S = W.segs[s];
   if (S.done || !S.dirty) return;
   const int p0 = s * C.seg, p1 = (p0 + C.seg < C.npix) ? p0 + C.seg : C.npix;
-  float e[DM][4], w[DM];                                   // the queue (e[0] = oldest box) and initWeights(DITHER_MAX)
+  float e[DM + NQS_U][NCH];                                // the queue window, e[0] = oldest box
   int from = p0;
-#pragma unroll
-  for (int k = 0; k < DM; ++k) w[k] = C.w[k];
   if (S.exact && p0 > 0) {
 #pragma unroll
-    for (int k = 0; k < DM; ++k) { e[k][0] = S.qstart[k][0]; e[k][1] = S.qstart[k][1]; e[k][2] = S.qstart[k][2]; e[k][3] = S.qstart[k][3]; }
+    for (int k = 0; k < DM; ++k)
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) e[k][j] = S.qstart[k][j];
   } else {
 #pragma unroll
-    for (int k = 0; k < DM; ++k) { e[k][0] = 0.f; e[k][1] = 0.f; e[k][2] = 0.f; e[k][3] = 0.f; }
+    for (int k = 0; k < DM; ++k)
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) e[k][j] = 0.f;
     if (!S.exact) { const long long w = (long long)C.warm * (long long)S.warmMul; from = (long long)p0 - w > 0 ? (int)((long long)p0 - w) : 0; }
   }
-  const float fDitherMax = (float)C.ditherMax, fDitherMax1 = (float)(C.ditherMax - 1);
-  const float divisor = (float)(1 + nqm::sqrt_((double)C.ditherMax));
-  const bool illusion0 = W.bn[0] > C.thresold;             // yDiff == 1 in this mode: bn[(int)4096.0 & 4095] (GC:251-252)
-  int draws = 0;
+  RunEnv X;
+  X.C = &C; X.W = &W; X.S = &S; X.pal = pal; X.tanhTab = tanhTab;
+  X.fDitherMax = (float)C.ditherMax; X.fDitherMax1 = (float)(C.ditherMax - 1);
+  X.divisor = (float)(1 + nqm::sqrt_((double)C.ditherMax));
+  X.illusion0 = W.bn[0] > C.thresold;                      // yDiff == 1 in this mode: bn[(int)4096.0 & 4095] (GC:251-252)
+  X.draws = 0;
   S.nnotes = 0;
   S.nreads = 0;
   S.mispos = -1;
-  // position of the NEXT record to fetch in the segment-interleaved layout, advanced without a division per pixel
-  const int segLen = C.seg, nsegs = C.nseg;
-  int rrow = (from < p1 ? from : 0) % segLen, rcol = (from < p1 ? from : 0) / segLen;
-  const SpecRec* const recs = W.rec;
-  SpecRec nxt = recs[(size_t)rrow * (size_t)nsegs + (size_t)rcol];
-  for (int n = from; n < p1; ++n) {
-    if (n == p0) {
+  if (from < p0) run_span<DM, DMI, NCH, false>(X, e, from, p0);    // warm-up: nothing is written, notes are not kept
 #pragma unroll
-      for (int k = 0; k < DM; ++k) { S.qwarm[k][0] = e[k][0]; S.qwarm[k][1] = e[k][1]; S.qwarm[k][2] = e[k][2]; S.qwarm[k][3] = e[k][3]; }
-      draws = 0;
-    }
-    const bool owned = n >= p0;
-    const SpecRec rc = nxt;
-    if (n + 1 < p1) {                                         // one pixel ahead of its use
-      if (++rrow == segLen) { rrow = 0; ++rcol; }
-      nxt = recs[(size_t)rrow * (size_t)nsegs + (size_t)rcol];
-    }
-    const uint32_t px = rc.px;
-    // ---- error.p = pixel + sum(queue[i].p * weights[i]), oldest box first (GC:190-204)
-    float a0 = (float)c_red(px), a1 = (float)c_green(px), a2 = (float)c_blue(px), a3 = (float)c_alpha(px);
-    float maxErr = (float)(DM - 1);
+  for (int k = 0; k < DM; ++k) { S.qwarm[k][0] = e[k][0]; S.qwarm[k][1] = e[k][1]; S.qwarm[k][2] = e[k][2]; S.qwarm[k][3] = NCH == 4 ? e[k][NCH - 1] : 0.f; }
+  X.draws = 0;
+  run_span<DM, DMI, NCH, true>(X, e, p0, p1);
 #pragma unroll
-    for (int k = 0; k < DM; ++k) {
-      a0 = a0 + e[k][0] * w[k]; if (a0 > maxErr) maxErr = a0;
-      a1 = a1 + e[k][1] * w[k]; if (a1 > maxErr) maxErr = a1;
-      a2 = a2 + e[k][2] * w[k]; if (a2 > maxErr) maxErr = a2;
-      a3 = a3 + e[k][3] * w[k]; if (a3 > maxErr) maxErr = a3;
-    }
-    const int r_pix = (int)fminf(255.f, fmaxf(a0, 0.f)), g_pix = (int)fminf(255.f, fmaxf(a1, 0.f));
-    const int b_pix = (int)fminf(255.f, fmaxf(a2, 0.f)), a_pix = (int)fminf(255.f, fmaxf(a3, 0.f));
-    const unsigned flag = (rc.qf >> 16) & 0xFFu;
-    const int bidx = (int)rc.bidx;
-    // ---- quantize (GC:211-229)
-    int qi;
-    if (flag & NQS_F_PRE) {
-      qi = (int)(rc.qf & 0xFFFFu);
-      if (flag & NQS_F_DRAW) ++draws;
-    } else {
-      const int x = bidx % C.width, y = bidx / C.width;
-      const uint32_t c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
-      const float sal = saliency_of(C, W, px);
-      uint32_t c = c2;
-      if (!(C.plen >= 256 && sal > .99f)) c = slow_colour(C, W, x, y, px, sal, color_y(px, W.lut), c2);
-      bool drew;
-      qi = slow_lookup(C, W, S, n, c, owned, &draws, &drew);
-      if (owned && S.mispos < 0 && drew != ((flag & NQS_F_DRAW) != 0)) S.mispos = n;   // every later draw index is off by one
-    }
-    const uint32_t pc = C.pal[qi];
-    if (owned) W.out[bidx] = pc;                           // dither == true: the palette colour (GC:278-279)
-    // ---- error of this pixel and its shaping (GC:236-264)
-    float e0 = (float)(r_pix - c_red(pc)), e1 = (float)(g_pix - c_green(pc)), e2 = (float)(b_pix - c_blue(pc)), e3 = (float)(a_pix - c_alpha(pc));
-    const bool s0 = fabsf_(e0) >= fDitherMax, s1 = fabsf_(e1) >= fDitherMax, s2 = fabsf_(e2) >= fDitherMax;
-    if (s0 || s1 || s2) {
-      if ((rc.qf >> 24) & 1u) {                              // diffuse = TELL_BLUE_NOISE[bidx & 4095] > thresold (GC:250)
-        if (s0) e0 = tanh_f((double)(e0 / maxErr * 20.f)) * fDitherMax1;
-        if (s1) e1 = tanh_f((double)(e1 / maxErr * 20.f)) * fDitherMax1;
-        if (s2) e2 = tanh_f((double)(e2 / maxErr * 20.f)) * fDitherMax1;
-      } else if (illusion0) {
-        if (s0) e0 = (float)((double)(e0 / maxErr) * 1.0) * fDitherMax1;
-        if (s1) e1 = (float)((double)(e1 / maxErr) * 1.0) * fDitherMax1;
-        if (s2) e2 = (float)((double)(e2 / maxErr) * 1.0) * fDitherMax1;
-      } else {
-        if (s0) e0 /= divisor;
-        if (s1) e1 /= divisor;
-        if (s2) e2 /= divisor;
-      }
-    }
-    // ---- errorq.poll(); errorq.add(error) (GC:231, 276)
-#pragma unroll
-    for (int k = 0; k + 1 < DM; ++k) { e[k][0] = e[k + 1][0]; e[k][1] = e[k + 1][1]; e[k][2] = e[k + 1][2]; e[k][3] = e[k + 1][3]; }
-    e[DM - 1][0] = e0; e[DM - 1][1] = e1; e[DM - 1][2] = e2; e[DM - 1][3] = e3;
-  }
-  if (p0 >= p1) {
-#pragma unroll
-    for (int k = 0; k < DM; ++k) { S.qwarm[k][0] = e[k][0]; S.qwarm[k][1] = e[k][1]; S.qwarm[k][2] = e[k][2]; S.qwarm[k][3] = e[k][3]; }
-  }
-#pragma unroll
-  for (int k = 0; k < DM; ++k) { S.qout[k][0] = e[k][0]; S.qout[k][1] = e[k][1]; S.qout[k][2] = e[k][2]; S.qout[k][3] = e[k][3]; }
-  S.draws = draws;
+  for (int k = 0; k < DM; ++k) { S.qout[k][0] = e[k][0]; S.qout[k][1] = e[k][1]; S.qout[k][2] = e[k][2]; S.qout[k][3] = NCH == 4 ? e[k][NCH - 1] : 0.f; }
+  S.draws = X.draws;
   S.dirty = 0;
 }
-NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s) {
-  if (C.DM == 25) stage_run_t<25>(C, W, s);
-  else if (C.DM == 16) stage_run_t<16>(C, W, s);
-  else if (C.DM == 9) stage_run_t<9>(C, W, s);
+NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s, const uint32_t* pal, const float* tanhTab) {
+  if (C.opaque) {
+    if (C.DM == 25) stage_run_t<25, 2, 3>(C, W, s, pal, tanhTab);
+    else if (C.DM == 16) stage_run_t<16, 1, 3>(C, W, s, pal, tanhTab);
+    else if (C.DM == 9) stage_run_t<9, 0, 3>(C, W, s, pal, tanhTab);
+  } else {
+    if (C.DM == 25) stage_run_t<25, 2, 4>(C, W, s, pal, tanhTab);
+    else if (C.DM == 16) stage_run_t<16, 1, 4>(C, W, s, pal, tanhTab);
+    else if (C.DM == 9) stage_run_t<9, 0, 4>(C, W, s, pal, tanhTab);
+  }
 }
 
 // ---- stage 7: ordered validation of one image. Returns the number of segments still open. ------------------------
@@ -696,21 +809,25 @@ NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
 
 #if defined(__CUDACC__) || defined(NQS_EMULATE)   // NQS_EMULATE: tests/spec_host_harness.cpp runs the kernels thread by thread on the CPU
 // =====================================================================================================================
-// Kernels: indexing only, every body is one of the stage functions above. One SpecImage per image of the batch;
-// the work arrays of image i live in wave slot i % wave (nq_api.cu), waves run one after the other.
+// Kernels: indexing only, every body is one of the stage functions above. One SpecImage per image of the batch. The
+// per-pixel work arrays live in a pool of slots; an image is bound to a free slot when it is admitted (k_spec_admit)
+// and gives it back when it is finished or handed back, so images of different ages share every launch ("rolling
+// admission", spec_drive): grid.y indexes a LIST of images, not the batch.
 // =====================================================================================================================
 struct SpecImage {
   SpecConst C;
   SpecWork W;
   int eligible;
+  int rounds;                    // validation rounds this image has been through
 };
 #define NQS_ACTIVE(P) ((P).eligible && !(P).W.state[1])
+#define NQS_CHUNK 8192           // pixels per block of the draw-count prefix sum (stage 2)
 
 // GilbertCurve / quantizer constants of every image, and which images this path takes (one thread per image)
-__global__ void k_spec_setup(const NqImage* imgs, const NqSlot* slots, SpecImage* sp, const uint32_t* order, int nimg, int seg, int warm, int* eligOut) {
+__global__ void k_spec_setup(NqImage* imgs, const NqSlot* slots, SpecImage* sp, const uint32_t* order, int nimg, int seg, int warm, int* eligOut) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nimg) return;
-  const NqImage& I = imgs[i];
+  NqImage& I = imgs[i];
   SpecImage& P = sp[i];
   SpecConst& C = P.C;
   const int plen = I.paletteLen;
@@ -719,9 +836,12 @@ __global__ void k_spec_setup(const NqImage* imgs, const NqSlot* slots, SpecImage
   // error in the queue for ever: alpha is never shaped, GC:248), ditherPixel lookups independent of the diffused colour
   P.eligible = I.kind == NQ_KIND_LAB && I.dither && I.gUseSal && !I.gSorted && !I.gHasAlpha && !I.hasSemi && I.transIdx < 0 && !I.error &&
                plen > 64 && 2 * acceptedDiff > 101 && I.nmax > 2 && slots[i].cells != nullptr && I.npix >= 4 * seg;
-  // 1 = taken; 2 = not taken and k_dither_fifo will run its serial chain for it anyway; 0 = another kernel's image
+  P.rounds = 0;
+  // 1 = taken; 2 = not taken and k_dither_fifo runs its serial chain for it; 0 = another kernel's image
   eligOut[i] = P.eligible ? 1 : ((plen > 0 && !I.error && !I.gSorted) ? 2 : 0);
+  I.specDone = P.eligible ? 2 : 0;                // 2 = pending here: k_dither_fifo leaves it alone until k_spec_finish has spoken
   if (!P.eligible) return;
+  if (I.gDitherMaxQ != 9 && I.gDitherMaxQ != 16 && I.gDitherMaxQ != 25) { P.eligible = 0; eligOut[i] = 2; I.specDone = 0; return; }
   C.plen = plen; C.margin = I.gMargin; C.thresold = I.gThresold; C.DM = I.gDitherMaxQ; C.ditherMax = I.gDitherMax;
   C.width = I.width; C.npix = I.npix;
   C.isNano = I.isNano; C.hasTrans = I.transIdx >= 0; C.salReplaced = I.nmax < 128 && I.nmax > 2;
@@ -732,74 +852,159 @@ __global__ void k_spec_setup(const NqImage* imgs, const NqSlot* slots, SpecImage
   JRandom r; r.set_seed(I.seed);
   C.seed0 = r.seed;
   for (int k = 0; k < NQ_MAXQ; ++k) C.w[k] = k < C.DM ? I.gWeights[k] : 0.f;
-  for (int k = 0; k < plen; ++k) C.pal[k] = I.palette[k];
+  int opaque = I.nonOpaque == 0;
+  for (int k = 0; k < plen; ++k) { C.pal[k] = I.palette[k]; opaque &= (I.palette[k] >> 24) == 0xFFu; }
+  C.opaque = opaque;
+  // which instantiation of stage 6 runs this image: bits 8.. of the verdict (spec_drive groups the images by it)
+  eligOut[i] |= (((C.DM == 25 ? 2 : (C.DM == 16 ? 1 : 0)) << 1) | (opaque ? 0 : 1)) << 8;
   P.W.order = order; P.W.in = slots[i].in; P.W.out = slots[i].out; P.W.cells = slots[i].cells;
   P.W.lut = g_gammaLut; P.W.bn = g_blueNoise;
   fill_tables(C, g_gammaLut);
 }
-// memo tables, segment records, state (grid: x strides, y = image)
-__global__ void __launch_bounds__(256) k_spec_init(SpecImage* sp) {
-  SpecImage& P = sp[blockIdx.y];
+// binds the images of `list` to their work-array slots: pool[slotOf[k]] holds the array pointers of that slot
+__global__ void k_spec_admit(SpecImage* sp, const int* list, const int* slotOf, int cnt, const SpecWork* pool) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  SpecImage& P = sp[list[k]];
+  const SpecWork& T = pool[slotOf[k]];
+  SpecWork& W = P.W;
+  W.cpx = T.cpx; W.ccol = T.ccol; W.ck0 = T.ck0; W.ck1 = T.ck1; W.cq = T.cq; W.cflag = T.cflag; W.rec = T.rec; W.cdraw = T.cdraw;
+  W.firstPos = T.firstPos; W.memo = T.memo; W.slowPos = T.slowPos; W.slowVal = T.slowVal; W.segs = T.segs; W.state = T.state;
+  W.chunkSum = T.chunkSum;
+}
+// memo tables, segment records, state (grid: x strides, y = list entry)
+__global__ void __launch_bounds__(256) k_spec_init(SpecImage* sp, const int* list) {
+  SpecImage& P = sp[list[blockIdx.y]];
   if (!P.eligible) return;
   const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   for (int k = t; k < 65536; k += nt) { P.W.firstPos[k] = NQS_NOPOS; P.W.slowPos[k] = NQS_NOPOS; P.W.memo[k] = 0xFFFF; P.W.slowVal[k] = 0; }
   for (int s = t; s < P.C.nseg; s += nt) { SpecSeg& S = P.W.segs[s]; S.exact = s == 0; S.dirty = 1; S.done = 0; S.draws = 0; S.nnotes = 0; S.nreads = 0; S.mispos = -1; S.warmMul = 1; }
   if (t < 16) P.W.state[t] = 0;
 }
-__global__ void __launch_bounds__(256) k_spec_pre(SpecImage* sp) {
-  const SpecImage& P = sp[blockIdx.y];
+__global__ void __launch_bounds__(256) k_spec_pre(SpecImage* sp, const int* list) {
+  const SpecImage& P = sp[list[blockIdx.y]];
   if (!P.eligible) return;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_pre(P.C, P.W, n);
 }
-// stage 2: exclusive prefix sum of the predicted draws, one CTA of 1024 threads per image, 8 pixels per thread and tile
+// stage 2: exclusive prefix sum of the predicted draws in three steps: draws per NQS_CHUNK pixels (a), prefix of those per
+// image (b), cdraw of every pixel (c). redo != 0: only images that asked for a re-resolve (state[5]).
+#define NQS_SCAN_SKIP(P, redo) (!(P).eligible || ((redo) && (!(P).W.state[5] || (P).W.state[1])))
 #if defined(NQS_EMULATE)
-__global__ void k_spec_scan(SpecImage* sp, int redo) {         // the block scan needs real warps: sequential stand-in
-  const SpecImage& P = sp[blockIdx.x];
-  if (threadIdx.x || !P.eligible || (redo && (!P.W.state[5] || P.W.state[1]))) return;
+__global__ void k_spec_scan_a(SpecImage*, const int*, int) {}
+__global__ void k_spec_scan_b(SpecImage*, const int*, int) {}
+__global__ void k_spec_scan_c(SpecImage* sp, const int* list, int redo) {     // the block scan needs real warps: sequential stand-in
+  const SpecImage& P = sp[list[blockIdx.y]];
+  if (threadIdx.x || blockIdx.x || NQS_SCAN_SKIP(P, redo)) return;
   unsigned d = 0;
   for (int n = 0; n < P.C.npix; ++n) { P.W.cdraw[n] = d; d += (P.W.cflag[n] & NQS_F_DRAW) ? 1u : 0u; }
   P.W.cdraw[P.C.npix] = d;
 }
 #else
-__global__ void __launch_bounds__(1024) k_spec_scan(SpecImage* sp, int redo) {
+__global__ void __launch_bounds__(256) k_spec_scan_a(SpecImage* sp, const int* list, int redo) {
+  __shared__ int sWarp[8];
+  const SpecImage& P = sp[list[blockIdx.y]];
+  if (NQS_SCAN_SKIP(P, redo)) return;
+  const int npix = P.C.npix, nchunk = (npix + NQS_CHUNK - 1) / NQS_CHUNK;
+  for (int c = blockIdx.x; c < nchunk; c += gridDim.x) {
+    const int n0 = c * NQS_CHUNK, n1 = min(npix, n0 + NQS_CHUNK);
+    int cnt = 0;
+    for (int n = n0 + 4 * (int)threadIdx.x; n < n1; n += 1024) {
+      if (n + 4 <= n1) {                                      // cflag + n0 is 4-byte aligned: NQS_CHUNK and the array base are
+        const unsigned v = *reinterpret_cast<const unsigned*>(P.W.cflag + n) & (0x01010101u * NQS_F_DRAW);
+        cnt += __popc(v);
+      } else
+        for (int k = n; k < n1; ++k) cnt += (P.W.cflag[k] & NQS_F_DRAW) ? 1 : 0;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) sWarp[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < 8; ++k) t += sWarp[k]; P.W.chunkSum[c] = (unsigned)t; }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(1024) k_spec_scan_b(SpecImage* sp, const int* list, int redo) {
   __shared__ int sWarp[33];
-  const SpecImage& P = sp[blockIdx.x];
-  if (!P.eligible || (redo && (!P.W.state[5] || P.W.state[1]))) return;
-  const int npix = P.C.npix;
+  const SpecImage& P = sp[list[blockIdx.x]];
+  if (NQS_SCAN_SKIP(P, redo)) return;
+  const int npix = P.C.npix, nchunk = (npix + NQS_CHUNK - 1) / NQS_CHUNK;
   unsigned carry = 0;
-  for (int base = 0; base < npix; base += 8192) {
-    const int n0 = base + (int)threadIdx.x * 8;
-    unsigned bits = 0;
-    for (int k = 0; k < 8; ++k) if (n0 + k < npix && (P.W.cflag[n0 + k] & NQS_F_DRAW)) bits |= 1u << k;
+  for (int base = 0; base < nchunk; base += 1024) {
+    const int c = base + (int)threadIdx.x;
+    const int v = c < nchunk ? (int)P.W.chunkSum[c] : 0;
     int total;
-    const int excl = block_excl_scan_1024(__popc(bits), &total, sWarp);
-    unsigned d = carry + (unsigned)excl;
-    for (int k = 0; k < 8; ++k) if (n0 + k < npix) { P.W.cdraw[n0 + k] = d; d += (bits >> k) & 1u; }
+    const int excl = block_excl_scan_1024(v, &total, sWarp);
+    if (c < nchunk) P.W.chunkSum[c] = carry + (unsigned)excl;
     carry += (unsigned)total;
   }
   if (threadIdx.x == 0) P.W.cdraw[npix] = carry;
 }
+__global__ void __launch_bounds__(256) k_spec_scan_c(SpecImage* sp, const int* list, int redo) {
+  __shared__ int sWarp[8];
+  const SpecImage& P = sp[list[blockIdx.y]];
+  if (NQS_SCAN_SKIP(P, redo)) return;
+  const int npix = P.C.npix, nchunk = (npix + NQS_CHUNK - 1) / NQS_CHUNK;
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int c = blockIdx.x; c < nchunk; c += gridDim.x) {
+    const int n0 = c * NQS_CHUNK + (int)threadIdx.x * 32;     // 32 consecutive pixels per thread
+    unsigned bits = 0;
+    if (n0 + 32 <= npix) {
+      const uint4* f = reinterpret_cast<const uint4*>(P.W.cflag + n0);
+      const uint4 a = f[0], b = f[1];
+      const unsigned wds[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bits |= ((wds[q] >> (8 * j)) & NQS_F_DRAW ? 1u : 0u) << (4 * q + j);
+    } else
+      for (int k = 0; k < 32; ++k) if (n0 + k < npix && (P.W.cflag[n0 + k] & NQS_F_DRAW)) bits |= 1u << k;
+    const int mine = __popc(bits);
+    int x = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+    if (lane == 31) sWarp[w] = x;
+    __syncthreads();
+    unsigned d = P.W.chunkSum[c] + (unsigned)(x - mine);
+    for (unsigned k = 0; k < w; ++k) d += (unsigned)sWarp[k];
+    if (n0 + 32 <= npix) {
+      uint4* o = reinterpret_cast<uint4*>(P.W.cdraw + n0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint4 v;
+        v.x = d; d += (bits >> (4 * q)) & 1u;
+        v.y = d; d += (bits >> (4 * q + 1)) & 1u;
+        v.z = d; d += (bits >> (4 * q + 2)) & 1u;
+        v.w = d; d += (bits >> (4 * q + 3)) & 1u;
+        o[q] = v;
+      }
+    } else
+      for (int k = 0; k < 32; ++k) if (n0 + k < npix) { P.W.cdraw[n0 + k] = d; d += (bits >> k) & 1u; }
+    __syncthreads();
+  }
+}
 #endif
-__global__ void __launch_bounds__(256) k_spec_resolve(SpecImage* sp) {
-  const SpecImage& P = sp[blockIdx.y];
+__global__ void __launch_bounds__(256) k_spec_resolve(SpecImage* sp, const int* list) {
+  const SpecImage& P = sp[list[blockIdx.y]];
   if (!P.eligible) return;
+  int risk = 0, slow = 0;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) {
     int key;
-    if (P.W.cflag[n] & NQS_F_RISK) atomicAdd(&P.W.state[7], 1);
-    if (!(P.W.cflag[n] & NQS_F_PRE)) atomicAdd(&P.W.state[8], 1);
+    risk += (P.W.cflag[n] & NQS_F_RISK) ? 1 : 0;
+    slow += (P.W.cflag[n] & NQS_F_PRE) ? 0 : 1;
     if (!stage_resolve(P.C, P.W, n, &key)) P.W.state[1] = 1;      // a nextInt that draws twice (2 in 2^31): leave the image to the serial kernel
     if (key >= 0) atomicMin(&P.W.firstPos[key], n);
   }
+  if (risk) atomicAdd(&P.W.state[7], risk);
+  if (slow) atomicAdd(&P.W.state[8], slow);
 }
 // re-resolve behind a draw misprediction (images with state[5] != 0): a = reset keys, b = stages 3, c = stage 4, d = stage 5
-__global__ void __launch_bounds__(256) k_spec_redo_a(SpecImage* sp) {
-  const SpecImage& P = sp[blockIdx.y];
+__global__ void __launch_bounds__(256) k_spec_redo_a(SpecImage* sp, const int* list) {
+  const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P) || !P.W.state[5]) return;
   const int from = P.W.state[5] - 1;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 65536; k += gridDim.x * blockDim.x) stage_rekey(P.W, k, from);
 }
-__global__ void __launch_bounds__(256) k_spec_redo_b(SpecImage* sp) {
-  const SpecImage& P = sp[blockIdx.y];
+__global__ void __launch_bounds__(256) k_spec_redo_b(SpecImage* sp, const int* list) {
+  const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P) || !P.W.state[5]) return;
   const int from = P.W.state[5] - 1;
   for (int n = from + 1 + blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) {
@@ -808,84 +1013,123 @@ __global__ void __launch_bounds__(256) k_spec_redo_b(SpecImage* sp) {
     if (key >= 0) atomicMin(&P.W.firstPos[key], n);
   }
 }
-__global__ void __launch_bounds__(256) k_spec_redo_c(SpecImage* sp) {
-  const SpecImage& P = sp[blockIdx.y];
+__global__ void __launch_bounds__(256) k_spec_redo_c(SpecImage* sp, const int* list) {
+  const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P) || !P.W.state[5]) return;
   const int from = P.W.state[5] - 1;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 65536; k += gridDim.x * blockDim.x) stage_memo(P.C, P.W, k, from);
 }
-__global__ void __launch_bounds__(256) k_spec_redo_d(SpecImage* sp) {
-  const SpecImage& P = sp[blockIdx.y];
+// d = stage 5 + 5b behind the misprediction (the records in front of it are unchanged)
+__global__ void __launch_bounds__(256) k_spec_redo_d(SpecImage* sp, const int* list) {
+  const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P) || !P.W.state[5]) return;
   const int from = P.W.state[5] - 1;
-  for (int n = from + 1 + blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_fill(P.C, P.W, n);
+  for (int n = from + blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) { if (n > from) stage_fill(P.C, P.W, n); stage_pack(P.C, P.W, n); }
 }
-__global__ void __launch_bounds__(256) k_spec_memo(SpecImage* sp) {
-  const SpecImage& P = sp[blockIdx.y];
+__global__ void __launch_bounds__(256) k_spec_memo(SpecImage* sp, const int* list) {
+  const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P)) return;
   if (blockIdx.x == 0 && threadIdx.x == 0) stage_gate(P.C, P.W);   // seen by every later launch (NQS_ACTIVE)
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 65536; k += gridDim.x * blockDim.x) stage_memo(P.C, P.W, k, -1);
 }
-__global__ void __launch_bounds__(256) k_spec_fill(SpecImage* sp) {
-  const SpecImage& P = sp[blockIdx.y];
+__global__ void __launch_bounds__(256) k_spec_fill(SpecImage* sp, const int* list) {
+  const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P)) return;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) { stage_fill(P.C, P.W, n); stage_pack(P.C, P.W, n); }   // stages 5 and 5b
 }
-// stage 5b alone; `only` = 0: every active image, 1: images with a pending patch or re-resolve
-__global__ void __launch_bounds__(256) k_spec_pack(SpecImage* sp, int only) {
-  const SpecImage& P = sp[blockIdx.y];
-  if (!NQS_ACTIVE(P) || (only && !P.W.state[2] && !P.W.state[5])) return;
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_pack(P.C, P.W, n);
+// stage 5b alone for the images with a pending patch (a patch may touch any pixel behind its position)
+__global__ void __launch_bounds__(256) k_spec_pack(SpecImage* sp, const int* list) {
+  const SpecImage& P = sp[list[blockIdx.y]];
+  if (!NQS_ACTIVE(P) || !P.W.state[2]) return;
+  const int from = P.W.state[3];
+  for (int n = from + blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_pack(P.C, P.W, n);
 }
-// stage 6: one thread per segment
-__global__ void __launch_bounds__(64) k_spec_run(SpecImage* sp) {
-  const SpecImage& P = sp[blockIdx.y];
+// stage 6: one thread per segment; one instantiation per (DITHER_MAX, opaque or not), each with its own list of images
+#define NQS_RUN_THREADS 128
+#define NQS_VARIANTS 6
+#if defined(NQS_EMULATE)
+template <int DM, int DMI, int NCH>
+__global__ void k_spec_run(SpecImage* sp, const int* list, const float* tanhTab) {
+  const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P)) return;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < P.C.nseg) stage_run(P.C, P.W, s);
+  if (s < P.C.nseg) stage_run_t<DM, DMI, NCH>(P.C, P.W, s, P.C.pal, tanhTab);
 }
-__global__ void __launch_bounds__(64) k_spec_compare(SpecImage* sp) {
-  const SpecImage& P = sp[blockIdx.y];
+#else
+template <int DM, int DMI, int NCH>
+__global__ void __launch_bounds__(NQS_RUN_THREADS, (DM + NQS_U) * NCH <= 96 ? 3 : 2) k_spec_run(SpecImage* sp, const int* list, const float* tanhTab) {
+  __shared__ uint32_t sPal[NQ_MAXK];
+  __shared__ float sTanh[512];
+  const SpecImage& P = sp[list[blockIdx.y]];
+  if (!NQS_ACTIVE(P)) return;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  // nothing to do for a whole block is the common case in the later rounds: look before loading the tables
+  const bool work = s < P.C.nseg && !P.W.segs[s].done && P.W.segs[s].dirty;
+  if (!__syncthreads_or(work)) return;
+  for (int k = threadIdx.x; k < NQ_MAXK; k += blockDim.x) sPal[k] = k < P.C.plen ? P.C.pal[k] : 0u;
+  for (int k = threadIdx.x; k < 511; k += blockDim.x) sTanh[k] = tanhTab[k];
+  __syncthreads();
+  if (work) stage_run_t<DM, DMI, NCH>(P.C, P.W, s, sPal, sTanh);
+}
+#endif
+template <class Backend>
+void spec_launch_run(Backend& be, int variant, dim3 grid, SpecImage* sp, const int* list, const float* tanhTab) {
+  switch (variant) {
+    case 0: be.launch_run(k_spec_run<9, 0, 3>, grid, NQS_RUN_THREADS, sp, list, tanhTab); break;
+    case 1: be.launch_run(k_spec_run<9, 0, 4>, grid, NQS_RUN_THREADS, sp, list, tanhTab); break;
+    case 2: be.launch_run(k_spec_run<16, 1, 3>, grid, NQS_RUN_THREADS, sp, list, tanhTab); break;
+    case 3: be.launch_run(k_spec_run<16, 1, 4>, grid, NQS_RUN_THREADS, sp, list, tanhTab); break;
+    case 4: be.launch_run(k_spec_run<25, 2, 3>, grid, NQS_RUN_THREADS, sp, list, tanhTab); break;
+    default: be.launch_run(k_spec_run<25, 2, 4>, grid, NQS_RUN_THREADS, sp, list, tanhTab); break;
+  }
+}
+__global__ void __launch_bounds__(64) k_spec_compare(SpecImage* sp, const int* list) {
+  const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P)) return;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s < P.C.nseg) stage_compare(P.C, P.W, s);
 }
-// stage 7: one thread per image; counters[0] += images with open segments, [1] += patch requests, [2] += re-resolve requests,
-// [3] += images left to the serial kernel
-__global__ void k_spec_validate(SpecImage* sp, int nimg, int* counters) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nimg) return;
-  const SpecImage& P = sp[i];
-  if (!P.eligible) return;
-  if (P.W.state[1]) { atomicAdd(&counters[3], 1); return; }    // left to the serial kernel
-  P.W.state[2] = 0;
-  P.W.state[5] = 0;
-  const int open = stage_validate(P.C, P.W);
-  if (open > 0 && !P.W.state[1]) atomicAdd(&counters[0], 1);
-  if (P.W.state[2]) atomicAdd(&counters[1], 1);
-  if (P.W.state[5] && !P.W.state[1]) atomicAdd(&counters[2], 1);
-  if (P.W.state[1]) atomicAdd(&counters[3], 1);
+// stage 7: one thread per listed image. status[k]: bit 0 = segments still open, 1 = patch requested, 2 = re-resolve
+// requested, 3 = left to the serial kernel
+__global__ void k_spec_validate(SpecImage* sp, const int* list, int cnt, int* status) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  SpecImage& P = sp[list[k]];
+  int st = 0;
+  if (P.eligible && !P.W.state[1]) {
+    P.W.state[2] = 0;
+    P.W.state[5] = 0;
+    ++P.rounds;
+    const int open = stage_validate(P.C, P.W);
+    if (open > 0) st |= 1;
+    if (P.W.state[2]) st |= 2;
+    if (P.W.state[5]) st |= 4;
+  }
+  if (!P.eligible || P.W.state[1]) st = 8;
+  status[k] = st;
 }
-__global__ void __launch_bounds__(256) k_spec_patch(SpecImage* sp) {
-  const SpecImage& P = sp[blockIdx.y];
+__global__ void __launch_bounds__(256) k_spec_patch(SpecImage* sp, const int* list) {
+  const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P) || !P.W.state[2]) return;
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_patch(P.C, P.W, n);
+  const int from = P.W.state[3];
+  for (int n = from + 1 + blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_patch(P.C, P.W, n);
 }
-// images that were completed here are skipped by k_dither_fifo; the others (not eligible, contradicted, round cap) are not
-__global__ void k_spec_finish(NqImage* imgs, SpecImage* sp, int nimg, int* doneCount) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nimg) return;
+// images that leave the pool: completed ones are marked specDone = 1 (k_dither_fifo skips them), the others 3 (handed back)
+__global__ void k_spec_finish(NqImage* imgs, SpecImage* sp, const int* list, int cnt) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  const int i = list[k];
   const SpecImage& P = sp[i];
   if (NQS_ACTIVE(P) && P.W.state[0] == P.C.nseg) {
     imgs[i].specDone = 1;
     imgs[i].rngDraws = P.W.cdraw[P.C.npix];
-    atomicAdd(doneCount, 1);
-  }
+  } else
+    imgs[i].specDone = 3;
 }
 
-// ---- host side: layout of one wave slot, binding of the work arrays, and the wave / round loop -------------------------
+// ---- host side: layout of one slot of the pool, and the admission / round loop -------------------------------------
 struct SpecLayout {
-  size_t cpx, ccol, ck0, ck1, cdraw, cq, cflag, firstPos, slowPos, memo, slowVal, segs, state, rec, perSlot;
+  size_t cpx, ccol, ck0, ck1, cdraw, cq, cflag, firstPos, slowPos, memo, slowVal, segs, state, rec, chunkSum, perSlot;
   int nseg;
 };
 inline SpecLayout spec_layout(int npix, int seg) {
@@ -894,81 +1138,139 @@ inline SpecLayout spec_layout(int npix, int seg) {
   auto take = [&](size_t bytes) { size_t r = o; o = (o + bytes + 255) / 256 * 256; return r; };
   L.nseg = (npix + seg - 1) / seg;
   L.cpx = take((size_t)npix * 4); L.ccol = take((size_t)npix * 4); L.ck0 = take((size_t)npix * 4); L.ck1 = take((size_t)npix * 4);
-  L.cdraw = take(((size_t)npix + 1) * 4); L.cq = take((size_t)npix * 2); L.cflag = take((size_t)npix);
+  L.cdraw = take(((size_t)npix + 1) * 4); L.cq = take((size_t)npix * 2); L.cflag = take((size_t)npix + 64);
   L.firstPos = take(65536 * 4); L.slowPos = take(65536 * 4); L.memo = take(65536 * 2); L.slowVal = take(65536 * 2);
   L.segs = take(sizeof(SpecSeg) * (size_t)L.nseg); L.state = take(64); L.rec = take(sizeof(SpecRec) * (size_t)L.nseg * (size_t)seg);
+  L.chunkSum = take(((size_t)npix / NQS_CHUNK + 2) * 4);
   L.perSlot = o;
   return L;
 }
-// work arrays of image i = wave slot i % wave of `buf` (host copy of the SpecImage array, uploaded before k_spec_setup)
-inline void spec_bind(SpecImage* h, int n, unsigned char* buf, const SpecLayout& L, int wave) {
-  for (int i = 0; i < n; ++i) {
-    unsigned char* b = buf + L.perSlot * (size_t)(i % wave);
-    SpecWork& W = h[i].W;
+// array pointers of slot k of `buf` (host copy of the pool table that k_spec_admit reads)
+inline void spec_bind_pool(SpecWork* pool, int nslots, unsigned char* buf, const SpecLayout& L) {
+  for (int k = 0; k < nslots; ++k) {
+    unsigned char* b = buf + L.perSlot * (size_t)k;
+    SpecWork& W = pool[k];
+    memset(&W, 0, sizeof(W));
     W.cpx = reinterpret_cast<uint32_t*>(b + L.cpx); W.ccol = reinterpret_cast<uint32_t*>(b + L.ccol);
     W.ck0 = reinterpret_cast<uint32_t*>(b + L.ck0); W.ck1 = reinterpret_cast<uint32_t*>(b + L.ck1);
     W.cdraw = reinterpret_cast<uint32_t*>(b + L.cdraw); W.cq = reinterpret_cast<unsigned short*>(b + L.cq); W.cflag = b + L.cflag;
     W.firstPos = reinterpret_cast<int*>(b + L.firstPos); W.slowPos = reinterpret_cast<int*>(b + L.slowPos);
     W.memo = reinterpret_cast<unsigned short*>(b + L.memo); W.slowVal = reinterpret_cast<unsigned short*>(b + L.slowVal);
     W.segs = reinterpret_cast<SpecSeg*>(b + L.segs); W.state = reinterpret_cast<int*>(b + L.state); W.rec = reinterpret_cast<SpecRec*>(b + L.rec);
+    W.chunkSum = reinterpret_cast<unsigned*>(b + L.chunkSum);
   }
 }
-struct SpecStats { unsigned long long done = 0, rounds = 0, handedBack = 0, patches = 0, redos = 0; bool abandoned = false; };
-// The wave / round loop. `be` launches kernels and moves a few ints: launch(kernel, grid, block, args...), zero_ints(ptr, n),
-// read_ints(host, dev, n) (synchronises), lap(name). dInts: 4 counters. elig: host copy of k_spec_setup's verdicts.
+struct SpecStats { unsigned long long done = 0, rounds = 0, handedBack = 0, patches = 0, redos = 0; };
+// The admission / round loop. `be` launches kernels and moves a few ints: launch(kernel, grid, block, args...),
+// write_ints(dev, host, n), read_ints(host, dev, n) (synchronises), lap(name), note(round, ...). Device scratch dInts:
+// 4 lists of `nslots` ints (fresh images, their slots, active images, status). elig: host copy of k_spec_setup's verdicts.
+// handedBack (optional): the images this path took and could not finish, for the serial kernel.
 template <class Backend>
-void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const int* elig, int n, int npix, int seg, int wave, int* dInts,
-                int smCount, SpecStats* st) {
+void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* dPool, const int* elig, int n, int npix, int seg, int nslots,
+                int* dInts, const float* dTanh, int smCount, SpecStats* st, int* handedBack = nullptr) {
   const int nseg = (npix + seg - 1) / seg;
   const int roundCap = nseg / 4 + 96;
-  for (int base = 0; base < n; base += wave) {
-    const int m = wave < n - base ? wave : n - base;
-    int any = 0;
-    for (int i = 0; i < m; ++i) any += elig[base + i] == 1;
-    if (!any) continue;
-    if (st->abandoned) { st->handedBack += (unsigned long long)any; continue; }
-    SpecImage* sp = dSpec + base;
+  int* dFresh = dInts; int* dFreshSlot = dInts + nslots; int* dActive = dInts + 2 * nslots; int* dStatus = dInts + 3 * nslots;
+  // host mirrors
+  int* active = new int[nslots]; int* slotOfActive = new int[nslots]; int* fresh = new int[nslots]; int* freshSlot = new int[nslots];
+  int* status = new int[nslots]; int* freeSlots = new int[nslots]; int* rounds = new int[nslots]; int* leaving = new int[nslots];
+  int nActive = 0, nFree = nslots, next = 0, nHanded = 0;
+  for (int k = 0; k < nslots; ++k) freeSlots[k] = nslots - 1 - k;
+  const int nchunk = (npix + NQS_CHUNK - 1) / NQS_CHUNK;
+  auto pgrid = [&](int m) {
     int gx = (npix + 256 * 8 - 1) / (256 * 8);
     const int cap = (smCount * 8) / m > 1 ? (smCount * 8) / m : 1;
-    if (gx > cap) gx = cap;
-    const dim3 pg(gx, m), kg(8, m), sg((nseg + 63) / 64, m);
-    be.launch(k_spec_init, kg, 256, sp); be.lap("init");
-    be.launch(k_spec_pre, pg, 256, sp); be.lap("pre");
-    be.launch(k_spec_scan, dim3(m), 1024, sp, 0); be.lap("scan");
-    be.launch(k_spec_resolve, pg, 256, sp); be.lap("resolve");
-    be.launch(k_spec_memo, kg, 256, sp); be.lap("memo");
-    be.launch(k_spec_fill, pg, 256, sp); be.lap("fill+pack");
-    for (int round = 0; round < roundCap; ++round) {
-      be.zero_ints(dInts, 4);
-      be.launch(k_spec_run, sg, 64, sp); be.lap("run");
-      be.launch(k_spec_compare, sg, 64, sp); be.lap("compare");
-      be.launch(k_spec_validate, dim3((m + 63) / 64), 64, sp, m, dInts); be.lap("validate");
-      int counters[4] = {0, 0, 0, 0};
-      be.read_ints(counters, dInts, 4);
-      ++st->rounds;
-      st->patches += (unsigned long long)counters[1]; st->redos += (unsigned long long)counters[2];
-      be.note(round, counters);
-      if (counters[1]) { be.launch(k_spec_patch, pg, 256, sp); be.lap("patch"); }
-      if (counters[2]) {   // a draw misprediction: prefix sum again, then stages 3-5 behind it, for the images that asked
-        be.launch(k_spec_scan, dim3(m), 1024, sp, 1);
-        be.launch(k_spec_redo_a, kg, 256, sp);
-        be.launch(k_spec_redo_b, pg, 256, sp);
-        be.launch(k_spec_redo_c, kg, 256, sp);
-        be.launch(k_spec_redo_d, pg, 256, sp); be.lap("re-resolve");
-      }
-      if (counters[1] || counters[2]) { be.launch(k_spec_pack, pg, 256, sp, 1); be.lap("pack"); }
-      // One image on k_dither_fifo costs the batch that kernel's whole serial chain, whatever else was done here: once an
-      // image has been left to it, finishing the others speculatively only adds time.
-      if (counters[3]) { st->abandoned = true; break; }
-      if (!counters[0]) break;
+    return dim3((unsigned)(gx > cap ? cap : gx), (unsigned)m);
+  };
+  auto cgrid = [&](int m) {
+    const int cap = (smCount * 16) / m > 1 ? (smCount * 16) / m : 1;
+    return dim3((unsigned)(nchunk > cap ? cap : nchunk), (unsigned)m);
+  };
+  for (int round = 0;; ++round) {
+    // ---- admit images into the free slots: stages 1-5 for them
+    int nFresh = 0;
+    while (nFree > 0 && next < n) {
+      const int i = next++;
+      if ((elig[i] & 255) != 1) continue;
+      const int slot = freeSlots[--nFree];
+      fresh[nFresh] = i; freshSlot[nFresh] = slot; ++nFresh;
+      active[nActive] = i; slotOfActive[nActive] = slot; rounds[nActive] = 0; ++nActive;
     }
-    be.zero_ints(dInts + 3, 1);
-    be.launch(k_spec_finish, dim3((m + 63) / 64), 64, dImgs + base, sp, m, dInts + 3);
-    int done = 0;
-    be.read_ints(&done, dInts + 3, 1);
-    st->done += (unsigned long long)done;                      // completed here; the rest goes through k_dither_fifo
-    st->handedBack += (unsigned long long)(any - done);
+    if (nFresh) {
+      be.write_ints(dFresh, fresh, nFresh); be.write_ints(dFreshSlot, freshSlot, nFresh);
+      const dim3 pg = pgrid(nFresh), kg(8, (unsigned)nFresh), cg = cgrid(nFresh);
+      be.launch(k_spec_admit, dim3((unsigned)((nFresh + 63) / 64)), 64, dSpec, (const int*)dFresh, (const int*)dFreshSlot, nFresh, dPool);
+      be.launch(k_spec_init, kg, 256, dSpec, (const int*)dFresh); be.lap("init");
+      be.launch(k_spec_pre, pg, 256, dSpec, (const int*)dFresh); be.lap("pre");
+      be.launch(k_spec_scan_a, cg, 256, dSpec, (const int*)dFresh, 0);
+      be.launch(k_spec_scan_b, dim3((unsigned)nFresh), 1024, dSpec, (const int*)dFresh, 0);
+      be.launch(k_spec_scan_c, cg, 256, dSpec, (const int*)dFresh, 0); be.lap("scan");
+      be.launch(k_spec_resolve, pg, 256, dSpec, (const int*)dFresh); be.lap("resolve");
+      be.launch(k_spec_memo, kg, 256, dSpec, (const int*)dFresh); be.lap("memo");
+      be.launch(k_spec_fill, pg, 256, dSpec, (const int*)dFresh); be.lap("fill+pack");
+    }
+    if (!nActive) break;
+    // ---- one round for everything in the pool: stages 6, 6b, 7. The list is kept grouped by stage-6 instantiation.
+    {
+      int at = 0;
+      for (int v = 0; v < NQS_VARIANTS; ++v)
+        for (int k = at; k < nActive; ++k)
+          if (((elig[active[k]] >> 8) & 7) == v) {
+            const int a = active[k], b = slotOfActive[k], r = rounds[k];
+            active[k] = active[at]; slotOfActive[k] = slotOfActive[at]; rounds[k] = rounds[at];
+            active[at] = a; slotOfActive[at] = b; rounds[at] = r; ++at;
+          }
+    }
+    be.write_ints(dActive, active, nActive);
+    const dim3 s64((unsigned)((nseg + 63) / 64), (unsigned)nActive);
+    for (int k0 = 0; k0 < nActive;) {
+      const int v = (elig[active[k0]] >> 8) & 7;
+      int k1 = k0;
+      while (k1 < nActive && ((elig[active[k1]] >> 8) & 7) == v) ++k1;
+      spec_launch_run(be, v, dim3((unsigned)((nseg + NQS_RUN_THREADS - 1) / NQS_RUN_THREADS), (unsigned)(k1 - k0)), dSpec, (const int*)dActive + k0, dTanh);
+      k0 = k1;
+    }
+    be.lap("run");
+    be.launch(k_spec_compare, s64, 64, dSpec, (const int*)dActive); be.lap("compare");
+    be.launch(k_spec_validate, dim3((unsigned)((nActive + 63) / 64)), 64, dSpec, (const int*)dActive, nActive, dStatus); be.lap("validate");
+    be.read_ints(status, dStatus, nActive);
+    ++st->rounds;
+    int nOpen = 0, nPatch = 0, nRedo = 0, nLeave = 0;
+    for (int k = 0; k < nActive; ++k) {
+      ++rounds[k];
+      if ((status[k] & 1) && rounds[k] >= roundCap) status[k] = 8;      // not converging: the serial kernel takes it
+      nOpen += (status[k] & 1) && !(status[k] & 8); nPatch += (status[k] & 2) != 0; nRedo += (status[k] & 4) != 0;
+    }
+    st->patches += (unsigned long long)nPatch; st->redos += (unsigned long long)nRedo;
+    be.note(round, nActive, nOpen, nPatch, nRedo);
+    const dim3 pa = pgrid(nActive), ka(8, (unsigned)nActive), ca = cgrid(nActive);
+    if (nPatch) { be.launch(k_spec_patch, pa, 256, dSpec, (const int*)dActive); be.launch(k_spec_pack, pa, 256, dSpec, (const int*)dActive); be.lap("patch"); }
+    if (nRedo) {   // a draw misprediction: prefix sum again, then stages 3-5 behind it, for the images that asked
+      be.launch(k_spec_scan_a, ca, 256, dSpec, (const int*)dActive, 1);
+      be.launch(k_spec_scan_b, dim3((unsigned)nActive), 1024, dSpec, (const int*)dActive, 1);
+      be.launch(k_spec_scan_c, ca, 256, dSpec, (const int*)dActive, 1);
+      be.launch(k_spec_redo_a, ka, 256, dSpec, (const int*)dActive);
+      be.launch(k_spec_redo_b, pa, 256, dSpec, (const int*)dActive);
+      be.launch(k_spec_redo_c, ka, 256, dSpec, (const int*)dActive);
+      be.launch(k_spec_redo_d, pa, 256, dSpec, (const int*)dActive); be.lap("re-resolve");
+    }
+    // ---- images that leave: completed (no segment open) or handed back; their slots are free for the next round
+    int keep = 0;
+    for (int k = 0; k < nActive; ++k) {
+      const bool leave = (status[k] & 8) || !(status[k] & 1);
+      if (leave) {
+        leaving[nLeave++] = active[k];
+        freeSlots[nFree++] = slotOfActive[k];
+        if (status[k] & 8) { ++st->handedBack; if (handedBack) handedBack[nHanded] = active[k]; ++nHanded; } else ++st->done;
+      } else { active[keep] = active[k]; slotOfActive[keep] = slotOfActive[k]; rounds[keep] = rounds[k]; ++keep; }
+    }
+    nActive = keep;
+    if (nLeave) {
+      be.write_ints(dFresh, leaving, nLeave);               // (dFresh is free again: stream order)
+      be.launch(k_spec_finish, dim3((unsigned)((nLeave + 63) / 64)), 64, dImgs, dSpec, (const int*)dFresh, nLeave);
+    }
   }
+  delete[] active; delete[] slotOfActive; delete[] fresh; delete[] freshSlot; delete[] status; delete[] freeSlots; delete[] rounds; delete[] leaving;
 }
 #endif  // __CUDACC__ || NQS_EMULATE
 

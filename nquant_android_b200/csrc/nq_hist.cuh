@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_alpha_scan(NqImage* imgs, const NqSlot*
   const int img = blockIdx.y;
   const int n = imgs[img].npix;
   const uint32_t* in = slots[img].in;
-  unsigned semi = 0;
+  unsigned semi = 0, nonop = 0;
   int last = -1;
   const bool vec = ((uintptr_t)in & 15) == 0;
   const int n4 = vec ? (n >> 2) : 0;
@@ -58,14 +58,18 @@ __global__ void __launch_bounds__(256) k_alpha_scan(NqImage* imgs, const NqSlot*
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       unsigned a = px[k] >> 24;
-      if (a < 0xE0) {
-        if (a == 0) last = 4 * q + k;
-        else if (a > 0xF) ++semi;
+      if (a != 0xFF) {
+        ++nonop;
+        if (a < 0xE0) {
+          if (a == 0) last = 4 * q + k;
+          else if (a > 0xF) ++semi;
+        }
       }
     }
   }
   for (int i = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     unsigned a = in[i] >> 24;
+    nonop += a != 0xFF;
     if (a < 0xE0) {
       if (a == 0) last = max(last, i);
       else if (a > 0xF) ++semi;
@@ -74,10 +78,12 @@ __global__ void __launch_bounds__(256) k_alpha_scan(NqImage* imgs, const NqSlot*
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
     semi += __shfl_xor_sync(0xffffffffu, semi, o);
+    nonop += __shfl_xor_sync(0xffffffffu, nonop, o);
     last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
   }
   if (lane_id() == 0) {
     if (semi) atomicAdd(&imgs[img].semiCount, semi);
+    if (nonop) atomicAdd(&imgs[img].nonOpaque, nonop);
     if (last >= 0) atomicMax(&imgs[img].transIdx, last);
   }
 }

@@ -43,8 +43,9 @@ struct NqImage {
   // merge-loop phase clocks (SM cycles, thread 0): 0 heap/top, 1 first-32, 2 block tests, 3 screen, 4 full+resolve, 5 merge+rebuild
   unsigned long long statCyc[6], statLiveBlocks, statScreened;
   unsigned long long statDither[3];   // FIFO dither: consumer cycles, consumer cycles waiting for the producer, producer cycles waiting
-  int specDone;            // dithered by the speculative segment-parallel path (nq_dither_spec.cuh); k_dither_fifo skips it
-  int pad0;
+  int specDone;            // speculative segment-parallel dither (nq_dither_spec.cuh): 0 not its image, 1 dithered by it, 2 pending there,
+                           // 3 handed back to k_dither_fifo
+  unsigned int nonOpaque;  // pixels whose alpha is not 255 (alpha scan)
 };
 
 // Per-image slot of the workspace (device pointers into one big allocation).

@@ -89,8 +89,17 @@ class Context:
         return out
 
     def set_stream(self, cuda_stream):
-        """Run on a caller-owned stream (e.g. torch.cuda.current_stream().cuda_stream); 0/None restores our own."""
-        self._check(self._L.nq_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+        """Order the context's work with a caller-owned stream, e.g. torch.cuda.current_stream().cuda_stream. Handle 0
+        is CUDA's legacy default stream (torch's default stream), NOT the context's own: use reset_stream() for that."""
+        self._check(self._L.nq_set_stream(self._h, ctypes.c_void_p(int(cuda_stream or 0))))
+
+    def reset_stream(self):
+        """Back to the context's private non-blocking stream (the state after creation)."""
+        self._check(self._L.nq_reset_stream(self._h))
+
+    def set_chunk_images(self, images):
+        """Images per pipeline chunk of a batch call (0 = automatic)."""
+        self._check(self._L.nq_set_chunk_images(self._h, int(images)))
 
     def set_spec_dither(self, on, segment=8192, warmup=1024):
         """Speculative segment-parallel error diffusion for the images that qualify (include/nquant_b200.h); results are
@@ -142,6 +151,15 @@ class Context:
         ln = np.zeros(6, dtype=np.uint64)
         self._check(self._L.nq_get_stage_times(self._h, _p(ms), _p(ln), int(bool(reset))))
         return {s: (float(ms[i]), int(ln[i])) for i, s in enumerate(self.STAGES)}
+
+    KERNELS = ["k_spec_run", "k_dither_fifo", "k_dither_sorted", "k_merge"]
+
+    def kernel_times(self, reset=False):
+        """{kernel: (device ms, launches)} of the kernels that are timed on their own (CUDA events around each launch)."""
+        ms = np.zeros(4, dtype=np.float64)
+        ln = np.zeros(4, dtype=np.uint64)
+        self._check(self._L.nq_get_kernel_times(self._h, _p(ms), _p(ln), int(bool(reset))))
+        return {s: (float(ms[i]), int(ln[i])) for i, s in enumerate(self.KERNELS)}
 
     def math(self, fn, x, y=None):
         names = ["pow", "exp", "tanh", "cbrt", "atan2", "sin", "cos"]

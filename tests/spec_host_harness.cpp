@@ -111,6 +111,11 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   std::vector<double> lut(256);
   for (int v = 0; v < 256; ++v) lut[v] = nq::gamma_to_linear(v);
   fill_tables(C, lut.data());
+  C.opaque = 1;
+  for (int i = 0; i < npix; ++i) C.opaque &= ((uint32_t)cPixels[i] >> 24) == 0xFFu;
+  for (int i = 0; i < plen; ++i) C.opaque &= (C.pal[i] >> 24) == 0xFFu;
+  std::vector<float> tanhTab(512, 0.f);   // the table k_spec_tables builds on the device (shape_tanh)
+  for (int t = 0; t < 511; ++t) tanhTab[t] = tanh_f((double)((float)(t - 255) / 255.f * 20.f));
 
   OrderOnly oo;
   oo.width = width;
@@ -141,6 +146,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
     I.gMargin = gc.margin; I.gThresold = gc.thresold; I.gDitherMaxQ = gc.DITHER_MAX; I.gDitherMax = gc.ditherMax;
     I.gSorted = gc.sortedByYDiff; I.gHasAlpha = gc.hasAlpha; I.gUseSal = q.hasSaliencies; I.gBeta = gc.beta; I.gWeight = gc.weight;
     for (int k = 0; k < C.DM; ++k) I.gWeights[k] = gc.weights[k];
+    for (int i = 0; i < npix; ++i) I.nonOpaque += ((uint32_t)cPixels[i] >> 24) != 0xFFu;
     B.in.resize(npix); B.ref.resize(npix);
     for (int i = 0; i < npix; ++i) { B.in[i] = (uint32_t)cPixels[i]; B.ref[i] = (uint32_t)reference[i]; }
     build_cells(C, B.cells);
@@ -173,7 +179,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   int open = C.nseg;
   while (open > 0 && !state[1] && R.rounds < 100000) {
     ++R.rounds;
-    for (int s = 0; s < C.nseg; ++s) { if (!segs[s].done && segs[s].dirty) ++R.segRuns; stage_run(C, W, s); }   // stage 6
+    for (int s = 0; s < C.nseg; ++s) { if (!segs[s].done && segs[s].dirty) ++R.segRuns; stage_run(C, W, s, C.pal, tanhTab.data()); }   // stage 6
     for (int s = 0; s < C.nseg; ++s) stage_compare(C, W, s);                             // stage 6b
     open = stage_validate(C, W);                                                         // stage 7
     if (getenv("NQ_SPEC_DEBUG") && open > 0 && !state[1]) {
@@ -262,10 +268,12 @@ struct EmuBackend {
       }
     ++launches;
   }
-  void zero_ints(int* p, int n) { memset(p, 0, sizeof(int) * (size_t)n); }
+  template <class... P, class... A>
+  void launch_run(void (*kernel)(P...), dim3 grid, int block, A... args) { launch(kernel, grid, block, args...); }
+  void write_ints(int* dev, const int* host, int n) { memcpy(dev, host, sizeof(int) * (size_t)n); }
   void read_ints(int* host, const int* dev, int n) { memcpy(host, dev, sizeof(int) * (size_t)n); }
   void lap(const char*) {}
-  void note(int, const int*) {}
+  void note(int, int, int, int, int) {}
 };
 }  // namespace
 
@@ -314,16 +322,19 @@ extern "C" int nqs_spec_batch_run(int seg, int warm, int wave, long long* out /*
   std::vector<unsigned char> buf(L.perSlot * (size_t)wave);
   std::vector<SpecImage> sp(n);
   memset(sp.data(), 0, sizeof(SpecImage) * (size_t)n);
-  spec_bind(sp.data(), n, buf.data(), L, wave);
-  std::vector<int> ints(n + 4, 0);
+  std::vector<SpecWork> pool(wave);
+  spec_bind_pool(pool.data(), wave, buf.data(), L);
+  std::vector<int> elig(n, 0), ints(4 * wave + 4, 0), handed(n, 0);
+  std::vector<float> tanhTab(512, 0.f);
+  for (int t = 0; t < 511; ++t) tanhTab[t] = tanh_f((double)((float)(t - 255) / 255.f * 20.f));
   EmuBackend be;
-  be.launch(k_spec_setup, dim3((n + 63) / 64), 64, (const NqImage*)imgs.data(), (const NqSlot*)slots.data(), sp.data(), (const uint32_t*)order.data(), n, seg, warm, ints.data() + 4);
+  be.launch(k_spec_setup, dim3((n + 63) / 64), 64, imgs.data(), (const NqSlot*)slots.data(), sp.data(), (const uint32_t*)order.data(), n, seg, warm, elig.data());
   SpecStats st;
-  spec_drive(be, imgs.data(), sp.data(), ints.data() + 4, n, npix, seg, wave, ints.data(), 148, &st);
+  spec_drive(be, imgs.data(), sp.data(), (const SpecWork*)pool.data(), (const int*)elig.data(), n, npix, seg, wave, ints.data(), (const float*)tanhTab.data(), 148, &st, handed.data());
   long long eligible = 0, wrong = 0;
   for (int i = 0; i < n; ++i) {
-    eligible += ints[4 + i] == 1;
-    if (imgs[i].specDone) {
+    eligible += (elig[i] & 255) == 1;
+    if (imgs[i].specDone == 1) {
       long long bad = 0;
       for (int k = 0; k < npix; ++k) bad += outs[i][k] != g_batch[i].ref[k];
       wrong += bad != 0;

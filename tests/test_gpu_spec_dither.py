@@ -1,10 +1,8 @@
-"""GPU parity of the speculative segment-parallel dither (csrc/nq_dither_spec.cuh, opt-in through
-nq_set_spec_dither): the result must be bit-identical to the oracle's sequential GilbertCurve, and the path must
-actually have taken the images it is meant for (nq_get_spec_stats). The stage bodies are checked on the CPU in
-tests/test_spec_dither_host.py; these tests add the kernels and the orchestration around them.
-
-The path is opt-in (nq_set_spec_dither); round 1's GPU probes of it are under profiles/r1_spec_probe*.log. Set
-NQ_SPEC_DITHER_TEST=0 to skip these tests."""
+"""GPU parity of the speculative segment-parallel dither (csrc/nq_dither_spec.cuh, the default path for the images
+that qualify): the result must be bit-identical to the oracle's sequential GilbertCurve, and the path must actually
+have taken the images it is meant for (nq_get_spec_stats). The stage bodies are checked on the CPU in
+tests/test_spec_dither_host.py; these tests add the kernels and the orchestration around them (rolling admission into
+a pool of work-array slots, the serial kernels running next to it). Set NQ_SPEC_DITHER_TEST=0 to skip these tests."""
 import os
 
 import numpy as np
@@ -72,13 +70,38 @@ def test_spec_dither_batch_and_mixed_eligibility(spec_ctx, oracle):
         assert np.array_equal(pal[i, :plen[i]], ref.palette), i
         assert np.array_equal(out[i], ref.out), i
     assert spec_ctx.spec_stats()["images"] == 3       # the PriorityQueue-mode image belongs to k_dither_sorted
-    # with an image that k_dither_fifo has to do anyway (a transparent pixel), the path stands aside for the whole batch
+    # an image that k_dither_fifo has to do (a transparent pixel) runs NEXT to the speculative rounds of the others
     imgs2 = np.stack([imgs[0], make_image(w, h, "rand", "transparent")])
     out2, pal2, plen2, _ = spec_ctx.convert_batch(1, imgs2, w, h, 256, True, seeds=[11, 15])
     for i, sd in enumerate([11, 15]):
         ref = oracle.convert(1, imgs2[i], w, h, 256, True, seed=sd, trace=False)
         assert np.array_equal(out2[i], ref.out), i
-    assert spec_ctx.spec_stats()["images"] == 3
+    assert spec_ctx.spec_stats()["images"] == 4
+
+
+def test_spec_dither_slot_reuse_and_chunks(oracle, monkeypatch):
+    """More images than work-array slots (NQ_SPEC_SLOTS=3: images are admitted as slots free up, every launch mixes images
+    of different ages) and more than one pipeline chunk (nq_set_chunk_images): bit-identical to the oracle, all completed
+    by the speculative path."""
+    from nquant_android_b200.quantizer import Context
+    monkeypatch.setenv("NQ_SPEC_SLOTS", "3")
+    ctx = Context(0)
+    try:
+        w, h, n = 256, 192, 11
+        imgs = np.stack([make_image(w, h, "noisy" if i % 3 else "rand", "opaque", seed=0x5EED0000 + i) for i in range(n)])
+        seeds = [100 + i for i in range(n)]
+        ctx.set_spec_dither(True, 2048, 512)
+        ctx.set_chunk_images(6)
+        out, pal, plen, _ = ctx.convert_batch(1, imgs, w, h, 256, True, seeds=seeds)
+        for i in range(n):
+            ref = oracle.convert(1, imgs[i], w, h, 256, True, seed=seeds[i], trace=False)
+            assert np.array_equal(pal[i, :plen[i]], ref.palette), i
+            assert np.array_equal(out[i], ref.out), i
+            assert ctx.image_info(i)["rng_draws"] == ref.scalars["rng_draws"], i
+        st = ctx.spec_stats()
+        assert st["images"] == n and st["fallbacks"] == 0, st
+    finally:
+        ctx.close()
 
 
 def test_spec_dither_leaves_other_quantizers_alone(spec_ctx, oracle):
