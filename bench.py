@@ -9,8 +9,9 @@ palette + Gilbert dither) on batches of synthetic 4K images, one process per GPU
 
 A step is one pass of convert() over this rank's batch of images. `value` is measured with the
 pixels already resident in HBM (nq_convert_batch_device), `e2e` through the host-buffer entry point
-(nq_convert_batch: pinned host -> device -> host inside the timed region). Weak scaling: every rank
-owns `--batch` images. Prints ONE JSON line on rank 0.
+(nq_convert_batch: pinned host -> device -> host inside the timed region). The headline line is weak
+scaling (every rank owns `--batch` images: BASELINE.json configs[3], 1024 x 4K, at N = 1); for N > 1 the
+same run also times configs[3]'s fixed batch split over the ranks (`strong`). Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -35,8 +36,12 @@ STAGE_BYTES = {"alpha_scan": 4, "histogram": 4, "find_nn_sweep": 0, "merge": 0, 
 NCU_DRAM_BYTES_PER_PIXEL = {
     # profiles/r1_final_ncu_lab_8x1080p.md: k_dither_fifo read 236.1 MB + wrote 58.8 MB for 8 x 1920x1080 pixels
     # (8 B/px algorithmic + visiting-order table, RGB->Lab table sectors, candidate lists)
-    ("lab", "dither"): (236.132352e6 + 58.803712e6) / (8 * 1920 * 1080),
+    "k_dither_fifo": (236.132352e6 + 58.803712e6) / (8 * 1920 * 1080),
 }
+try:   # per-kernel DRAM bytes per pixel from this round's `ncu --set full` captures (tools/summarize_ncu.py writes it)
+    NCU_DRAM_BYTES_PER_PIXEL.update(json.load(open(os.path.join(HERE, "profiles", "ncu_dram_bytes_per_pixel.json"))))
+except Exception:
+    pass
 
 
 def parse():
@@ -45,24 +50,26 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("NQ_BENCH_BATCH", "592")),
-                    help="images per GPU per step (592 = 4 merge CTAs on each of the 148 SMs)")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("NQ_BENCH_BATCH", "1024")),
+                    help="images per GPU per step (1024 = BASELINE.json configs[3] on one GPU)")
+    ap.add_argument("--strong-batch", type=int, default=1024, help="N > 1: fixed batch that is also timed split over the ranks (0 = skip)")
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
     ap.add_argument("--kind", default="lab", choices=list(KINDS))
     ap.add_argument("--colors", type=int, default=256)
     ap.add_argument("--dither", type=int, default=1)
     ap.add_argument("--cls", default="noisy", choices=list(CLASSES))
-    ap.add_argument("--spec-dither", type=int, default=int(os.environ.get("NQ_SPEC_DITHER", "0")),
-                    help="1: speculative segment-parallel dither for the images that qualify (DESIGN.md 7.1; bit-identical results). "
-                         "Off by default until its GPU tests have run on a B200")
-    ap.add_argument("--spec-segment", type=int, default=8192)
+    ap.add_argument("--spec-dither", type=int, default=int(os.environ.get("NQ_SPEC_DITHER", "1")),
+                    help="1 (default): speculative segment-parallel dither for the images that qualify (DESIGN.md 7.1; bit-identical "
+                         "results); 0: every image through the serial kernels")
+    ap.add_argument("--spec-segment", type=int, default=0, help="0 = chosen from the size of the job")
+    ap.add_argument("--chunk", type=int, default=0, help="images per pipeline chunk (0 = automatic)")
     ap.add_argument("--spec-warmup", type=int, default=1024)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-workers", type=int, default=0, help="reference arm: worker processes (0 = all cores)")
-    ap.add_argument("--cpu-width", type=int, default=1920, help="CPU legs: width of the bounded sample image")
-    ap.add_argument("--cpu-height", type=int, default=1080, help="CPU legs: height of the bounded sample image")
+    ap.add_argument("--cpu-width", type=int, default=0, help="CPU legs: width of the sample image (0 = the workload's own)")
+    ap.add_argument("--cpu-height", type=int, default=0, help="CPU legs: height of the sample image (0 = the workload's own)")
     return ap.parse_args()
 
 
@@ -138,47 +145,56 @@ def _cpu_one(job):
     return time.perf_counter() - t0
 
 
+def _cpu_size(a):
+    return (min(a.cpu_width, a.width) if a.cpu_width else a.width), (min(a.cpu_height, a.height) if a.cpu_height else a.height)
+
+
 def cpu_single(a):
-    """one image, one thread: the like-for-like figure (the reference creates no threads). Bounded sample: one
-    image of the workload's class and quantizer at --cpu-width x --cpu-height (a 4K CIELAB image costs the oracle
-    about a minute; Mpixels/s is the unit, so the sample scales)."""
+    """one image, one thread: the like-for-like figure (the reference creates no threads). Bounded sample: ONE image of
+    the workload itself (same size, class, quantizer, colours, dither) -- about 45-90 s for a 4K CIELAB image."""
     from oracle import pyoracle
     pyoracle.build()
-    w, h = min(a.cpu_width, a.width), min(a.cpu_height, a.height)
+    w, h = _cpu_size(a)
     dt = _cpu_one((KINDS[a.kind], a.cls, w, h, a.colors, a.dither, 0xC0FFEE, 0))
     return {"value": w * h / dt / 1e6, "unit": "Mpixels/s", "cores": 1, "kind": "port",
-            "sample": f"1 image of the workload's class ({a.cls}, {workload_quantizer(a)}, {a.colors} colours, dither {a.dither}) at {w}x{h}, "
+            "sample": f"1 image of the workload ({a.cls}, {workload_quantizer(a)}, {a.colors} colours, dither {a.dither}) at {w}x{h}, "
                       f"oracle/nq_oracle.cpp -O2, 1 thread, {dt:.1f} s; C++ restatement of the Java core (no JVM in the image)"}
 
 
 def run_reference(a, rank):
-    """--impl reference: the oracle (C++ restatement of the reference's Java core) on all host cores. Every step
-    converts one bounded-sample image (--cpu-width x --cpu-height, the workload's class/quantizer/colours) per
-    worker process."""
+    """--impl reference: the oracle (C++ restatement of the reference's Java core; no JVM exists in the image) on all host
+    cores, on the workload's own image size. The reference is single-threaded per image, so the host is filled with one
+    worker process per core, each converting whole images; the --steps K steps are K equal shares of
+    workers * ceil(K / workers) images dealt to the pool (a step = that many images / K), so that every core is busy for the
+    whole timed region and the run ends within minutes. Warm-up steps convert 256x256 images."""
     if rank != 0:
         return
     import multiprocessing as mp
     from oracle import pyoracle
     pyoracle.build()
+    pyoracle.lib()     # the checker's library is mapped in THIS process too (the workers are forks of it)
     workers = a.cpu_workers or (os.cpu_count() or 1)
     kind = KINDS[a.kind]
-    w, h = min(a.cpu_width, a.width), min(a.cpu_height, a.height)
+    w, h = _cpu_size(a)
+    _cpu_one((kind, a.cls, 64, 64, a.colors, a.dither, 0xC0FFEE, 0))
+    rounds = max(1, -(-a.steps // workers))
+    total = workers * rounds
     ctx = mp.get_context("fork")
     with ctx.Pool(workers) as pool:
         for _ in range(a.warmup):   # untimed, on a small sample
             pool.map(_cpu_one, [(kind, a.cls, 256, 256, a.colors, a.dither, 0xC0FFEE, i) for i in range(workers)])
         t0 = time.perf_counter()
-        for s in range(a.steps):
-            pool.map(_cpu_one, [(kind, a.cls, w, h, a.colors, a.dither, 0xC0FFEE, s * workers + i) for i in range(workers)])
+        per = list(pool.imap_unordered(_cpu_one, [(kind, a.cls, w, h, a.colors, a.dither, 0xC0FFEE, i) for i in range(total)], chunksize=1))
         dt = time.perf_counter() - t0
-    px = a.steps * workers * w * h
+    px = total * w * h
     val = px / dt / 1e6
-    sample = (f"{workers} images per step (one per worker process) of the workload's class at {w}x{h} "
-              f"({a.cls}, {workload_quantizer(a)}, {a.colors} colours, dither {a.dither}); warm-up steps use 256x256 images")
+    sample = (f"{total} images of the workload ({a.cls}, {workload_quantizer(a)}, {a.colors} colours, dither {a.dither}) at {w}x{h}, "
+              f"one worker process per core ({workers}), {rounds} image(s) per worker; a step = {total / a.steps:.2f} images; "
+              f"{statistics.mean(per):.1f} s per image and core; warm-up steps use 256x256 images")
     line = {"metric": METRIC, "value": val, "unit": "Mpixels/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload_name(a), "sample": sample},
+            "config": {"workload": workload_name(a), "sample": sample, "image_size": f"{w}x{h}"},
             "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": workers, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -188,6 +204,23 @@ def run_reference(a, rank):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+def _golden_check(a, ctx, din, dout, n, rank, seeds):
+    """Outside the timed region: image 0 of rank 0's batch against the oracle's frozen output (tests/golden/
+    oracle_big_cases.json, tools/make_golden_big.py) when the workload is the one the fixture was made for."""
+    import hashlib
+    import torch
+    if rank != 0 or not (a.kind == "lab" and a.cls == "noisy" and a.colors == 256 and a.dither and (a.width, a.height) == (3840, 2160)):
+        return None
+    try:
+        cases = {c["name"]: c for c in json.load(open(os.path.join(HERE, "tests", "golden", "oracle_big_cases.json")))}
+        c = cases["config3_4k_lab_img0"]
+    except Exception:
+        return None
+    npix = a.width * a.height
+    got = hashlib.sha256(dout[:npix].cpu().numpy().astype("<u4").tobytes()).hexdigest()
+    return {"case": "config3_4k_lab_img0", "output_matches_oracle": got == c["output_sha"]}
+
+
 def run_ours(a, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -198,8 +231,9 @@ def run_ours(a, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = Context(local_rank)
     stream = torch.cuda.current_stream()
-    ctx.set_stream(stream.cuda_stream)
+    ctx.set_stream(stream.cuda_stream)       # handle 0 = the legacy default stream: the events below see the library's work
     ctx.set_spec_dither(bool(a.spec_dither), a.spec_segment, a.spec_warmup)
+    ctx.set_chunk_images(a.chunk)
     kind, cls = KINDS[a.kind], CLASSES[a.cls]
     npix = a.width * a.height
     n = a.batch
@@ -213,32 +247,55 @@ def run_ours(a, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        ctx.convert_batch_ptr(kind, din.data_ptr(), dout.data_ptr(), n, a.width, a.height, a.colors, a.dither, seeds=seeds, device=True)
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1)
+
+    def step_device(m=n):
+        ctx.convert_batch_ptr(kind, din.data_ptr(), dout.data_ptr(), m, a.width, a.height, a.colors, a.dither, seeds=seeds[:m], device=True)
 
     for _ in range(a.warmup):
         step_device()
+    golden = _golden_check(a, ctx, din, dout, n, rank, seeds)
     ctx.stage_times(reset=True)
+    ctx.kernel_times(reset=True)
+    s0 = ctx.spec_stats()
     l0 = ctx.kernel_launches()
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(a.steps):
-        step_device()
-    e1.record(stream)
-    barrier()
+    ms = timed(step_device, a.steps)
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
     launches = ctx.kernel_launches() - l0
     stages = ctx.stage_times()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    kernels = ctx.kernel_times()
+    s1 = ctx.spec_stats()
+    ms_max = max_over_ranks(ms)
     total_px = world * n * npix * a.steps
     value = total_px / (ms_max / 1e3) / 1e6
+
+    # ---- BASELINE.json configs[3] as written: ONE batch of --strong-batch images split over the ranks (N > 1 only; at N = 1
+    #      it is the headline line itself when --batch equals it)
+    strong = None
+    if world > 1 and a.strong_batch > 0 and a.strong_batch // world >= 1:
+        m = min(n, a.strong_batch // world)
+        for _ in range(max(1, a.warmup // 2)):
+            step_device(m)
+        sms = max_over_ranks(timed(lambda: step_device(m), a.steps))
+        strong = {"scaling": "strong", "global_batch_images": m * world, "images_per_gpu": m, "ms_per_step": sms / a.steps,
+                  "value": world * m * npix * a.steps / (sms / 1e3) / 1e6, "unit": "Mpixels/s",
+                  "note": "rank r converts the first m images of its own shard (same synthetic class; the images of a batch are independent)"}
 
     # ---- end to end: pinned host buffers through nq_convert_batch
     e2e = None
@@ -266,23 +323,15 @@ def run_ours(a, rank, world, local_rank):
                                   device=False, palettes=pal, palette_lens=plen)
 
         step_host()   # allocates the staging buffers
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for _ in range(a.steps):
-            step_host()
-        f1.record(stream)
-        barrier()
-        t2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t2.item())
-        same = bool(torch.equal(hout.cuda(), dout[:ne * npix]))
+        e2e_ms = max_over_ranks(timed(step_host, a.steps))
+        same = bool(torch.equal(hout.cuda(), dout[:ne * npix])) if ne == n else bool(torch.equal(hout[:npix].cuda(), dout[:npix]))
         e2e = {"value": world * ne * npix * a.steps / (e2e_ms / 1e3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": ne * npix * 4,
                "d2h_bytes_per_step": ne * npix * 4 + ne * 256 * 4 + ne * 4, "ms_per_step": e2e_ms / a.steps,
-               "matches_device_path": same, "batch_images_per_gpu": ne}
+               "matches_device_path": same, "batch_images_per_gpu": ne,
+               "overlap": "host->device, kernels and device->host of consecutive chunks of the batch run on separate streams"}
         if ne != n:
             e2e["note"] = f"host memory holds pinned buffers for {ne} of the {n} images per GPU: end-to-end leg run on the smaller batch"
+        del hin, hout
 
     if rank == 0:
         peaks = {}
@@ -293,39 +342,55 @@ def run_ours(a, rank, world, local_rank):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
         per_stage = {}
-        dom, dom_ms = None, -1.0          # dominant stage among those that move pixel bytes
         top, top_ms = None, -1.0          # dominant stage overall
         for name, (sms, ln) in stages.items():
             bytes_total = STAGE_BYTES[name] * n * npix * a.steps
             gbs = bytes_total / (sms / 1e3) / 1e9 if sms > 0 else 0.0
-            per_stage[name] = {"ms_per_step": sms / a.steps, "launches_per_step": ln / a.steps, "share": sms / ms if ms > 0 else 0,
+            per_stage[name] = {"ms_per_step": sms / a.steps, "launches_per_step": ln / a.steps, "share_of_stage_sum": 0.0,
                                "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
             if sms > top_ms:
                 top, top_ms = name, sms
-            if STAGE_BYTES[name] > 0 and sms > dom_ms:
-                dom, dom_ms = name, sms
-        dom_launches = max(1, stages[dom][1])
-        dom_bytes_per_launch = STAGE_BYTES[dom] * n * npix * a.steps / dom_launches
-        achieved = dom_bytes_per_launch / (dom_ms / dom_launches / 1e3) / 1e9 if dom_ms > 0 else 0.0
-        # DRAM bytes per pixel of the stage's kernels from one `ncu --set full` capture (profiles/), scaled to this launch
-        tpp = NCU_DRAM_BYTES_PER_PIXEL.get((a.kind, dom))
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": (tpp * n * npix * a.steps / dom_launches) if tpp else None, "peak_source": peak_src,
-                    "note": "largest stage that moves pixel bytes; it is a distance-1 recurrence per image (dependent-issue latency bound, "
-                            "DESIGN.md 4.1/4.2), so the HBM fraction is structurally tiny. The pixel passes' fractions are under `stages`.",
-                    "dominant_by_time": {"stage": top, "share": top_ms / ms if ms > 0 else 0,
+        stage_sum = sum(v[0] for v in stages.values()) or 1.0
+        for name, (sms, _) in stages.items():
+            per_stage[name]["share_of_stage_sum"] = sms / stage_sum
+        # The dominant kernel among those that move pixel bytes: the error-diffusion kernel of the dither stage (8 B per pixel:
+        # 4 read + 4 written). Whichever of k_spec_run / k_dither_fifo / k_dither_sorted took the most device time, each timed
+        # by its own CUDA events around every launch on the stream it runs on. Launches that did no work are not counted.
+        dk = max(("k_spec_run", "k_dither_fifo", "k_dither_sorted"), key=lambda k: kernels[k][0])
+        dk_ms, dk_launches = kernels[dk]
+        dk_launches = max(1, dk_launches)
+        bytes_per_launch = 8.0 * n * npix * a.steps / dk_launches
+        achieved = bytes_per_launch / (dk_ms / dk_launches / 1e3) / 1e9 if dk_ms > 0 else 0.0
+        tpp = NCU_DRAM_BYTES_PER_PIXEL.get(dk)
+        roofline = {"bound": "hbm", "kernel": dk, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": (tpp * n * npix * a.steps / dk_launches) if tpp else None, "peak_source": peak_src,
+                    "launches_per_step": dk_launches / a.steps, "avg_launch_ms": dk_ms / dk_launches,
+                    "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "note": "dominant kernel among those that move pixel bytes (8 B per pixel: the dither reads and writes each pixel once). "
+                            "It is an FP32 recurrence of ~300 instructions per pixel (25 taps x 3 channels of mul, add, max in the reference's "
+                            "order), issue bound, not HBM bound; the pixel passes' own fractions are under `stages`.",
+                    "dominant_by_time": {"stage": top, "share_of_stage_sum": top_ms / stage_sum,
                                          "note": "find_nn sweep and merge loop work on histogram bins (<= 65 536 per image), not pixels: "
-                                                 "0 algorithmic pixel bytes; issue/latency evidence in profiles/*_ncu_merge_sweep.md"},
+                                                 "0 algorithmic pixel bytes; issue/latency evidence in profiles/"},
                     "end_to_end_frac": (12.0 * total_px / (ms_max / 1e3) / 1e9) / (peak * world)}
+        spec = {k: s1[k] - s0[k] for k in s1}
         line = {"metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(a), "global_batch_images": world * n, "pixels_per_step": world * n * npix,
+                           "image_size": f"{a.width}x{a.height}",
                            "parallelism": f"one image shard per GPU x{world}, no collective",
                            "l2": "inputs larger than L2 (batch x 33 MB per image)",
-                           "dither_path": ("speculative segments %d/%d (%s)" % (a.spec_segment, a.spec_warmup, ctx.spec_stats())) if a.spec_dither
-                                          else "serial chain per image"},
-                "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "stages": per_stage}
+                           "dither_path": (f"speculative segments: {spec['images']} of {n * a.steps} images completed by it, "
+                                           f"{spec['fallbacks']} handed back to the serial kernel, {spec['rounds']} rounds") if a.spec_dither
+                                          else "serial chain per image",
+                           "stage_times": "stages of different chunks overlap (multi-stream pipeline): their sum exceeds ms_per_step"},
+                "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "stages": per_stage,
+                "kernels": {k: {"ms_per_step": v[0] / a.steps, "launches_per_step": v[1] / a.steps} for k, v in kernels.items()}}
+        if golden:
+            line["golden"] = golden
+        if strong:
+            line["strong"] = strong
         if e2e:
             line["e2e"] = e2e
         if not a.no_cpu and world == 1:

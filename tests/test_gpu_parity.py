@@ -297,3 +297,63 @@ def test_mirror_classes(oracle):
         out = q.convert(32, True)
         ref = oracle.convert(kind, img, W, H, 32, True, seed=3, trace=False)
         assert q.hasAlpha() and np.array_equal(out, ref.out) and np.array_equal(q.palette, ref.palette)
+
+
+def test_reference_demo_picture(gpu_ctx):
+    """The one real image the reference ships (its demo's sample.jpg, here as the lossless tests/golden/sample_495x438.png,
+    tools/make_sample_fixture.py) through imageio.load_argb, as the demo converts it (MainActivity.java:190-194:
+    PnnQuantizer, 256 colours, dither) and four other settings, against the oracle's frozen palette and output."""
+    from nquant_android_b200.imageio import load_argb
+    argb, w, h = load_argb(os.path.join(HERE, "golden", "sample_495x438.png"))
+    for c in json.load(open(os.path.join(HERE, "golden", "sample_cases.json"))):
+        assert (w, h) == (c["w"], c["h"]) and sha(argb) == c["input_sha"]
+        out, pal, plen, _ = gpu_ctx.convert_batch(c["kind"], argb[None, :], w, h, c["k"], bool(c["dither"]), seeds=[c["seed"]])
+        assert [int(v) for v in pal[0, :plen[0]]] == c["palette"], c
+        assert sha(out[0]) == c["output_sha"], (c["kind"], c["k"], c["dither"])
+        assert gpu_ctx.image_info(0)["rng_draws"] == c["rng_draws"]
+
+
+def test_caller_stream_orders_input_and_output(gpu_ctx):
+    """nq_set_stream: the library's work starts after what the caller's stream already holds and the stream continues only
+    after the call. Handle 0 is CUDA's legacy default stream (torch's default stream), not the context's own: a torch kernel
+    that PRODUCES the input immediately before convert_batch_ptr(device=True) must be seen, on the default stream and on a
+    side stream."""
+    import torch
+    W, H, K = 256, 128, 64
+    img = make_image(W, H, "noisy", "opaque")
+    ref_out, ref_pal, ref_len, _ = gpu_ctx.convert_batch(1, img[None, :], W, H, K, True, seeds=[3])
+    src = torch.from_numpy(img.view(np.int32)).cuda()
+    try:
+        for stream in (torch.cuda.default_stream(), torch.cuda.Stream()):
+            gpu_ctx.set_stream(stream.cuda_stream)
+            with torch.cuda.stream(stream):
+                din = torch.zeros_like(src)
+                dout = torch.empty_like(src)
+                big = torch.empty(1 << 28, dtype=torch.int32, device="cuda")
+                for _ in range(4):
+                    big.fill_(1)                 # keeps the stream busy so an unordered library would read zeros
+                din.copy_(src + big[:src.numel()] - 1)
+                gpu_ctx.convert_batch_ptr(1, din.data_ptr(), dout.data_ptr(), 1, W, H, K, True, seeds=np.array([3], dtype=np.uint64), device=True)
+                res = dout.clone()               # enqueued on the caller's stream right behind the call
+            stream.synchronize()
+            assert np.array_equal(res.cpu().numpy().view(np.uint32), ref_out[0]), stream
+            del big
+    finally:
+        gpu_ctx.reset_stream()
+
+
+def test_debug_records_survive_small_workspaces(oracle):
+    """Debug mode with more images than workspace slots would index the records of a later group with the group-local
+    index; here: several images in debug mode, every image's merge sequence must be its own."""
+    from nquant_android_b200.quantizer import Context
+    ctx = Context(0)
+    try:
+        W, H, K = 64, 48, 16
+        imgs = np.stack([make_image(W, H, "noisy", "opaque", seed=0x5EED0000 + i) for i in range(5)])
+        ctx.set_debug(True)
+        ctx.convert_batch(0, imgs, W, H, K, True)
+        for i in range(5):
+            ref = oracle.convert(0, imgs[i], W, H, K, True)
+            assert np.array_equal(ctx.debug_merges(i), ref.merges), i
+    finally:
+        ctx.close()

@@ -232,3 +232,20 @@ def test_libm_mode_agrees_closely(oracle):
     cols = rng.integers(0, 1 << 24, 20000) | 0xFF000000
     same = sum(np.array_equal(oracle.rgb2lab(int(c), 0), oracle.rgb2lab(int(c), 1)) for c in cols)
     assert same >= 19990
+
+
+def test_big_golden_file_is_complete_and_reproducible(oracle):
+    """tests/golden/oracle_big_cases.json (the frozen oracle outputs at the benchmarked sizes): every case of
+    tools/make_golden_big.py is present, and the two cheapest are re-run here so that a change to the oracle or to the
+    synthetic generator cannot leave the file stale silently."""
+    import hashlib, json, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import make_golden_big as g
+    have = {c["name"]: c for c in json.load(open(g.PATH))}
+    assert set(have) == {c["name"] for c in g.cases()}
+    assert have["q3_8192_lab_256_on"]["error"].startswith("alpha must be between 0 and 255")
+    for name in ("config0_512_smooth", "config0_512_noisy"):
+        c = have[name]
+        r = g.run_case({k: c[k] for k in ("name", "kind", "cls", "alpha", "w", "h", "k", "dither", "img_seed", "seed")})
+        assert r["input_sha"] == c["input_sha"] and r["output_sha"] == c["output_sha"] and r["palette"] == c["palette"], name
