@@ -315,6 +315,12 @@ def run_ours(a, rank, world, local_rank):
         hout = torch.empty(ne * npix, dtype=torch.int32, pin_memory=True)
         hin.copy_(din[:ne * npix])
         torch.cuda.synchronize()
+        # the device-resident leg is over: its buffers make room for the library's own staging (2 x batch); a few output
+        # images stay for the comparison below
+        keep = [0, ne // 2, ne - 1]
+        ref_out = {i: dout[i * npix:(i + 1) * npix].clone() for i in keep}
+        del din, dout
+        torch.cuda.empty_cache()
         pal = np.zeros((ne, 256), dtype=np.uint32)
         plen = np.zeros(ne, dtype=np.int32)
 
@@ -324,10 +330,10 @@ def run_ours(a, rank, world, local_rank):
 
         step_host()   # allocates the staging buffers
         e2e_ms = max_over_ranks(timed(step_host, a.steps))
-        same = bool(torch.equal(hout.cuda(), dout[:ne * npix])) if ne == n else bool(torch.equal(hout[:npix].cuda(), dout[:npix]))
+        same = all(bool(torch.equal(hout[i * npix:(i + 1) * npix].cuda(), ref_out[i])) for i in keep)
         e2e = {"value": world * ne * npix * a.steps / (e2e_ms / 1e3) / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": ne * npix * 4,
                "d2h_bytes_per_step": ne * npix * 4 + ne * 256 * 4 + ne * 4, "ms_per_step": e2e_ms / a.steps,
-               "matches_device_path": same, "batch_images_per_gpu": ne,
+               "matches_device_path": same, "compared_images": keep, "batch_images_per_gpu": ne,
                "overlap": "host->device, kernels and device->host of consecutive chunks of the batch run on separate streams"}
         if ne != n:
             e2e["note"] = f"host memory holds pinned buffers for {ne} of the {n} images per GPU: end-to-end leg run on the smaller batch"

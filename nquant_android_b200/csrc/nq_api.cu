@@ -195,7 +195,7 @@ struct nq_ctx {
   unsigned char* sortPool = nullptr;    // NQ_FRONT_STREAMS x sortSets sets of CIELAB sort scratch
   size_t zeroSlotBytes = 0, memoSlotBytes = 0, sortSetBytes = 0, sortABytes = 0;
   int wsSlots = 0, wsNpix = 0, wsKind = -1, sortSets = 0;
-  bool wsDebug = false, wsBits = false;
+  bool wsDebug = false, wsBits = false, wsIdx = false;
   std::vector<NqSlot> hSlots;
   // staging for host-buffer calls
   uint32_t* dIn = nullptr;
@@ -230,9 +230,9 @@ namespace {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SlotLayout {
-  size_t keyOff, sal, bD, bF, bCnt, bErr, bNn, bTm, bMtm, heap, mergeLog, cells, bits, total;
+  size_t keyOff, sal, bD, bF, bCnt, bErr, bNn, bTm, bMtm, heap, mergeLog, cells, bits, idx, total;
 };
-SlotLayout slot_layout(int kind, int npix, bool debug, bool needBits) {
+SlotLayout slot_layout(int kind, int npix, bool debug, bool needBits, bool needIdx) {
   SlotLayout L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
@@ -250,6 +250,7 @@ SlotLayout slot_layout(int kind, int npix, bool debug, bool needBits) {
   L.mergeLog = take(debug ? (size_t)2 * NQ_NBINS * 4 : 0);
   L.cells = take(lab ? (size_t)32768 * 32 : 0);
   L.bits = take(needBits ? ((size_t)1 << 29) : 0);      // one bit per ARGB value
+  L.idx = take(needIdx ? (size_t)npix * 2 : 0);         // first-pass indices + pending marks of the per-pixel BlueNoise pass
   L.total = o;
   return L;
 }
@@ -259,8 +260,8 @@ SlotLayout slot_layout(int kind, int npix, bool debug, bool needBits) {
 // batch instead of giving every image its own. Every front stream owns NQ_SORT_POOL of them.
 #define NQ_SORT_POOL 32
 
-int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots, bool needBits) {
-  SlotLayout L = slot_layout(kind, npix, c->debug, needBits);
+int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots, bool needBits, bool needIdx) {
+  SlotLayout L = slot_layout(kind, npix, c->debug, needBits, needIdx);
   const bool lab = kind == NQ_KIND_LAB;
   const size_t nruns = ((size_t)npix + NQ_RUN - 1) / NQ_RUN;
   const size_t sortA = align_up((size_t)npix * 4, 256);
@@ -275,7 +276,7 @@ int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots, bool needBits
   if (NQ_FRONT_STREAMS * pool * sortSet + perImage > budget) return fail(NQ_ERR_NOMEM, "not enough device memory for one image workspace");
   const int maxSlots = (int)std::min<size_t>((budget - NQ_FRONT_STREAMS * pool * sortSet) / perImage, 8192);
   const int slots = std::min(wantSlots, maxSlots);
-  if (c->ws && c->wsKind == kind && c->wsNpix == npix && c->wsSlots >= slots && c->wsDebug == c->debug && c->wsBits == needBits) return NQ_OK;
+  if (c->ws && c->wsKind == kind && c->wsNpix == npix && c->wsSlots >= slots && c->wsDebug == c->debug && c->wsBits == needBits && c->wsIdx == needIdx) return NQ_OK;
   if (c->ws) { CU(cudaDeviceSynchronize()); cudaFree(c->ws); c->ws = nullptr; c->wsBytes = 0; c->wsSlots = 0; }
   const size_t imgsB = align_up(sizeof(NqImage) * slots, 256), slotsB = align_up(sizeof(NqSlot) * slots, 256);
   const size_t liveB = align_up((size_t)slots * NQ_NBINS * 4, 256);
@@ -313,9 +314,9 @@ int ensure_workspace(nq_ctx* c, int kind, int npix, int wantSlots, bool needBits
     S.memo = reinterpret_cast<unsigned short*>(c->memoPlane + memoSlot * s);
     S.cells = lab ? b + L.cells : nullptr;
     S.bits = needBits ? reinterpret_cast<unsigned int*>(b + L.bits) : nullptr;
-    S.idx = nullptr;
+    S.idx = needIdx ? reinterpret_cast<unsigned short*>(b + L.idx) : nullptr;
   }
-  c->wsSlots = slots; c->wsNpix = npix; c->wsKind = kind; c->sortSets = pool; c->wsDebug = c->debug; c->wsBits = needBits;
+  c->wsSlots = slots; c->wsNpix = npix; c->wsKind = kind; c->sortSets = pool; c->wsDebug = c->debug; c->wsBits = needBits; c->wsIdx = needIdx;
   return NQ_OK;
 }
 
@@ -684,6 +685,12 @@ int run_dither(nq_ctx* c, Chunk& ch, const GroupArgs& A, const uint32_t* dOrder)
   cudaEventRecord(ch.evK[4], ax);
   nq::k_dither_sorted<<<n, 32, 0, ax>>>(dI, dS, dOrder); ++c->launches;
   cudaEventRecord(ch.evK[5], ax);
+  if (kind == NQ_KIND_RGB && !A.dither && A.nmax > 32) {   // BlueNoise.dither second pass, one thread per pixel (images flagged bnParallel)
+    nq::k_bn_rgb_init<<<dim3(8, n), 256, 0, ax>>>(dI, dS); ++c->launches;
+    nq::k_bn_rgb_a<<<pg, 256, 0, ax>>>(dI, dS); ++c->launches;
+    nq::k_bn_rgb_b<<<dim3(16, n), 256, 0, ax>>>(dI, dS); ++c->launches;
+    nq::k_bn_rgb_c<<<pg, 256, 0, ax>>>(dI, dS); ++c->launches;
+  }
   if (spec) {
     int rc = spec_rounds(c, ch, st, npix, plan, elig, handed);
     if (rc) return rc;
@@ -814,7 +821,9 @@ int convert_device(nq_ctx* c, int kind, const uint32_t* dIn, int n, int w, int h
   const int npix = w * h;
   // the BlueNoise second pass of PnnLABQuantizer weighs by pixelMap.size() (PL:511-513): track it only then
   const bool needBits = kind == NQ_KIND_LAB && !dither && nmax > 32;
-  int rc = ensure_workspace(c, kind, npix, n, needBits);
+  // PnnQuantizer's BlueNoise second pass runs one thread per pixel and keeps the first-pass indices next to the output
+  const bool needIdx = kind == NQ_KIND_RGB && !dither && nmax > 32;
+  int rc = ensure_workspace(c, kind, npix, n, needBits, needIdx);
   if (rc) return rc;
   if (c->debug) c->dbg.assign(n, DebugImage{});
   int firstErr = 0;

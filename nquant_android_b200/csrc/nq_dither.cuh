@@ -546,6 +546,9 @@ __global__ void k_dither_setup(NqImage* imgs, const NqSlot* slots, int nimg) {
   init_weights(I.gW3, 3);
   init_weights(I.gW7, 7);
   I.bnWeight = 1.0f;
+  // PnnQuantizer: BlueNoise.dither's lookups (closestColorIndex, PQ:313-375) are pure per pixel except for the first-seen memo
+  // of the nearestColorIndex fall-back: done by the per-pixel kernels k_bn_rgb_* after the Gilbert pass
+  I.bnParallel = (!lab && !I.dither && plen > 32 && slots[img].idx != nullptr) ? 1 : 0;
   // pixelMap.size() is only tracked exactly when getLab's call pattern does not depend on the scan order (PL:347-349)
   if (lab && !I.dither && plen > 32 && I.hasSemi && !I.error) I.error = 4;
 }
@@ -1175,7 +1178,7 @@ __global__ void __launch_bounds__(64) k_dither_fifo(NqImage* imgs, const NqSlot*
 
   if (lane == 0) { I.statDither[0] = (unsigned long long)(clock64() - cstart); I.statDither[1] = (unsigned long long)cwait; }
   E.rng.seed = ring.rngSeed; E.draws = ring.draws;
-  if (!dither && plen > 32) bluenoise_pass(I, D);
+  if (!dither && plen > 32 && !I.bnParallel) bluenoise_pass(I, D);
   if (lane == 0) I.rngDraws = E.draws;
 }
 
@@ -1351,8 +1354,149 @@ __global__ void __launch_bounds__(32) k_dither_sorted(NqImage* imgs, const NqSlo
     }
   }
 
-  if (!dither && plen > 32) bluenoise_pass(I, D);
+  if (!dither && plen > 32 && !I.bnParallel) bluenoise_pass(I, D);
   if (lane == 0) I.rngDraws = E.draws;
+}
+
+
+// -------------------------------------------------------------------------------------------------
+// BlueNoise.dither (BN:207-222) for PnnQuantizer, one THREAD per pixel. The second pass perturbs every original pixel
+// away from its first-pass colour and looks the result up again with closestColorIndex (PQ:313-375), which is a pure
+// function of (colour, position) -- its cache is written under another key than it is read with (PQ:320 vs 362) -- except
+// where it falls back to nearestColorIndex (PQ:372), whose memo under the reduced key keeps the FIRST colour seen in a
+// bucket (PQ:271-274), in raster order here (BN:212-219), after whatever the Gilbert pass left in it (PQ:398-404).
+//   a: every pixel; fall-backs that miss the memo of the first pass post (raster position, colour) to their bucket with
+//      a 64-bit atomicMin and mark the pixel (bit 15 of the index plane)
+//   b: one thread per bucket that was posted to: the entry its first colour creates
+//   c: the marked pixels read their bucket
+// -------------------------------------------------------------------------------------------------
+struct BnRgb {
+  int plen, hasTrans, semi, isNano, fixA0, width, npix;
+  uint32_t transColor;
+  double PR, PG, PB, PA;
+};
+__device__ __forceinline__ BnRgb bn_rgb_consts(const NqImage& I) {
+  BnRgb B;
+  B.plen = I.paletteLen; B.hasTrans = I.transIdx >= 0; B.semi = I.hasSemi != 0; B.isNano = I.isNano != 0; B.fixA0 = I.fixA0;
+  B.width = I.width; B.npix = I.npix; B.transColor = I.transColor;
+  B.PR = I.PR; B.PG = I.PG; B.PB = I.PB; B.PA = I.PA;
+  if (B.plen < 3) B.PR = B.PG = B.PB = B.PA = 1;
+  return B;
+}
+// PnnQuantizer.nearestColorIndex without its memo (PQ:276-310), one thread
+__device__ int nearest_rgb_thread(const BnRgb& B, const uint32_t* pal, uint32_t c) {
+  int k = 0;
+  if (c_alpha(c) <= 0xF) c = B.transColor;
+  if (B.plen > 2 && B.hasTrans && c_alpha(c) > 0xF) k = 1;
+  const int ca = c_alpha(c), cr = c_red(c), cg = c_green(c), cb = c_blue(c);
+  double best = 1e300;
+  int bi = -1;
+  for (int i = k; i < B.plen; ++i) {
+    const uint32_t c2 = pal[i];
+    const double da = (double)(c_alpha(c2) - ca), dr = (double)(c_red(c2) - cr), dg = (double)(c_green(c2) - cg), db = (double)(c_blue(c2) - cb);
+    double cur = B.PA * (da * da);
+    cur += B.PR * (dr * dr);
+    cur += B.PG * (dg * dg);
+    cur += B.PB * (db * db);
+    if (cur <= best) { best = cur; bi = i; }            // strict > pruning: the last minimal index wins (PQ:291-307)
+  }
+  if (!(best <= 2147483647.0) || bi < 0) bi = k;         // mindist starts at Integer.MAX_VALUE (PQ:286)
+  return bi;
+}
+// PnnQuantizer.closestColorIndex (PQ:313-375), one thread; -1 = falls back to nearestColorIndex(c)
+__device__ int closest_rgb_thread(const BnRgb& B, const uint32_t* pal, uint32_t c, int pos) {
+  if (c_alpha(c) <= 0xF) return -1;
+  const int ca = c_alpha(c), cr = c_red(c), cg = c_green(c), cb = c_blue(c);
+  Top2 t = {1 << 30, 1 << 30, T2_NONE, T2_NONE};
+  for (int k = 0; k < B.plen; ++k) {
+    const uint32_t c2 = pal[k];
+    const double dr = (double)(c_red(c2) - cr), dg = (double)(c_green(c2) - cg), db = (double)(c_blue(c2) - cb);
+    double err = B.PR * (dr * dr);
+    err += B.PG * (dg * dg);
+    err += B.PB * (db * db);
+    if (B.semi) { const double da = (double)(c_alpha(c2) - ca); err += B.PA * (da * da); }
+    const int d = j2i(err);
+    if (d != T2_NONE) t2_insert(t, d, k);
+  }
+  const int c0 = t.d0 == T2_NONE ? 0 : t.i0, e0 = t.d0;
+  const int c1 = t.d1 == T2_NONE ? c0 : t.i1, e1 = t.d1;     // PQ:359-360
+  const int MAX_ERR = B.plen << 2;
+  int idx = (pos + 1) % 2;
+  if ((double)e1 * .67 < (double)(e1 - e0)) idx = 0;
+  else if (c0 > c1) idx = pos % 2;
+  const int ci = idx ? c1 : c0, ei = idx ? e1 : e0;
+  if (ei >= MAX_ERR || (B.hasTrans && ci == 0)) return -1;
+  return ci;
+}
+#define NQ_BN_PENDING 0x8000u
+__global__ void __launch_bounds__(256) k_bn_rgb_init(const NqImage* imgs, const NqSlot* slots) {
+  const NqImage& I = imgs[blockIdx.y];
+  if (!I.bnParallel || I.error || I.paletteLen <= 0) return;
+  unsigned long long* first = slots[blockIdx.y].hSum;       // 65 536 buckets; the histogram sums are long dead
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < NQ_NBINS; k += gridDim.x * blockDim.x) first[k] = ~0ULL;
+}
+__global__ void __launch_bounds__(256) k_bn_rgb_a(NqImage* imgs, const NqSlot* slots) {
+  __shared__ uint32_t pal[NQ_MAXK];
+  NqImage& I = imgs[blockIdx.y];
+  if (!I.bnParallel || I.error || I.paletteLen <= 0) return;
+  const NqSlot& S = slots[blockIdx.y];
+  const BnRgb B = bn_rgb_consts(I);
+  for (int k = threadIdx.x; k < NQ_MAXK; k += blockDim.x) pal[k] = k < B.plen ? I.palette[k] : 0u;
+  __syncthreads();
+  unsigned long long* first = S.hSum;
+  const float strength = 1 / 3.f;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < B.npix; n += gridDim.x * blockDim.x) {
+    const uint32_t px = eff_pixel(S.in[n], B.fixA0);
+    const unsigned q0 = S.out[n] & 0xFFFFu;                  // the Gilbert pass stored indices (GC:278-279)
+    const int x = n % B.width, y = n / B.width;
+    const uint32_t c1 = bn_diffuse(px, pal[q0 < (unsigned)B.plen ? q0 : 0], 1.0f, strength, x, y, g_blueNoise);
+    int qi = closest_rgb_thread(B, pal, c1, n);
+    unsigned mark = q0;
+    if (qi < 0) {
+      if (!B.isNano) qi = nearest_rgb_thread(B, pal, c1);    // full-colour key: the memo is a pure cache (PQ:271)
+      else {
+        const int key = color_index(c1, B.semi, B.hasTrans);
+        const unsigned short got = S.memo[key];
+        if (got != 0xFFFF) qi = got;
+        else { atomicMin(&first[key], ((unsigned long long)(unsigned)n << 32) | (unsigned long long)c1); mark |= NQ_BN_PENDING; }
+      }
+    }
+    S.idx[n] = (unsigned short)mark;
+    if (qi >= 0) S.out[n] = pal[qi];
+  }
+}
+__global__ void __launch_bounds__(256) k_bn_rgb_b(const NqImage* imgs, const NqSlot* slots) {
+  __shared__ uint32_t pal[NQ_MAXK];
+  const NqImage& I = imgs[blockIdx.y];
+  if (!I.bnParallel || I.error || I.paletteLen <= 0 || !I.isNano) return;
+  const NqSlot& S = slots[blockIdx.y];
+  const BnRgb B = bn_rgb_consts(I);
+  for (int k = threadIdx.x; k < NQ_MAXK; k += blockDim.x) pal[k] = k < B.plen ? I.palette[k] : 0u;
+  __syncthreads();
+  const unsigned long long* first = S.hSum;
+  for (int key = blockIdx.x * blockDim.x + threadIdx.x; key < NQ_NBINS; key += gridDim.x * blockDim.x) {
+    const unsigned long long f = first[key];
+    if (f != ~0ULL) S.memo[key] = (unsigned short)nearest_rgb_thread(B, pal, (uint32_t)f);
+  }
+}
+__global__ void __launch_bounds__(256) k_bn_rgb_c(const NqImage* imgs, const NqSlot* slots) {
+  __shared__ uint32_t pal[NQ_MAXK];
+  const NqImage& I = imgs[blockIdx.y];
+  if (!I.bnParallel || I.error || I.paletteLen <= 0 || !I.isNano) return;
+  const NqSlot& S = slots[blockIdx.y];
+  const BnRgb B = bn_rgb_consts(I);
+  for (int k = threadIdx.x; k < NQ_MAXK; k += blockDim.x) pal[k] = k < B.plen ? I.palette[k] : 0u;
+  __syncthreads();
+  const float strength = 1 / 3.f;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < B.npix; n += gridDim.x * blockDim.x) {
+    const unsigned m = S.idx[n];
+    if (!(m & NQ_BN_PENDING)) continue;
+    const unsigned q0 = m & 0x7FFFu;
+    const uint32_t px = eff_pixel(S.in[n], B.fixA0);
+    const int x = n % B.width, y = n / B.width;
+    const uint32_t c1 = bn_diffuse(px, pal[q0 < (unsigned)B.plen ? q0 : 0], 1.0f, strength, x, y, g_blueNoise);
+    S.out[n] = pal[S.memo[color_index(c1, B.semi, B.hasTrans)]];
+  }
 }
 
 }  // namespace nq

@@ -40,8 +40,8 @@ namespace spec {
 #define NQS_F_DRAW 2u           // the lookup is predicted to call Random.nextInt (PL:467)
 #define NQS_F_RISK 8u           // error-dependent lookup predicted NOT to draw: the pixel is (nearly) a palette colour, any diffused
                                 // error makes it draw (PL:467) and every later draw index moves
-#define NQS_MAXRISK 16          // more such pixels than this: the image is left to the serial kernel before any segment runs
-#define NQS_MAXREDO 24          // draw mispredictions corrected per image before giving up
+#define NQS_MAXRISK 4096        // more such pixels than this: the image is left to the serial kernel before any segment runs
+#define NQS_MAXREDO 256         // rounds with a draw misprediction per image before giving up
 #define NQS_F_NEAR 4u           // resolved through nearestColorIndex's memo (PL:470-472), key = memo_key(ccol)
 
 // Constants of one image: what GilbertCurve's constructor and the quantizer hold while dithering.
@@ -81,9 +81,9 @@ struct SpecSeg {
 // consecutive 16-byte records.
 struct alignas(16) SpecRec {
   uint32_t px;                           // source pixel
-  uint32_t bidx;                         // x + y * width
+  uint32_t xy;                           // x | y << 16
   uint32_t qf;                           // palette index | flags << 16 | (TELL_BLUE_NOISE[bidx & 4095] > thresold) << 24
-  uint32_t pad;
+  float sal;                             // saliency of the pixel, for error-dependent lookups only (0 otherwise)
 };
 struct SpecWork {
   const uint32_t* order;                 // x | y << 16 per curve position
@@ -186,35 +186,45 @@ NQ_HD double closest_err(const SpecConst& C, uint32_t c2, int cr, int cg, int cb
   }
   return err;
 }
-NQ_HD unsigned top2_key(const SpecConst& C, int k, int cr, int cg, int cb) {
-  const uint32_t c2 = C.pal[k];
+// where the top-2 scan reads the palette and the per-channel cost tables from (global memory: SpecConst; stage 6 keeps
+// copies in shared memory)
+struct ScanTabs { const uint32_t* pal; const double *Tr, *Tg, *Tb; int plen; };
+NQ_HD ScanTabs scan_tabs(const SpecConst& C) { ScanTabs T; T.pal = C.pal; T.Tr = C.Tr; T.Tg = C.Tg; T.Tb = C.Tb; T.plen = C.plen; return T; }
+NQ_HD unsigned top2_key(const SpecConst& C, const ScanTabs& T, int k, int cr, int cg, int cb) {
+  const uint32_t c2 = T.pal[k];
   const int ar = c_red(c2) - cr, ag = c_green(c2) - cg, ab = c_blue(c2) - cb;
-  const double a = C.Tr[ar < 0 ? -ar : ar] + C.Tg[ag < 0 ? -ag : ag] + C.Tb[ab < 0 ? -ab : ab];
+  const double a = T.Tr[ar < 0 ? -ar : ar] + T.Tg[ag < 0 ? -ag : ag] + T.Tb[ab < 0 ? -ab : ab];
   int d = j2i(a);
   const double fr = a - (double)d;
   if (fr < 1e-6 || fr > 1.0 - 1e-6) d = j2i(closest_err(C, c2, cr, cg, cb));   // only floor(err) is compared (PL:448-456)
   return ((unsigned)d << 8) | (unsigned)k;
 }
 // the two smallest (floor(err), index) pairs = closest[0..3] of PL:418-458
-NQ_HD void top2(const SpecConst& C, const unsigned char* cells, uint32_t c, unsigned* k0, unsigned* k1) {
+NQ_HD void top2(const SpecConst& C, const ScanTabs& T, const unsigned char* cells, uint32_t c, unsigned* k0, unsigned* k1) {
   const int cr = c_red(c), cg = c_green(c), cb = c_blue(c);
   unsigned a0 = NQS_NONE, a1 = NQS_NONE;
   int cnt = 255;
-  const unsigned char* cell = nullptr;
+  unsigned w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cells) {
-    cell = cells + 32 * (size_t)(((cr >> 3) << 10) | ((cg >> 3) << 5) | (cb >> 3));
-    cnt = cell[0];
+    const unsigned* cell = reinterpret_cast<const unsigned*>(cells + 32 * (size_t)(((cr >> 3) << 10) | ((cg >> 3) << 5) | (cb >> 3)));
+#if defined(__CUDA_ARCH__)
+    const uint4 lo = __ldg(reinterpret_cast<const uint4*>(cell)), hi = __ldg(reinterpret_cast<const uint4*>(cell) + 1);
+    w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w; w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+#else
+    for (int q = 0; q < 8; ++q) w[q] = cell[q];
+#endif
+    cnt = (int)(w[0] & 255u);
   }
   if (cnt != 255) {
     for (int j = 1; j <= cnt; ++j) {
-      const unsigned key = top2_key(C, cell[j], cr, cg, cb);
+      const unsigned key = top2_key(C, T, (int)((w[j >> 2] >> (8 * (j & 3))) & 255u), cr, cg, cb);
       const unsigned t = key > a0 ? key : a0;
       a0 = key < a0 ? key : a0;
       a1 = a1 < t ? a1 : t;
     }
   } else {
-    for (int k = 0; k < C.plen; ++k) {
-      const unsigned key = top2_key(C, k, cr, cg, cb);
+    for (int k = 0; k < T.plen; ++k) {
+      const unsigned key = top2_key(C, T, k, cr, cg, cb);
       const unsigned t = key > a0 ? key : a0;
       a0 = key < a0 ? key : a0;
       a1 = a1 < t ? a1 : t;
@@ -222,6 +232,7 @@ NQ_HD void top2(const SpecConst& C, const unsigned char* cells, uint32_t c, unsi
   }
   *k0 = a0; *k1 = a1;
 }
+NQ_HD void top2(const SpecConst& C, const unsigned char* cells, uint32_t c, unsigned* k0, unsigned* k1) { top2(C, scan_tabs(C), cells, c, k0, k1); }
 
 // PnnLABQuantizer.nearestColorIndex without its memo (PL:337-401), palettes of more than 32 colours, no semi-transparency
 NQ_HD int nearest_nomemo(const SpecConst& C, uint32_t c, const double* lut) {
@@ -415,7 +426,7 @@ NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firs
 // ---- gate after stage 3 (state[7] = pixels flagged NQS_F_RISK): too many likely mispredictions, do not start
 NQ_HD void stage_gate(const SpecConst& C, const SpecWork& W) {
   if (W.state[7] > NQS_MAXRISK) W.state[1] = 1;
-  if (W.state[8] > (C.npix >> 8)) W.state[1] = 1;           // state[8] = error-dependent lookups: past 0.4 % their draws are mispredicted too often
+  if (W.state[8] > (C.npix >> 3)) W.state[1] = 1;           // state[8] = error-dependent lookups: past an eighth of the image little is left to speculate on
 }
 // ---- stage 4: one memo key ------------------------------------------------------------------------------------
 // `after`: only entries first seen behind that curve position (-1 = all); the others are settled
@@ -435,9 +446,9 @@ NQ_HD void stage_pack(const SpecConst& C, const SpecWork& W, int n) {
   const int bidx = (int)(xy & 0xFFFF) + (int)(xy >> 16) * C.width;
   SpecRec r;
   r.px = W.cpx[n];
-  r.bidx = (uint32_t)bidx;
+  r.xy = xy;
   r.qf = (uint32_t)W.cq[n] | ((uint32_t)W.cflag[n] << 16) | (W.bn[bidx & 4095] > C.thresold ? 1u << 24 : 0u);
-  r.pad = 0;
+  r.sal = (W.cflag[n] & NQS_F_PRE) ? 0.f : saliency_of(C, W, r.px);
   W.rec[rec_index(C, n)] = r;
 }
 // ---- re-resolve after a draw misprediction at curve position `from` = state[5] - 1 (stage_validate has corrected the
@@ -461,17 +472,31 @@ NQ_HD void stage_patch(const SpecConst& C, const SpecWork& W, int n) {
 // ---- stage 6: one segment ---------------------------------------------------------------------------------------
 // An error-dependent lookup (GC:214-216 with the diffused colour c2): closestColorIndex with the draw this pixel
 // was predicted to make, nearestColorIndex through the memo. `owned` = the pixel belongs to the segment (notes kept).
-NQ_HD int slow_lookup(const SpecConst& C, const SpecWork& W, SpecSeg& S, int n, uint32_t c, bool owned, int* draws, bool* drew) {
+// java.util.Random addressed by draw index, for a caller that asks for (mostly) increasing indices: the state of the last
+// index is kept and stepped forward; only a long way ahead (or back) takes the O(log) jump from the seed.
+struct LcgCursor { unsigned long long state; unsigned idx; int valid; };
+NQ_HD unsigned long long lcg_state_at(const SpecConst& C, LcgCursor& L, unsigned idx) {   // state after `idx` steps
+  const unsigned long long MASK = (1ULL << 48) - 1;
+  if (L.valid && idx >= L.idx && idx - L.idx <= 24u) {
+    for (unsigned k = L.idx; k < idx; ++k) L.state = (L.state * 0x5DEECE66DULL + 0xBULL) & MASK;
+  } else
+    L.state = lcg_jump(C.jmpA, C.jmpC, C.seed0, (unsigned long long)idx);
+  L.idx = idx; L.valid = 1;
+  return L.state;
+}
+// `drawIdx` = draws predicted in front of this pixel (cdraw[n])
+NQ_HD int slow_lookup(const SpecConst& C, const ScanTabs& T, const SpecWork& W, SpecSeg& S, LcgCursor& L, int n, unsigned drawIdx, uint32_t c, bool owned,
+                      int* draws, bool* drew) {
   *drew = false;
   bool needNear = true;
   int qi = 0;
   if (c_alpha(c) > 0xF) {
     unsigned k0, k1;
-    top2(C, W.cells, c, &k0, &k1);
+    top2(C, T, W.cells, c, &k0, &k1);
     int r = 0;
     if ((k0 >> 8) != 0u) {
       bool rej;
-      r = next_int_from(lcg_jump(C.jmpA, C.jmpC, C.seed0, (unsigned long long)W.cdraw[n] + 1ULL), &rej);
+      r = next_int_from(lcg_state_at(C, L, drawIdx + 1u), &rej);
       if (rej) S.nnotes = NQS_NOTES + 1;                   // never seen; handled as an overflow = not validated
       ++*draws;
       *drew = true;
@@ -531,45 +556,52 @@ NQ_HD float shape_tanh(float e, float maxErr, const float* tab) {
   return shape_tanh_eval(e, maxErr);
 }
 
-struct RunEnv {                 // what the pixel step needs besides the queue: loop-invariant
+struct RunEnv {                 // what the pixel step needs besides the queue
   const SpecConst* C;
   const SpecWork* W;
   SpecSeg* S;
-  const uint32_t* pal;          // C->pal (shared memory copy on the device)
+  ScanTabs T;                   // palette and cost tables (shared memory copies on the device)
   const float* tanhTab;         // shape_tanh
   float fDitherMax, fDitherMax1, divisor;
   bool illusion0;
-  int draws;
+  int draws;                    // draws made by the pixels of the current span
+  unsigned drawIdx;             // draws PREDICTED in front of the current pixel = cdraw[n], kept up from the records' flags
+  LcgCursor lcg;
 };
 
 // the quantization of an error-dependent lookup (GC:211-229 with the diffused colour), kept out of the hot loop
-NQ_HD int run_slow_pixel_body(RunEnv& X, int n, uint32_t px, int bidx, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned) {
+NQ_HD int run_slow_pixel_body(RunEnv& X, int n, uint32_t px, uint32_t xy, float sal, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned) {
   const SpecConst& C = *X.C;
   const SpecWork& W = *X.W;
-  const int x = bidx % C.width, y = bidx / C.width;
+  const int x = (int)(xy & 0xFFFFu), y = (int)(xy >> 16);
   const uint32_t c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
-  const float sal = saliency_of(C, W, px);
   uint32_t c = c2;
   if (!(C.plen >= 256 && sal > .99f)) c = slow_colour(C, W, x, y, px, sal, color_y(px, W.lut), c2);
   bool drew;
-  const int qi = slow_lookup(C, W, *X.S, n, c, owned, &X.draws, &drew);
-  if (owned && X.S->mispos < 0 && drew != ((flag & NQS_F_DRAW) != 0)) X.S->mispos = n;   // every later draw index is off by one
+  const int qi = slow_lookup(C, X.T, W, *X.S, X.lcg, n, X.drawIdx, c, owned, &X.draws, &drew);
+  if (owned && drew != ((flag & NQS_F_DRAW) != 0)) {
+    // A draw against the prediction (PL:467): every later draw index of the image is off by one. The prediction is corrected
+    // here, for every such pixel of the segment (the first one is what stage 7 reports); what this thread computes behind
+    // it is discarded with the segment.
+    if (X.S->mispos < 0) X.S->mispos = n;
+    W.cflag[n] = (unsigned char)(flag ^ NQS_F_DRAW);
+  }
   return qi;
 }
 #if defined(__CUDA_ARCH__)
-__device__ NQS_NOINLINE int run_slow_pixel(RunEnv& X, int n, uint32_t px, int bidx, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned) {
-  return run_slow_pixel_body(X, n, px, bidx, flag, a_pix, r_pix, g_pix, b_pix, owned);
+__device__ NQS_NOINLINE int run_slow_pixel(RunEnv& X, int n, uint32_t px, uint32_t xy, float sal, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned) {
+  return run_slow_pixel_body(X, n, px, xy, sal, flag, a_pix, r_pix, g_pix, b_pix, owned);
 }
 #else
-inline int run_slow_pixel(RunEnv& X, int n, uint32_t px, int bidx, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned) {
-  return run_slow_pixel_body(X, n, px, bidx, flag, a_pix, r_pix, g_pix, b_pix, owned);
+inline int run_slow_pixel(RunEnv& X, int n, uint32_t px, uint32_t xy, float sal, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned) {
+  return run_slow_pixel_body(X, n, px, xy, sal, flag, a_pix, r_pix, g_pix, b_pix, owned);
 }
 #endif
 
 // One pixel at window offset u: the queue is e[u .. u + DM - 1] (oldest first), the new box goes to e[u + DM].
 template <int DM, int DMI, int NCH, int u, bool OWNED>
 NQ_HD void run_pixel(RunEnv& X, float (&e)[DM + NQS_U][NCH], const SpecRec& rc, int n) {
-  const SpecConst& C = *X.C; (void)C;
+  const SpecConst& C = *X.C;
   const uint32_t px = rc.px;
   // ---- error.p = pixel + sum(queue[i].p * weights[i]), oldest box first (GC:190-204)
   float a0 = (float)c_red(px), a1 = (float)c_green(px), a2 = (float)c_blue(px), a3 = (float)c_alpha(px);
@@ -593,9 +625,10 @@ NQ_HD void run_pixel(RunEnv& X, float (&e)[DM + NQS_U][NCH], const SpecRec& rc, 
     qi = (int)(rc.qf & 0xFFFFu);
     X.draws += (flag & NQS_F_DRAW) ? 1 : 0;
   } else
-    qi = run_slow_pixel(X, n, px, (int)rc.bidx, flag, a_pix, r_pix, g_pix, b_pix, OWNED);
-  const uint32_t pc = X.pal[qi];
-  if (OWNED) X.W->out[rc.bidx] = pc;                       // dither == true: the palette colour (GC:278-279)
+    qi = run_slow_pixel(X, n, px, rc.xy, rc.sal, flag, a_pix, r_pix, g_pix, b_pix, OWNED);
+  X.drawIdx += (flag & NQS_F_DRAW) ? 1u : 0u;               // the prefix every pre-lookup behind this pixel was resolved with
+  const uint32_t pc = X.T.pal[qi];
+  if (OWNED) X.W->out[(rc.xy & 0xFFFFu) + (rc.xy >> 16) * (uint32_t)C.width] = pc;   // dither == true: the palette colour (GC:278-279)
   // ---- error of this pixel and its shaping (GC:236-264)
   float e0 = (float)(r_pix - c_red(pc)), e1 = (float)(g_pix - c_green(pc)), e2 = (float)(b_pix - c_blue(pc));
   const bool s0 = fabsf_(e0) >= X.fDitherMax, s1 = fabsf_(e1) >= X.fDitherMax, s2 = fabsf_(e2) >= X.fDitherMax;
@@ -635,6 +668,7 @@ NQ_HD void run_span(RunEnv& X, float (&e)[DM + NQS_U][NCH], int n0, int n1) {
   const SpecRec* const recs = X.W->rec;
   const int segLen = C.seg, nsegs = C.nseg;
   int n = n0;
+  if (n0 < n1) X.drawIdx = X.W->cdraw[n0];
   if (n + NQS_U <= n1) {
     // record (row, col) of pixel n in the segment-interleaved layout, advanced without a division per pixel
     int row = n % segLen, col = n / segLen;
@@ -673,7 +707,7 @@ NQ_HD void run_span(RunEnv& X, float (&e)[DM + NQS_U][NCH], int n0, int n1) {
 static_assert(NQS_U == 4, "run_span spells out the NQS_U pixel steps");
 
 template <int DM, int DMI, int NCH>
-NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s, const uint32_t* pal, const float* tanhTab) {
+NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s, const ScanTabs& T, const float* tanhTab) {
   SpecSeg& S = W.segs[s];
   if (S.done || !S.dirty) return;
   const int p0 = s * C.seg, p1 = (p0 + C.seg < C.npix) ? p0 + C.seg : C.npix;
@@ -692,7 +726,8 @@ NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s, const uint3
     if (!S.exact) { const long long w = (long long)C.warm * (long long)S.warmMul; from = (long long)p0 - w > 0 ? (int)((long long)p0 - w) : 0; }
   }
   RunEnv X;
-  X.C = &C; X.W = &W; X.S = &S; X.pal = pal; X.tanhTab = tanhTab;
+  X.C = &C; X.W = &W; X.S = &S; X.T = T; X.tanhTab = tanhTab;
+  X.lcg.valid = 0; X.lcg.idx = 0; X.lcg.state = 0; X.drawIdx = 0;
   X.fDitherMax = (float)C.ditherMax; X.fDitherMax1 = (float)(C.ditherMax - 1);
   X.divisor = (float)(1 + nqm::sqrt_((double)C.ditherMax));
   X.illusion0 = W.bn[0] > C.thresold;                      // yDiff == 1 in this mode: bn[(int)4096.0 & 4095] (GC:251-252)
@@ -710,15 +745,16 @@ NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s, const uint3
   S.draws = X.draws;
   S.dirty = 0;
 }
-NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s, const uint32_t* pal, const float* tanhTab) {
+NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s, const float* tanhTab) {
+  const ScanTabs T = scan_tabs(C);
   if (C.opaque) {
-    if (C.DM == 25) stage_run_t<25, 2, 3>(C, W, s, pal, tanhTab);
-    else if (C.DM == 16) stage_run_t<16, 1, 3>(C, W, s, pal, tanhTab);
-    else if (C.DM == 9) stage_run_t<9, 0, 3>(C, W, s, pal, tanhTab);
+    if (C.DM == 25) stage_run_t<25, 2, 3>(C, W, s, T, tanhTab);
+    else if (C.DM == 16) stage_run_t<16, 1, 3>(C, W, s, T, tanhTab);
+    else if (C.DM == 9) stage_run_t<9, 0, 3>(C, W, s, T, tanhTab);
   } else {
-    if (C.DM == 25) stage_run_t<25, 2, 4>(C, W, s, pal, tanhTab);
-    else if (C.DM == 16) stage_run_t<16, 1, 4>(C, W, s, pal, tanhTab);
-    else if (C.DM == 9) stage_run_t<9, 0, 4>(C, W, s, pal, tanhTab);
+    if (C.DM == 25) stage_run_t<25, 2, 4>(C, W, s, T, tanhTab);
+    else if (C.DM == 16) stage_run_t<16, 1, 4>(C, W, s, T, tanhTab);
+    else if (C.DM == 9) stage_run_t<9, 0, 4>(C, W, s, T, tanhTab);
   }
 }
 
@@ -751,7 +787,7 @@ NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
       // colour but not for the pixel, or the reverse). Up to that pixel the segment is exact; behind it every draw index
       // moves by one. Correct the pixel's flag, ask for a re-resolve of everything behind it (stage_rekey and stages
       // 2-5), and run this segment and all later ones again.
-      W.cflag[S.mispos] = (unsigned char)(W.cflag[S.mispos] ^ NQS_F_DRAW);
+      // (stage 6 has already corrected the flag of that pixel and of every later misprediction it saw)
       W.state[5] = S.mispos + 1;
       for (int t = s; t < C.nseg; ++t) W.segs[t].dirty = 1;
       if (++W.state[6] > NQS_MAXREDO) { W.state[1] = 1; return 0; }
@@ -1053,23 +1089,29 @@ __global__ void k_spec_run(SpecImage* sp, const int* list, const float* tanhTab)
   const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P)) return;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < P.C.nseg) stage_run_t<DM, DMI, NCH>(P.C, P.W, s, P.C.pal, tanhTab);
+  if (s < P.C.nseg) stage_run_t<DM, DMI, NCH>(P.C, P.W, s, scan_tabs(P.C), tanhTab);
 }
 #else
 template <int DM, int DMI, int NCH>
 __global__ void __launch_bounds__(NQS_RUN_THREADS, (DM + NQS_U) * NCH <= 96 ? 3 : 2) k_spec_run(SpecImage* sp, const int* list, const float* tanhTab) {
   __shared__ uint32_t sPal[NQ_MAXK];
   __shared__ float sTanh[512];
+  __shared__ double sT[3][256];
   const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P)) return;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   // nothing to do for a whole block is the common case in the later rounds: look before loading the tables
   const bool work = s < P.C.nseg && !P.W.segs[s].done && P.W.segs[s].dirty;
   if (!__syncthreads_or(work)) return;
-  for (int k = threadIdx.x; k < NQ_MAXK; k += blockDim.x) sPal[k] = k < P.C.plen ? P.C.pal[k] : 0u;
+  for (int k = threadIdx.x; k < NQ_MAXK; k += blockDim.x) {
+    sPal[k] = k < P.C.plen ? P.C.pal[k] : 0u;
+    sT[0][k] = P.C.Tr[k]; sT[1][k] = P.C.Tg[k]; sT[2][k] = P.C.Tb[k];
+  }
   for (int k = threadIdx.x; k < 511; k += blockDim.x) sTanh[k] = tanhTab[k];
   __syncthreads();
-  if (work) stage_run_t<DM, DMI, NCH>(P.C, P.W, s, sPal, sTanh);
+  ScanTabs T;
+  T.pal = sPal; T.Tr = sT[0]; T.Tg = sT[1]; T.Tb = sT[2]; T.plen = P.C.plen;
+  if (work) stage_run_t<DM, DMI, NCH>(P.C, P.W, s, T, sTanh);
 }
 #endif
 template <class Backend>

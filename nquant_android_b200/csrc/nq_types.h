@@ -46,6 +46,8 @@ struct NqImage {
   int specDone;            // speculative segment-parallel dither (nq_dither_spec.cuh): 0 not its image, 1 dithered by it, 2 pending there,
                            // 3 handed back to k_dither_fifo
   unsigned int nonOpaque;  // pixels whose alpha is not 255 (alpha scan)
+  int bnParallel;          // BlueNoise.dither second pass done by the per-pixel kernels k_bn_* instead of the serial warp
+  int pad1;
 };
 
 // Per-image slot of the workspace (device pointers into one big allocation).

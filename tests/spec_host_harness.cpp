@@ -179,7 +179,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   int open = C.nseg;
   while (open > 0 && !state[1] && R.rounds < 100000) {
     ++R.rounds;
-    for (int s = 0; s < C.nseg; ++s) { if (!segs[s].done && segs[s].dirty) ++R.segRuns; stage_run(C, W, s, C.pal, tanhTab.data()); }   // stage 6
+    for (int s = 0; s < C.nseg; ++s) { if (!segs[s].done && segs[s].dirty) ++R.segRuns; stage_run(C, W, s, tanhTab.data()); }   // stage 6
     for (int s = 0; s < C.nseg; ++s) stage_compare(C, W, s);                             // stage 6b
     open = stage_validate(C, W);                                                         // stage 7
     if (getenv("NQ_SPEC_DEBUG") && open > 0 && !state[1]) {
