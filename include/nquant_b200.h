@@ -88,6 +88,17 @@ int nq_convert_batch(nq_ctx* ctx, int kind, const uint32_t* argb_in, int n_image
                      int dither, const uint64_t* rng_seeds, uint32_t* argb_out, uint32_t* palettes_out, int* palette_lens,
                      int* has_alpha);
 
+/* The same batch over SEVERAL GPUs of one node: contexts[g] was created with nq_create(device g) (or several contexts on one
+ * device). The images are independent (every `convert` of the reference is, PnnQuantizer.java:18-33), so there is no
+ * collective: one host thread per context pulls pieces of `queue_images` images from a shared queue and converts them
+ * with nq_convert_batch; a context that finishes early takes the next piece. queue_images == 0 cuts the batch into one
+ * piece per context (best when the images cost about the same: the merge loop and the dither want hundreds of images
+ * in flight per GPU); smaller pieces balance batches whose images differ a lot in occupied histogram bins. Results land
+ * at the image's own index whichever GPU converted it. Host buffers (pinned memory makes the copies overlap). */
+int nq_convert_batch_multi(nq_ctx** contexts, int n_contexts, int kind, const uint32_t* argb_in, int n_images, int width, int height,
+                           int n_max_colors, int dither, const uint64_t* rng_seeds, uint32_t* argb_out, uint32_t* palettes_out,
+                           int* palette_lens, int* has_alpha, int queue_images);
+
 /* As nq_convert_batch, but argb_in / argb_out are DEVICE pointers on the context's GPU (16-byte
  * aligned). For callers that already hold the pixels in HBM; rng_seeds, palettes_out, palette_lens and
  * has_alpha stay host pointers. Work is enqueued on the context's stream and the call returns after

@@ -40,8 +40,47 @@ final class NQuantNative {
 	static final MethodHandle nq_convert = h("nq_convert", FunctionDescriptor.of(I, P, I, P, I, I, I, I, L, P, P, P, P));
 	// int nq_convert_batch(ctx, kind, argb_in, n_images, width, height, n_max_colors, dither, rng_seeds, argb_out, palettes_out, palette_lens, has_alpha)
 	static final MethodHandle nq_convert_batch = h("nq_convert_batch", FunctionDescriptor.of(I, P, I, P, I, I, I, I, I, P, P, P, P, P));
-	// int nq_set_spec_dither(ctx, on, segment, warmup): opt-in speculative segment-parallel error diffusion (DESIGN.md 7.1)
+	// int nq_convert_batch_multi(contexts, n_contexts, kind, argb_in, n_images, width, height, n_max_colors, dither, rng_seeds,
+	//                            argb_out, palettes_out, palette_lens, has_alpha, queue_images): one batch over several GPUs
+	static final MethodHandle nq_convert_batch_multi = h("nq_convert_batch_multi",
+		FunctionDescriptor.of(I, P, I, I, P, I, I, I, I, I, P, P, P, P, P, I));
+	// int nq_device_count(void)
+	static final MethodHandle nq_device_count = h("nq_device_count", FunctionDescriptor.of(I));
+	// int nq_set_spec_dither(ctx, on, segment, warmup): speculative segment-parallel error diffusion, on by default (DESIGN.md 7.1)
 	static final MethodHandle nq_set_spec_dither = h("nq_set_spec_dither", FunctionDescriptor.of(I, P, I, I, I));
+
+	/**
+	 * One nq_ctx per (thread, GPU), shared by every quantizer object of that thread: a context owns the device workspace
+	 * (about 7.5 MB per image in flight plus the 256 MiB RGB->Lab table per device), so it is created once and reused,
+	 * not once per image. Contexts are not re-entrant, like the reference's quantizer objects (PnnQuantizer.java:18-33).
+	 */
+	static final ThreadLocal<java.util.HashMap<Integer, MemorySegment>> CONTEXTS = ThreadLocal.withInitial(java.util.HashMap::new);
+
+	static MemorySegment context(int device) {
+		return CONTEXTS.get().computeIfAbsent(device, d -> {
+			try {
+				MemorySegment c = (MemorySegment) nq_create.invokeExact((int) d);
+				if (c.equals(MemorySegment.NULL))
+					throw new IllegalStateException("nq_create: " + lastError());
+				return c;
+			} catch (RuntimeException e) {
+				throw e;
+			} catch (Throwable t) {
+				throw new IllegalStateException(t);
+			}
+		});
+	}
+
+	/** Destroys this thread's contexts (device memory is returned); they are re-created on demand. */
+	static void releaseContexts() {
+		for (MemorySegment c : CONTEXTS.get().values()) {
+			try {
+				nq_destroy.invokeExact(c);
+			} catch (Throwable ignored) {
+			}
+		}
+		CONTEXTS.get().clear();
+	}
 
 	static String lastError() {
 		try {

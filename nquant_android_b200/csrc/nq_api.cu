@@ -11,6 +11,8 @@
 #include <utility>
 #include <algorithm>
 #include <mutex>
+#include <thread>
+#include <atomic>
 #include <nvtx3/nvToolsExt.h>
 
 #include "../../include/nquant_b200.h"
@@ -179,6 +181,7 @@ struct nq_ctx {
   unsigned long long launches = 0;
   bool debug = false;
   int chunkImages = 0;                // images per chunk (0 = automatic)
+  int mergeRot = 1;                   // rotate the logical warp ids of the merge kernels by the CTA index (NQ_MERGE_ROT=0: off)
   // Gilbert orders by (w,h), least recently used first in orderLru
   std::map<std::pair<int, int>, uint32_t*> orders;
   std::vector<std::pair<int, int>> orderLru;
@@ -633,9 +636,9 @@ int enqueue_front(nq_ctx* c, Chunk& ch, const GroupArgs& A, const uint32_t* dIn,
     int* live = c->dLive + (size_t)ch.base * NQ_NBINS;
     int* pos = c->dPos + (size_t)ch.base * NQ_NBINS;
     if (kind == NQ_KIND_RGB) {
-      nq::k_merge_rgb<<<n, NQ_RGB_THREADS, (size_t)NQ_RGB_HEAP_SMEM * 8, st>>>(dI, dS, live, pos, c->debug ? 1 : 0); ++c->launches;
+      nq::k_merge_rgb<<<n, NQ_RGB_THREADS, (size_t)NQ_RGB_HEAP_SMEM * 8, st>>>(dI, dS, live, pos, c->debug ? 1 : 0, c->mergeRot); ++c->launches;
     } else {
-      nq::k_merge_lab<<<n, NQ_LAB_THREADS, (size_t)NQ_LAB_HEAP_SMEM * 8, st>>>(dI, dS, live, pos, c->debug ? 1 : 0); ++c->launches;
+      nq::k_merge_lab<<<n, NQ_LAB_THREADS, (size_t)NQ_LAB_HEAP_SMEM * 8, st>>>(dI, dS, live, pos, c->debug ? 1 : 0, c->mergeRot); ++c->launches;
     }
   } else { mark(2); mark(3); }
   mark(4);
@@ -933,6 +936,7 @@ nq_ctx* nq_create(int device) {
   if (const char* e = getenv("NQ_SPEC_DITHER")) c->specDither = atoi(e) != 0;
   if (const char* e = getenv("NQ_CHUNK")) c->chunkImages = atoi(e);
   if (const char* e = getenv("NQ_SPEC_SLOTS")) c->specSlotsMax = atoi(e);
+  if (const char* e = getenv("NQ_MERGE_ROT")) c->mergeRot = atoi(e) != 0;
   bool haveLut = false;
   {
     DevBuf dBn, dW;
@@ -999,6 +1003,44 @@ int nq_convert_batch(nq_ctx* c, int kind, const uint32_t* in, int n, int w, int 
   rc = convert_device(c, kind, c->dIn, n, w, h, nmax, dither, seeds, c->dOut, palettes, plens, hasAlpha, nullptr, 0, in, out);
   if (rc) return rc;
   CU(cudaStreamSynchronize(c->stream));
+  return NQ_OK;
+}
+
+// One worker thread per context pulls pieces of the batch from a shared counter (a dynamic queue: a GPU that finishes early
+// takes the next piece) and runs nq_convert_batch on its piece. No collective: the images are independent.
+int nq_convert_batch_multi(nq_ctx** ctxs, int nctx, int kind, const uint32_t* in, int n, int w, int h, int nmax, int dither,
+                           const uint64_t* seeds, uint32_t* out, uint32_t* palettes, int* plens, int* hasAlpha, int queueImages) {
+  if (!ctxs || nctx <= 0) return fail(NQ_ERR_ARG, "no contexts");
+  for (int g = 0; g < nctx; ++g) if (!ctxs[g]) return fail(NQ_ERR_ARG, "null context in the list");
+  int rc = check_args(ctxs[0], kind, in, n, w, h, nmax, out);
+  if (rc) return rc;
+  if (queueImages < 0) return fail(NQ_ERR_ARG, "queue_images must be >= 0");
+  const int piece = queueImages > 0 ? queueImages : (n + nctx - 1) / nctx;   // default: one piece per context
+  const size_t npix = (size_t)w * h;
+  std::atomic<int> next(0), firstRc(NQ_OK);
+  std::mutex errMutex;
+  std::string errMsg;
+  auto worker = [&](int g) {
+    for (;;) {
+      const int base = next.fetch_add(piece);
+      if (base >= n || firstRc.load() != NQ_OK) return;
+      const int m = std::min(piece, n - base);
+      const int r = nq_convert_batch(ctxs[g], kind, in + (size_t)base * npix, m, w, h, nmax, dither, seeds ? seeds + base : nullptr,
+                                     out + (size_t)base * npix, palettes ? palettes + (size_t)base * NQ_MAXK : nullptr,
+                                     plens ? plens + base : nullptr, hasAlpha ? hasAlpha + base : nullptr);
+      if (r != NQ_OK) {
+        std::lock_guard<std::mutex> lk(errMutex);
+        int expected = NQ_OK;
+        if (firstRc.compare_exchange_strong(expected, r)) errMsg = "context " + std::to_string(g) + ", images " + std::to_string(base) + ".." + std::to_string(base + m - 1) + ": " + nq_last_error();
+        return;
+      }
+    }
+  };
+  std::vector<std::thread> threads;
+  for (int g = 1; g < nctx; ++g) threads.emplace_back(worker, g);
+  worker(0);
+  for (auto& t : threads) t.join();
+  if (firstRc.load() != NQ_OK) return fail(firstRc.load(), errMsg);
   return NQ_OK;
 }
 

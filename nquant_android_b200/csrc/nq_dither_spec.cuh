@@ -30,7 +30,7 @@
 namespace nq {
 namespace spec {
 
-#define NQS_NOTES 48            // memo entries a segment may create through error-dependent lookups
+#define NQS_NOTES 256           // memo entries a segment may create through error-dependent lookups
 #define NQS_READS 64            // memo entries of the pre-lookups its error-dependent lookups may read
 #define NQS_NOPOS 0x7fffffff
 #define NQS_NONE 0xFFFFFFFFu    // absent top-2 key
@@ -40,15 +40,19 @@ namespace spec {
 #define NQS_F_DRAW 2u           // the lookup is predicted to call Random.nextInt (PL:467)
 #define NQS_F_RISK 8u           // error-dependent lookup predicted NOT to draw: the pixel is (nearly) a palette colour, any diffused
                                 // error makes it draw (PL:467) and every later draw index moves
-#define NQS_MAXRISK 4096        // more such pixels than this: the image is left to the serial kernel before any segment runs
+#define NQS_MAXRISK 0x3fffffff  // (no limit: a run from the exact state handles any number of them, stage 7)
 #define NQS_MAXREDO 256         // rounds with a draw misprediction per image before giving up
 #define NQS_F_NEAR 4u           // resolved through nearestColorIndex's memo (PL:470-472), key = memo_key(ccol)
+// What stage 6 saw an error-dependent lookup do. NQS_F_DRAW stays the prediction the CURRENT prefix sums, pre-lookups and
+// packed records were made with; the next re-resolve adopts the observation as the prediction (stage_adopt) before its prefix sum.
+#define NQS_F_SEEN 32u          // an outcome has been recorded since the last re-resolve
+#define NQS_F_ACT 16u           // ... and it was a draw
 
 // Constants of one image: what GilbertCurve's constructor and the quantizer hold while dithering.
 struct SpecConst {
   int plen, margin, thresold, DM, ditherMax, width, npix;
   int isNano, hasTrans, salReplaced;
-  int opaque;                            // every pixel and every palette entry has alpha 255: stage 6 drops the alpha channel
+  int opaque;                            // every pixel has alpha 255 and every palette entry 254 or 255: stage 6 keeps the alpha errors as bits
   int seg, warm, nseg;
   uint32_t transColor;
   double gWeight, PR, PG, PB, ratio;
@@ -75,7 +79,14 @@ struct SpecSeg {
   int noteKey[NQS_NOTES], notePos[NQS_NOTES], noteVal[NQS_NOTES];
   int nreads;                            // > NQS_READS: overflow (treated as "may have read any key")
   int readKey[NQS_READS];
+  int nslow;                             // error-dependent lookups among the owned pixels (last run)
+  int chain;                             // exact segment: how many segments (this one included) its thread runs in a row
+  int chained;                           // run by the thread of an earlier segment (its chain): the own thread stands aside
+  int dev;                               // sequential run: curve position of the chain's first draw against its prediction, or NQS_NOPOS
+  unsigned idx0;                         // sequential run: draws made in front of the segment (the index its first draw continues from)
 };
+#define NQS_MAXCHAIN 32
+#define NQS_MAXPATCH 24          // memo entries corrected per round and image
 // What stage 6 reads per pixel, packed by stage 5b and stored SEGMENT-INTERLEAVED: record of curve position n lives at
 // (n % seg) * nseg + n / seg, so the threads of a warp (consecutive segments, same offset inside the segment) read
 // consecutive 16-byte records.
@@ -105,6 +116,7 @@ struct SpecWork {
   const double* lut;                     // gammaToLinear table
   const signed char* bn;                 // TELL_BLUE_NOISE
   unsigned* chunkSum;                    // [npix / NQS_CHUNK + 1] draws predicted in front of each block of NQS_CHUNK pixels (stage 2)
+  int* patch;                            // [2 * NQS_MAXPATCH] (key, position) pairs of the pending patches, count in state[2]
   SpecSeg* segs;
   int* state;                            // [16]: firstOpen, anomaly, patch key + 1 (0 = none), patch position, failed validations,
                                          //      re-resolve position + 1 (0 = none), re-resolves so far, pixels flagged NQS_F_RISK, error-dependent lookups
@@ -426,13 +438,15 @@ NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firs
 // ---- gate after stage 3 (state[7] = pixels flagged NQS_F_RISK): too many likely mispredictions, do not start
 NQ_HD void stage_gate(const SpecConst& C, const SpecWork& W) {
   if (W.state[7] > NQS_MAXRISK) W.state[1] = 1;
-  if (W.state[8] > (C.npix >> 3)) W.state[1] = 1;           // state[8] = error-dependent lookups: past an eighth of the image little is left to speculate on
+  if (W.state[8] > (C.npix >> 4)) W.state[1] = 1;           // state[8] = error-dependent lookups: past 6 % of the image the sequential runs (and their notes) outgrow this scheme
 }
 // ---- stage 4: one memo key ------------------------------------------------------------------------------------
 // `after`: only entries first seen behind that curve position (-1 = all); the others are settled
 NQ_HD void stage_memo(const SpecConst& C, const SpecWork& W, int key, int after) {
   const int n = W.firstPos[key];
   if (n != NQS_NOPOS && n <= after) return;
+  // an entry that an error-dependent lookup of a validated segment created in front of the first pre-lookup stands (PL:402)
+  if (W.slowPos[key] != NQS_NOPOS && (n == NQS_NOPOS || W.slowPos[key] < n)) { W.memo[key] = W.slowVal[key]; return; }
   W.memo[key] = n == NQS_NOPOS ? (unsigned short)0xFFFF : (unsigned short)nearest_nomemo(C, W.ccol[n], W.lut);
 }
 // ---- stage 5 ------------------------------------------------------------------------------------------------------
@@ -451,21 +465,32 @@ NQ_HD void stage_pack(const SpecConst& C, const SpecWork& W, int n) {
   r.sal = (W.cflag[n] & NQS_F_PRE) ? 0.f : saliency_of(C, W, r.px);
   W.rec[rec_index(C, n)] = r;
 }
+// ---- first step of a re-resolve: what stage 6 saw the error-dependent lookups do becomes the prediction
+NQ_HD void stage_adopt(const SpecWork& W, int n) {
+  const unsigned f = W.cflag[n];
+  if (f & NQS_F_SEEN) W.cflag[n] = (unsigned char)((f & (15u & ~NQS_F_DRAW)) | ((f & NQS_F_ACT) ? NQS_F_DRAW : 0u));
+}
 // ---- re-resolve after a draw misprediction at curve position `from` = state[5] - 1 (stage_validate has corrected the
 //      pixel's flag): stage 2 again, then per memo key this reset, then stages 3-5 for the pixels behind `from`
+// (entries first seen at or behind curve position state[10] <= from + 1 are dropped: behind a draw that went against its
+//  prediction inside a sequential run the pre-lookups were decided again by that run, and what they created are its notes)
 NQ_HD void stage_rekey(const SpecWork& W, int key, int from) {
-  if (W.firstPos[key] != NQS_NOPOS && W.firstPos[key] > from) { W.firstPos[key] = NQS_NOPOS; W.memo[key] = 0xFFFF; }
+  const int rk = W.state[10] > 0 && W.state[10] <= from ? W.state[10] - 1 : from;
+  if (W.firstPos[key] != NQS_NOPOS && W.firstPos[key] > rk) { W.firstPos[key] = NQS_NOPOS; W.memo[key] = 0xFFFF; }
 }
 // ---- patch: an error-dependent lookup at curve position state[3] created memo entry state[2] - 1 BEFORE the first
 //      pre-lookup that needs it, with another value than stage 4 gave it (PL:402: the first colour of a bucket fixes
 //      it). stage_validate has already corrected memo/firstPos; every later pre-lookup of that key is redirected and
 //      its segment re-runs. One call per pixel.
 NQ_HD void stage_patch(const SpecConst& C, const SpecWork& W, int n) {
-  const int key = W.state[2] - 1, pos = W.state[3];
-  if (key < 0 || n <= pos) return;
-  if ((W.cflag[n] & NQS_F_NEAR) && memo_key(C, W.ccol[n]) == key) {
-    W.cq[n] = W.memo[key];
-    W.segs[n / C.seg].dirty = 1;                           // benign race on the device: every writer stores 1
+  const int cnt = W.state[2];
+  if (cnt <= 0 || n <= W.state[3] || !(W.cflag[n] & NQS_F_NEAR)) return;
+  const int mine = memo_key(C, W.ccol[n]);
+  for (int i = 0; i < cnt; ++i) {
+    if (W.patch[2 * i] == mine && n > W.patch[2 * i + 1]) {
+      W.cq[n] = W.memo[mine];
+      W.segs[n / C.seg].dirty = 1;                           // benign race on the device: every writer stores 1
+    }
   }
 }
 
@@ -484,31 +509,20 @@ NQ_HD unsigned long long lcg_state_at(const SpecConst& C, LcgCursor& L, unsigned
   L.idx = idx; L.valid = 1;
   return L.state;
 }
-// `drawIdx` = draws predicted in front of this pixel (cdraw[n])
-NQ_HD int slow_lookup(const SpecConst& C, const ScanTabs& T, const SpecWork& W, SpecSeg& S, LcgCursor& L, int n, unsigned drawIdx, uint32_t c, bool owned,
-                      int* draws, bool* drew) {
-  *drew = false;
-  bool needNear = true;
-  int qi = 0;
-  if (c_alpha(c) > 0xF) {
-    unsigned k0, k1;
-    top2(C, T, W.cells, c, &k0, &k1);
-    int r = 0;
-    if ((k0 >> 8) != 0u) {
-      bool rej;
-      r = next_int_from(lcg_state_at(C, L, drawIdx + 1u), &rej);
-      if (rej) S.nnotes = NQS_NOTES + 1;                   // never seen; handled as an overflow = not validated
-      ++*draws;
-      *drew = true;
-    }
-    qi = closest_pick(C, c, k0, k1, r, &needNear);
-  }
-  if (!needNear) return qi;
+// nearestColorIndex through the first-seen memo for a lookup made inside stage 6 (PL:332-335, 402). `trust` = pre-lookup
+// entries (firstPos / memo) first seen before that curve position are the sequential run's too. Entries created by
+// stage-6 lookups are notes: of this segment, of the earlier segments of the same chain (chainFirst .. S - 1), and of
+// validated segments (slowPos / slowVal).
+NQ_HD int near_lookup(const SpecConst& C, const SpecWork& W, SpecSeg& S, int chainFirst, int n, int trust, uint32_t c, bool owned) {
   if (!C.isNano) return nearest_nomemo(C, c, W.lut);
   const int key = color_index(c, false, C.hasTrans != 0);
-  if (owned) for (int i = 0; i < S.nnotes && i < NQS_NOTES; ++i) if (S.noteKey[i] == key) return S.noteVal[i];
+  if (owned) {
+    for (int i = 0; i < S.nnotes && i < NQS_NOTES; ++i) if (S.noteKey[i] == key) return S.noteVal[i];
+    for (const SpecSeg* P = &S - 1; P >= W.segs + chainFirst; --P)
+      for (int i = 0; i < P->nnotes && i < NQS_NOTES; ++i) if (P->noteKey[i] == key) return P->noteVal[i];
+  }
   if (W.slowPos[key] < n) return W.slowVal[key];           // created by an error-dependent lookup of a validated segment
-  if (W.firstPos[key] < n || (!owned && W.firstPos[key] != NQS_NOPOS)) {
+  if (W.firstPos[key] < trust || (!owned && W.firstPos[key] != NQS_NOPOS)) {
     if (owned) {                                           // remembered: a later patch of this key invalidates the segment
       if (S.nreads < NQS_READS) S.readKey[S.nreads] = key;
       ++S.nreads;
@@ -522,13 +536,33 @@ NQ_HD int slow_lookup(const SpecConst& C, const ScanTabs& T, const SpecWork& W, 
   }
   return v;
 }
+// closestColorIndex (PL:406-474) for colour c whose top-2 keys are known, with the draw of index drawIdx + 1
+NQ_HD int pick_lookup(const SpecConst& C, const SpecWork& W, SpecSeg& S, LcgCursor& L, int chainFirst, int n, int trust, unsigned drawIdx,
+                      uint32_t c, unsigned k0, unsigned k1, bool owned, bool* drew) {
+  *drew = false;
+  bool needNear = true;
+  int qi = 0;
+  if (c_alpha(c) > 0xF) {
+    int r = 0;
+    if ((k0 >> 8) != 0u) {
+      bool rej;
+      r = next_int_from(lcg_state_at(C, L, drawIdx + 1u), &rej);
+      if (rej) S.nnotes = NQS_NOTES + 1;                   // never seen; handled as an overflow = not validated
+      *drew = true;
+    }
+    qi = closest_pick(C, c, k0, k1, r, &needNear);
+  }
+  if (!needNear) return qi;
+  return near_lookup(C, W, S, chainFirst, n, trust, c, owned);
+}
 
 // ---- stage 6 proper -----------------------------------------------------------------------------------------------------
 // DM is a template constant (DITHER_MAX is 9, 16 or 25, GC:96): the queue lives in registers as a window of DM + NQS_U boxes
 // that slides one box per pixel and is moved back every NQS_U pixels, the weights are compile-time-indexed operands (constant
-// bank on the device), and for images whose pixels all have alpha 255 (OPAQUE) the alpha channel is dropped: its error is
-// always 0 (a_pix = (int) min(255, 255 + 0) and every palette alpha is 255) and all its partial sums are exactly 255.0f, so
-// it only contributes "maxErr >= 255" (GC:192-201), which is how maxErr is seeded below.
+// bank on the device). For images whose pixels all have alpha 255 and whose palette alphas are 254 or 255 (NCH == 3) the
+// alpha channel shrinks to one bit per box: the alpha sum 255 + (errors >= 0) never drops below 255, so a_pix is always 255
+// and the error of a box is 255 - palette alpha = 0 or 1 (a palette alpha of 254 is the reference's float mean of 255s,
+// PL:301-305); the sum itself still feeds maxErr (GC:192-201).
 #define NQS_U 4                 // pixels per group: one slide of the register window per NQS_U pixels
 
 #if defined(__CUDACC__)
@@ -565,37 +599,63 @@ struct RunEnv {                 // what the pixel step needs besides the queue
   float fDitherMax, fDitherMax1, divisor;
   bool illusion0;
   int draws;                    // draws made by the pixels of the current span
+  int nslow;                    // error-dependent lookups of the current span
+  bool seq;                     // sequential truth: the run started from an exact state and addresses java.util.Random by the
+                                // draws it has really made (actIdx), re-deciding the pre-lookups behind a deviation
+  int chainFirst;               // first segment of the chain this thread runs
+  int devPos;                   // seq: curve position of the first draw that went against its prediction (NQS_NOPOS: none yet)
+  unsigned actIdx;              // seq: draws really made in front of the current pixel
   unsigned drawIdx;             // draws PREDICTED in front of the current pixel = cdraw[n], kept up from the records' flags
+  unsigned amask;               // three-channel variant: alpha error (0 or 1) of queue box k in bit k, oldest box first
   LcgCursor lcg;
 };
 
 // the quantization of an error-dependent lookup (GC:211-229 with the diffused colour), kept out of the hot loop
-NQ_HD int run_slow_pixel_body(RunEnv& X, int n, uint32_t px, uint32_t xy, float sal, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned) {
+NQ_HD int run_slow_pixel_body(RunEnv& X, int n, uint32_t px, uint32_t xy, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned,
+                              int* drawn) {
   const SpecConst& C = *X.C;
   const SpecWork& W = *X.W;
+  const float sal = W.rec[rec_index(C, n)].sal;            // (kept out of the registers of the hot loop)
   const int x = (int)(xy & 0xFFFFu), y = (int)(xy >> 16);
   const uint32_t c2 = c_argb(a_pix, r_pix, g_pix, b_pix);
   uint32_t c = c2;
   if (!(C.plen >= 256 && sal > .99f)) c = slow_colour(C, W, x, y, px, sal, color_y(px, W.lut), c2);
+  unsigned k0 = NQS_NONE, k1 = NQS_NONE;
+  if (c_alpha(c) > 0xF) top2(C, X.T, W.cells, c, &k0, &k1);
   bool drew;
-  const int qi = slow_lookup(C, X.T, W, *X.S, X.lcg, n, X.drawIdx, c, owned, &X.draws, &drew);
-  if (owned && drew != ((flag & NQS_F_DRAW) != 0)) {
-    // A draw against the prediction (PL:467): every later draw index of the image is off by one. The prediction is corrected
-    // here, for every such pixel of the segment (the first one is what stage 7 reports); what this thread computes behind
-    // it is discarded with the segment.
-    if (X.S->mispos < 0) X.S->mispos = n;
-    W.cflag[n] = (unsigned char)(flag ^ NQS_F_DRAW);
+  const int trust = X.seq && X.devPos < n ? X.devPos : n;
+  const int qi = pick_lookup(C, W, *X.S, X.lcg, X.chainFirst, n, trust, X.seq ? X.actIdx : X.drawIdx, c, k0, k1, owned, &drew);
+  *drawn = drew ? 1 : 0;
+  if (owned) {
+    // What this lookup did is the prediction from now on (the flag in the packed record is the one this run was resolved with).
+    W.cflag[n] = (unsigned char)((flag & 15u) | NQS_F_SEEN | (drew ? NQS_F_ACT : 0u));
+    if (drew != ((flag & NQS_F_DRAW) != 0)) {
+      // A draw against the prediction (PL:467): every later draw index of the image is off by one. A speculative segment
+      // reports the first such pixel and is run again, from its predecessor's exact state, as sequential truth (stage 7);
+      // a sequential run just goes on with the index it has really reached.
+      if (!X.seq) { if (X.S->mispos < 0) X.S->mispos = n; }
+      else if (X.devPos == NQS_NOPOS) X.devPos = n;
+    }
   }
   return qi;
 }
+// sequential truth behind a deviation: the pre-lookup of pixel n decided again with the draw it really gets
+NQ_HD int run_seq_pre_body(RunEnv& X, int n, bool owned) {
+  const SpecWork& W = *X.W;
+  bool drew;
+  const int trust = X.devPos < n ? X.devPos : n;
+  return pick_lookup(*X.C, W, *X.S, X.lcg, X.chainFirst, n, trust, X.actIdx, W.ccol[n], W.ck0[n], W.ck1[n], owned, &drew);
+}
 #if defined(__CUDA_ARCH__)
-__device__ NQS_NOINLINE int run_slow_pixel(RunEnv& X, int n, uint32_t px, uint32_t xy, float sal, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned) {
-  return run_slow_pixel_body(X, n, px, xy, sal, flag, a_pix, r_pix, g_pix, b_pix, owned);
+__device__ NQS_NOINLINE int run_slow_pixel(RunEnv& X, int n, uint32_t px, uint32_t xy, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned, int* drawn) {
+  return run_slow_pixel_body(X, n, px, xy, flag, a_pix, r_pix, g_pix, b_pix, owned, drawn);
 }
+__device__ NQS_NOINLINE int run_seq_pre(RunEnv& X, int n, bool owned) { return run_seq_pre_body(X, n, owned); }
 #else
-inline int run_slow_pixel(RunEnv& X, int n, uint32_t px, uint32_t xy, float sal, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned) {
-  return run_slow_pixel_body(X, n, px, xy, sal, flag, a_pix, r_pix, g_pix, b_pix, owned);
+inline int run_slow_pixel(RunEnv& X, int n, uint32_t px, uint32_t xy, unsigned flag, int a_pix, int r_pix, int g_pix, int b_pix, bool owned, int* drawn) {
+  return run_slow_pixel_body(X, n, px, xy, flag, a_pix, r_pix, g_pix, b_pix, owned, drawn);
 }
+inline int run_seq_pre(RunEnv& X, int n, bool owned) { return run_seq_pre_body(X, n, owned); }
 #endif
 
 // One pixel at window offset u: the queue is e[u .. u + DM - 1] (oldest first), the new box goes to e[u + DM].
@@ -605,7 +665,7 @@ NQ_HD void run_pixel(RunEnv& X, float (&e)[DM + NQS_U][NCH], const SpecRec& rc, 
   const uint32_t px = rc.px;
   // ---- error.p = pixel + sum(queue[i].p * weights[i]), oldest box first (GC:190-204)
   float a0 = (float)c_red(px), a1 = (float)c_green(px), a2 = (float)c_blue(px), a3 = (float)c_alpha(px);
-  float maxErr = NCH == 3 ? 255.f : (float)(DM - 1);
+  float maxErr = (float)(DM - 1);
 #pragma unroll
   for (int k = 0; k < DM; ++k) {
     const float wk = NQS_W(C, DMI, k);
@@ -614,18 +674,28 @@ NQ_HD void run_pixel(RunEnv& X, float (&e)[DM + NQS_U][NCH], const SpecRec& rc, 
     a2 = a2 + e[u + k][2] * wk;
     maxErr = max3f(maxErr, a0, a1);
     if (NCH == 4) { a3 = a3 + e[u + k][NCH - 1] * wk; maxErr = max3f(maxErr, a2, a3); }
-    else maxErr = fmaxf(maxErr, a2);
+    else {
+      // alpha error of box k is 0 or 1 (bit k of amask): 1.0f * w == w and a3 + 0.0f == a3, so this is the reference's sum
+      a3 = a3 + (((X.amask >> k) & 1u) ? wk : 0.f);
+      maxErr = fmaxf(maxErr, a2);
+    }
   }
+  if (NCH == 3) maxErr = fmaxf(maxErr, a3);                 // alpha partial sums never decrease: their maximum is the last one
   const int r_pix = (int)fminf(255.f, fmaxf(a0, 0.f)), g_pix = (int)fminf(255.f, fmaxf(a1, 0.f));
   const int b_pix = (int)fminf(255.f, fmaxf(a2, 0.f)), a_pix = NCH == 4 ? (int)fminf(255.f, fmaxf(a3, 0.f)) : 255;
   const unsigned flag = (rc.qf >> 16) & 0xFFu;
   // ---- quantize (GC:211-229)
-  int qi;
+  int qi, drawn;
   if (flag & NQS_F_PRE) {
-    qi = (int)(rc.qf & 0xFFFFu);
-    X.draws += (flag & NQS_F_DRAW) ? 1 : 0;
-  } else
-    qi = run_slow_pixel(X, n, px, rc.xy, rc.sal, flag, a_pix, r_pix, g_pix, b_pix, OWNED);
+    drawn = (flag & NQS_F_DRAW) ? 1 : 0;                    // whether a pre-lookup draws depends on its colour alone (PL:467)
+    if (X.seq && X.actIdx != X.drawIdx) qi = run_seq_pre(X, n, OWNED);
+    else qi = (int)(rc.qf & 0xFFFFu);
+  } else {
+    qi = run_slow_pixel(X, n, px, rc.xy, flag, a_pix, r_pix, g_pix, b_pix, OWNED, &drawn);
+    ++X.nslow;
+  }
+  X.draws += drawn;
+  X.actIdx += (unsigned)drawn;
   X.drawIdx += (flag & NQS_F_DRAW) ? 1u : 0u;               // the prefix every pre-lookup behind this pixel was resolved with
   const uint32_t pc = X.T.pal[qi];
   if (OWNED) X.W->out[(rc.xy & 0xFFFFu) + (rc.xy >> 16) * (uint32_t)C.width] = pc;   // dither == true: the palette colour (GC:278-279)
@@ -650,6 +720,7 @@ NQ_HD void run_pixel(RunEnv& X, float (&e)[DM + NQS_U][NCH], const SpecRec& rc, 
   // ---- errorq.poll(); errorq.add(error) (GC:231, 276): the window slides
   e[u + DM][0] = e0; e[u + DM][1] = e1; e[u + DM][2] = e2;
   if (NCH == 4) e[u + DM][NCH - 1] = (float)(a_pix - c_alpha(pc));
+  else X.amask = (X.amask >> 1) | ((unsigned)(255 - c_alpha(pc)) << (DM - 1));   // a_pix is 255, palette alphas are 254 or 255
 }
 template <int DM, int NCH, int BY>
 NQ_HD void run_slide(float (&e)[DM + NQS_U][NCH]) {
@@ -708,42 +779,64 @@ static_assert(NQS_U == 4, "run_span spells out the NQS_U pixel steps");
 
 template <int DM, int DMI, int NCH>
 NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s, const ScanTabs& T, const float* tanhTab) {
-  SpecSeg& S = W.segs[s];
-  if (S.done || !S.dirty) return;
-  const int p0 = s * C.seg, p1 = (p0 + C.seg < C.npix) ? p0 + C.seg : C.npix;
+  SpecSeg& S0 = W.segs[s];
+  if (S0.done || !S0.dirty || S0.chained) return;
+  const int p0 = s * C.seg;
   float e[DM + NQS_U][NCH];                                // the queue window, e[0] = oldest box
+  unsigned amask0 = 0u;
   int from = p0;
-  if (S.exact && p0 > 0) {
+  const bool seq = S0.exact != 0;                          // started from the exact state: this run IS the sequential algorithm
+  if (S0.exact && p0 > 0) {
 #pragma unroll
     for (int k = 0; k < DM; ++k)
 #pragma unroll
-      for (int j = 0; j < NCH; ++j) e[k][j] = S.qstart[k][j];
+      for (int j = 0; j < NCH; ++j) e[k][j] = S0.qstart[k][j];
+    if (NCH == 3) for (int k = 0; k < DM; ++k) amask0 |= (S0.qstart[k][3] != 0.f ? 1u : 0u) << k;
   } else {
 #pragma unroll
     for (int k = 0; k < DM; ++k)
 #pragma unroll
       for (int j = 0; j < NCH; ++j) e[k][j] = 0.f;
-    if (!S.exact) { const long long w = (long long)C.warm * (long long)S.warmMul; from = (long long)p0 - w > 0 ? (int)((long long)p0 - w) : 0; }
+    if (!S0.exact) { const long long w = (long long)C.warm * (long long)S0.warmMul; from = (long long)p0 - w > 0 ? (int)((long long)p0 - w) : 0; }
   }
   RunEnv X;
-  X.C = &C; X.W = &W; X.S = &S; X.T = T; X.tanhTab = tanhTab;
-  X.lcg.valid = 0; X.lcg.idx = 0; X.lcg.state = 0; X.drawIdx = 0;
+  X.C = &C; X.W = &W; X.S = &S0; X.T = T; X.tanhTab = tanhTab;
+  X.lcg.valid = 0; X.lcg.idx = 0; X.lcg.state = 0; X.drawIdx = 0; X.amask = amask0;
+  X.seq = seq; X.chainFirst = s; X.devPos = NQS_NOPOS; X.actIdx = 0; X.nslow = 0;
   X.fDitherMax = (float)C.ditherMax; X.fDitherMax1 = (float)(C.ditherMax - 1);
   X.divisor = (float)(1 + nqm::sqrt_((double)C.ditherMax));
   X.illusion0 = W.bn[0] > C.thresold;                      // yDiff == 1 in this mode: bn[(int)4096.0 & 4095] (GC:251-252)
   X.draws = 0;
-  S.nnotes = 0;
-  S.nreads = 0;
-  S.mispos = -1;
+  S0.nnotes = 0;
+  S0.nreads = 0;
+  S0.mispos = -1;
   if (from < p0) run_span<DM, DMI, NCH, false>(X, e, from, p0);    // warm-up: nothing is written, notes are not kept
+  // a chain: the thread of an exact segment goes on through the following segments that hold error-dependent lookups
+  // (stage 7 decides how many), handing each the exact state it needs
+  int nchain = seq && S0.chain > 1 ? S0.chain : 1;
+  if (s + nchain > C.nseg) nchain = C.nseg - s;
+  X.actIdx = W.cdraw[p0];
+  for (int c = 0; c < nchain; ++c) {
+    SpecSeg& S = W.segs[s + c];
+    const int q0 = (s + c) * C.seg, q1 = (q0 + C.seg < C.npix) ? q0 + C.seg : C.npix;
+    X.S = &S;
+    if (c > 0) {
+      S.exact = 1; S.nnotes = 0; S.nreads = 0; S.mispos = -1;
 #pragma unroll
-  for (int k = 0; k < DM; ++k) { S.qwarm[k][0] = e[k][0]; S.qwarm[k][1] = e[k][1]; S.qwarm[k][2] = e[k][2]; S.qwarm[k][3] = NCH == 4 ? e[k][NCH - 1] : 0.f; }
-  X.draws = 0;
-  run_span<DM, DMI, NCH, true>(X, e, p0, p1);
+      for (int k = 0; k < DM; ++k) { S.qstart[k][0] = e[k][0]; S.qstart[k][1] = e[k][1]; S.qstart[k][2] = e[k][2]; S.qstart[k][3] = NCH == 4 ? e[k][NCH - 1] : (float)((X.amask >> k) & 1u); }
+    }
 #pragma unroll
-  for (int k = 0; k < DM; ++k) { S.qout[k][0] = e[k][0]; S.qout[k][1] = e[k][1]; S.qout[k][2] = e[k][2]; S.qout[k][3] = NCH == 4 ? e[k][NCH - 1] : 0.f; }
-  S.draws = X.draws;
-  S.dirty = 0;
+    for (int k = 0; k < DM; ++k) { S.qwarm[k][0] = e[k][0]; S.qwarm[k][1] = e[k][1]; S.qwarm[k][2] = e[k][2]; S.qwarm[k][3] = NCH == 4 ? e[k][NCH - 1] : (float)((X.amask >> k) & 1u); }
+    X.draws = 0; X.nslow = 0;
+    S.idx0 = X.actIdx;
+    run_span<DM, DMI, NCH, true>(X, e, q0, q1);
+#pragma unroll
+    for (int k = 0; k < DM; ++k) { S.qout[k][0] = e[k][0]; S.qout[k][1] = e[k][1]; S.qout[k][2] = e[k][2]; S.qout[k][3] = NCH == 4 ? e[k][NCH - 1] : (float)((X.amask >> k) & 1u); }
+    S.draws = X.draws;
+    S.nslow = X.nslow;
+    S.dev = seq ? X.devPos : NQS_NOPOS;
+    S.dirty = 0;
+  }
 }
 NQ_HD void stage_run(const SpecConst& C, const SpecWork& W, int s, const float* tanhTab) {
   const ScanTabs T = scan_tabs(C);
@@ -777,70 +870,101 @@ NQ_HD void stage_compare(const SpecConst& C, const SpecWork& W, int s) {
 NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
   int s = W.state[0];
   if (W.state[1]) return 0;
+  int delta = 0;                            // draws really made minus draws predicted, over the exact segments accepted in this call
+  int minDev = NQS_NOPOS;                   // first draw against its prediction inside those segments
   for (; s < C.nseg; ++s) {
     SpecSeg& S = W.segs[s];
     const int p0 = s * C.seg, p1 = (p0 + C.seg < C.npix) ? p0 + C.seg : C.npix;
-    bool ok = S.nnotes <= NQS_NOTES;
+    if ((delta != 0 || minDev != NQS_NOPOS) && !S.exact) break;   // behind a shift of the draw indices only sequential truth counts: re-resolve first
+    bool ok = S.nnotes <= NQS_NOTES && !S.dirty;            // (dirty: a patch touched it after its last run)
     if (ok && s > 0) ok = S.qok != 0;
-    if (ok && S.mispos >= 0) {
-      // An error-dependent lookup drew (or did not draw) against its prediction (PL:467: closest[2] == 0 for the diffused
-      // colour but not for the pixel, or the reverse). Up to that pixel the segment is exact; behind it every draw index
-      // moves by one. Correct the pixel's flag, ask for a re-resolve of everything behind it (stage_rekey and stages
-      // 2-5), and run this segment and all later ones again.
-      // (stage 6 has already corrected the flag of that pixel and of every later misprediction it saw)
-      W.state[5] = S.mispos + 1;
-      for (int t = s; t < C.nseg; ++t) W.segs[t].dirty = 1;
-      if (++W.state[6] > NQS_MAXREDO) { W.state[1] = 1; return 0; }
-      break;
-    }
+    // An error-dependent lookup of a SPECULATIVE segment drew (or did not draw) against its prediction (PL:467: closest[2]
+    // == 0 for the diffused colour but not for the pixel, or the reverse): behind that pixel the segment used wrong
+    // draw indices. It is run again as sequential truth (below).
+    if (ok && !S.exact && S.mispos >= 0) ok = false;
+    // a sequential run is the truth only if it also started from the right draw index (a chain hands it on; the head of an
+    // earlier chain may have been run again since)
+    if (ok && S.exact && S.idx0 != W.cdraw[p0] + (unsigned)delta) ok = false;
+    int predicted = 0;
     if (ok) {
       // the draws of the owned pixels against the prediction every later pre-lookup was computed with
-      const int predicted = (int)(W.cdraw[p1] - W.cdraw[p0]);   // cdraw has npix + 1 entries
-      if (S.draws != predicted) { W.state[1] = 1; return 0; }      // cannot happen without a mispos; kept as a guard
+      predicted = (int)(W.cdraw[p1] - W.cdraw[p0]);   // cdraw has npix + 1 entries
+      if (S.draws != predicted && !S.exact) { W.state[1] = 1; return 0; }      // cannot happen without a mispos; kept as a guard
       for (int i = 0; i < S.nnotes; ++i) {
         const int key = S.noteKey[i], pos = S.notePos[i], val = S.noteVal[i];
         if (W.slowPos[key] < pos && W.slowVal[key] != val) { ok = false; break; }
       }
     }
+#if defined(NQS_TRACE)
+    if (!ok) fprintf(stderr, "  validate: segment %d fails (exact %d chained %d dirty %d qok %d mispos %d notes %d draws %d predicted %d)\n", s, S.exact, S.chained, S.dirty, S.qok, S.mispos, S.nnotes, S.draws, (int)(W.cdraw[p1] - W.cdraw[p0]));
+#endif
     if (!ok) {
       if (S.exact && S.nnotes > NQS_NOTES) { W.state[1] = 1; return 0; }     // even the exact run overflows its notes
-      // every failure costs a round in which one segment runs alone: past a quarter of the segments the serial kernel is cheaper
+      // every failure costs a round in which one thread runs alone: past a quarter of the segments the serial kernel is cheaper
       if (++W.state[4] > (C.nseg >> 2) + 4) { W.state[1] = 1; return 0; }
-      S.exact = 1; S.dirty = 1;
+      S.exact = 1; S.dirty = 1; S.chained = 0;
       if (s > 0) for (int k = 0; k < C.DM; ++k) for (int j = 0; j < 4; ++j) S.qstart[k][j] = W.segs[s - 1].qout[k][j];
+      // its thread goes on through the following segments that hold error-dependent lookups: their draws are as uncertain
+      int n = 1;
+      while (n < NQS_MAXCHAIN && s + n < C.nseg && W.segs[s + n].nslow > 0 && !W.segs[s + n].done) {
+        SpecSeg& N = W.segs[s + n];
+        N.chained = 1; N.dirty = 1; N.exact = 1;
+        ++n;
+      }
+      S.chain = n;
       break;
     }
     {
-      // an entry first created by an error-dependent lookup which the pre-lookups after it resolved differently:
-      // correct the memo, ask for stage_patch, and re-run this segment (its own later pixels read the entry too)
-      bool patched = false;
-      for (int i = 0; i < S.nnotes; ++i) {
+      // entries first created by an error-dependent lookup which the pre-lookups after it resolved differently: correct the
+      // memo, ask for stage_patch (all of the segment's at once), and run the segment -- with its chain -- again (its own later
+      // pixels read the entries too). Behind a draw that went against its prediction a sequential run decides the
+      // pre-lookups itself and the re-resolve that follows drops what they had created (stage_rekey): nothing to patch there.
+      int npatch = 0, first = NQS_NOPOS;
+      for (int i = 0; i < S.nnotes && npatch < NQS_MAXPATCH; ++i) {
         const int key = S.noteKey[i], pos = S.notePos[i], val = S.noteVal[i];
+        if (S.exact && S.dev != NQS_NOPOS && pos > S.dev) continue;
         if (W.slowPos[key] != NQS_NOPOS && W.slowPos[key] < pos) continue;      // agrees with an earlier entry (checked above)
         if (W.firstPos[key] != NQS_NOPOS && W.firstPos[key] > pos && W.memo[key] != (unsigned short)val) {
           W.memo[key] = (unsigned short)val; W.firstPos[key] = pos;
-          W.state[2] = key + 1; W.state[3] = pos;
-          S.dirty = 1;
+          W.patch[2 * npatch] = key; W.patch[2 * npatch + 1] = pos;
+          ++npatch;
+          if (pos < first) first = pos;
           for (int t = s + 1; t < C.nseg; ++t) {           // later segments whose error-dependent lookups read the old entry
             SpecSeg& T = W.segs[t];
             bool hit = T.nreads > NQS_READS;
             for (int r = 0; !hit && r < T.nreads; ++r) hit = T.readKey[r] == key;
-            if (hit) T.dirty = 1;
+            if (hit) { T.dirty = 1; if (!T.exact) { T.chained = 0; T.chain = 1; } }
           }
-          patched = true;
-          break;
         }
       }
-      if (patched) break;
+      if (npatch) {
+        W.state[2] = npatch; W.state[3] = first;
+        S.dirty = 1;
+        if (S.exact && S.chain > 1) for (int t = 1; t < S.chain && s + t < C.nseg; ++t) { SpecSeg& N = W.segs[s + t]; if (!N.done) { N.chained = 1; N.dirty = 1; N.exact = 1; } }
+        break;
+      }
     }
     for (int i = 0; i < S.nnotes; ++i) {
       const int key = S.noteKey[i], pos = S.notePos[i], val = S.noteVal[i];
       if (W.slowPos[key] == NQS_NOPOS) { W.slowPos[key] = pos; W.slowVal[key] = (unsigned short)val; }
     }
     S.done = 1;
+    S.chained = 0;
+    delta += S.draws - predicted;
+    if (S.exact && S.dev != NQS_NOPOS && S.dev < minDev) minDev = S.dev;
+  }
+  if (delta != 0 || minDev != NQS_NOPOS) {
+    // The exact segments accepted above made another number of draws than predicted (stage 6 has corrected the flags of
+    // their pixels): every draw index behind them moves. Ask for the prefix sum and stages 3-5 again behind position
+    // s * seg - 1 (k_spec_redo_*) and run everything behind again.
+    const int from = (s * C.seg < C.npix ? s * C.seg : C.npix) - 1;
+    W.state[5] = from + 1;
+    W.state[10] = minDev != NQS_NOPOS ? minDev + 1 : 0;
+    for (int t = s; t < C.nseg; ++t) { SpecSeg& T = W.segs[t]; T.dirty = 1; T.chained = 0; T.chain = 1; if (T.exact && t > s) T.exact = 0; }
+    if (++W.state[6] > NQS_MAXREDO) { W.state[1] = 1; return 0; }
   }
   W.state[0] = s;
-  return C.nseg - s;
+  return C.nseg - s + (W.state[5] ? 1 : 0);   // a pending re-resolve keeps the image open even when every segment is done
 }
 
 #if defined(__CUDACC__) || defined(NQS_EMULATE)   // NQS_EMULATE: tests/spec_host_harness.cpp runs the kernels thread by thread on the CPU
@@ -888,8 +1012,8 @@ __global__ void k_spec_setup(NqImage* imgs, const NqSlot* slots, SpecImage* sp, 
   JRandom r; r.set_seed(I.seed);
   C.seed0 = r.seed;
   for (int k = 0; k < NQ_MAXQ; ++k) C.w[k] = k < C.DM ? I.gWeights[k] : 0.f;
-  int opaque = I.nonOpaque == 0;
-  for (int k = 0; k < plen; ++k) { C.pal[k] = I.palette[k]; opaque &= (I.palette[k] >> 24) == 0xFFu; }
+  int opaque = I.nonOpaque == 0;                  // ... and palette alphas of 254 or 255 (a mean of 255s can round to 254.99998, PL:301)
+  for (int k = 0; k < plen; ++k) { C.pal[k] = I.palette[k]; opaque &= (I.palette[k] >> 24) >= 0xFEu; }
   C.opaque = opaque;
   // which instantiation of stage 6 runs this image: bits 8.. of the verdict (spec_drive groups the images by it)
   eligOut[i] |= (((C.DM == 25 ? 2 : (C.DM == 16 ? 1 : 0)) << 1) | (opaque ? 0 : 1)) << 8;
@@ -906,7 +1030,7 @@ __global__ void k_spec_admit(SpecImage* sp, const int* list, const int* slotOf, 
   SpecWork& W = P.W;
   W.cpx = T.cpx; W.ccol = T.ccol; W.ck0 = T.ck0; W.ck1 = T.ck1; W.cq = T.cq; W.cflag = T.cflag; W.rec = T.rec; W.cdraw = T.cdraw;
   W.firstPos = T.firstPos; W.memo = T.memo; W.slowPos = T.slowPos; W.slowVal = T.slowVal; W.segs = T.segs; W.state = T.state;
-  W.chunkSum = T.chunkSum;
+  W.chunkSum = T.chunkSum; W.patch = T.patch;
 }
 // memo tables, segment records, state (grid: x strides, y = list entry)
 __global__ void __launch_bounds__(256) k_spec_init(SpecImage* sp, const int* list) {
@@ -914,7 +1038,7 @@ __global__ void __launch_bounds__(256) k_spec_init(SpecImage* sp, const int* lis
   if (!P.eligible) return;
   const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
   for (int k = t; k < 65536; k += nt) { P.W.firstPos[k] = NQS_NOPOS; P.W.slowPos[k] = NQS_NOPOS; P.W.memo[k] = 0xFFFF; P.W.slowVal[k] = 0; }
-  for (int s = t; s < P.C.nseg; s += nt) { SpecSeg& S = P.W.segs[s]; S.exact = s == 0; S.dirty = 1; S.done = 0; S.draws = 0; S.nnotes = 0; S.nreads = 0; S.mispos = -1; S.warmMul = 1; }
+  for (int s = t; s < P.C.nseg; s += nt) { SpecSeg& S = P.W.segs[s]; S.exact = s == 0; S.dirty = 1; S.done = 0; S.draws = 0; S.nnotes = 0; S.nreads = 0; S.mispos = -1; S.warmMul = 1; S.nslow = 0; S.chain = 1; S.chained = 0; }
   if (t < 16) P.W.state[t] = 0;
 }
 __global__ void __launch_bounds__(256) k_spec_pre(SpecImage* sp, const int* list) {
@@ -1032,7 +1156,13 @@ __global__ void __launch_bounds__(256) k_spec_resolve(SpecImage* sp, const int* 
   if (risk) atomicAdd(&P.W.state[7], risk);
   if (slow) atomicAdd(&P.W.state[8], slow);
 }
-// re-resolve behind a draw misprediction (images with state[5] != 0): a = reset keys, b = stages 3, c = stage 4, d = stage 5
+// re-resolve behind a draw misprediction (images with state[5] != 0): adopt = observed draws become the prediction (before the
+// prefix sum), a = reset keys, b = stages 3, c = stage 4, d = stage 5
+__global__ void __launch_bounds__(256) k_spec_adopt(SpecImage* sp, const int* list) {
+  const SpecImage& P = sp[list[blockIdx.y]];
+  if (!NQS_ACTIVE(P) || !P.W.state[5]) return;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_adopt(P.W, n);
+}
 __global__ void __launch_bounds__(256) k_spec_redo_a(SpecImage* sp, const int* list) {
   const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P) || !P.W.state[5]) return;
@@ -1171,7 +1301,7 @@ __global__ void k_spec_finish(NqImage* imgs, SpecImage* sp, const int* list, int
 
 // ---- host side: layout of one slot of the pool, and the admission / round loop -------------------------------------
 struct SpecLayout {
-  size_t cpx, ccol, ck0, ck1, cdraw, cq, cflag, firstPos, slowPos, memo, slowVal, segs, state, rec, chunkSum, perSlot;
+  size_t cpx, ccol, ck0, ck1, cdraw, cq, cflag, firstPos, slowPos, memo, slowVal, segs, state, rec, chunkSum, patch, perSlot;
   int nseg;
 };
 inline SpecLayout spec_layout(int npix, int seg) {
@@ -1184,6 +1314,7 @@ inline SpecLayout spec_layout(int npix, int seg) {
   L.firstPos = take(65536 * 4); L.slowPos = take(65536 * 4); L.memo = take(65536 * 2); L.slowVal = take(65536 * 2);
   L.segs = take(sizeof(SpecSeg) * (size_t)L.nseg); L.state = take(64); L.rec = take(sizeof(SpecRec) * (size_t)L.nseg * (size_t)seg);
   L.chunkSum = take(((size_t)npix / NQS_CHUNK + 2) * 4);
+  L.patch = take(sizeof(int) * 2 * NQS_MAXPATCH);
   L.perSlot = o;
   return L;
 }
@@ -1200,6 +1331,7 @@ inline void spec_bind_pool(SpecWork* pool, int nslots, unsigned char* buf, const
     W.memo = reinterpret_cast<unsigned short*>(b + L.memo); W.slowVal = reinterpret_cast<unsigned short*>(b + L.slowVal);
     W.segs = reinterpret_cast<SpecSeg*>(b + L.segs); W.state = reinterpret_cast<int*>(b + L.state); W.rec = reinterpret_cast<SpecRec*>(b + L.rec);
     W.chunkSum = reinterpret_cast<unsigned*>(b + L.chunkSum);
+    W.patch = reinterpret_cast<int*>(b + L.patch);
   }
 }
 struct SpecStats { unsigned long long done = 0, rounds = 0, handedBack = 0, patches = 0, redos = 0; };
@@ -1288,6 +1420,7 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* d
     const dim3 pa = pgrid(nActive), ka(8, (unsigned)nActive), ca = cgrid(nActive);
     if (nPatch) { be.launch(k_spec_patch, pa, 256, dSpec, (const int*)dActive); be.launch(k_spec_pack, pa, 256, dSpec, (const int*)dActive); be.lap("patch"); }
     if (nRedo) {   // a draw misprediction: prefix sum again, then stages 3-5 behind it, for the images that asked
+      be.launch(k_spec_adopt, pa, 256, dSpec, (const int*)dActive);
       be.launch(k_spec_scan_a, ca, 256, dSpec, (const int*)dActive, 1);
       be.launch(k_spec_scan_b, dim3((unsigned)nActive), 1024, dSpec, (const int*)dActive, 1);
       be.launch(k_spec_scan_c, ca, 256, dSpec, (const int*)dActive, 1);

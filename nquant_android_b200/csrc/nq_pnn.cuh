@@ -539,7 +539,7 @@ __device__ __forceinline__ int rebuild_live_lab(const NqSlot& S, const LabScratc
   return total;
 }
 
-__global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, const NqSlot* slots, int* liveBuf, int* posBuf, int logMerges) {
+__global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, const NqSlot* slots, int* liveBuf, int* posBuf, int logMerges, int rot) {
   extern __shared__ unsigned char smemRaw[];
   float* sErr = reinterpret_cast<float*>(smemRaw);
   unsigned* sId = reinterpret_cast<unsigned*>(smemRaw + (size_t)NQ_LAB_HEAP_SMEM * 4);
@@ -559,7 +559,10 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
   if (I.kind != NQ_KIND_LAB || I.nmax <= 2 || I.skipPnn) return;
   const NqSlot& S = slots[img];
   const LabScratch X = lab_scratch(S);
-  const int t = threadIdx.x;
+  // The serial phases (heap top, ordered replay) belong to logical warp 0. Several CTAs share an SM, and the hardware
+  // places warp k of every CTA on the same scheduler: rotating the logical warp ids by the CTA index spreads the serial
+  // warps of co-resident images over the four schedulers.
+  const int t = (int)((threadIdx.x + 32u * (rot ? (blockIdx.x & 3u) : 0u)) & 127u);
   const unsigned lane = lane_id(), w = t >> 5;
   const int W = NQ_LAB_THREADS / 32;
   const int maxbins = I.maxbins, extbins = I.extbins;
@@ -954,7 +957,7 @@ __device__ __forceinline__ void rgb_accept_in_order(const RgbProbe& P, double ga
 
 static_assert(NQ_RGB_THREADS == NQ_LAB_THREADS, "block_excl_scan_128 is shared");
 
-__global__ void __launch_bounds__(NQ_RGB_THREADS, 4) k_merge_rgb(NqImage* imgs, const NqSlot* slots, int* liveBuf, int* posBuf, int logMerges) {
+__global__ void __launch_bounds__(NQ_RGB_THREADS, 4) k_merge_rgb(NqImage* imgs, const NqSlot* slots, int* liveBuf, int* posBuf, int logMerges, int rot) {
   extern __shared__ unsigned char smemRaw[];
   float* sErr = reinterpret_cast<float*>(smemRaw);
   unsigned* sId = reinterpret_cast<unsigned*>(smemRaw + (size_t)NQ_RGB_HEAP_SMEM * 4);
@@ -971,7 +974,10 @@ __global__ void __launch_bounds__(NQ_RGB_THREADS, 4) k_merge_rgb(NqImage* imgs, 
   if (I.kind != NQ_KIND_RGB || I.nmax <= 2 || I.skipPnn) return;
   const NqSlot& S = slots[img];
   const RgbScratch X = rgb_scratch(S);
-  const int t = threadIdx.x;
+  // The serial phases (heap top, ordered replay) belong to logical warp 0. Several CTAs share an SM, and the hardware
+  // places warp k of every CTA on the same scheduler: rotating the logical warp ids by the CTA index spreads the serial
+  // warps of co-resident images over the four schedulers.
+  const int t = (int)((threadIdx.x + 32u * (rot ? (blockIdx.x & 3u) : 0u)) & 127u);
   const unsigned lane = lane_id(), w = t >> 5;
   const int W = NQ_RGB_THREADS / 32;
   const int maxbins = I.maxbins, extbins = I.extbins;

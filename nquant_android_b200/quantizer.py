@@ -182,6 +182,25 @@ class Context:
         self._check(self._L.nq_synth_device(self._h, ctypes.c_void_p(out_ptr), n, width, height, cls, alpha_mode, seed0))
 
 
+def convert_batch_multi(contexts, kind, argb, width, height, n_max_colors, dither, seeds=None, queue_images=0):
+    """nq_convert_batch_multi: one batch over several contexts (one per GPU of the node, normally), pieces of
+    `queue_images` images handed out dynamically (0 = one piece per context). Returns (out, palettes, palette_lens, has_alpha)."""
+    L = _lib.load()
+    argb = np.ascontiguousarray(argb, dtype=np.uint32).reshape(-1, width * height)
+    n = argb.shape[0]
+    out = np.empty_like(argb)
+    pal = np.zeros((n, 256), dtype=np.uint32)
+    plen = np.zeros(n, dtype=np.int32)
+    ha = np.zeros(n, dtype=np.int32)
+    sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+    handles = (ctypes.c_void_p * len(contexts))(*[c._h for c in contexts])
+    rc = L.nq_convert_batch_multi(handles, len(contexts), kind, _p(argb), n, width, height, int(n_max_colors), int(bool(dither)),
+                                  _p(sd), _p(out), _p(pal), _p(plen), _p(ha), int(queue_images))
+    if rc != 0:
+        raise NQuantError(rc, L.nq_last_error().decode())
+    return out, pal, plen, ha
+
+
 def default_context(device=0):
     """Per-thread, per-device context cache (one nq_ctx per (thread, GPU))."""
     cache = getattr(_tls, "ctx", None)

@@ -728,6 +728,8 @@ struct Trace {
   GilbertParams gp{};
   std::vector<float> gweights;
   int64_t rng_draws = 0, pixelMapSize = 0;
+  bool keep_draws = false;          // debugging aid of tests/spec_host_harness.cpp: the pixel (bidx) of every draw, in order
+  std::vector<int32_t> draw_bidx;
   float bn_weight = 0;
 };
 
@@ -1452,6 +1454,7 @@ class PnnLABQuantizer : public PnnQuantizer {
     if (closest[2] == 0) idx = 0;
     else {
       ++trace.rng_draws;
+      if (trace.keep_draws) trace.draw_bidx.push_back(pos);
       if ((random.nextInt(32767) % iadd(closest[3], closest[2])) <= closest[3]) idx = 0;
     }
 

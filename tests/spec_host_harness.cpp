@@ -113,7 +113,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   fill_tables(C, lut.data());
   C.opaque = 1;
   for (int i = 0; i < npix; ++i) C.opaque &= ((uint32_t)cPixels[i] >> 24) == 0xFFu;
-  for (int i = 0; i < plen; ++i) C.opaque &= (C.pal[i] >> 24) == 0xFFu;
+  for (int i = 0; i < plen; ++i) C.opaque &= (C.pal[i] >> 24) >= 0xFEu;
   std::vector<float> tanhTab(512, 0.f);   // the table k_spec_tables builds on the device (shape_tanh)
   for (int t = 0; t < 511; ++t) tanhTab[t] = tanh_f((double)((float)(t - 255) / 255.f * 20.f));
 
@@ -133,6 +133,11 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   memset(segs.data(), 0, sizeof(SpecSeg) * segs.size());
   for (auto& s : segs) { s.dirty = 1; s.warmMul = 1; s.mispos = -1; }
   segs[0].exact = 1;
+  if (getenv("NQ_SPEC_FORCECHAIN")) {   // debugging aid: the whole image as ONE sequential chain from the first pixel
+    const int k = std::min(C.nseg, atoi(getenv("NQ_SPEC_FORCECHAIN")));
+    segs[0].chain = k;
+    for (int t = 1; t < k; ++t) { segs[t].chained = 1; segs[t].exact = 1; }
+  }
   if (H.useCells) build_cells(C, cells);
   if (g_collect) {   // what k_dither_setup leaves in NqImage for this image (the fields k_spec_setup reads)
     Collected B;
@@ -160,6 +165,8 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   W.cq = cq.data(); W.cflag = cflag.data(); W.cdraw = cdraw.data(); W.firstPos = firstPos.data(); W.memo = memo.data();
   W.slowPos = slowPos.data(); W.slowVal = slowVal.data(); W.cells = H.useCells ? cells.data() : nullptr; W.lut = lut.data(); W.bn = bn;
   W.segs = segs.data(); W.state = state.data(); W.rec = rec.data();
+  std::vector<int> patchList(2 * NQS_MAXPATCH, 0);
+  W.patch = patchList.data();
 
   for (int n = 0; n < npix; ++n) stage_pre(C, W, n);                                     // stage 1
   { uint32_t d = 0; for (int n = 0; n < npix; ++n) { cdraw[n] = d; d += (cflag[n] & NQS_F_DRAW) ? 1u : 0u; } cdraw[npix] = d; }   // stage 2
@@ -182,7 +189,8 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
     for (int s = 0; s < C.nseg; ++s) { if (!segs[s].done && segs[s].dirty) ++R.segRuns; stage_run(C, W, s, tanhTab.data()); }   // stage 6
     for (int s = 0; s < C.nseg; ++s) stage_compare(C, W, s);                             // stage 6b
     open = stage_validate(C, W);                                                         // stage 7
-    if (getenv("NQ_SPEC_DEBUG") && open > 0 && !state[1]) {
+    if (getenv("NQ_SPEC_DEBUG")) fprintf(stderr, "round %lld: validated up to segment %d, open %d, patch %d, redo from %d (rekey %d)\n", R.rounds, state[0], open, state[2], state[5] - 1, state[10] - 1);
+    if (getenv("NQ_SPEC_DEBUG2") && open > 0 && !state[1]) {
       const int s = state[0];
       int diff = 0;
       if (s > 0) for (int k = 0; k < C.DM; ++k) for (int j = 0; j < 4; ++j) diff += segs[s].qwarm[k][j] != segs[s - 1].qout[k][j];
@@ -194,6 +202,7 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
     if (state[5] && !state[1]) {                                                         // draw misprediction: re-resolve behind it
       ++R.redos;
       const int from = state[5] - 1;
+      for (int n = 0; n < npix; ++n) stage_adopt(W, n);
       { uint32_t d = 0; for (int n = 0; n < npix; ++n) { cdraw[n] = d; d += (cflag[n] & NQS_F_DRAW) ? 1u : 0u; } cdraw[npix] = d; }
       for (int key = 0; key < 65536; ++key) stage_rekey(W, key, from);
       for (int n = from + 1; n < npix; ++n) {
@@ -211,6 +220,40 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   R.anomaly = state[1];
   if (getenv("NQ_SPEC_DEBUG")) fprintf(stderr, "risk pixels %d, error-dependent lookups %d of %d\n", state[7], state[8], npix);
   for (auto& s : segs) R.notes += std::min(s.nnotes, NQS_NOTES);
+  if (!state[1] && getenv("NQ_SPEC_DEBUG") && !q.trace.draw_bidx.empty()) {
+    // the oracle's draws per pixel against the flags the path ended with
+    std::vector<unsigned char> truth(npix, 0);
+    for (int32_t b : q.trace.draw_bidx) truth[b] = 1;
+    int shown = 0;
+    unsigned d = 0;
+    for (int n = 0; n < npix && shown < 8; ++n) {
+      const int bidx = (int)(order[n] & 0xFFFF) + (int)(order[n] >> 16) * width;
+      const int mine = (cflag[n] & NQS_F_DRAW) ? 1 : 0;
+      if (mine != truth[bidx] || cdraw[n] != d) {
+        fprintf(stderr, "draw flag / prefix differs at curve position %d (segment %d offset %d): flag %u (truth draws %d), cdraw %u (truth %u)\n", n, n / C.seg, n % C.seg, (unsigned)cflag[n], truth[bidx], cdraw[n], d);
+        ++shown;
+      }
+      d += truth[bidx];
+    }
+  }
+  if (!state[1] && getenv("NQ_SPEC_DEBUG")) {
+    int shown = 0;
+    for (int n = 0; n < npix && shown < 6; ++n) {
+      const int bidx = (int)(order[n] & 0xFFFF) + (int)(order[n] >> 16) * width;
+      if (out[bidx] != (uint32_t)reference[bidx]) {
+        const int sg = n / C.seg;
+        fprintf(stderr, "first mismatch at curve position %d (segment %d, offset %d): flag %u cq %d cdraw %u; seg exact %d chain %d chained %d dev %d draws %d nslow %d notes %d\n", n, sg, n % C.seg,
+                (unsigned)cflag[n], (int)cq[n], cdraw[n], segs[sg].exact, segs[sg].chain, segs[sg].chained, segs[sg].dev, segs[sg].draws, segs[sg].nslow, segs[sg].nnotes);
+        int mi = -1, ri = -1;
+        for (int k = 0; k < plen; ++k) { if (C.pal[k] == out[bidx]) mi = k; if (C.pal[k] == (uint32_t)reference[bidx]) ri = k; }
+        const SpecRec& rr = rec[rec_index(C, n)];
+        fprintf(stderr, "   ours %08x (palette %d), reference %08x (palette %d); record qf %08x; ck0 %u/%u ck1 %u/%u ccol %08x\n", out[bidx], mi, (uint32_t)reference[bidx], ri, rr.qf,
+                ck0[n] >> 8, ck0[n] & 255, ck1[n] >> 8, ck1[n] & 255, ccol[n]);
+        ++shown;
+        n = (sg + 1) * C.seg - 1;
+      }
+    }
+  }
   if (!state[1]) {
     for (int i = 0; i < npix; ++i) R.mismatches += out[i] != (uint32_t)reference[i];
     R.exact = R.mismatches == 0;
@@ -241,6 +284,7 @@ extern "C" int nqs_spec_host(const uint32_t* argb, int w, int h, int nmax, int d
   try {
     HostLab q(argb, w, h);
     q.rngSeed = seed; q.nMax = nmax;
+    q.trace.keep_draws = getenv("NQ_SPEC_DEBUG") != nullptr;
     q.convert(nmax, dither != 0);
   } catch (const std::exception& e) {
     fprintf(stderr, "spec host harness: %s\n", e.what());

@@ -357,3 +357,27 @@ def test_debug_records_survive_small_workspaces(oracle):
             assert np.array_equal(ctx.debug_merges(i), ref.merges), i
     finally:
         ctx.close()
+
+
+def test_convert_batch_multi_dynamic_queue():
+    """nq_convert_batch_multi: several contexts pull pieces of one batch from a shared queue (one context per GPU of the
+    node; on a single-GPU box two contexts on device 0 exercise the same threads and queue). Every image must land at its
+    own index with the result a single-context call gives."""
+    import torch
+    from nquant_android_b200.quantizer import Context, convert_batch_multi, NQuantError
+    W, H, K, n = 96, 64, 64, 13
+    imgs = np.stack([make_image(W, H, ["noisy", "smooth", "rand"][i % 3], "opaque", seed=0x5EED0000 + i) for i in range(n)])
+    seeds = np.arange(n, dtype=np.uint64) + 21
+    ndev = torch.cuda.device_count()
+    ctxs = [Context(g % ndev) for g in range(max(2, min(ndev, 4)))]
+    try:
+        ref = ctxs[0].convert_batch(1, imgs, W, H, K, True, seeds=seeds)
+        for q in (0, 3, 1):
+            got = convert_batch_multi(ctxs, 1, imgs, W, H, K, True, seeds=seeds, queue_images=q)
+            for a, b in zip(ref, got):
+                assert np.array_equal(a, b), q
+        with pytest.raises(NQuantError):
+            convert_batch_multi(ctxs, 1, imgs, W, H, 1, True)
+    finally:
+        for c in ctxs:
+            c.close()

@@ -113,3 +113,21 @@ def test_spec_dither_leaves_other_quantizers_alone(spec_ctx, oracle):
         out, pal, plen, _ = spec_ctx.convert_batch(kind, img[None, :], w, h, nmax, dither, seeds=[3])
         assert np.array_equal(out[0], ref.out), (kind, nmax, dither)
     assert spec_ctx.spec_stats()["images"] == 0
+
+
+def test_spec_dither_hard_image_sequential_chains(spec_ctx, oracle):
+    """A saturated bright corner: thousands of pixels that are exactly a palette colour, whose error-dependent lookups draw
+    or not depending on the diffused error, so the draw prediction fails hundreds of times. The mispredicted stretch is
+    re-run as the sequential algorithm from its predecessor's exact state (a chain of segments on one thread) and everything
+    behind it re-resolved: the path finishes the image itself, bit-identical, in a handful of rounds."""
+    from test_spec_dither_host import _saturated_corner
+    w = h = 512
+    img = _saturated_corner(w, h, 0x5EED0001, 30)
+    ref = oracle.convert(1, img, w, h, 256, True, seed=0xC0FFEE, trace=False)
+    spec_ctx.set_spec_dither(True, 2048, 1024)
+    out, pal, plen, _ = spec_ctx.convert_batch(1, img[None, :], w, h, 256, True, seeds=[0xC0FFEE])
+    assert np.array_equal(pal[0, :plen[0]], ref.palette)
+    assert np.array_equal(out[0], ref.out)
+    assert spec_ctx.image_info(0)["rng_draws"] == ref.scalars["rng_draws"]
+    st = spec_ctx.spec_stats()
+    assert st["images"] == 1 and st["fallbacks"] == 0 and st["rounds"] <= 12, st

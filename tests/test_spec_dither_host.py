@@ -81,3 +81,29 @@ def test_kernels_and_wave_loop_emulated_on_a_batch(lib):
     assert r["images"] == 5 and r["eligible"] == 5 and r["completed"] == 5 and r["handed_back"] == 0, r
     assert r["wrong"] == 0, r
     assert r["patches"] >= 1 and r["rounds"] >= 4, r       # three waves, at least one extra round for the patches
+
+
+def _saturated_corner(w, h, seed, boost):
+    """The noisy class with its bright corner pushed into saturation: thousands of pixels that are exactly a palette colour
+    (white), whose error-dependent lookups draw or not depending on the diffused error -- the case the draw PREDICTION gets
+    wrong hundreds of times."""
+    img = make_image(w, h, "noisy", "opaque", seed=seed).astype(np.int64)
+    x, y = np.arange(w * h) % w, np.arange(w * h) // w
+    m = (x > 0.55 * w) & (y > 0.55 * h)
+    ch = [np.where(m, np.minimum(255, c + boost), c) for c in ((img >> 16) & 255, (img >> 8) & 255, img & 255)]
+    return np.ascontiguousarray(((255 << 24) | (ch[0] << 16) | (ch[1] << 8) | ch[2]).astype(np.uint32))
+
+
+def test_hard_image_is_finished_by_sequential_chains(lib):
+    """An image whose draws are mispredicted hundreds of times (1 025 'risk' pixels, 2 % error-dependent lookups) used to need
+    one validation round per misprediction (257 rounds, then handed back). The first mispredicted segment is now run again
+    from its predecessor's exact state as the sequential algorithm itself, its thread going on through the following
+    segments that hold error-dependent lookups (a chain), after which everything behind is re-resolved once: a handful of
+    rounds, bit-identical to the oracle."""
+    w = h = 512
+    img = _saturated_corner(w, h, 0x5EED0001, 30)
+    out = np.zeros(12, np.int64)
+    assert lib.nqs_spec_host(img.ctypes.data, w, h, 256, 1, 0xC0FFEE, 2048, 1024, 1, out.ctypes.data) == 0
+    r = dict(zip(KEYS, [int(v) for v in out]))
+    assert r["eligible"] == 1 and r["anomaly"] == 0 and r["mismatches"] == 0 and r["exact"] == 1, r
+    assert r["rounds"] <= 12 and r["redos"] >= 1, r
