@@ -181,7 +181,8 @@ struct nq_ctx {
   unsigned long long launches = 0;
   bool debug = false;
   int chunkImages = 0;                // images per chunk (0 = automatic)
-  int mergeRot = 1;                   // rotate the logical warp ids of the merge kernels by the CTA index (NQ_MERGE_ROT=0: off)
+  int mergeRot = 0;                   // NQ_MERGE_ROT=1: rotate the logical warp ids of the merge kernels by the CTA index (measured: no
+                                      // effect, the hardware already spreads the warps of co-resident CTAs over the schedulers)
   // Gilbert orders by (w,h), least recently used first in orderLru
   std::map<std::pair<int, int>, uint32_t*> orders;
   std::vector<std::pair<int, int>> orderLru;
@@ -801,6 +802,9 @@ int convert_group(nq_ctx* c, const GroupArgs& A, int n, const uint32_t* dIn, uin
     if (cudaEventElapsedTime(&ms, ch.ev[3], ch.ev[4]) == cudaSuccess) { c->kernelMs[3] += ms; ++c->kernelLaunches[3]; }
   }
   cudaGetLastError();
+  if (getenv("NQ_SPEC_TIMING") || getenv("NQ_SPEC_REASONS"))
+    for (int i = 0; i < n; ++i)
+      if (c->lastImgs[i].specDone == 3) fprintf(stderr, "[nq spec] image %d handed back to the serial kernel, reason %d\n", i, c->lastImgs[i].pad1);
   if (c->debug) {
     for (int i = 0; i < n; ++i) {
       DebugImage& D = c->dbg[dbgBase + i];

@@ -33,6 +33,7 @@ namespace spec {
 #define NQS_NOTES 256           // memo entries a segment may create through error-dependent lookups
 #define NQS_READS 64            // memo entries of the pre-lookups its error-dependent lookups may read
 #define NQS_NOPOS 0x7fffffff
+#define NQS_MAXREJ 8             // generator steps whose value nextInt(32767) rejects, per image (expected: 0.008 for a 4K image)
 #define NQS_NONE 0xFFFFFFFFu    // absent top-2 key
 
 // per-pixel flags (curve order)
@@ -63,6 +64,11 @@ struct SpecConst {
   Lab4 palLab[NQ_MAXK];                  // getLab(palette[i]) (PL:352)
   double Tr[256], Tg[256], Tb[256];      // closestColorIndex cost of one channel difference (see nq_dither.cuh)
   unsigned long long jmpA[40], jmpC[40]; // java.util.Random: state after 2^i more steps = jmpA[i] * state + jmpC[i] (mod 2^48)
+  // Random.nextInt(32767) draws AGAIN when next(31) is one of the two top values (2 in 2^31 per draw: a few images of every
+  // large batch). Which steps of the generator do that depends on the seed alone: they are listed here (1-based step
+  // indices, ascending; k_spec_rejects), and draw d is the d-th step that is not in the list (lcg_step_of).
+  int nrej;
+  unsigned rej[NQS_MAXREJ];
 };
 
 // Per-image work arrays (curve order, npix entries unless noted) and segment records.
@@ -85,7 +91,7 @@ struct SpecSeg {
   int dev;                               // sequential run: curve position of the chain's first draw against its prediction, or NQS_NOPOS
   unsigned idx0;                         // sequential run: draws made in front of the segment (the index its first draw continues from)
 };
-#define NQS_MAXCHAIN 32
+#define NQS_MAXCHAIN 4            // segments one thread runs in a row: bounds the time a round waits for its slowest thread
 #define NQS_MAXPATCH 24          // memo entries corrected per round and image
 // What stage 6 reads per pixel, packed by stage 5b and stored SEGMENT-INTERLEAVED: record of curve position n lives at
 // (n % seg) * nseg + n / seg, so the threads of a warp (consecutive segments, same offset inside the segment) read
@@ -145,6 +151,14 @@ NQ_HD int next_int_from(unsigned long long s, bool* rejected) {
   return r;
 }
 
+NQ_HD bool lcg_rejects(unsigned long long s) { return (unsigned)(s >> 17) >= 0x7FFFFFFEu; }   // next(31) in {2^31 - 2, 2^31 - 1}: u - u % 32767 + 32766 overflows
+// generator step that delivers draw d (1-based): the d-th step nextInt does not reject
+template <class SC>
+NQ_HD unsigned long long lcg_step_of(const SC& C, unsigned long long d) {
+  unsigned long long j = 0;
+  while (j < (unsigned long long)C.nrej && (unsigned long long)C.rej[j] <= d + j) ++j;
+  return d + j;
+}
 NQ_HD Lab4 lab_at(uint32_t c, const double* lut) {
 #if defined(__CUDA_ARCH__)
   return lab_of(c);                      // 2^24-entry table (nq_hist.cuh)
@@ -420,7 +434,7 @@ NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firs
     int r = 0;
     if (flag & NQS_F_DRAW) {
       bool rej;
-      r = next_int_from(lcg_jump(C.jmpA, C.jmpC, C.seed0, (unsigned long long)W.cdraw[n] + 1ULL), &rej);
+      r = next_int_from(lcg_jump(C.jmpA, C.jmpC, C.seed0, lcg_step_of(C, (unsigned long long)W.cdraw[n] + 1ULL)), &rej);
       ok = !rej;
     }
     qi = closest_pick(C, c, W.ck0[n], W.ck1[n], r, &needNear);
@@ -437,8 +451,8 @@ NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firs
 }
 // ---- gate after stage 3 (state[7] = pixels flagged NQS_F_RISK): too many likely mispredictions, do not start
 NQ_HD void stage_gate(const SpecConst& C, const SpecWork& W) {
-  if (W.state[7] > NQS_MAXRISK) W.state[1] = 1;
-  if (W.state[8] > (C.npix >> 4)) W.state[1] = 1;           // state[8] = error-dependent lookups: past 6 % of the image the sequential runs (and their notes) outgrow this scheme
+  if (W.state[7] > NQS_MAXRISK) { W.state[1] = 1; W.state[11] = 1; }
+  if (W.state[8] > (C.npix >> 4)) { W.state[1] = 1; W.state[11] = 2; }           // state[8] = error-dependent lookups: past 6 % of the image the sequential runs (and their notes) outgrow this scheme
 }
 // ---- stage 4: one memo key ------------------------------------------------------------------------------------
 // `after`: only entries first seen behind that curve position (-1 = all); the others are settled
@@ -500,8 +514,9 @@ NQ_HD void stage_patch(const SpecConst& C, const SpecWork& W, int n) {
 // java.util.Random addressed by draw index, for a caller that asks for (mostly) increasing indices: the state of the last
 // index is kept and stepped forward; only a long way ahead (or back) takes the O(log) jump from the seed.
 struct LcgCursor { unsigned long long state; unsigned idx; int valid; };
-NQ_HD unsigned long long lcg_state_at(const SpecConst& C, LcgCursor& L, unsigned idx) {   // state after `idx` steps
+NQ_HD unsigned long long lcg_state_at(const SpecConst& C, LcgCursor& L, unsigned draw) {   // state that delivers draw `draw` (1-based)
   const unsigned long long MASK = (1ULL << 48) - 1;
+  const unsigned idx = (unsigned)lcg_step_of(C, (unsigned long long)draw);                 // generator steps from the seed
   if (L.valid && idx >= L.idx && idx - L.idx <= 24u) {
     for (unsigned k = L.idx; k < idx; ++k) L.state = (L.state * 0x5DEECE66DULL + 0xBULL) & MASK;
   } else
@@ -889,7 +904,7 @@ NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
     if (ok) {
       // the draws of the owned pixels against the prediction every later pre-lookup was computed with
       predicted = (int)(W.cdraw[p1] - W.cdraw[p0]);   // cdraw has npix + 1 entries
-      if (S.draws != predicted && !S.exact) { W.state[1] = 1; return 0; }      // cannot happen without a mispos; kept as a guard
+      if (S.draws != predicted && !S.exact) { W.state[1] = 1; W.state[11] = 3; return 0; }      // cannot happen without a mispos; kept as a guard
       for (int i = 0; i < S.nnotes; ++i) {
         const int key = S.noteKey[i], pos = S.notePos[i], val = S.noteVal[i];
         if (W.slowPos[key] < pos && W.slowVal[key] != val) { ok = false; break; }
@@ -899,9 +914,9 @@ NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
     if (!ok) fprintf(stderr, "  validate: segment %d fails (exact %d chained %d dirty %d qok %d mispos %d notes %d draws %d predicted %d)\n", s, S.exact, S.chained, S.dirty, S.qok, S.mispos, S.nnotes, S.draws, (int)(W.cdraw[p1] - W.cdraw[p0]));
 #endif
     if (!ok) {
-      if (S.exact && S.nnotes > NQS_NOTES) { W.state[1] = 1; return 0; }     // even the exact run overflows its notes
+      if (S.exact && S.nnotes > NQS_NOTES) { W.state[1] = 1; W.state[11] = 4; return 0; }     // even the exact run overflows its notes
       // every failure costs a round in which one thread runs alone: past a quarter of the segments the serial kernel is cheaper
-      if (++W.state[4] > (C.nseg >> 2) + 4) { W.state[1] = 1; return 0; }
+      if (++W.state[4] > (C.nseg >> 2) + 4) { W.state[1] = 1; W.state[11] = 5; return 0; }
       S.exact = 1; S.dirty = 1; S.chained = 0;
       if (s > 0) for (int k = 0; k < C.DM; ++k) for (int j = 0; j < 4; ++j) S.qstart[k][j] = W.segs[s - 1].qout[k][j];
       // its thread goes on through the following segments that hold error-dependent lookups: their draws are as uncertain
@@ -961,7 +976,7 @@ NQ_HD int stage_validate(const SpecConst& C, const SpecWork& W) {
     W.state[5] = from + 1;
     W.state[10] = minDev != NQS_NOPOS ? minDev + 1 : 0;
     for (int t = s; t < C.nseg; ++t) { SpecSeg& T = W.segs[t]; T.dirty = 1; T.chained = 0; T.chain = 1; if (T.exact && t > s) T.exact = 0; }
-    if (++W.state[6] > NQS_MAXREDO) { W.state[1] = 1; return 0; }
+    if (++W.state[6] > NQS_MAXREDO) { W.state[1] = 1; W.state[11] = 6; return 0; }
   }
   W.state[0] = s;
   return C.nseg - s + (W.state[5] ? 1 : 0);   // a pending re-resolve keeps the image open even when every segment is done
@@ -1011,6 +1026,7 @@ __global__ void k_spec_setup(NqImage* imgs, const NqSlot* slots, SpecImage* sp, 
   C.beta = I.gBeta;
   JRandom r; r.set_seed(I.seed);
   C.seed0 = r.seed;
+  C.nrej = 0;
   for (int k = 0; k < NQ_MAXQ; ++k) C.w[k] = k < C.DM ? I.gWeights[k] : 0.f;
   int opaque = I.nonOpaque == 0;                  // ... and palette alphas of 254 or 255 (a mean of 255s can round to 254.99998, PL:301)
   for (int k = 0; k < plen; ++k) { C.pal[k] = I.palette[k]; opaque &= (I.palette[k] >> 24) >= 0xFEu; }
@@ -1031,6 +1047,38 @@ __global__ void k_spec_admit(SpecImage* sp, const int* list, const int* slotOf, 
   W.cpx = T.cpx; W.ccol = T.ccol; W.ck0 = T.ck0; W.ck1 = T.ck1; W.cq = T.cq; W.cflag = T.cflag; W.rec = T.rec; W.cdraw = T.cdraw;
   W.firstPos = T.firstPos; W.memo = T.memo; W.slowPos = T.slowPos; W.slowVal = T.slowVal; W.segs = T.segs; W.state = T.state;
   W.chunkSum = T.chunkSum; W.patch = T.patch;
+}
+// The generator steps whose value Random.nextInt(32767) rejects, among the first npix + NQS_MAXREJ + 1 (every pixel draws at
+// most once): 64 steps per thread from a jump to its first one. k_spec_rejsort orders the few that exist.
+__global__ void __launch_bounds__(256) k_spec_rejects(SpecImage* sp, const int* list) {
+  SpecImage& P = sp[list[blockIdx.y]];
+  if (!P.eligible) return;
+  const unsigned long long MASK = (1ULL << 48) - 1;
+  const unsigned long long total = (unsigned long long)P.C.npix + NQS_MAXREJ + 1;
+  for (unsigned long long base = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 64ULL; base < total;
+       base += (unsigned long long)gridDim.x * blockDim.x * 64ULL) {
+    unsigned long long st = lcg_jump(P.C.jmpA, P.C.jmpC, P.C.seed0, base);
+    for (int k = 1; k <= 64 && base + (unsigned long long)k <= total; ++k) {
+      st = (st * 0x5DEECE66DULL + 0xBULL) & MASK;
+      if (lcg_rejects(st)) {
+        const int at = atomicAdd(&P.C.nrej, 1);
+        if (at < NQS_MAXREJ) P.C.rej[at] = (unsigned)(base + (unsigned long long)k);
+      }
+    }
+  }
+}
+__global__ void k_spec_rejsort(SpecImage* sp, const int* list, int cnt) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  SpecImage& P = sp[list[k]];
+  if (!P.eligible) return;
+  if (P.C.nrej > NQS_MAXREJ) { P.C.nrej = 0; P.W.state[1] = 1; P.W.state[11] = 7; return; }   // (2 in 2^31 per step: never seen)
+  for (int i = 1; i < P.C.nrej; ++i) {
+    const unsigned v = P.C.rej[i];
+    int j = i - 1;
+    for (; j >= 0 && P.C.rej[j] > v; --j) P.C.rej[j + 1] = P.C.rej[j];
+    P.C.rej[j + 1] = v;
+  }
 }
 // memo tables, segment records, state (grid: x strides, y = list entry)
 __global__ void __launch_bounds__(256) k_spec_init(SpecImage* sp, const int* list) {
@@ -1150,7 +1198,7 @@ __global__ void __launch_bounds__(256) k_spec_resolve(SpecImage* sp, const int* 
     int key;
     risk += (P.W.cflag[n] & NQS_F_RISK) ? 1 : 0;
     slow += (P.W.cflag[n] & NQS_F_PRE) ? 0 : 1;
-    if (!stage_resolve(P.C, P.W, n, &key)) P.W.state[1] = 1;      // a nextInt that draws twice (2 in 2^31): leave the image to the serial kernel
+    if (!stage_resolve(P.C, P.W, n, &key)) { P.W.state[1] = 1; P.W.state[11] = 7; }   // a nextInt that draws twice (2 in 2^31): leave the image to the serial kernel
     if (key >= 0) atomicMin(&P.W.firstPos[key], n);
   }
   if (risk) atomicAdd(&P.W.state[7], risk);
@@ -1175,7 +1223,7 @@ __global__ void __launch_bounds__(256) k_spec_redo_b(SpecImage* sp, const int* l
   const int from = P.W.state[5] - 1;
   for (int n = from + 1 + blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) {
     int key;
-    if (!stage_resolve(P.C, P.W, n, &key)) P.W.state[1] = 1;
+    if (!stage_resolve(P.C, P.W, n, &key)) { P.W.state[1] = 1; P.W.state[11] = 7; }
     if (key >= 0) atomicMin(&P.W.firstPos[key], n);
   }
 }
@@ -1295,8 +1343,12 @@ __global__ void k_spec_finish(NqImage* imgs, SpecImage* sp, const int* list, int
   if (NQS_ACTIVE(P) && P.W.state[0] == P.C.nseg) {
     imgs[i].specDone = 1;
     imgs[i].rngDraws = P.W.cdraw[P.C.npix];
-  } else
+  } else {
     imgs[i].specDone = 3;
+    // why (nq_get_spec_stats' fallbacks; NQ_SPEC_TIMING prints it): 1 risk gate, 2 too many error-dependent lookups, 3 draw guard,
+    // 4 a sequential run overflowed its notes, 5 too many failed validations, 6 too many re-resolves, 7 a nextInt drew twice, 8 round cap
+    imgs[i].pad1 = P.eligible ? (P.W.state[11] ? P.W.state[11] : 8) : 0;
+  }
 }
 
 // ---- host side: layout of one slot of the pool, and the admission / round loop -------------------------------------
@@ -1374,7 +1426,9 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* d
       be.write_ints(dFresh, fresh, nFresh); be.write_ints(dFreshSlot, freshSlot, nFresh);
       const dim3 pg = pgrid(nFresh), kg(8, (unsigned)nFresh), cg = cgrid(nFresh);
       be.launch(k_spec_admit, dim3((unsigned)((nFresh + 63) / 64)), 64, dSpec, (const int*)dFresh, (const int*)dFreshSlot, nFresh, dPool);
-      be.launch(k_spec_init, kg, 256, dSpec, (const int*)dFresh); be.lap("init");
+      be.launch(k_spec_init, kg, 256, dSpec, (const int*)dFresh);
+      be.launch(k_spec_rejects, cg, 256, dSpec, (const int*)dFresh);
+      be.launch(k_spec_rejsort, dim3((unsigned)((nFresh + 63) / 64)), 64, dSpec, (const int*)dFresh, nFresh); be.lap("init");
       be.launch(k_spec_pre, pg, 256, dSpec, (const int*)dFresh); be.lap("pre");
       be.launch(k_spec_scan_a, cg, 256, dSpec, (const int*)dFresh, 0);
       be.launch(k_spec_scan_b, dim3((unsigned)nFresh), 1024, dSpec, (const int*)dFresh, 0);

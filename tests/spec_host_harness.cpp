@@ -111,6 +111,15 @@ void run_spec(PnnLABQuantizer& q, const std::vector<int32_t>& cPixels, const std
   std::vector<double> lut(256);
   for (int v = 0; v < 256; ++v) lut[v] = nq::gamma_to_linear(v);
   fill_tables(C, lut.data());
+  {   // the generator steps nextInt(32767) rejects (k_spec_rejects / k_spec_rejsort on the device)
+    const unsigned long long MASK = (1ULL << 48) - 1;
+    unsigned long long st = C.seed0;
+    C.nrej = 0;
+    for (unsigned long long t = 1; t <= (unsigned long long)npix + NQS_MAXREJ + 1; ++t) {
+      st = (st * 0x5DEECE66DULL + 0xBULL) & MASK;
+      if (lcg_rejects(st) && C.nrej < NQS_MAXREJ) C.rej[C.nrej++] = (unsigned)t;
+    }
+  }
   C.opaque = 1;
   for (int i = 0; i < npix; ++i) C.opaque &= ((uint32_t)cPixels[i] >> 24) == 0xFFu;
   for (int i = 0; i < plen; ++i) C.opaque &= (C.pal[i] >> 24) >= 0xFEu;

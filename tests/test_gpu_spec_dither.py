@@ -131,3 +131,21 @@ def test_spec_dither_hard_image_sequential_chains(spec_ctx, oracle):
     assert spec_ctx.image_info(0)["rng_draws"] == ref.scalars["rng_draws"]
     st = spec_ctx.spec_stats()
     assert st["images"] == 1 and st["fallbacks"] == 0 and st["rounds"] <= 12, st
+
+
+def test_spec_dither_follows_a_rejected_nextint(spec_ctx, oracle):
+    """Random.nextInt(32767) draws again when next(31) is one of its two top values (2 in 2^31 per draw: a few 4K images of a
+    1024-image batch meet one). The path maps draw indices to generator steps around such steps (k_spec_rejects,
+    lcg_step_of) instead of handing the image to the serial kernel. Seed built so that the 100 000th step is rejected."""
+    from test_spec_dither_host import seed_with_rejected_step
+    seed = seed_with_rejected_step(100000)
+    w = h = 512
+    img = make_image(w, h, "noisy", "opaque")
+    ref = oracle.convert(1, img, w, h, 256, True, seed=seed, trace=False)
+    for spec in (True, False):                 # the speculative path and the serial kernels must both follow it
+        spec_ctx.set_spec_dither(spec, 2048, 1024)
+        out, pal, plen, _ = spec_ctx.convert_batch(1, img[None, :], w, h, 256, True, seeds=[seed])
+        assert np.array_equal(out[0], ref.out), spec
+        assert spec_ctx.image_info(0)["rng_draws"] == ref.scalars["rng_draws"]
+    st = spec_ctx.spec_stats()
+    assert st["images"] == 1 and st["fallbacks"] == 0, st

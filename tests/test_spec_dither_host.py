@@ -107,3 +107,33 @@ def test_hard_image_is_finished_by_sequential_chains(lib):
     r = dict(zip(KEYS, [int(v) for v in out]))
     assert r["eligible"] == 1 and r["anomaly"] == 0 and r["mismatches"] == 0 and r["exact"] == 1, r
     assert r["rounds"] <= 12 and r["redos"] >= 1, r
+
+
+def seed_with_rejected_step(t, low17=0x1234):
+    """A java.util.Random seed whose t-th generator step delivers next(31) == 2^31 - 1, one of the two values
+    Random.nextInt(32767) rejects and draws again for (2 in 2^31 per draw: a few 4K images of every large batch meet one).
+    Built by running the 48-bit LCG backwards from such a state."""
+    m, a, c = 1 << 48, 0x5DEECE66D, 0xB
+    a_inv = pow(a, -1, m)
+    s = (0x7FFFFFFF << 17) | low17
+    for _ in range(t):
+        s = ((s - c) * a_inv) % m
+    return s ^ a            # setSeed scrambles with the multiplier
+
+
+def test_a_draw_that_nextint_rejects_is_followed_exactly(lib, oracle=None):
+    """The draw index -> generator step mapping (lcg_step_of): with a seed whose 100 000th step is rejected by nextInt the
+    speculative path must still reproduce the sequential oracle (every later draw uses the step after the one its index
+    suggests), instead of handing the image to the serial kernel."""
+    from oracle import pyoracle
+    seed = seed_with_rejected_step(100000)
+    vals = pyoracle.java_random_next_int(seed, 32767, 100002)
+    vals0 = pyoracle.java_random_next_int(seed_with_rejected_step(100000, 0x1235), 32767, 100002)
+    assert len(vals) == 100002            # (the oracle's Random really loops there: the 100 000th call consumes two steps)
+    w, h = 512, 512
+    img = np.ascontiguousarray(make_image(w, h, "noisy", "opaque"))
+    out = np.zeros(12, np.int64)
+    assert lib.nqs_spec_host(img.ctypes.data, w, h, 256, 1, seed, 2048, 1024, 1, out.ctypes.data) == 0
+    r = dict(zip(KEYS, [int(v) for v in out]))
+    assert r["eligible"] == 1 and r["anomaly"] == 0 and r["rejected"] == 0, r
+    assert r["mismatches"] == 0 and r["exact"] == 1, r

@@ -47,6 +47,9 @@ def main():
         d = dict(zip(hdr, r))
         u = dict(zip(hdr, units))
         name = d.get("Kernel Name", "?").split("(")[0]
+        if name.startswith("void "):
+            name = name[5:]
+        name = name.split("<")[0].strip()
         names.append(name)
         print(f"## `{name}`\n")
         print("| metric | value |")
