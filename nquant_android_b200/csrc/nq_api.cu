@@ -745,12 +745,11 @@ int convert_group(nq_ctx* c, const GroupArgs& A, int n, const uint32_t* dIn, uin
   if (rc) return rc;
   int per = c->chunkImages;
   if (per <= 0) {
-    // automatic: whole batches up to 640 images in one piece (the merge loop wants >= 4 images per SM in flight); larger
-    // ones, and host-buffer calls (whose copies should overlap the kernels), in equal pieces of at most 512 / 256 images
-    const int cap = A.hIn ? 256 : 512;
-    per = (n <= 640 && !A.hIn) ? n : (n + ((n + cap - 1) / cap) - 1) / ((n + cap - 1) / cap);
-    if (A.hIn && n <= 8) per = n;
-  }
+    // automatic: the merge loop wants >= 4 images per SM in flight, so chunks stay as large as possible: batches up to 640
+    // images in one piece, larger ones in equal pieces of at most 512. Host-buffer calls are cut in at least two pieces
+    // (from 32 images on) so that the copies of one piece overlap the kernels of the other.
+    const int pieces = std::max((n + 511) / 512, (A.hIn && n >= 32) ? 2 : 1);
+    per = (n <= 640 && pieces == 1) ? n : (n + pieces - 1) / pieces;
   if (c->debug) per = n;
   per = std::max(1, std::min(per, n));
   const int nch = (n + per - 1) / per;

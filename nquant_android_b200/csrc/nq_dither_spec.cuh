@@ -382,7 +382,7 @@ NQ_HD int closest_pick(const SpecConst& C, uint32_t c, unsigned k0, unsigned k1,
 }
 
 // ---- stage 1: one pixel of the curve ------------------------------------------------------------------------
-NQ_HD void stage_pre(const SpecConst& C, const SpecWork& W, int n) {
+NQ_HD void stage_pre(const SpecConst& C, const ScanTabs& T, const SpecWork& W, int n) {
   const uint32_t xy = W.order[n];
   const int x = (int)(xy & 0xFFFF), y = (int)(xy >> 16);
   const uint32_t px = W.in[x + y * C.width];
@@ -396,7 +396,7 @@ NQ_HD void stage_pre(const SpecConst& C, const SpecWork& W, int n) {
   unsigned k0 = NQS_NONE, k1 = NQS_NONE;
   const bool viaClosest = c_alpha(c) > 0xF;                // PL:407-408
   if (viaClosest) {
-    top2(C, W.cells, c, &k0, &k1);
+    top2(C, T, W.cells, c, &k0, &k1);
     if ((k0 >> 8) != 0u) flag |= NQS_F_DRAW;               // short-circuit: no draw when closest[2] == 0 (PL:467)
     else if (!(flag & NQS_F_PRE)) {
       // The pixel itself costs 0 (it is a palette colour): the reference draws unless the DIFFUSED colour is that colour
@@ -408,7 +408,7 @@ NQ_HD void stage_pre(const SpecConst& C, const SpecWork& W, int n) {
         const uint32_t pxy = W.order[n - 1];
         const uint32_t ppx = W.in[(int)(pxy & 0xFFFF) + (int)(pxy >> 16) * C.width];
         unsigned p0 = NQS_NONE, p1 = NQS_NONE;
-        if (c_alpha(ppx) > 0xF) top2(C, W.cells, ppx, &p0, &p1);
+        if (c_alpha(ppx) > 0xF) top2(C, T, W.cells, ppx, &p0, &p1);
         flat = (p0 >> 8) == 0u;
       }
       if (flat) flag |= NQS_F_RISK; else flag |= NQS_F_DRAW;
@@ -418,10 +418,12 @@ NQ_HD void stage_pre(const SpecConst& C, const SpecWork& W, int n) {
   W.cflag[n] = (unsigned char)flag;
 }
 
+NQ_HD void stage_pre(const SpecConst& C, const SpecWork& W, int n) { stage_pre(C, scan_tabs(C), W, n); }
+
 // ---- stage 3: the draw, the choice between the two candidates, first-seen positions of the memo keys -------
 // (stage 2 = exclusive prefix sum of NQS_F_DRAW into cdraw). Returns false when a nextInt would have rejected.
 NQ_HD int memo_key(const SpecConst& C, uint32_t c) { return color_index(c, false, C.hasTrans != 0); }   // PL:332
-NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firstPosOut /* key or -1 */) {
+NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firstPosOut /* key or -1 */, const unsigned long long* state = nullptr) {
   *firstPosOut = -1;
   const unsigned flag = W.cflag[n] & ~NQS_F_NEAR;          // (a re-resolve after a draw misprediction starts over)
   W.cflag[n] = (unsigned char)flag;
@@ -434,7 +436,7 @@ NQ_HD bool stage_resolve(const SpecConst& C, const SpecWork& W, int n, int* firs
     int r = 0;
     if (flag & NQS_F_DRAW) {
       bool rej;
-      r = next_int_from(lcg_jump(C.jmpA, C.jmpC, C.seed0, lcg_step_of(C, (unsigned long long)W.cdraw[n] + 1ULL)), &rej);
+      r = next_int_from(state ? *state : lcg_jump(C.jmpA, C.jmpC, C.seed0, lcg_step_of(C, (unsigned long long)W.cdraw[n] + 1ULL)), &rej);
       ok = !rej;
     }
     qi = closest_pick(C, c, W.ck0[n], W.ck1[n], r, &needNear);
@@ -1089,11 +1091,35 @@ __global__ void __launch_bounds__(256) k_spec_init(SpecImage* sp, const int* lis
   for (int s = t; s < P.C.nseg; s += nt) { SpecSeg& S = P.W.segs[s]; S.exact = s == 0; S.dirty = 1; S.done = 0; S.draws = 0; S.nnotes = 0; S.nreads = 0; S.mispos = -1; S.warmMul = 1; S.nslow = 0; S.chain = 1; S.chained = 0; }
   if (t < 16) P.W.state[t] = 0;
 }
-__global__ void __launch_bounds__(256) k_spec_pre(SpecImage* sp, const int* list) {
+#if defined(NQS_EMULATE)
+__global__ void k_spec_pre(SpecImage* sp, const int* list) {
   const SpecImage& P = sp[list[blockIdx.y]];
   if (!P.eligible) return;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_pre(P.C, P.W, n);
 }
+#else
+// the palette, the three cost tables, the gamma table and the blue-noise mask of the image in shared memory: stage 1 reads
+// each of them several times per pixel
+__global__ void __launch_bounds__(256) k_spec_pre(SpecImage* sp, const int* list) {
+  __shared__ uint32_t sPal[NQ_MAXK];
+  __shared__ double sT[3][256], sLut[256];
+  __shared__ signed char sBn[4096];
+  const SpecImage& P = sp[list[blockIdx.y]];
+  if (!P.eligible) return;
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+    sPal[k] = k < P.C.plen ? P.C.pal[k] : 0u;
+    sT[0][k] = P.C.Tr[k]; sT[1][k] = P.C.Tg[k]; sT[2][k] = P.C.Tb[k];
+    sLut[k] = P.W.lut[k];
+  }
+  for (int k = threadIdx.x; k < 4096; k += blockDim.x) sBn[k] = P.W.bn[k];
+  __syncthreads();
+  SpecWork W = P.W;
+  W.lut = sLut; W.bn = sBn;
+  ScanTabs T;
+  T.pal = sPal; T.Tr = sT[0]; T.Tg = sT[1]; T.Tb = sT[2]; T.plen = P.C.plen;
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) stage_pre(P.C, T, W, n);
+}
+#endif
 // stage 2: exclusive prefix sum of the predicted draws in three steps: draws per NQS_CHUNK pixels (a), prefix of those per
 // image (b), cdraw of every pixel (c). redo != 0: only images that asked for a re-resolve (state[5]).
 #define NQS_SCAN_SKIP(P, redo) (!(P).eligible || ((redo) && (!(P).W.state[5] || (P).W.state[1])))
@@ -1190,7 +1216,8 @@ __global__ void __launch_bounds__(256) k_spec_scan_c(SpecImage* sp, const int* l
   }
 }
 #endif
-__global__ void __launch_bounds__(256) k_spec_resolve(SpecImage* sp, const int* list) {
+#if defined(NQS_EMULATE)
+__global__ void k_spec_resolve(SpecImage* sp, const int* list) {
   const SpecImage& P = sp[list[blockIdx.y]];
   if (!P.eligible) return;
   int risk = 0, slow = 0;
@@ -1198,12 +1225,64 @@ __global__ void __launch_bounds__(256) k_spec_resolve(SpecImage* sp, const int* 
     int key;
     risk += (P.W.cflag[n] & NQS_F_RISK) ? 1 : 0;
     slow += (P.W.cflag[n] & NQS_F_PRE) ? 0 : 1;
-    if (!stage_resolve(P.C, P.W, n, &key)) { P.W.state[1] = 1; P.W.state[11] = 7; }   // a nextInt that draws twice (2 in 2^31): leave the image to the serial kernel
+    if (!stage_resolve(P.C, P.W, n, &key)) { P.W.state[1] = 1; P.W.state[11] = 7; }
     if (key >= 0) atomicMin(&P.W.firstPos[key], n);
   }
   if (risk) atomicAdd(&P.W.state[7], risk);
   if (slow) atomicAdd(&P.W.state[8], slow);
 }
+#else
+// Stage 3 with the generator state carried along: every warp owns spans of NQS_RSPAN consecutive pixels, jumps to the state
+// of the span's first draw once (O(log n)) and from there reaches the draw of each pixel with ONE multiply-add
+// (state after k more steps = A^k state + C_k, k <= 48 from a shared table).
+#define NQS_RSPAN 2048
+__global__ void __launch_bounds__(256) k_spec_resolve(SpecImage* sp, const int* list) {
+  __shared__ unsigned long long sA[64], sC[64];
+  const SpecImage& P = sp[list[blockIdx.y]];
+  if (!P.eligible) return;
+  const unsigned long long MASK = (1ULL << 48) - 1;
+  if (threadIdx.x == 0) {
+    unsigned long long a = 1ULL, c = 0ULL;
+    for (int k = 0; k < 64; ++k) { sA[k] = a; sC[k] = c; a = (a * 0x5DEECE66DULL) & MASK; c = (c * 0x5DEECE66DULL + 0xBULL) & MASK; }
+  }
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31;
+  const int warpsPerGrid = (int)(gridDim.x * (blockDim.x >> 5)), warp = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+  const int npix = P.C.npix, nspan = (npix + NQS_RSPAN - 1) / NQS_RSPAN;
+  int risk = 0, slow = 0;
+  for (int sp_ = warp; sp_ < nspan; sp_ += warpsPerGrid) {
+    const int n0 = sp_ * NQS_RSPAN, n1 = min(npix, n0 + NQS_RSPAN);
+    unsigned long long curStep = lcg_step_of(P.C, (unsigned long long)P.W.cdraw[n0]);        // generator steps behind the draws in front of the span
+    unsigned long long curState = lcg_jump(P.C.jmpA, P.C.jmpC, P.C.seed0, curStep);
+    for (int base = n0; base < n1; base += 32) {
+      const int n = base + (int)lane;
+      const int nn = min(base + 32, npix);                                                    // cdraw has npix + 1 entries
+      const unsigned long long nextStep = lcg_step_of(P.C, (unsigned long long)P.W.cdraw[nn]);
+      if (n < n1) {
+        const unsigned flag = P.W.cflag[n];
+        risk += (flag & NQS_F_RISK) ? 1 : 0;
+        slow += (flag & NQS_F_PRE) ? 0 : 1;
+        unsigned long long st = 0ULL;
+        const unsigned long long* stp = nullptr;
+        if ((flag & NQS_F_PRE) && (flag & NQS_F_DRAW)) {
+          const unsigned long long k = lcg_step_of(P.C, (unsigned long long)P.W.cdraw[n] + 1ULL) - curStep;
+          if (k < 64ULL) { st = (sA[k] * curState + sC[k]) & MASK; stp = &st; }              // (else: the jump inside stage_resolve)
+        }
+        int key;
+        if (!stage_resolve(P.C, P.W, n, &key, stp)) { P.W.state[1] = 1; P.W.state[11] = 7; }
+        if (key >= 0) atomicMin(&P.W.firstPos[key], n);
+      }
+      const unsigned long long k2 = nextStep - curStep;
+      curState = k2 < 64ULL ? (sA[k2] * curState + sC[k2]) & MASK : lcg_jump(P.C.jmpA, P.C.jmpC, P.C.seed0, nextStep);
+      curStep = nextStep;
+    }
+  }
+  risk = __reduce_add_sync(0xffffffffu, risk);
+  slow = __reduce_add_sync(0xffffffffu, slow);
+  if (lane == 0 && risk) atomicAdd(&P.W.state[7], risk);
+  if (lane == 0 && slow) atomicAdd(&P.W.state[8], slow);
+}
+#endif
 // re-resolve behind a draw misprediction (images with state[5] != 0): adopt = observed draws become the prediction (before the
 // prefix sum), a = reset keys, b = stages 3, c = stage 4, d = stage 5
 __global__ void __launch_bounds__(256) k_spec_adopt(SpecImage* sp, const int* list) {
@@ -1246,11 +1325,56 @@ __global__ void __launch_bounds__(256) k_spec_memo(SpecImage* sp, const int* lis
   if (blockIdx.x == 0 && threadIdx.x == 0) stage_gate(P.C, P.W);   // seen by every later launch (NQS_ACTIVE)
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < 65536; k += gridDim.x * blockDim.x) stage_memo(P.C, P.W, k, -1);
 }
-__global__ void __launch_bounds__(256) k_spec_fill(SpecImage* sp, const int* list) {
+#if defined(NQS_EMULATE)
+__global__ void k_spec_fill(SpecImage* sp, const int* list) {
   const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P)) return;
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < P.C.npix; n += gridDim.x * blockDim.x) { stage_fill(P.C, P.W, n); stage_pack(P.C, P.W, n); }   // stages 5 and 5b
 }
+#else
+// Stages 5 and 5b. The packed records are stored segment-interleaved (record of curve position n at (n % seg) * nseg + n / seg),
+// i.e. TRANSPOSED against the curve order the work arrays are in: a tile of 32 segments x 32 offsets goes through shared
+// memory so that both the reads (32 consecutive curve positions) and the writes (32 consecutive records) are coalesced.
+__device__ __forceinline__ SpecRec make_rec(const SpecConst& C, const SpecWork& W, int n) {
+  const uint32_t xy = W.order[n];
+  const int bidx = (int)(xy & 0xFFFF) + (int)(xy >> 16) * C.width;
+  SpecRec r;
+  r.px = W.cpx[n];
+  r.xy = xy;
+  r.qf = (uint32_t)W.cq[n] | ((uint32_t)W.cflag[n] << 16) | (W.bn[bidx & 4095] > C.thresold ? 1u << 24 : 0u);
+  r.sal = (W.cflag[n] & NQS_F_PRE) ? 0.f : saliency_of(C, W, r.px);
+  return r;
+}
+__global__ void __launch_bounds__(256) k_spec_fill(SpecImage* sp, const int* list) {
+  __shared__ uint4 tile[32][33];
+  const SpecImage& P = sp[list[blockIdx.y]];
+  if (!NQS_ACTIVE(P)) return;
+  const int seg = P.C.seg, nseg = P.C.nseg, npix = P.C.npix;
+  const int tilesR = (seg + 31) >> 5, tilesC = (nseg + 31) >> 5;
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint4* const recs = reinterpret_cast<uint4*>(P.W.rec);
+  for (int t = blockIdx.x; t < tilesR * tilesC; t += gridDim.x) {
+    const int r0 = (t % tilesR) << 5, c0 = (t / tilesR) << 5;
+    for (int k = (int)w; k < 32; k += 8) {                 // segment c0 + k, offsets r0 .. r0 + 31: consecutive curve positions
+      const int c = c0 + k, r = r0 + (int)lane;
+      const long long n = (long long)c * seg + r;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (c < nseg && r < seg && n < npix) {
+        stage_fill(P.C, P.W, (int)n);
+        const SpecRec rec = make_rec(P.C, P.W, (int)n);
+        v = make_uint4(rec.px, rec.xy, rec.qf, __float_as_uint(rec.sal));
+      }
+      tile[k][lane] = v;
+    }
+    __syncthreads();
+    for (int j = (int)w; j < 32; j += 8) {                 // offset r0 + j, segments c0 .. c0 + 31: consecutive records
+      const int r = r0 + j, c = c0 + (int)lane;
+      if (r < seg && c < nseg && (long long)c * seg + r < npix) recs[(size_t)r * (size_t)nseg + (size_t)c] = tile[lane][j];
+    }
+    __syncthreads();
+  }
+}
+#endif
 // stage 5b alone for the images with a pending patch (a patch may touch any pixel behind its position)
 __global__ void __launch_bounds__(256) k_spec_pack(SpecImage* sp, const int* list) {
   const SpecImage& P = sp[list[blockIdx.y]];
@@ -1435,7 +1559,7 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* d
       be.launch(k_spec_scan_c, cg, 256, dSpec, (const int*)dFresh, 0); be.lap("scan");
       be.launch(k_spec_resolve, pg, 256, dSpec, (const int*)dFresh); be.lap("resolve");
       be.launch(k_spec_memo, kg, 256, dSpec, (const int*)dFresh); be.lap("memo");
-      be.launch(k_spec_fill, pg, 256, dSpec, (const int*)dFresh); be.lap("fill+pack");
+      be.launch(k_spec_fill, dim3((unsigned)((smCount * 16) / nFresh > 1 ? (smCount * 16) / nFresh : 1), (unsigned)nFresh), 256, dSpec, (const int*)dFresh); be.lap("fill+pack");
     }
     if (!nActive) break;
     // ---- one round for everything in the pool: stages 6, 6b, 7. The list is kept grouped by stage-6 instantiation.
