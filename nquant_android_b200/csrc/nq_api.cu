@@ -750,6 +750,7 @@ int convert_group(nq_ctx* c, const GroupArgs& A, int n, const uint32_t* dIn, uin
     // (from 32 images on) so that the copies of one piece overlap the kernels of the other.
     const int pieces = std::max((n + 511) / 512, (A.hIn && n >= 32) ? 2 : 1);
     per = (n <= 640 && pieces == 1) ? n : (n + pieces - 1) / pieces;
+  }
   if (c->debug) per = n;
   per = std::max(1, std::min(per, n));
   const int nch = (n + per - 1) / per;
