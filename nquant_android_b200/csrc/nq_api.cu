@@ -173,8 +173,9 @@ struct nq_ctx {
   cudaStream_t stream = nullptr;      // where the caller's order and timing live (nq_set_stream)
   cudaStream_t ownStream = nullptr;
   // internal streams of a call (convert_group): front = scan .. merge of a chunk, dith = dither of the chunks in order,
-  // aux = the serial dither kernels next to the speculative rounds, copyOut = device -> host of finished chunks
-  cudaStream_t sFront[NQ_FRONT_STREAMS] = {}, sDith = nullptr, sAux = nullptr, sOut = nullptr;
+  // aux = the serial dither kernels next to the speculative rounds, copyOut / copyIn = device -> host of finished chunks and
+  // host -> device of the coming ones
+  cudaStream_t sFront[NQ_FRONT_STREAMS] = {}, sDith = nullptr, sAux = nullptr, sOut = nullptr, sIn = nullptr;
   std::vector<cudaEvent_t> evPool;    // grows on demand, reused by every call
   size_t evUsed = 0;
   int smCount = 148;
@@ -387,6 +388,7 @@ struct Chunk {
   int base = 0, n = 0;
   cudaStream_t front = nullptr;
   int frontIdx = 0;
+  cudaEvent_t evIn = nullptr;      // host-buffer calls: the chunk's pixels have arrived (copy-in stream)
   cudaEvent_t ev[5] = {};          // on `front`: start, after scan, after histogram, after the find_nn sweep, after the merge loop
   cudaEvent_t evD[3] = {};         // on the dither stream: start, after setup, end
   cudaEvent_t evK[2 * NQ_NKERNELS] = {};   // pairs around the kernels timed on their own (0 when not recorded)
@@ -535,7 +537,7 @@ int enqueue_front(nq_ctx* c, Chunk& ch, const GroupArgs& A, const uint32_t* dIn,
   cudaStream_t st = ch.front;
   NqImage* dI = c->dImgs + ch.base;
   NqSlot* dS = c->dSlots + ch.base;
-  if (A.hIn) CU(cudaMemcpyAsync(const_cast<uint32_t*>(dIn) + (size_t)ch.base * npix, A.hIn + (size_t)ch.base * npix, (size_t)n * npix * 4, cudaMemcpyHostToDevice, st));
+  if (ch.evIn) CU(cudaStreamWaitEvent(st, ch.evIn, 0));
   std::vector<NqImage> hImgs(n);
   for (int i = 0; i < n; ++i) {
     NqImage& I = hImgs[i];
@@ -743,17 +745,23 @@ int convert_group(nq_ctx* c, const GroupArgs& A, int n, const uint32_t* dIn, uin
   const uint32_t* dOrder = nullptr;
   int rc = ensure_order(c, A.w, A.h, &dOrder);
   if (rc) return rc;
-  int per = c->chunkImages;
-  if (per <= 0) {
-    // automatic: the merge loop wants >= 4 images per SM in flight, so chunks stay as large as possible: batches up to 640
-    // images in one piece, larger ones in equal pieces of at most 512. Host-buffer calls are cut in at least two pieces
-    // (from 32 images on) so that the copies of one piece overlap the kernels of the other.
-    const int pieces = std::max((n + 511) / 512, (A.hIn && n >= 32) ? 2 : 1);
-    per = (n <= 640 && pieces == 1) ? n : (n + pieces - 1) / pieces;
+  // Chunk sizes. The merge loop wants >= 4 images per SM in flight, so chunks stay large: batches up to 640 images in one
+  // piece, larger ones in equal pieces of at most 512. Host-buffer calls (from 32 images on) get a short first and a short
+  // last piece (an eighth of the batch each) so that little of the first host->device and of the last device->host copy is
+  // left uncovered by kernels.
+  std::vector<int> sizes;
+  if (c->debug) sizes.push_back(n);
+  else if (c->chunkImages > 0) { for (int b = 0; b < n; b += c->chunkImages) sizes.push_back(std::min(c->chunkImages, n - b)); }
+  else if (A.hIn && n >= 32) {
+    const int edge = std::max(1, n / 8), mid = n - 2 * edge, pieces = std::max(1, (mid + 511) / 512);
+    sizes.push_back(edge);
+    for (int k = 0; k < pieces; ++k) sizes.push_back(mid / pieces + (k < mid % pieces ? 1 : 0));
+    sizes.push_back(edge);
+  } else {
+    const int pieces = n <= 640 ? 1 : (n + 511) / 512;
+    for (int k = 0; k < pieces; ++k) sizes.push_back(n / pieces + (k < n % pieces ? 1 : 0));
   }
-  if (c->debug) per = n;
-  per = std::max(1, std::min(per, n));
-  const int nch = (n + per - 1) / per;
+  const int nch = (int)sizes.size();
   c->evUsed = 0;
   std::vector<Chunk> chunks(nch);
   cudaEvent_t evStart = take_event(c), evOut = take_event(c), evEnd = take_event(c);
@@ -761,20 +769,25 @@ int convert_group(nq_ctx* c, const GroupArgs& A, int n, const uint32_t* dIn, uin
   for (int k = 0; k < NQ_FRONT_STREAMS; ++k) CU(cudaStreamWaitEvent(c->sFront[k], evStart, 0));
   CU(cudaStreamWaitEvent(c->sDith, evStart, 0));
   CU(cudaStreamWaitEvent(c->sOut, evStart, 0));
-  for (int k = 0; k < nch; ++k) {
+  CU(cudaStreamWaitEvent(c->sIn, evStart, 0));
+  for (int k = 0, base = 0; k < nch; base += sizes[k], ++k) {
     Chunk& ch = chunks[k];
-    ch.base = k * per; ch.n = std::min(per, n - ch.base);
+    ch.base = base; ch.n = sizes[k];
     ch.frontIdx = k % NQ_FRONT_STREAMS; ch.front = c->sFront[ch.frontIdx];
     for (auto& e : ch.ev) e = take_event(c);
     for (auto& e : ch.evD) e = take_event(c);
+    if (A.hIn) {   // every chunk's pixels are copied in on their own stream, in order, as early as the copy engine allows
+      ch.evIn = take_event(c);
+      CU(cudaMemcpyAsync(const_cast<uint32_t*>(dIn) + (size_t)ch.base * npix, A.hIn + (size_t)ch.base * npix, (size_t)ch.n * npix * 4, cudaMemcpyHostToDevice, c->sIn));
+      CU(cudaEventRecord(ch.evIn, c->sIn));
+    }
   }
   if (c->debug) for (int i = 0; i < n; ++i) c->dbg[dbgBase + i] = DebugImage{};
   GroupArgs G = A;
-  // fronts are enqueued one chunk ahead of the dither that consumes them (the speculative rounds block this thread)
-  rc = enqueue_front(c, chunks[0], G, dIn, dOut);
-  if (rc) return rc;
+  // every front is enqueued before the first dither (the speculative rounds block this thread); consecutive chunks
+  // alternate between the front streams, so at most two merge loops run next to each other and next to a dither
+  for (int k = 0; k < nch; ++k) { rc = enqueue_front(c, chunks[k], G, dIn, dOut); if (rc) return rc; }
   for (int k = 0; k < nch; ++k) {
-    if (k + 1 < nch) { rc = enqueue_front(c, chunks[k + 1], G, dIn, dOut); if (rc) return rc; }
     rc = run_dither(c, chunks[k], G, dOrder);
     if (rc) return rc;
     if (A.hOut) {   // device -> host of the finished chunk on its own stream
@@ -791,6 +804,7 @@ int convert_group(nq_ctx* c, const GroupArgs& A, int n, const uint32_t* dIn, uin
   CU(cudaStreamSynchronize(c->sDith));
   for (int k = 0; k < NQ_FRONT_STREAMS; ++k) CU(cudaStreamSynchronize(c->sFront[k]));
   CU(cudaStreamSynchronize(c->sAux));
+  CU(cudaStreamSynchronize(c->sIn));
   for (Chunk& ch : chunks) {
     float ms = 0.f;
     for (int k = 0; k < 4; ++k) if (cudaEventElapsedTime(&ms, ch.ev[k], ch.ev[k + 1]) == cudaSuccess) c->stageMs[k] += ms;
@@ -890,6 +904,7 @@ void destroy_ctx(nq_ctx* c, bool dropLut) {
   if (c->sDith) cudaStreamDestroy(c->sDith);
   if (c->sAux) cudaStreamDestroy(c->sAux);
   if (c->sOut) cudaStreamDestroy(c->sOut);
+  if (c->sIn) cudaStreamDestroy(c->sIn);
   if (c->ownStream) cudaStreamDestroy(c->ownStream);
   delete c;
 }
@@ -935,6 +950,7 @@ nq_ctx* nq_create(int device) {
   ok = ok && cudaStreamCreateWithFlags(&c->sDith, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&c->sAux, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&c->sOut, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&c->sIn, cudaStreamNonBlocking) == cudaSuccess;
   if (!ok) { fail(NQ_ERR_CUDA, "cudaStreamCreate failed"); destroy_ctx(c, false); return nullptr; }
   c->stream = c->ownStream;
   if (const char* e = getenv("NQ_SPEC_DITHER")) c->specDither = atoi(e) != 0;
