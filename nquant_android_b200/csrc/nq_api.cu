@@ -394,6 +394,11 @@ struct Chunk {
   cudaEvent_t evK[2 * NQ_NKERNELS] = {};   // pairs around the kernels timed on their own (0 when not recorded)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> evRuns;   // around every k_spec_run launch
   unsigned long long launches[NQ_NSTAGES] = {};
+  // host-buffer calls: images [0, copied) of the chunk are already on their way to the host (progressive copy-out)
+  int copied = 0;
+  uint32_t* hOut = nullptr;        // host destination of the chunk's first image, or nullptr
+  const uint32_t* dOut = nullptr;  // device source of the chunk's first image
+  size_t imageBytes = 0;
 };
 
 // launches and small copies of the admission / round loop (spec_drive in nq_dither_spec.cuh) on the dither stream
@@ -436,6 +441,16 @@ struct SpecCudaBackend {
     cudaEventElapsedTime(&ms, t0, t1);
     fprintf(stderr, "[nq spec] %-14s %9.3f ms\n", what, ms);
     cudaEventRecord(t0, st);
+  }
+  // images [0, prefix) of the chunk are complete: copy them out on the copy-out stream while the rest is still being dithered
+  void done_prefix(int prefix) {
+    if (!ch->hOut || prefix - ch->copied < 16) return;
+    cudaEvent_t e = take_event(c);
+    keep(cudaEventRecord(e, st));
+    keep(cudaStreamWaitEvent(c->sOut, e, 0));
+    keep(cudaMemcpyAsync(ch->hOut + (size_t)ch->copied * (ch->imageBytes / 4), ch->dOut + (size_t)ch->copied * (ch->imageBytes / 4),
+                         (size_t)(prefix - ch->copied) * ch->imageBytes, cudaMemcpyDeviceToHost, c->sOut));
+    ch->copied = prefix;
   }
   void note(int round, int active, int open, int patches, int redos) {
     if (timing) fprintf(stderr, "[nq spec] round %d: %d image(s) in the pool, %d open, %d patch(es), %d re-resolve(s)\n", round, active, open, patches, redos);
@@ -746,19 +761,14 @@ int convert_group(nq_ctx* c, const GroupArgs& A, int n, const uint32_t* dIn, uin
   int rc = ensure_order(c, A.w, A.h, &dOrder);
   if (rc) return rc;
   // Chunk sizes. The merge loop wants >= 4 images per SM in flight, so chunks stay large: batches up to 640 images in one
-  // piece, larger ones in equal pieces of at most 512. Host-buffer calls (from 32 images on) get a short first and a short
-  // last piece (an eighth of the batch each) so that little of the first host->device and of the last device->host copy is
-  // left uncovered by kernels.
+  // piece, larger ones in equal pieces of at most 512; host-buffer calls (from 32 images on) in at least two, so that the copies
+  // of one piece overlap the kernels of the other (a short first and last piece was tried and lost more in the merge loop than
+  // it hid). The device->host copy of a chunk starts while its dither is still running (SpecCudaBackend::done_prefix).
   std::vector<int> sizes;
   if (c->debug) sizes.push_back(n);
   else if (c->chunkImages > 0) { for (int b = 0; b < n; b += c->chunkImages) sizes.push_back(std::min(c->chunkImages, n - b)); }
-  else if (A.hIn && n >= 32) {
-    const int edge = std::max(1, n / 8), mid = n - 2 * edge, pieces = std::max(1, (mid + 511) / 512);
-    sizes.push_back(edge);
-    for (int k = 0; k < pieces; ++k) sizes.push_back(mid / pieces + (k < mid % pieces ? 1 : 0));
-    sizes.push_back(edge);
-  } else {
-    const int pieces = n <= 640 ? 1 : (n + 511) / 512;
+  else {
+    const int pieces = std::max(n <= 640 ? 1 : (n + 511) / 512, (A.hIn && n >= 32) ? 2 : 1);
     for (int k = 0; k < pieces; ++k) sizes.push_back(n / pieces + (k < n % pieces ? 1 : 0));
   }
   const int nch = (int)sizes.size();
@@ -788,11 +798,14 @@ int convert_group(nq_ctx* c, const GroupArgs& A, int n, const uint32_t* dIn, uin
   // alternate between the front streams, so at most two merge loops run next to each other and next to a dither
   for (int k = 0; k < nch; ++k) { rc = enqueue_front(c, chunks[k], G, dIn, dOut); if (rc) return rc; }
   for (int k = 0; k < nch; ++k) {
+    if (A.hOut) { chunks[k].hOut = A.hOut + (size_t)chunks[k].base * npix; chunks[k].dOut = dOut + (size_t)chunks[k].base * npix; chunks[k].imageBytes = (size_t)npix * 4; }
     rc = run_dither(c, chunks[k], G, dOrder);
     if (rc) return rc;
-    if (A.hOut) {   // device -> host of the finished chunk on its own stream
-      CU(cudaStreamWaitEvent(c->sOut, chunks[k].evD[2], 0));
-      CU(cudaMemcpyAsync(A.hOut + (size_t)chunks[k].base * npix, dOut + (size_t)chunks[k].base * npix, (size_t)chunks[k].n * npix * 4, cudaMemcpyDeviceToHost, c->sOut));
+    if (A.hOut && chunks[k].copied < chunks[k].n) {   // device -> host of what the progressive copy-out has not taken yet
+      Chunk& ch = chunks[k];
+      CU(cudaStreamWaitEvent(c->sOut, ch.evD[2], 0));
+      CU(cudaMemcpyAsync(A.hOut + (size_t)(ch.base + ch.copied) * npix, dOut + (size_t)(ch.base + ch.copied) * npix, (size_t)(ch.n - ch.copied) * npix * 4,
+                         cudaMemcpyDeviceToHost, c->sOut));
     }
   }
   CU(cudaEventRecord(evOut, c->sOut));

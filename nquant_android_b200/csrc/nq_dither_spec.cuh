@@ -1524,7 +1524,9 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* d
   // host mirrors
   int* active = new int[nslots]; int* slotOfActive = new int[nslots]; int* fresh = new int[nslots]; int* freshSlot = new int[nslots];
   int* status = new int[nslots]; int* freeSlots = new int[nslots]; int* rounds = new int[nslots]; int* leaving = new int[nslots];
-  int nActive = 0, nFree = nslots, next = 0, nHanded = 0;
+  int nActive = 0, nFree = nslots, next = 0, nHanded = 0, prefix = 0;
+  unsigned char* finished = new unsigned char[n];   // images this path will not touch again (not its own, completed, handed back)
+  for (int i = 0; i < n; ++i) finished[i] = (elig[i] & 255) == 1 ? 0 : 2;
   for (int k = 0; k < nslots; ++k) freeSlots[k] = nslots - 1 - k;
   const int nchunk = (npix + NQS_CHUNK - 1) / NQS_CHUNK;
   auto pgrid = [&](int m) {
@@ -1614,15 +1616,22 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* d
       if (leave) {
         leaving[nLeave++] = active[k];
         freeSlots[nFree++] = slotOfActive[k];
-        if (status[k] & 8) { ++st->handedBack; if (handedBack) handedBack[nHanded] = active[k]; ++nHanded; } else ++st->done;
+        if (status[k] & 8) { ++st->handedBack; if (handedBack) handedBack[nHanded] = active[k]; ++nHanded; finished[active[k]] = 2; }
+        else { ++st->done; finished[active[k]] = 1; }
       } else { active[keep] = active[k]; slotOfActive[keep] = slotOfActive[k]; rounds[keep] = rounds[k]; ++keep; }
     }
     nActive = keep;
     if (nLeave) {
       be.write_ints(dFresh, leaving, nLeave);               // (dFresh is free again: stream order)
       be.launch(k_spec_finish, dim3((unsigned)((nLeave + 63) / 64)), 64, dImgs, dSpec, (const int*)dFresh, nLeave);
+      // the leading run of images that are COMPLETE (a caller with host buffers starts copying them out while the rest is
+      // still in the pool); it stops at the first image another kernel has to dither
+      int p = prefix;
+      while (p < n && finished[p] == 1) ++p;
+      if (p > prefix) { prefix = p; be.done_prefix(prefix); }
     }
   }
+  delete[] finished;
   delete[] active; delete[] slotOfActive; delete[] fresh; delete[] freshSlot; delete[] status; delete[] freeSlots; delete[] rounds; delete[] leaving;
 }
 #endif  // __CUDACC__ || NQS_EMULATE

@@ -327,6 +327,7 @@ struct EmuBackend {
   void read_ints(int* host, const int* dev, int n) { memcpy(host, dev, sizeof(int) * (size_t)n); }
   void lap(const char*) {}
   void note(int, int, int, int, int) {}
+  void done_prefix(int) {}
 };
 }  // namespace
 
