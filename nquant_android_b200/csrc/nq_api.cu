@@ -215,6 +215,7 @@ struct nq_ctx {
   // speculative segment-parallel dither (nq_dither_spec.cuh); on unless nq_set_spec_dither(0) / NQ_SPEC_DITHER=0
   bool specDither = true;
   int specSeg = 0, specWarm = 1024;
+  size_t specPoolMaxBytes = 0;     // NQ_SPEC_POOL_GB: cap on the pool's memory (0 = 96 GB)
   int specSlotsMax = 0;            // cap on the pool of work-array slots (0 = none; NQ_SPEC_SLOTS, tests force slot reuse with it)
   nq::spec::SpecImage* dSpec = nullptr;
   int specCap = 0;                 // images dSpec holds
@@ -486,9 +487,12 @@ int spec_prepare(nq_ctx* c, Chunk& ch, cudaStream_t st, int npix, const uint32_t
   const SpecLayout L = spec_layout(npix, seg);
   size_t freeB = 0, totalB = 0;
   CU(cudaMemGetInfo(&freeB, &totalB));
-  // the pool only has to fill the machine (one thread per segment: ~150 4K images); the rest of the memory stays the caller's
-  const size_t budget = std::min<size_t>((size_t)((double)(freeB + c->specBufBytes) * 0.5), (size_t)48 << 30);
-  const long long wantThreads = (long long)c->smCount * 1024;                       // segments in flight that fill the SMs twice over
+  // The rounds are latency bound (a round lasts as long as its slowest thread: a chain of segments run sequentially), so the
+  // throughput of the path is images in the pool / (rounds per image x round time): the pool takes up to 300 4K images
+  // (one thread per segment: the SMs filled four times over) and up to half of the free memory, at most 96 GB.
+  const size_t poolCap = c->specPoolMaxBytes ? c->specPoolMaxBytes : ((size_t)96 << 30);
+  const size_t budget = std::min<size_t>((size_t)((double)(freeB + c->specBufBytes) * 0.5), poolCap);
+  const long long wantThreads = (long long)c->smCount * 2048;
   int nslots = (int)std::min<long long>(n, std::max<long long>(8, (wantThreads + L.nseg - 1) / L.nseg));
   nslots = (int)std::min<size_t>((size_t)nslots, budget / L.perSlot);
   if (c->specSlotsMax > 0) nslots = std::min(nslots, c->specSlotsMax);
@@ -969,6 +973,7 @@ nq_ctx* nq_create(int device) {
   if (const char* e = getenv("NQ_SPEC_DITHER")) c->specDither = atoi(e) != 0;
   if (const char* e = getenv("NQ_CHUNK")) c->chunkImages = atoi(e);
   if (const char* e = getenv("NQ_SPEC_SLOTS")) c->specSlotsMax = atoi(e);
+  if (const char* e = getenv("NQ_SPEC_POOL_GB")) c->specPoolMaxBytes = (size_t)atoi(e) << 30;
   if (const char* e = getenv("NQ_MERGE_ROT")) c->mergeRot = atoi(e) != 0;
   bool haveLut = false;
   {

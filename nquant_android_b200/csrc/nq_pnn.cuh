@@ -151,23 +151,6 @@ __device__ __forceinline__ bool lab_block_skip_v(const LabProbe& P, const float4
   const float lb = (P.ratioLo * nerr2) * q * 0.9999f;
   return lb > Uup;
 }
-// the two quantities lab_block_skip_v compares with U, for a caller that does not know U yet. nerr2 = +inf: no live bin.
-__device__ __forceinline__ void lab_block_bounds(const LabProbe& P, const float4 s0, const float4 s1, float* nerr2Out, float* lbOut) {
-  const float cmin = s0.x;
-  if (!(cmin >= 0.f)) { *nerr2Out = __int_as_float(0x7f800000); *lbOut = 0.f; return; }
-  const float nerr2 = ((P.n1 * cmin) / (P.n1 + cmin)) * 0.9999f;
-  const float dl = fmaxf(0.f, fmaxf(s0.y - P.L1, P.L1 - s0.z));
-  const float da = fmaxf(0.f, fmaxf(s1.x - P.A1, P.A1 - s1.y));
-  const float db = fmaxf(0.f, fmaxf(s1.z - P.B1, P.B1 - s1.w));
-  const float cb = (0.75f * (P.C1 + s0.w)) * 1.00001f;
-  const float sc = (1.f + (0.045f * cb)) * 1.00001f;
-  const float rf = g_rtFac[min(255, (int)cb)];
-  const float d2 = fmaxf(0.f, (((da * da) + (db * db)) * 0.9999f) - 1e-4f);
-  const float t = dl * 0.57234f;                           // 1 / 1.7472 rounded down
-  const float q = (t * t) + __fdividef(rf * d2, (sc * sc) * 1.00001f) * 0.99999f;
-  *nerr2Out = nerr2;
-  *lbOut = (P.ratioLo * nerr2) * q * 0.9999f;
-}
 __device__ __forceinline__ bool lab_block_skip(const LabProbe& P, const LabView& V, int blk, double U) {
   return lab_block_skip_v(P, V.bs[2 * blk], V.bs[2 * blk + 1], U);
 }
@@ -506,8 +489,6 @@ __device__ __forceinline__ unsigned pack_idnn(int id, int nn) { return (unsigned
 // -------------------------------------------------------------------------------------------------
 #define NQ_LAB_THREADS 128
 #define NQ_LAB_HEAP_SMEM 5632   // 44 KB of heap: four CTAs fit one SM
-#define NQ_LAB_BATCH 64         // live blocks screened per batch (two scan entries per lane of warp 0)
-#define NQ_LAB_PRE 6            // block bounds per thread of warps 1-3 computed while warp 0 evaluates the first 32 candidates
 
 __device__ __forceinline__ int block_excl_scan_128(int v, int* total, int* sScan /*[8]*/) {
   const unsigned lane = lane_id(), w = threadIdx.x >> 5;
@@ -565,9 +546,9 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
   __shared__ int sScan[8];
   __shared__ unsigned sBits[64];             // live blocks of this rescan, one bit per block
   __shared__ unsigned short sBlk[2048];      // the same as an ordered list
-  __shared__ unsigned sMaskA[NQ_LAB_BATCH];  // bins that passed the cheap bound, per block of the current batch
-  __shared__ unsigned sMaskB[NQ_LAB_BATCH];  // ... of those, the ones that passed the screen, per 32 list entries
-  __shared__ int sOffA[NQ_LAB_BATCH + 1], sOffB[NQ_LAB_BATCH + 1];
+  __shared__ unsigned sMaskA[32];            // bins that passed the cheap bound, per block of the current batch
+  __shared__ unsigned sMaskB[32];            // ... of those, the ones that passed the screen, per 32 list entries
+  __shared__ int sOffA[33], sOffB[33];
   __shared__ double sGs[NQ_LAB_THREADS], sGw[NQ_LAB_THREADS], sF[NQ_LAB_THREADS];
   __shared__ int sPos[NQ_LAB_THREADS];       // position of a fully evaluated survivor, -1 = rejected
   __shared__ double sErrCur;
@@ -664,11 +645,7 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
       const LabProbe P = lab_probe(I, S, b1, ratioMerge);
       double err = 1e100;
       int nn = -1;                              // position in the live list
-      // -- 1. the first 32 candidates in full (warp 0); meanwhile warps 1-3 work out the summary bounds of the blocks behind
-      //       them -- everything of step 2 that does not need err yet (NQ_LAB_PRE blocks per thread, kept in registers)
-      const int stop = first + 32;
-      const int blkBeg = stop >> 5, nblk = (liveLen + 31) >> 5;
-      float pn[NQ_LAB_PRE], pl[NQ_LAB_PRE];
+      // -- 1. the first 32 candidates in full
       if (w == 0) {
         const int i = first + (int)lane;
         LabCand c;
@@ -676,30 +653,15 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
         lab_accept_in_order(alive, c, i, err, nn);
         fulls += i < liveLen;
         if (lane == 0) { sErrCur = err; sNnCur = nn; }
-      } else {
-#pragma unroll
-        for (int j = 0; j < NQ_LAB_PRE; ++j) {
-          const int blk = blkBeg + (t - 32) + j * (NQ_LAB_THREADS - 32);
-          pn[j] = __int_as_float(0x7f800000); pl[j] = 0.f;
-          if (blk < nblk) lab_block_bounds(P, V.bs[2 * blk], V.bs[2 * blk + 1], &pn[j], &pl[j]);
-        }
       }
       __syncthreads();
       tick(1);
       err = sErrCur; nn = sNnCur;
       // -- 2. block summaries of everything behind them
-      {
-        const float Uup = __double2float_ru(err);
-        if (w != 0) {
-#pragma unroll
-          for (int j = 0; j < NQ_LAB_PRE; ++j) {
-            const int blk = blkBeg + (t - 32) + j * (NQ_LAB_THREADS - 32);
-            if (blk < nblk && !(pn[j] >= Uup || pl[j] > Uup)) atomicOr(&sBits[blk >> 5], 1u << (blk & 31));
-          }
-        }
-        for (int blk = blkBeg + NQ_LAB_PRE * (NQ_LAB_THREADS - 32) + t; blk < nblk; blk += NQ_LAB_THREADS)
-          if (!lab_block_skip(P, V, blk, err)) atomicOr(&sBits[blk >> 5], 1u << (blk & 31));
-      }
+      const int stop = first + 32;
+      const int blkBeg = stop >> 5, nblk = (liveLen + 31) >> 5;
+      for (int blk = blkBeg + t; blk < nblk; blk += NQ_LAB_THREADS)
+        if (!lab_block_skip(P, V, blk, err)) atomicOr(&sBits[blk >> 5], 1u << (blk & 31));
       __syncthreads();
       if (w == 0) {                             // bit set -> ordered list
         const unsigned m0 = sBits[2 * lane], m1 = sBits[2 * lane + 1];
@@ -716,10 +678,10 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
       tick(2);
       const int nLive = sNLive;
       liveBlocks += nLive;
-      for (int g0 = 0; g0 < nLive; g0 += NQ_LAB_BATCH) {  // batches of 64 live blocks (<= 2048 bins), in list order
-        const int gn = min(NQ_LAB_BATCH, nLive - g0);
+      for (int g0 = 0; g0 < nLive; g0 += 32) {  // batches of 32 live blocks (<= 1024 bins), in list order
+        const int gn = min(32, nLive - g0);
         // -- 3a. per-candidate lower bound (lab_cheap_keep): one warp per block, one lane per bin
-        if (t < NQ_LAB_BATCH) { sMaskA[t] = 0u; sMaskB[t] = 0u; }
+        if (t < 32) { sMaskA[t] = 0u; sMaskB[t] = 0u; }
         __syncthreads();
         for (int r0 = w; r0 < gn; r0 += 4 * W) {     // four records in flight per lane: the loads come from L2
           float4 v[4];
@@ -737,19 +699,19 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
           }
         }
         __syncthreads();
-        if (w == 0) {                             // two entries per lane
-          const int c0 = __popc(sMaskA[2 * lane]), c1 = __popc(sMaskA[2 * lane + 1]);
-          int x = c0 + c1;
+        if (w == 0) {
+          const int c = __popc(sMaskA[lane]);
+          int x = c;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
-          sOffA[2 * lane + 1] = x - c1; sOffA[2 * lane + 2] = x;
+          sOffA[lane + 1] = x;
           if (lane == 0) sOffA[0] = 0;
         }
         __syncthreads();
-        const int totalA = sOffA[NQ_LAB_BATCH];
+        const int totalA = sOffA[32];
         // the s-th bin that passed 3a, in list order
         auto posA = [&](int sIdx) {
-          int lo = 0, hi = NQ_LAB_BATCH;          // largest r with sOffA[r] <= sIdx
+          int lo = 0, hi = 32;                    // largest r with sOffA[r] <= sIdx
           while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sOffA[mid] <= sIdx) lo = mid; else hi = mid; }
           return ((int)sBlk[g0 + lo] << 5) + (int)__fns(sMaskA[lo], 0, sIdx - sOffA[lo] + 1);
         };
@@ -763,23 +725,23 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
         }
         __syncthreads();
         if (w == 0) {
-          const int c0 = __popc(sMaskB[2 * lane]), c1 = __popc(sMaskB[2 * lane + 1]);
-          int x = c0 + c1;
+          const int c = __popc(sMaskB[lane]);
+          int x = c;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
-          sOffB[2 * lane + 1] = x - c1; sOffB[2 * lane + 2] = x;
+          sOffB[lane + 1] = x;
           if (lane == 0) sOffB[0] = 0;
         }
         __syncthreads();
         tick(3);
-        const int total = sOffB[NQ_LAB_BATCH];
+        const int total = sOffB[32];
         screened += total;
         // -- 4. survivors in full, packed; then resolved in order
         for (int base = 0; base < total; base += NQ_LAB_THREADS) {
           const int uIdx = base + t;
           int pos = -1;
           if (uIdx < total) {
-            int lo = 0, hi = NQ_LAB_BATCH;        // largest word with sOffB[word] <= uIdx
+            int lo = 0, hi = 32;                  // largest word with sOffB[word] <= uIdx
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sOffB[mid] <= uIdx) lo = mid; else hi = mid; }
             const int sIdx = (lo << 5) + (int)__fns(sMaskB[lo], 0, uIdx - sOffB[lo] + 1);   // index into the 3a list
             const int i = posA(sIdx);
