@@ -175,7 +175,7 @@ struct nq_ctx {
   // internal streams of a call (convert_group): front = scan .. merge of a chunk, dith = dither of the chunks in order,
   // aux = the serial dither kernels next to the speculative rounds, copyOut / copyIn = device -> host of finished chunks and
   // host -> device of the coming ones
-  cudaStream_t sFront[NQ_FRONT_STREAMS] = {}, sDith = nullptr, sAux = nullptr, sOut = nullptr, sIn = nullptr;
+  cudaStream_t sFront[NQ_FRONT_STREAMS] = {}, sDith = nullptr, sAux = nullptr, sOut = nullptr, sIn = nullptr, sChain = nullptr;
   std::vector<cudaEvent_t> evPool;    // grows on demand, reused by every call
   size_t evUsed = 0;
   int smCount = 148;
@@ -406,7 +406,8 @@ struct Chunk {
 struct SpecCudaBackend {
   nq_ctx* c;
   Chunk* ch;
-  cudaStream_t st;
+  cudaStream_t st;                 // where launches go: the dither stream, or the chain stream between chain_begin / chain_end
+  cudaStream_t mainSt = nullptr;
   bool timing = false;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   cudaError_t err = cudaSuccess;
@@ -443,6 +444,20 @@ struct SpecCudaBackend {
     fprintf(stderr, "[nq spec] %-14s %9.3f ms\n", what, ms);
     cudaEventRecord(t0, st);
   }
+  // launches that hold a sequential chain (one thread, tens of milliseconds) go to the chain stream, behind everything the
+  // dither stream holds so far; spec_drive parks the image until the event of its launch has fired
+  void chain_begin() {
+    mainSt = st;
+    cudaEvent_t e = take_event(c);
+    keep(cudaEventRecord(e, mainSt));
+    keep(cudaStreamWaitEvent(c->sChain, e, 0));
+    st = c->sChain;
+  }
+  void chain_end() { st = mainSt; }
+  void* chain_mark() { cudaEvent_t e = take_event(c); keep(cudaEventRecord(e, c->sChain)); return (void*)e; }
+  bool event_done(void* e) { return cudaEventQuery((cudaEvent_t)e) != cudaErrorNotReady; }
+  void event_wait_host(void* e) { keep(cudaEventSynchronize((cudaEvent_t)e)); }
+  void main_wait(void* e) { keep(cudaStreamWaitEvent(st, (cudaEvent_t)e, 0)); }
   // images [0, prefix) of the chunk are complete: copy them out on the copy-out stream while the rest is still being dithered
   void done_prefix(int prefix) {
     if (!ch->hOut || prefix - ch->copied < 16) return;
@@ -507,7 +522,7 @@ int spec_prepare(nq_ctx* c, Chunk& ch, cudaStream_t st, int npix, const uint32_t
     if (c->dSpecPool) { CU(cudaDeviceSynchronize()); cudaFree(c->dSpecPool); cudaFree(c->dSpecInts); }
     c->dSpecPool = nullptr; c->dSpecInts = nullptr; c->specPoolCap = 0;
     CU(cudaMalloc(&c->dSpecPool, sizeof(SpecWork) * (size_t)nslots));
-    CU(cudaMalloc(&c->dSpecInts, sizeof(int) * (size_t)(4 * nslots + 4)));
+    CU(cudaMalloc(&c->dSpecInts, sizeof(int) * (size_t)(5 * nslots + 4)));
     c->specPoolCap = nslots;
   }
   std::vector<SpecWork> pool(nslots);
@@ -822,6 +837,7 @@ int convert_group(nq_ctx* c, const GroupArgs& A, int n, const uint32_t* dIn, uin
   for (int k = 0; k < NQ_FRONT_STREAMS; ++k) CU(cudaStreamSynchronize(c->sFront[k]));
   CU(cudaStreamSynchronize(c->sAux));
   CU(cudaStreamSynchronize(c->sIn));
+  CU(cudaStreamSynchronize(c->sChain));
   for (Chunk& ch : chunks) {
     float ms = 0.f;
     for (int k = 0; k < 4; ++k) if (cudaEventElapsedTime(&ms, ch.ev[k], ch.ev[k + 1]) == cudaSuccess) c->stageMs[k] += ms;
@@ -922,6 +938,7 @@ void destroy_ctx(nq_ctx* c, bool dropLut) {
   if (c->sAux) cudaStreamDestroy(c->sAux);
   if (c->sOut) cudaStreamDestroy(c->sOut);
   if (c->sIn) cudaStreamDestroy(c->sIn);
+  if (c->sChain) cudaStreamDestroy(c->sChain);
   if (c->ownStream) cudaStreamDestroy(c->ownStream);
   delete c;
 }
@@ -968,6 +985,7 @@ nq_ctx* nq_create(int device) {
   ok = ok && cudaStreamCreateWithFlags(&c->sAux, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&c->sOut, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&c->sIn, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&c->sChain, cudaStreamNonBlocking) == cudaSuccess;
   if (!ok) { fail(NQ_ERR_CUDA, "cudaStreamCreate failed"); destroy_ctx(c, false); return nullptr; }
   c->stream = c->ownStream;
   if (const char* e = getenv("NQ_SPEC_DITHER")) c->specDither = atoi(e) != 0;

@@ -15,6 +15,23 @@ CLS = {"smooth": 0, "noisy": 1, "rand": 2}
 ALPHA = {"opaque": 0, "transparent": 1, "semi": 2}
 
 
+def _oracle_seconds():
+    """oracle_seconds of the frozen cases (tests/golden/oracle_big_cases.json): the CPU time of ONE image on one core of the
+    build container (measured while 4-5 oracle jobs shared its 8 cores, so a little high)."""
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "oracle_big_cases.json")
+    out = {}
+    try:
+        for c in json.load(open(path)):
+            out[(c["kind"], c["cls"], c["alpha"], c["w"], c["h"], c["k"], c["dither"])] = c.get("oracle_seconds")
+    except Exception:
+        pass
+    return out
+
+
+ORACLE_S = _oracle_seconds()
+
+
 def run(ctx, label, kind, cls, alpha, W, H, K, dither, batch):
     npix = W * H
     din = torch.empty(batch * npix, dtype=torch.int32, device="cuda")
@@ -32,8 +49,11 @@ def run(ctx, label, kind, cls, alpha, W, H, K, dither, batch):
     dt, st, info = best
     q = "PnnLABQuantizer" if kind else "PnnQuantizer"
     stages = " / ".join(f"{v[0]:.0f}" for v in st.values())
+    osec = ORACLE_S.get((kind, cls, alpha, W, H, K, int(bool(dither))))
+    cpu = f"{npix / osec / 1e6:.2f}" if osec else "-"
+    ratio = f"{(batch * npix / dt) / (npix / osec):.0f}x" if osec else "-"
     print(f"| {label} | {q} | {K} | {'on' if dither else 'off'} | {cls}/{alpha} | {W}x{H} | {batch} | {info['maxbins']} | "
-          f"{dt * 1e3:.0f} | {batch * npix / dt / 1e6:.1f} | {stages} |", flush=True)
+          f"{dt * 1e3:.0f} | {batch * npix / dt / 1e6:.1f} | {cpu} | {ratio} | {stages} |", flush=True)
     del din, dout
     torch.cuda.empty_cache()
 
@@ -41,8 +61,8 @@ def run(ctx, label, kind, cls, alpha, W, H, K, dither, batch):
 def main():
     big = "--big" in sys.argv
     ctx = Context(0)
-    print("| config | quantizer | colours | dither | class/alpha | size | images | bins | ms | Mpixels/s | stage ms (scan / histogram / sweep / merge / setup / dither) |")
-    print("|---|---|---:|---|---|---|---:|---:|---:|---:|---|")
+    print("| config | quantizer | colours | dither | class/alpha | size | images | bins | ms | Mpixels/s | oracle Mpixels/s (1 core) | GPU / oracle | stage ms (scan / histogram / sweep / merge / setup / dither) |")
+    print("|---|---|---:|---|---|---|---:|---:|---:|---:|---:|---:|---|")
     run(ctx, "configs[0]", 0, "noisy", "opaque", 512, 512, 256, 1, 1)
     run(ctx, "configs[1]", 1, "noisy", "opaque", 1920, 1080, 256, 1, 1)
     run(ctx, "configs[1] x592", 1, "noisy", "opaque", 1920, 1080, 256, 1, 592)
@@ -52,11 +72,11 @@ def main():
         run(ctx, f"class {cls}", 1, cls, "opaque", 3840, 2160, 256, 1, 148)
         run(ctx, f"class {cls}", 0, cls, "opaque", 3840, 2160, 256, 1, 148)
     if big:
-        for kind in (0, 1):
-            for K in (2, 16, 64, 256):
+        for kind in (1, 0):
+            for K in (256, 64, 16, 2):
                 run(ctx, "configs[4]", kind, "noisy", "opaque", 8192, 8192, K, 1, 1)
-            run(ctx, "configs[4]", kind, "noisy", "opaque", 8192, 8192, 256, 0, 1)
-            run(ctx, "configs[4]", kind, "noisy", "opaque", 8192, 8192, 64, 0, 1)
+            for K in (256, 64):
+                run(ctx, "configs[4]", kind, "noisy", "opaque", 8192, 8192, K, 0, 1)
 
 
 main()
