@@ -1525,7 +1525,8 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* d
   const int nseg = (npix + seg - 1) / seg;
   const int roundCap = nseg / 4 + 96;
   int* dFresh = dInts; int* dFreshSlot = dInts + nslots; int* dActive = dInts + 2 * nslots; int* dStatus = dInts + 3 * nslots;
-  int* dChain = dInts + 4 * nslots;          // one entry per slot: the list of a chain launch (must outlive the round)
+  int* dChain = dInts + 4 * nslots;          // ring of 2 * nslots entries: the lists of the chain launches (they outlive the round)
+  int chainAt = 0;
   // host mirrors. An entry of the pool is either in the round loop or PARKED: its dirty segments (a sequential chain among
   // them: one thread, tens of milliseconds) run in a launch of their own on the chain stream, and the entry comes back when
   // that launch's event has fired -- the rounds of everybody else do not wait for it.
@@ -1554,7 +1555,7 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* d
     // ---- parked entries whose launch has finished come back
     int nParked = 0;
     for (int k = 0; k < nActive; ++k)
-      if (parked[k]) { if (be.event_done(parkEv[k])) { be.main_wait(parkEv[k]); parked[k] = 0; } else ++nParked; }
+      if (parked[k]) { if (be.event_done(parkEv[k])) { be.main_wait(parkEv[k]); parked[k] = 0; parkEv[k] = nullptr; } else ++nParked; }
     // ---- admit images into the free slots: stages 1-5 for them
     int nFresh = 0;
     while (nFree > 0 && next < n) {
@@ -1626,17 +1627,24 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* d
       be.launch(k_spec_redo_c, ka, 256, dSpec, (const int*)dActive);
       be.launch(k_spec_redo_d, pa, 256, dSpec, (const int*)dActive); be.lap("re-resolve");
     }
-    // ---- images whose next run is a sequential chain: that run happens beside the round loop
+    // ---- images whose next run is a sequential chain: that run happens beside the round loop, ONE launch per round (and
+    //      stage-6 instantiation) on the next of the chain streams, so that launches of consecutive rounds overlap
     if (nChain) {
       be.chain_begin();                                     // the chain stream is ordered behind everything enqueued so far
-      for (int j = 0; j < nRun; ++j) {
-        if (!((status[j] & 16) && (status[j] & 1) && !(status[j] & 8))) continue;
-        const int k = runIdx[j], slot = slotOfActive[k];
-        be.write_ints(dChain + slot, &active[k], 1);
-        spec_launch_run(be, variant_of(active[k]), runGrid1, dSpec, (const int*)dChain + slot, dTanh);
-        parkEv[k] = be.chain_mark();
-        parked[k] = 1;
+      if (chainAt + nChain > 2 * nslots) chainAt = 0;       // ring of list entries: at most nslots images are parked at a time
+      int cnt = 0;
+      for (int v = 0; v < NQS_VARIANTS; ++v) {
+        const int first = cnt;
+        for (int j = 0; j < nRun; ++j)
+          if ((status[j] & 16) && (status[j] & 1) && !(status[j] & 8) && variant_of(runList[j]) == v) { fresh[cnt++] = runList[j]; parked[runIdx[j]] = 1; }
+        if (cnt > first) {
+          be.write_ints(dChain + chainAt + first, fresh + first, cnt - first);
+          spec_launch_run(be, v, dim3(runGrid1.x, (unsigned)(cnt - first)), dSpec, (const int*)dChain + chainAt + first, dTanh);
+        }
       }
+      void* ev = be.chain_mark();
+      for (int j = 0; j < nRun; ++j) if (parked[runIdx[j]] && parkEv[runIdx[j]] == nullptr) parkEv[runIdx[j]] = ev;
+      chainAt += cnt;
       be.chain_end();
     }
     // ---- images that leave: completed (no segment open) or handed back; their slots are free for the next round
