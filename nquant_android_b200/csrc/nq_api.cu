@@ -167,7 +167,6 @@ struct DebugImage {
 }  // namespace
 
 #define NQ_FRONT_STREAMS 2   // histogram / find_nn / merge of consecutive chunks alternate between these
-#define NQ_CHAIN_STREAMS 8
 
 struct nq_ctx {
   int device = 0;
@@ -177,8 +176,6 @@ struct nq_ctx {
   // aux = the serial dither kernels next to the speculative rounds, copyOut / copyIn = device -> host of finished chunks and
   // host -> device of the coming ones
   cudaStream_t sFront[NQ_FRONT_STREAMS] = {}, sDith = nullptr, sAux = nullptr, sOut = nullptr, sIn = nullptr;
-  cudaStream_t sChain[NQ_CHAIN_STREAMS] = {};   // launches that hold sequential chains, round robin
-  int chainNext = 0;
   std::vector<cudaEvent_t> evPool;    // grows on demand, reused by every call
   size_t evUsed = 0;
   int smCount = 148;
@@ -409,8 +406,7 @@ struct Chunk {
 struct SpecCudaBackend {
   nq_ctx* c;
   Chunk* ch;
-  cudaStream_t st;                 // where launches go: the dither stream, or the chain stream between chain_begin / chain_end
-  cudaStream_t mainSt = nullptr;
+  cudaStream_t st;
   bool timing = false;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   cudaError_t err = cudaSuccess;
@@ -447,22 +443,6 @@ struct SpecCudaBackend {
     fprintf(stderr, "[nq spec] %-14s %9.3f ms\n", what, ms);
     cudaEventRecord(t0, st);
   }
-  // launches that hold a sequential chain (one thread, tens of milliseconds) go to the chain stream, behind everything the
-  // dither stream holds so far; spec_drive parks the image until the event of its launch has fired
-  void chain_begin() {
-    mainSt = st;
-    cudaStream_t cs = c->sChain[c->chainNext];
-    c->chainNext = (c->chainNext + 1) % NQ_CHAIN_STREAMS;
-    cudaEvent_t e = take_event(c);
-    keep(cudaEventRecord(e, mainSt));
-    keep(cudaStreamWaitEvent(cs, e, 0));
-    st = cs;
-  }
-  void chain_end() { st = mainSt; }
-  void* chain_mark() { cudaEvent_t e = take_event(c); keep(cudaEventRecord(e, st)); return (void*)e; }
-  bool event_done(void* e) { return cudaEventQuery((cudaEvent_t)e) != cudaErrorNotReady; }
-  void event_wait_host(void* e) { keep(cudaEventSynchronize((cudaEvent_t)e)); }
-  void main_wait(void* e) { keep(cudaStreamWaitEvent(st, (cudaEvent_t)e, 0)); }
   // images [0, prefix) of the chunk are complete: copy them out on the copy-out stream while the rest is still being dithered
   void done_prefix(int prefix) {
     if (!ch->hOut || prefix - ch->copied < 16) return;
@@ -527,7 +507,7 @@ int spec_prepare(nq_ctx* c, Chunk& ch, cudaStream_t st, int npix, const uint32_t
     if (c->dSpecPool) { CU(cudaDeviceSynchronize()); cudaFree(c->dSpecPool); cudaFree(c->dSpecInts); }
     c->dSpecPool = nullptr; c->dSpecInts = nullptr; c->specPoolCap = 0;
     CU(cudaMalloc(&c->dSpecPool, sizeof(SpecWork) * (size_t)nslots));
-    CU(cudaMalloc(&c->dSpecInts, sizeof(int) * (size_t)(6 * nslots + 4)));
+    CU(cudaMalloc(&c->dSpecInts, sizeof(int) * (size_t)(4 * nslots + 4)));
     c->specPoolCap = nslots;
   }
   std::vector<SpecWork> pool(nslots);
@@ -842,7 +822,6 @@ int convert_group(nq_ctx* c, const GroupArgs& A, int n, const uint32_t* dIn, uin
   for (int k = 0; k < NQ_FRONT_STREAMS; ++k) CU(cudaStreamSynchronize(c->sFront[k]));
   CU(cudaStreamSynchronize(c->sAux));
   CU(cudaStreamSynchronize(c->sIn));
-  for (int k = 0; k < NQ_CHAIN_STREAMS; ++k) CU(cudaStreamSynchronize(c->sChain[k]));
   for (Chunk& ch : chunks) {
     float ms = 0.f;
     for (int k = 0; k < 4; ++k) if (cudaEventElapsedTime(&ms, ch.ev[k], ch.ev[k + 1]) == cudaSuccess) c->stageMs[k] += ms;
@@ -943,7 +922,6 @@ void destroy_ctx(nq_ctx* c, bool dropLut) {
   if (c->sAux) cudaStreamDestroy(c->sAux);
   if (c->sOut) cudaStreamDestroy(c->sOut);
   if (c->sIn) cudaStreamDestroy(c->sIn);
-  for (int k = 0; k < NQ_CHAIN_STREAMS; ++k) if (c->sChain[k]) cudaStreamDestroy(c->sChain[k]);
   if (c->ownStream) cudaStreamDestroy(c->ownStream);
   delete c;
 }
@@ -990,7 +968,6 @@ nq_ctx* nq_create(int device) {
   ok = ok && cudaStreamCreateWithFlags(&c->sAux, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&c->sOut, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&c->sIn, cudaStreamNonBlocking) == cudaSuccess;
-  for (int k = 0; ok && k < NQ_CHAIN_STREAMS; ++k) ok = cudaStreamCreateWithFlags(&c->sChain[k], cudaStreamNonBlocking) == cudaSuccess;
   if (!ok) { fail(NQ_ERR_CUDA, "cudaStreamCreate failed"); destroy_ctx(c, false); return nullptr; }
   c->stream = c->ownStream;
   if (const char* e = getenv("NQ_SPEC_DITHER")) c->specDither = atoi(e) != 0;

@@ -91,7 +91,7 @@ struct SpecSeg {
   int dev;                               // sequential run: curve position of the chain's first draw against its prediction, or NQS_NOPOS
   unsigned idx0;                         // sequential run: draws made in front of the segment (the index its first draw continues from)
 };
-#define NQS_MAXCHAIN 16           // segments one thread runs in a row (such launches run beside the round loop, see spec_drive)
+#define NQS_MAXCHAIN 4            // segments one thread runs in a row: bounds the time a round waits for its slowest thread
 #define NQS_MAXPATCH 24          // memo entries corrected per round and image
 // What stage 6 reads per pixel, packed by stage 5b and stored SEGMENT-INTERLEAVED: record of curve position n lives at
 // (n % seg) * nseg + n / seg, so the threads of a warp (consecutive segments, same offset inside the segment) read
@@ -1434,7 +1434,7 @@ __global__ void __launch_bounds__(64) k_spec_compare(SpecImage* sp, const int* l
   if (s < P.C.nseg) stage_compare(P.C, P.W, s);
 }
 // stage 7: one thread per listed image. status[k]: bit 0 = segments still open, 1 = patch requested, 2 = re-resolve
-// requested, 3 = left to the serial kernel, 4 = the next run of the image is a sequential chain
+// requested, 3 = left to the serial kernel
 __global__ void k_spec_validate(SpecImage* sp, const int* list, int cnt, int* status) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= cnt) return;
@@ -1448,10 +1448,6 @@ __global__ void k_spec_validate(SpecImage* sp, const int* list, int cnt, int* st
     if (open > 0) st |= 1;
     if (P.W.state[2]) st |= 2;
     if (P.W.state[5]) st |= 4;
-    // the first open segment is to be run as sequential truth (a chain on one thread): a long, lonely launch that
-    // spec_drive takes off the round loop
-    const int s0 = P.W.state[0];
-    if (s0 < P.C.nseg && P.W.segs[s0].exact && P.W.segs[s0].dirty) st |= 16;
   }
   if (!P.eligible || P.W.state[1]) st = 8;
   status[k] = st;
@@ -1525,16 +1521,9 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* d
   const int nseg = (npix + seg - 1) / seg;
   const int roundCap = nseg / 4 + 96;
   int* dFresh = dInts; int* dFreshSlot = dInts + nslots; int* dActive = dInts + 2 * nslots; int* dStatus = dInts + 3 * nslots;
-  int* dChain = dInts + 4 * nslots;          // ring of 2 * nslots entries: the lists of the chain launches (they outlive the round)
-  int chainAt = 0;
-  // host mirrors. An entry of the pool is either in the round loop or PARKED: its dirty segments (a sequential chain among
-  // them: one thread, tens of milliseconds) run in a launch of their own on the chain stream, and the entry comes back when
-  // that launch's event has fired -- the rounds of everybody else do not wait for it.
+  // host mirrors
   int* active = new int[nslots]; int* slotOfActive = new int[nslots]; int* fresh = new int[nslots]; int* freshSlot = new int[nslots];
   int* status = new int[nslots]; int* freeSlots = new int[nslots]; int* rounds = new int[nslots]; int* leaving = new int[nslots];
-  int* runList = new int[nslots]; int* runIdx = new int[nslots];
-  void** parkEv = new void*[nslots];
-  unsigned char* parked = new unsigned char[nslots];
   int nActive = 0, nFree = nslots, next = 0, nHanded = 0, prefix = 0;
   unsigned char* finished = new unsigned char[n];   // images this path will not touch again (not its own, completed, handed back)
   for (int i = 0; i < n; ++i) finished[i] = (elig[i] & 255) == 1 ? 0 : 2;
@@ -1549,13 +1538,7 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* d
     const int cap = (smCount * 16) / m > 1 ? (smCount * 16) / m : 1;
     return dim3((unsigned)(nchunk > cap ? cap : nchunk), (unsigned)m);
   };
-  auto variant_of = [&](int img) { return (elig[img] >> 8) & 7; };
-  const dim3 runGrid1((unsigned)((nseg + NQS_RUN_THREADS - 1) / NQS_RUN_THREADS), 1u);
   for (int round = 0;; ++round) {
-    // ---- parked entries whose launch has finished come back
-    int nParked = 0;
-    for (int k = 0; k < nActive; ++k)
-      if (parked[k]) { if (be.event_done(parkEv[k])) { be.main_wait(parkEv[k]); parked[k] = 0; parkEv[k] = nullptr; } else ++nParked; }
     // ---- admit images into the free slots: stages 1-5 for them
     int nFresh = 0;
     while (nFree > 0 && next < n) {
@@ -1563,7 +1546,7 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* d
       if ((elig[i] & 255) != 1) continue;
       const int slot = freeSlots[--nFree];
       fresh[nFresh] = i; freshSlot[nFresh] = slot; ++nFresh;
-      active[nActive] = i; slotOfActive[nActive] = slot; rounds[nActive] = 0; parked[nActive] = 0; parkEv[nActive] = nullptr; ++nActive;
+      active[nActive] = i; slotOfActive[nActive] = slot; rounds[nActive] = 0; ++nActive;
     }
     if (nFresh) {
       be.write_ints(dFresh, fresh, nFresh); be.write_ints(dFreshSlot, freshSlot, nFresh);
@@ -1581,88 +1564,64 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* d
       be.launch(k_spec_fill, dim3((unsigned)((smCount * 16) / nFresh > 1 ? (smCount * 16) / nFresh : 1), (unsigned)nFresh), 256, dSpec, (const int*)dFresh); be.lap("fill+pack");
     }
     if (!nActive) break;
-    // ---- the entries of this round, grouped by stage-6 instantiation
-    int nRun = 0;
-    for (int v = 0; v < NQS_VARIANTS; ++v)
-      for (int k = 0; k < nActive; ++k)
-        if (!parked[k] && variant_of(active[k]) == v) { runList[nRun] = active[k]; runIdx[nRun] = k; ++nRun; }
-    if (!nRun) {                                            // everything left is parked: wait for the first launch to finish
-      for (int k = 0; k < nActive; ++k) if (parked[k]) { be.event_wait_host(parkEv[k]); break; }
-      continue;
+    // ---- one round for everything in the pool: stages 6, 6b, 7. The list is kept grouped by stage-6 instantiation.
+    {
+      int at = 0;
+      for (int v = 0; v < NQS_VARIANTS; ++v)
+        for (int k = at; k < nActive; ++k)
+          if (((elig[active[k]] >> 8) & 7) == v) {
+            const int a = active[k], b = slotOfActive[k], r = rounds[k];
+            active[k] = active[at]; slotOfActive[k] = slotOfActive[at]; rounds[k] = rounds[at];
+            active[at] = a; slotOfActive[at] = b; rounds[at] = r; ++at;
+          }
     }
-    // ---- one round for them: stages 6, 6b, 7
-    be.write_ints(dActive, runList, nRun);
-    const dim3 s64((unsigned)((nseg + 63) / 64), (unsigned)nRun);
-    for (int k0 = 0; k0 < nRun;) {
-      const int v = variant_of(runList[k0]);
+    be.write_ints(dActive, active, nActive);
+    const dim3 s64((unsigned)((nseg + 63) / 64), (unsigned)nActive);
+    for (int k0 = 0; k0 < nActive;) {
+      const int v = (elig[active[k0]] >> 8) & 7;
       int k1 = k0;
-      while (k1 < nRun && variant_of(runList[k1]) == v) ++k1;
-      spec_launch_run(be, v, dim3(runGrid1.x, (unsigned)(k1 - k0)), dSpec, (const int*)dActive + k0, dTanh);
+      while (k1 < nActive && ((elig[active[k1]] >> 8) & 7) == v) ++k1;
+      spec_launch_run(be, v, dim3((unsigned)((nseg + NQS_RUN_THREADS - 1) / NQS_RUN_THREADS), (unsigned)(k1 - k0)), dSpec, (const int*)dActive + k0, dTanh);
       k0 = k1;
     }
     be.lap("run");
     be.launch(k_spec_compare, s64, 64, dSpec, (const int*)dActive); be.lap("compare");
-    be.launch(k_spec_validate, dim3((unsigned)((nRun + 63) / 64)), 64, dSpec, (const int*)dActive, nRun, dStatus); be.lap("validate");
-    be.read_ints(status, dStatus, nRun);
+    be.launch(k_spec_validate, dim3((unsigned)((nActive + 63) / 64)), 64, dSpec, (const int*)dActive, nActive, dStatus); be.lap("validate");
+    be.read_ints(status, dStatus, nActive);
     ++st->rounds;
-    int nOpen = 0, nPatch = 0, nRedo = 0, nLeave = 0, nChain = 0;
-    for (int j = 0; j < nRun; ++j) {
-      const int k = runIdx[j];
+    int nOpen = 0, nPatch = 0, nRedo = 0, nLeave = 0;
+    for (int k = 0; k < nActive; ++k) {
       ++rounds[k];
-      if ((status[j] & 1) && rounds[k] >= roundCap) status[j] = 8;      // not converging: the serial kernel takes it
-      nOpen += (status[j] & 1) && !(status[j] & 8); nPatch += (status[j] & 2) != 0; nRedo += (status[j] & 4) != 0;
-      nChain += (status[j] & 16) && (status[j] & 1) && !(status[j] & 8);
+      if ((status[k] & 1) && rounds[k] >= roundCap) status[k] = 8;      // not converging: the serial kernel takes it
+      nOpen += (status[k] & 1) && !(status[k] & 8); nPatch += (status[k] & 2) != 0; nRedo += (status[k] & 4) != 0;
     }
     st->patches += (unsigned long long)nPatch; st->redos += (unsigned long long)nRedo;
-    be.note(round, nRun, nOpen, nPatch, nRedo);
-    const dim3 pa = pgrid(nRun), ka(8, (unsigned)nRun), ca = cgrid(nRun);
+    be.note(round, nActive, nOpen, nPatch, nRedo);
+    const dim3 pa = pgrid(nActive), ka(8, (unsigned)nActive), ca = cgrid(nActive);
     if (nPatch) { be.launch(k_spec_patch, pa, 256, dSpec, (const int*)dActive); be.launch(k_spec_pack, pa, 256, dSpec, (const int*)dActive); be.lap("patch"); }
     if (nRedo) {   // a draw misprediction: prefix sum again, then stages 3-5 behind it, for the images that asked
       be.launch(k_spec_adopt, pa, 256, dSpec, (const int*)dActive);
       be.launch(k_spec_scan_a, ca, 256, dSpec, (const int*)dActive, 1);
-      be.launch(k_spec_scan_b, dim3((unsigned)nRun), 1024, dSpec, (const int*)dActive, 1);
+      be.launch(k_spec_scan_b, dim3((unsigned)nActive), 1024, dSpec, (const int*)dActive, 1);
       be.launch(k_spec_scan_c, ca, 256, dSpec, (const int*)dActive, 1);
       be.launch(k_spec_redo_a, ka, 256, dSpec, (const int*)dActive);
       be.launch(k_spec_redo_b, pa, 256, dSpec, (const int*)dActive);
       be.launch(k_spec_redo_c, ka, 256, dSpec, (const int*)dActive);
       be.launch(k_spec_redo_d, pa, 256, dSpec, (const int*)dActive); be.lap("re-resolve");
     }
-    // ---- images whose next run is a sequential chain: that run happens beside the round loop, ONE launch per round (and
-    //      stage-6 instantiation) on the next of the chain streams, so that launches of consecutive rounds overlap
-    if (nChain) {
-      be.chain_begin();                                     // the chain stream is ordered behind everything enqueued so far
-      if (chainAt + nChain > 2 * nslots) chainAt = 0;       // ring of list entries: at most nslots images are parked at a time
-      int cnt = 0;
-      for (int v = 0; v < NQS_VARIANTS; ++v) {
-        const int first = cnt;
-        for (int j = 0; j < nRun; ++j)
-          if ((status[j] & 16) && (status[j] & 1) && !(status[j] & 8) && variant_of(runList[j]) == v) { fresh[cnt++] = runList[j]; parked[runIdx[j]] = 1; }
-        if (cnt > first) {
-          be.write_ints(dChain + chainAt + first, fresh + first, cnt - first);
-          spec_launch_run(be, v, dim3(runGrid1.x, (unsigned)(cnt - first)), dSpec, (const int*)dChain + chainAt + first, dTanh);
-        }
-      }
-      void* ev = be.chain_mark();
-      for (int j = 0; j < nRun; ++j) if (parked[runIdx[j]] && parkEv[runIdx[j]] == nullptr) parkEv[runIdx[j]] = ev;
-      chainAt += cnt;
-      be.chain_end();
-    }
     // ---- images that leave: completed (no segment open) or handed back; their slots are free for the next round
-    for (int j = 0; j < nRun; ++j) {
-      const int k = runIdx[j];
-      const bool leave = (status[j] & 8) || !(status[j] & 1);
-      if (!leave) continue;
-      leaving[nLeave++] = active[k];
-      freeSlots[nFree++] = slotOfActive[k];
-      if (status[j] & 8) { ++st->handedBack; if (handedBack) handedBack[nHanded] = active[k]; ++nHanded; finished[active[k]] = 2; }
-      else { ++st->done; finished[active[k]] = 1; }
-      active[k] = -1;
+    int keep = 0;
+    for (int k = 0; k < nActive; ++k) {
+      const bool leave = (status[k] & 8) || !(status[k] & 1);
+      if (leave) {
+        leaving[nLeave++] = active[k];
+        freeSlots[nFree++] = slotOfActive[k];
+        if (status[k] & 8) { ++st->handedBack; if (handedBack) handedBack[nHanded] = active[k]; ++nHanded; finished[active[k]] = 2; }
+        else { ++st->done; finished[active[k]] = 1; }
+      } else { active[keep] = active[k]; slotOfActive[keep] = slotOfActive[k]; rounds[keep] = rounds[k]; ++keep; }
     }
+    nActive = keep;
     if (nLeave) {
-      int keep = 0;
-      for (int k = 0; k < nActive; ++k)
-        if (active[k] >= 0) { active[keep] = active[k]; slotOfActive[keep] = slotOfActive[k]; rounds[keep] = rounds[k]; parked[keep] = parked[k]; parkEv[keep] = parkEv[k]; ++keep; }
-      nActive = keep;
       be.write_ints(dFresh, leaving, nLeave);               // (dFresh is free again: stream order)
       be.launch(k_spec_finish, dim3((unsigned)((nLeave + 63) / 64)), 64, dImgs, dSpec, (const int*)dFresh, nLeave);
       // the leading run of images that are COMPLETE (a caller with host buffers starts copying them out while the rest is
@@ -1672,7 +1631,7 @@ void spec_drive(Backend& be, NqImage* dImgs, SpecImage* dSpec, const SpecWork* d
       if (p > prefix) { prefix = p; be.done_prefix(prefix); }
     }
   }
-  delete[] finished; delete[] runList; delete[] runIdx; delete[] parkEv; delete[] parked;
+  delete[] finished;
   delete[] active; delete[] slotOfActive; delete[] fresh; delete[] freshSlot; delete[] status; delete[] freeSlots; delete[] rounds; delete[] leaving;
 }
 #endif  // __CUDACC__ || NQS_EMULATE

@@ -328,13 +328,6 @@ struct EmuBackend {
   void lap(const char*) {}
   void note(int, int, int, int, int) {}
   void done_prefix(int) {}
-  // the emulation runs every launch to completion at once: nothing is ever parked for longer than a round
-  void chain_begin() {}
-  void chain_end() {}
-  void* chain_mark() { return (void*)this; }
-  bool event_done(void*) { return true; }
-  void event_wait_host(void*) {}
-  void main_wait(void*) {}
 };
 }  // namespace
 
@@ -385,7 +378,7 @@ extern "C" int nqs_spec_batch_run(int seg, int warm, int wave, long long* out /*
   memset(sp.data(), 0, sizeof(SpecImage) * (size_t)n);
   std::vector<SpecWork> pool(wave);
   spec_bind_pool(pool.data(), wave, buf.data(), L);
-  std::vector<int> elig(n, 0), ints(6 * wave + 4, 0), handed(n, 0);
+  std::vector<int> elig(n, 0), ints(4 * wave + 4, 0), handed(n, 0);
   std::vector<float> tanhTab(512, 0.f);
   for (int t = 0; t < 511; ++t) tanhTab[t] = tanh_f((double)((float)(t - 255) / 255.f * 20.f));
   EmuBackend be;
