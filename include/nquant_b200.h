@@ -114,6 +114,15 @@ int nq_convert_batch_device(nq_ctx* ctx, int kind, const uint32_t* d_argb_in, in
 int nq_dither_with_palette(nq_ctx* ctx, int kind, const uint32_t* argb_in, int width, int height, int n_max_colors,
                            int dither, uint64_t rng_seed, const uint32_t* palette_in, int palette_len, uint32_t* argb_out);
 
+/* Stage hook (parity + profiling): the front of pnnquan alone -- alpha scan (PnnQuantizer.java:411-436), the 65 536-bin
+ * histogram with compaction, means and getQuanFn (PnnQuantizer.java:137-191, PnnLABQuantizer.java:134-241) and the initial
+ * find_nn sweep (PnnQuantizer.java:196-197, PnnLABQuantizer.java:246-247) -- of one image in HOST memory; no merge loop, no
+ * dither. n_bins receives the number of occupied bins; bins5 (optional, capacity x 5 doubles: alpha, c1, c2, c3, count),
+ * init_err / init_nn (optional, capacity entries) the state at PnnQuantizer.java:192 and each bin's first nearest
+ * neighbour. The scalars (weight, ratio, quan_rt, ...) are available through nq_get_image_info(ctx, 0, ..) afterwards. */
+int nq_histogram(nq_ctx* ctx, int kind, const uint32_t* argb_in, int width, int height, int n_max_colors, int* n_bins,
+                 double* bins5, float* init_err, int* init_nn, int capacity);
+
 /* Generalized Hilbert visiting order for a width x height image (GilbertCurve.java:282-334,
  * 356-365): order_out[n] = x + y*width of the n-th pixel diffusePixel is called on. Host buffer. */
 int nq_gilbert_order(int width, int height, uint32_t* order_out);

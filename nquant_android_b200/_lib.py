@@ -12,7 +12,7 @@ SYMBOLS = [
     "nq_convert_batch_device", "nq_dither_with_palette", "nq_gilbert_order", "nq_get_image_info", "nq_set_debug",
     "nq_debug_get_bins", "nq_debug_get_merges", "nq_debug_get_saliencies", "nq_kernel_launches", "nq_debug_math",
     "nq_synth_device", "nq_get_stage_times", "nq_set_stream", "nq_debug_ciede", "nq_sizeof_image_info",
-    "nq_set_spec_dither", "nq_get_spec_stats", "nq_reset_stream", "nq_set_chunk_images", "nq_get_kernel_times", "nq_convert_batch_multi",
+    "nq_set_spec_dither", "nq_get_spec_stats", "nq_reset_stream", "nq_set_chunk_images", "nq_get_kernel_times", "nq_convert_batch_multi", "nq_histogram",
 ]
 
 NQ_KIND_PNN, NQ_KIND_PNNLAB = 0, 1
@@ -66,6 +66,7 @@ def load():
     L.nq_convert_batch_multi.argtypes = [vp, ci, ci, vp, ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, ci]
     L.nq_dither_with_palette.argtypes = [vp, ci, vp, ci, ci, ci, ci, u64, vp, ci, vp]
     L.nq_gilbert_order.argtypes = [ci, ci, vp]
+    L.nq_histogram.argtypes = [vp, ci, vp, ci, ci, ci, vp, vp, vp, vp, ci]
     L.nq_get_image_info.argtypes = [vp, ci, vp]
     L.nq_set_debug.argtypes = [vp, ci]
     L.nq_debug_get_bins.argtypes = [vp, ci, vp, vp, vp]

@@ -547,6 +547,7 @@ struct GroupArgs {
   int palInLen;
   const uint32_t* hIn;     // host pixels (nullptr: dIn is the caller's device buffer and already holds them)
   uint32_t* hOut;
+  bool stopAfterSweep = false;   // stage hook nq_histogram: no merge loop, no dither
 };
 
 // scan .. merge loop of one chunk, enqueued on its front stream (no host synchronisation unless the context is in debug mode)
@@ -655,6 +656,7 @@ int enqueue_front(nq_ctx* c, Chunk& ch, const GroupArgs& A, const uint32_t* dIn,
         CU(cudaMemcpy(D.initNn.data(), S.bNn, (size_t)mb * 4, cudaMemcpyDeviceToHost));
       }
     }
+    if (A.stopAfterSweep) { mark(4); CU(cudaGetLastError()); return NQ_OK; }
     int* live = c->dLive + (size_t)ch.base * NQ_NBINS;
     int* pos = c->dPos + (size_t)ch.base * NQ_NBINS;
     if (kind == NQ_KIND_RGB) {
@@ -802,6 +804,11 @@ int convert_group(nq_ctx* c, const GroupArgs& A, int n, const uint32_t* dIn, uin
   // alternate between the front streams, so at most two merge loops run next to each other and next to a dither
   for (int k = 0; k < nch; ++k) { rc = enqueue_front(c, chunks[k], G, dIn, dOut); if (rc) return rc; }
   for (int k = 0; k < nch; ++k) {
+    if (A.stopAfterSweep) {   // the dither stream only has to wait for the front
+      CU(cudaStreamWaitEvent(c->sDith, chunks[k].ev[4], 0));
+      for (auto& e : chunks[k].evD) CU(cudaEventRecord(e, c->sDith));
+      continue;
+    }
     if (A.hOut) { chunks[k].hOut = A.hOut + (size_t)chunks[k].base * npix; chunks[k].dOut = dOut + (size_t)chunks[k].base * npix; chunks[k].imageBytes = (size_t)npix * 4; }
     rc = run_dither(c, chunks[k], G, dOrder);
     if (rc) return rc;
@@ -854,7 +861,7 @@ int convert_group(nq_ctx* c, const GroupArgs& A, int n, const uint32_t* dIn, uin
 // chunk by chunk, overlapped with the kernels.
 int convert_device(nq_ctx* c, int kind, const uint32_t* dIn, int n, int w, int h, int nmax, int dither, const uint64_t* seeds,
                    uint32_t* dOut, uint32_t* palettes, int* plens, int* hasAlpha, const uint32_t* dPalIn, int palInLen,
-                   const uint32_t* hIn = nullptr, uint32_t* hOut = nullptr) {
+                   const uint32_t* hIn = nullptr, uint32_t* hOut = nullptr, bool stopAfterSweep = false) {
   CU(cudaSetDevice(c->device));
   const int npix = w * h;
   // the BlueNoise second pass of PnnLABQuantizer weighs by pixelMap.size() (PL:511-513): track it only then
@@ -871,6 +878,7 @@ int convert_device(nq_ctx* c, int kind, const uint32_t* dIn, int n, int w, int h
     const int m = std::min(c->wsSlots, n - base);
     GroupArgs A{kind, w, h, nmax, dither, seeds ? seeds + base : nullptr, dPalIn, palInLen,
                 hIn ? hIn + (size_t)base * npix : nullptr, hOut ? hOut + (size_t)base * npix : nullptr};
+    A.stopAfterSweep = stopAfterSweep;
     rc = convert_group(c, A, m, dIn + (size_t)base * npix, dOut + (size_t)base * npix, base);
     if (rc) return rc;
     collect_results(c, base, m, palettes, plens, hasAlpha, &firstErr);
@@ -1102,6 +1110,30 @@ int nq_dither_with_palette(nq_ctx* c, int kind, const uint32_t* in, int w, int h
   rc = convert_device(c, kind, c->dIn, 1, w, h, nmax, dither, &seed, c->dOut, nullptr, nullptr, nullptr, dPal.as<uint32_t>(), plen, in, out);
   if (rc) return rc;
   CU(cudaStreamSynchronize(c->stream));
+  return NQ_OK;
+}
+
+int nq_histogram(nq_ctx* c, int kind, const uint32_t* in, int w, int h, int nmax, int* nBins, double* bins5, float* initErr, int* initNn, int capacity) {
+  int rc = check_args(c, kind, in, 1, w, h, nmax, in);
+  if (rc) return rc;
+  if (!nBins) return fail(NQ_ERR_ARG, "n_bins must not be null");
+  CU(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)w * h * 4;
+  rc = ensure_stage(c, bytes);
+  if (rc) return rc;
+  const bool wasDebug = c->debug;
+  c->debug = true;                                   // the hook returns what debug mode records after the find_nn sweep
+  uint64_t seed = 0;
+  rc = convert_device(c, kind, c->dIn, 1, w, h, nmax, 1, &seed, c->dOut, nullptr, nullptr, nullptr, nullptr, 0, in, nullptr, true);
+  c->debug = wasDebug;
+  if (rc) return rc;
+  const DebugImage& D = c->dbg[0];
+  const int mb = (int)D.initErr.size();
+  *nBins = mb;
+  if (mb > capacity && (bins5 || initErr || initNn)) return fail(NQ_ERR_ARG, "capacity is smaller than the number of occupied bins (call with null outputs to size them)");
+  if (bins5) memcpy(bins5, D.bins5.data(), D.bins5.size() * 8);
+  if (initErr) memcpy(initErr, D.initErr.data(), D.initErr.size() * 4);
+  if (initNn) memcpy(initNn, D.initNn.data(), D.initNn.size() * 4);
   return NQ_OK;
 }
 

@@ -88,6 +88,18 @@ class Context:
                                                    int(seed), _p(palette), len(palette), _p(out)))
         return out
 
+    def histogram(self, kind, argb, width, height, n_max_colors):
+        """Stage hook nq_histogram: alpha scan + histogram + initial find_nn sweep of one image.
+        Returns (bins (n, 5) float64, init_err float32, init_nn int32); image_info(0) holds the scalars."""
+        argb = np.ascontiguousarray(argb, dtype=np.uint32)
+        nb = ctypes.c_int(0)
+        self._check(self._L.nq_histogram(self._h, kind, _p(argb), width, height, int(n_max_colors), ctypes.byref(nb), None, None, None, 0))
+        bins = np.zeros((nb.value, 5), dtype=np.float64)
+        err = np.zeros(nb.value, dtype=np.float32)
+        nn = np.zeros(nb.value, dtype=np.int32)
+        self._check(self._L.nq_histogram(self._h, kind, _p(argb), width, height, int(n_max_colors), ctypes.byref(nb), _p(bins), _p(err), _p(nn), nb.value))
+        return bins, err, nn
+
     def set_stream(self, cuda_stream):
         """Order the context's work with a caller-owned stream, e.g. torch.cuda.current_stream().cuda_stream. Handle 0
         is CUDA's legacy default stream (torch's default stream), NOT the context's own: use reset_stream() for that."""

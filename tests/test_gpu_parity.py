@@ -381,3 +381,19 @@ def test_convert_batch_multi_dynamic_queue():
     finally:
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_stage_hook_histogram(gpu_ctx, oracle, kind):
+    """nq_histogram: the front of pnnquan alone (alpha scan, histogram, initial find_nn sweep), against the oracle's bins and
+    first nearest neighbours; and the context still converts afterwards."""
+    W, H, K = 200, 150, 64
+    img = make_image(W, H, "noisy", "transparent")
+    ref = oracle.convert(kind, img, W, H, K, True, seed=9)
+    bins, err, nn = gpu_ctx.histogram(kind, img, W, H, K)
+    info = gpu_ctx.image_info(0)
+    assert info["maxbins"] == ref.scalars["maxbins"] == len(bins) and info["weight"] == ref.scalars["weight"]
+    assert np.array_equal(bins, ref.bins)
+    assert np.array_equal(err.view(np.uint32), ref.init_err.view(np.uint32)) and np.array_equal(nn, ref.init_nn)
+    out, pal, plen, _ = gpu_ctx.convert_batch(kind, img[None, :], W, H, K, True, seeds=[9])
+    assert np.array_equal(out[0], ref.out)
