@@ -167,6 +167,7 @@ struct DebugImage {
 }  // namespace
 
 #define NQ_FRONT_STREAMS 2   // histogram / find_nn / merge of consecutive chunks alternate between these
+#define NQ_SPEC_BULK_DEFAULT 0   // stage 6 record stream through cp.async.bulk + mbarrier (NQ_SPEC_BULK overrides)
 
 struct nq_ctx {
   int device = 0;
@@ -980,6 +981,11 @@ nq_ctx* nq_create(int device) {
   c->stream = c->ownStream;
   if (const char* e = getenv("NQ_SPEC_DITHER")) c->specDither = atoi(e) != 0;
   if (const char* e = getenv("NQ_CHUNK")) c->chunkImages = atoi(e);
+  {
+    const char* e = getenv("NQ_SPEC_BULK");
+    const int bulk = e ? (atoi(e) != 0) : NQ_SPEC_BULK_DEFAULT;
+    ok = ok && cudaMemcpyToSymbol(nq::spec::g_specBulk, &bulk, sizeof(bulk)) == cudaSuccess;
+  }
   if (const char* e = getenv("NQ_SPEC_SLOTS")) c->specSlotsMax = atoi(e);
   if (const char* e = getenv("NQ_SPEC_POOL_GB")) c->specPoolMaxBytes = (size_t)atoi(e) << 30;
   if (const char* e = getenv("NQ_MERGE_ROT")) c->mergeRot = atoi(e) != 0;

@@ -607,6 +607,7 @@ NQ_HD float shape_tanh(float e, float maxErr, const float* tab) {
   return shape_tanh_eval(e, maxErr);
 }
 
+struct WarpRing;                // the staged record stream of a warp (device only, below)
 struct RunEnv {                 // what the pixel step needs besides the queue
   const SpecConst* C;
   const SpecWork* W;
@@ -624,6 +625,8 @@ struct RunEnv {                 // what the pixel step needs besides the queue
   unsigned actIdx;              // seq: draws really made in front of the current pixel
   unsigned drawIdx;             // draws PREDICTED in front of the current pixel = cdraw[n], kept up from the records' flags
   unsigned amask;               // three-channel variant: alpha error (0 or 1) of queue box k in bit k, oldest box first
+  WarpRing* ring;               // device: this warp's staged record stream (nullptr: per-thread loads)
+  unsigned ringPhase;           // parity of the next phase of the ring's two mbarriers
   LcgCursor lcg;
 };
 
@@ -750,6 +753,40 @@ NQ_HD SpecRec run_fetch(const SpecRec* recs, int segLen, int nsegs, int n) {
   return recs[(size_t)(n % segLen) * (size_t)nsegs + (size_t)(n / segLen)];
 }
 // pixels [n0, n1) from the queue in e[0 .. DM - 1]; groups of NQS_U with the records of the next group in flight
+#if defined(__CUDACC__)
+// ---- the record stream of a warp through shared memory (sm_90+ bulk copies completing on an mbarrier) -------------------
+// When the 32 lanes of a warp run 32 consecutive segments in step (the first launch of an image: same warm-up, same length),
+// pixel k of the span needs ONE row of the segment-interleaved record matrix per warp: 32 x 16 = 512 contiguous bytes.
+// Lane 0 fetches NQS_TROWS rows per stage with cp.async.bulk into a two-stage ring; the copies complete on the stage's
+// mbarrier (complete_tx), every lane waits for its phase and reads its own 16-byte record with one LDS.128. Against the
+// register prefetch (four records ahead per thread) this takes 24 registers out of the loop and puts a whole tile of loads
+// in flight per instruction.
+#define NQS_TROWS 8
+__device__ int g_specBulk;       // 1: stage 6 streams its records through shared memory with bulk copies (nq_create: NQ_SPEC_BULK)
+struct WarpRing {
+  uint4 rec[2][NQS_TROWS][32];
+  unsigned long long bar[2];
+};
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+#endif
+
 template <int DM, int DMI, int NCH, bool OWNED>
 NQ_HD void run_span(RunEnv& X, float (&e)[DM + NQS_U][NCH], int n0, int n1) {
   const SpecConst& C = *X.C;
@@ -757,6 +794,53 @@ NQ_HD void run_span(RunEnv& X, float (&e)[DM + NQS_U][NCH], int n0, int n1) {
   const int segLen = C.seg, nsegs = C.nseg;
   int n = n0;
   if (n0 < n1) X.drawIdx = X.W->cdraw[n0];
+#if defined(__CUDA_ARCH__)
+  if (X.ring) {
+    // all 32 lanes here, consecutive segments, same offset and length, no wrap into the next column: the staged stream
+    const unsigned lane = threadIdx.x & 31;
+    const int len = n1 - n0, base = n0 - (int)lane * segLen;
+    bool uni = __activemask() == 0xffffffffu;
+    if (uni) uni = __all_sync(0xffffffffu, len >= 2 * NQS_TROWS && base == __shfl_sync(0xffffffffu, base, 0) && len == __shfl_sync(0xffffffffu, len, 0) &&
+                                               (n0 % segLen) + len <= segLen && !X.seq);
+    if (uni) {
+      WarpRing& R = *X.ring;
+      const int row0 = n0 % segLen, col0 = __shfl_sync(0xffffffffu, n0 / segLen, 0);
+      const int ntile = (len + NQS_TROWS - 1) / NQS_TROWS;
+      auto issue = [&](int t) {                              // lane 0: rows of tile t into stage t & 1
+        const int st = t & 1, r0 = t * NQS_TROWS, nr = len - r0 < NQS_TROWS ? len - r0 : NQS_TROWS;
+        mbar_expect_tx(&R.bar[st], (unsigned)nr * 512u);
+        for (int r = 0; r < nr; ++r) bulk_load(&R.rec[st][r][0], recs + ((size_t)(row0 + r0 + r) * (size_t)nsegs + (size_t)col0), 512u, &R.bar[st]);
+      };
+      if (lane == 0) { issue(0); if (ntile > 1) issue(1); }
+      for (int t = 0; t < ntile; ++t) {
+        const int st = t & 1, r0 = t * NQS_TROWS, nr = len - r0 < NQS_TROWS ? len - r0 : NQS_TROWS;
+        mbar_wait(&R.bar[st], (X.ringPhase >> st) & 1u);
+        X.ringPhase ^= 1u << st;
+        int r = 0;
+        for (; r + NQS_U <= nr; r += NQS_U) {
+          SpecRec rc[NQS_U];
+#pragma unroll
+          for (int u = 0; u < NQS_U; ++u) { const uint4 v = R.rec[st][r + u][lane]; rc[u].px = v.x; rc[u].xy = v.y; rc[u].qf = v.z; rc[u].sal = __uint_as_float(v.w); }
+          run_pixel<DM, DMI, NCH, 0, OWNED>(X, e, rc[0], n);
+          run_pixel<DM, DMI, NCH, 1, OWNED>(X, e, rc[1], n + 1);
+          run_pixel<DM, DMI, NCH, 2, OWNED>(X, e, rc[2], n + 2);
+          run_pixel<DM, DMI, NCH, 3, OWNED>(X, e, rc[3], n + 3);
+          run_slide<DM, NCH, NQS_U>(e);
+          n += NQS_U;
+        }
+        for (; r < nr; ++r, ++n) {
+          const uint4 v = R.rec[st][r][lane];
+          SpecRec rc; rc.px = v.x; rc.xy = v.y; rc.qf = v.z; rc.sal = __uint_as_float(v.w);
+          run_pixel<DM, DMI, NCH, 0, OWNED>(X, e, rc, n);
+          run_slide<DM, NCH, 1>(e);
+        }
+        __syncwarp();                                        // every lane has read the stage before it is refilled
+        if (lane == 0 && t + 2 < ntile) issue(t + 2);
+      }
+      return;
+    }
+  }
+#endif
   if (n + NQS_U <= n1) {
     // record (row, col) of pixel n in the segment-interleaved layout, advanced without a division per pixel
     int row = n % segLen, col = n / segLen;
@@ -795,7 +879,7 @@ NQ_HD void run_span(RunEnv& X, float (&e)[DM + NQS_U][NCH], int n0, int n1) {
 static_assert(NQS_U == 4, "run_span spells out the NQS_U pixel steps");
 
 template <int DM, int DMI, int NCH>
-NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s, const ScanTabs& T, const float* tanhTab) {
+NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s, const ScanTabs& T, const float* tanhTab, WarpRing* ring = nullptr) {
   SpecSeg& S0 = W.segs[s];
   if (S0.done || !S0.dirty || S0.chained) return;
   const int p0 = s * C.seg;
@@ -820,6 +904,7 @@ NQ_HD void stage_run_t(const SpecConst& C, const SpecWork& W, int s, const ScanT
   X.C = &C; X.W = &W; X.S = &S0; X.T = T; X.tanhTab = tanhTab;
   X.lcg.valid = 0; X.lcg.idx = 0; X.lcg.state = 0; X.drawIdx = 0; X.amask = amask0;
   X.seq = seq; X.chainFirst = s; X.devPos = NQS_NOPOS; X.actIdx = 0; X.nslow = 0;
+  X.ring = ring; X.ringPhase = 0u;
   X.fDitherMax = (float)C.ditherMax; X.fDitherMax1 = (float)(C.ditherMax - 1);
   X.divisor = (float)(1 + nqm::sqrt_((double)C.ditherMax));
   X.illusion0 = W.bn[0] > C.thresold;                      // yDiff == 1 in this mode: bn[(int)4096.0 & 4095] (GC:251-252)
@@ -1399,12 +1484,20 @@ __global__ void __launch_bounds__(NQS_RUN_THREADS, (DM + NQS_U) * NCH <= 96 ? 3 
   __shared__ uint32_t sPal[NQ_MAXK];
   __shared__ float sTanh[512];
   __shared__ double sT[3][256];
+  __shared__ WarpRing sRing[NQS_RUN_THREADS / 32];
   const SpecImage& P = sp[list[blockIdx.y]];
   if (!NQS_ACTIVE(P)) return;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   // nothing to do for a whole block is the common case in the later rounds: look before loading the tables
   const bool work = s < P.C.nseg && !P.W.segs[s].done && P.W.segs[s].dirty;
   if (!__syncthreads_or(work)) return;
+  const bool bulk = g_specBulk != 0;
+  if (bulk && (threadIdx.x & 31) == 0) {
+    mbar_init(&sRing[threadIdx.x >> 5].bar[0], 1u);
+    mbar_init(&sRing[threadIdx.x >> 5].bar[1], 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   for (int k = threadIdx.x; k < NQ_MAXK; k += blockDim.x) {
     sPal[k] = k < P.C.plen ? P.C.pal[k] : 0u;
     sT[0][k] = P.C.Tr[k]; sT[1][k] = P.C.Tg[k]; sT[2][k] = P.C.Tb[k];
@@ -1413,7 +1506,7 @@ __global__ void __launch_bounds__(NQS_RUN_THREADS, (DM + NQS_U) * NCH <= 96 ? 3 
   __syncthreads();
   ScanTabs T;
   T.pal = sPal; T.Tr = sT[0]; T.Tg = sT[1]; T.Tb = sT[2]; T.plen = P.C.plen;
-  if (work) stage_run_t<DM, DMI, NCH>(P.C, P.W, s, T, sTanh);
+  if (work) stage_run_t<DM, DMI, NCH>(P.C, P.W, s, T, sTanh, bulk ? &sRing[threadIdx.x >> 5] : nullptr);
 }
 #endif
 template <class Backend>
