@@ -169,9 +169,6 @@ struct DebugImage {
 #define NQ_FRONT_STREAMS 2   // histogram / find_nn / merge of consecutive chunks alternate between these
 #define NQ_SPEC_BULK_DEFAULT 0   // stage 6 record stream through cp.async.bulk + mbarrier (NQ_SPEC_BULK overrides)
 
-#ifndef NQ_MERGE_MODE_DEFAULT
-#define NQ_MERGE_MODE_DEFAULT 0
-#endif
 struct nq_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;      // where the caller's order and timing live (nq_set_stream)
@@ -186,10 +183,8 @@ struct nq_ctx {
   unsigned long long launches = 0;
   bool debug = false;
   int chunkImages = 0;                // images per chunk (0 = automatic)
-  int mergeRot = NQ_MERGE_MODE_DEFAULT;   // bit 0 (NQ_MERGE_ROT=1): rotate the logical warp ids of the merge kernels by the CTA index (measured: no
-                                      // effect, the hardware already spreads the warps of co-resident CTAs over the schedulers); k_merge_lab also reads
-                                      // bit 1 = full evaluation straight after the cheap bound when one pass holds the candidates, bits 2-3 = blocks per
-                                      // batch 32 << n (NQ_MERGE_MODE sets all four bits)
+  int mergeRot = 0;                   // NQ_MERGE_ROT=1: rotate the logical warp ids of the merge kernels by the CTA index (measured: no
+                                      // effect, the hardware already spreads the warps of co-resident CTAs over the schedulers)
   // Gilbert orders by (w,h), least recently used first in orderLru
   std::map<std::pair<int, int>, uint32_t*> orders;
   std::vector<std::pair<int, int>> orderLru;
@@ -993,8 +988,7 @@ nq_ctx* nq_create(int device) {
   }
   if (const char* e = getenv("NQ_SPEC_SLOTS")) c->specSlotsMax = atoi(e);
   if (const char* e = getenv("NQ_SPEC_POOL_GB")) c->specPoolMaxBytes = (size_t)atoi(e) << 30;
-  if (const char* e = getenv("NQ_MERGE_ROT")) c->mergeRot = (c->mergeRot & ~1) | (atoi(e) != 0);
-  if (const char* e = getenv("NQ_MERGE_MODE")) c->mergeRot = atoi(e) & 15;
+  if (const char* e = getenv("NQ_MERGE_ROT")) c->mergeRot = atoi(e) != 0;
   bool haveLut = false;
   {
     DevBuf dBn, dW;

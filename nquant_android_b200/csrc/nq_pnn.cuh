@@ -489,7 +489,6 @@ __device__ __forceinline__ unsigned pack_idnn(int id, int nn) { return (unsigned
 // -------------------------------------------------------------------------------------------------
 #define NQ_LAB_THREADS 128
 #define NQ_LAB_HEAP_SMEM 5632   // 44 KB of heap: four CTAs fit one SM
-#define NQ_LAB_GBMAX 128         // most live blocks of a rescan handled in one batch
 
 __device__ __forceinline__ int block_excl_scan_128(int v, int* total, int* sScan /*[8]*/) {
   const unsigned lane = lane_id(), w = threadIdx.x >> 5;
@@ -547,9 +546,9 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
   __shared__ int sScan[8];
   __shared__ unsigned sBits[64];             // live blocks of this rescan, one bit per block
   __shared__ unsigned short sBlk[2048];      // the same as an ordered list
-  __shared__ unsigned sMaskA[NQ_LAB_GBMAX];  // bins that passed the cheap bound, per block of the current batch
-  __shared__ unsigned sMaskB[NQ_LAB_GBMAX];  // ... of those, the ones that passed the screen, per 32 list entries
-  __shared__ int sOffA[NQ_LAB_GBMAX + 1], sOffB[NQ_LAB_GBMAX + 1];
+  __shared__ unsigned sMaskA[32];            // bins that passed the cheap bound, per block of the current batch
+  __shared__ unsigned sMaskB[32];            // ... of those, the ones that passed the screen, per 32 list entries
+  __shared__ int sOffA[33], sOffB[33];
   __shared__ double sGs[NQ_LAB_THREADS], sGw[NQ_LAB_THREADS], sF[NQ_LAB_THREADS];
   __shared__ int sPos[NQ_LAB_THREADS];       // position of a fully evaluated survivor, -1 = rejected
   __shared__ double sErrCur;
@@ -563,14 +562,9 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
   // The serial phases (heap top, ordered replay) belong to logical warp 0. Several CTAs share an SM, and the hardware
   // places warp k of every CTA on the same scheduler: rotating the logical warp ids by the CTA index spreads the serial
   // warps of co-resident images over the four schedulers.
-  const int t = (int)((threadIdx.x + 32u * ((rot & 1) ? (blockIdx.x & 3u) : 0u)) & 127u);
+  const int t = (int)((threadIdx.x + 32u * (rot ? (blockIdx.x & 3u) : 0u)) & 127u);
   const unsigned lane = lane_id(), w = t >> 5;
   const int W = NQ_LAB_THREADS / 32;
-  // rot bit 1: candidates that passed 3a go straight to the full evaluation when one pass of the CTA holds them all
-  // (the screen's tests are the first tests of the full evaluation: screening first only pays when it saves passes);
-  // rot bits 2-3: blocks per batch = 32 << bits (fewer barrier rounds per rescan, looser err for the later blocks)
-  const bool directFull = (rot & 2) != 0;
-  const int GB = min(NQ_LAB_GBMAX, 32 << ((rot >> 2) & 3));
   const int maxbins = I.maxbins, extbins = I.extbins;
   int* live = liveBuf + (size_t)img * NQ_NBINS;
   int* posOf = posBuf + (size_t)img * NQ_NBINS;
@@ -609,19 +603,6 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
   long long cyc[6] = {0, 0, 0, 0, 0, 0};
   long long tk = clock64();
   auto tick = [&](int k) { const long long now = clock64(); cyc[k] += now - tk; tk = now; };
-
-  // warp 0: off[r] = set bits in mask[0 .. r), r <= GB
-  auto mask_offsets = [&](const unsigned* mask, int* off) {
-    const int per = GB >> 5;
-    int c = 0;
-    for (int k = 0; k < per; ++k) c += __popc(mask[(int)lane * per + k]);
-    int x = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
-    int at = x - c;
-    for (int k = 0; k < per; ++k) { off[(int)lane * per + k] = at; at += __popc(mask[(int)lane * per + k]); }
-    if (lane == 31) off[GB] = x;
-  };
 
   for (;;) {
     // ---- thread 0: look at the heap top (PL:271-283)
@@ -679,20 +660,8 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
       // -- 2. block summaries of everything behind them
       const int stop = first + 32;
       const int blkBeg = stop >> 5, nblk = (liveLen + 31) >> 5;
-      for (int blk0 = blkBeg + t; blk0 < nblk; blk0 += 4 * NQ_LAB_THREADS) {   // four summaries in flight per thread (L2 latency)
-        float4 s0[4], s1[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int blk = blk0 + u * NQ_LAB_THREADS;
-          if (blk < nblk) { s0[u] = V.bs[2 * blk]; s1[u] = V.bs[2 * blk + 1]; }
-          else s0[u] = s1[u] = make_float4(-1.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int blk = blk0 + u * NQ_LAB_THREADS;
-          if (!lab_block_skip_v(P, s0[u], s1[u], err)) atomicOr(&sBits[blk >> 5], 1u << (blk & 31));
-        }
-      }
+      for (int blk = blkBeg + t; blk < nblk; blk += NQ_LAB_THREADS)
+        if (!lab_block_skip(P, V, blk, err)) atomicOr(&sBits[blk >> 5], 1u << (blk & 31));
       __syncthreads();
       if (w == 0) {                             // bit set -> ordered list
         const unsigned m0 = sBits[2 * lane], m1 = sBits[2 * lane + 1];
@@ -709,10 +678,10 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
       tick(2);
       const int nLive = sNLive;
       liveBlocks += nLive;
-      for (int g0 = 0; g0 < nLive; g0 += GB) {  // batches of GB live blocks (32 x GB bins), in list order
-        const int gn = min(GB, nLive - g0);
+      for (int g0 = 0; g0 < nLive; g0 += 32) {  // batches of 32 live blocks (<= 1024 bins), in list order
+        const int gn = min(32, nLive - g0);
         // -- 3a. per-candidate lower bound (lab_cheap_keep): one warp per block, one lane per bin
-        if (t < GB) { sMaskA[t] = 0u; sMaskB[t] = 0u; }
+        if (t < 32) { sMaskA[t] = 0u; sMaskB[t] = 0u; }
         __syncthreads();
         for (int r0 = w; r0 < gn; r0 += 4 * W) {     // four records in flight per lane: the loads come from L2
           float4 v[4];
@@ -730,13 +699,19 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
           }
         }
         __syncthreads();
-        if (w == 0) mask_offsets(sMaskA, sOffA);
+        if (w == 0) {
+          const int c = __popc(sMaskA[lane]);
+          int x = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+          sOffA[lane + 1] = x;
+          if (lane == 0) sOffA[0] = 0;
+        }
         __syncthreads();
-        const int totalA = sOffA[GB];
-        const bool direct = directFull && totalA <= NQ_LAB_THREADS;
+        const int totalA = sOffA[32];
         // the s-th bin that passed 3a, in list order
         auto posA = [&](int sIdx) {
-          int lo = 0, hi = GB;                    // largest r with sOffA[r] <= sIdx
+          int lo = 0, hi = 32;                    // largest r with sOffA[r] <= sIdx
           while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sOffA[mid] <= sIdx) lo = mid; else hi = mid; }
           return ((int)sBlk[g0 + lo] << 5) + (int)__fns(sMaskA[lo], 0, sIdx - sOffA[lo] + 1);
         };
@@ -744,22 +719,29 @@ __global__ void __launch_bounds__(NQ_LAB_THREADS, 4) k_merge_lab(NqImage* imgs, 
         for (int base = 0; base < totalA; base += NQ_LAB_THREADS) {
           const int sIdx = base + t;
           LabCand dummy;
-          const bool keep = sIdx < totalA && (direct || lab_eval_t<true>(P, V, posA(sIdx), err, &dummy));
+          const bool keep = sIdx < totalA && lab_eval_t<true>(P, V, posA(sIdx), err, &dummy);
           const unsigned m = __ballot_sync(0xffffffffu, keep);
           if (lane == 0) sMaskB[(base >> 5) + w] = m;
         }
         __syncthreads();
-        if (w == 0) mask_offsets(sMaskB, sOffB);
+        if (w == 0) {
+          const int c = __popc(sMaskB[lane]);
+          int x = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+          sOffB[lane + 1] = x;
+          if (lane == 0) sOffB[0] = 0;
+        }
         __syncthreads();
         tick(3);
-        const int total = sOffB[GB];
+        const int total = sOffB[32];
         screened += total;
         // -- 4. survivors in full, packed; then resolved in order
         for (int base = 0; base < total; base += NQ_LAB_THREADS) {
           const int uIdx = base + t;
           int pos = -1;
           if (uIdx < total) {
-            int lo = 0, hi = GB;                  // largest word with sOffB[word] <= uIdx
+            int lo = 0, hi = 32;                  // largest word with sOffB[word] <= uIdx
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sOffB[mid] <= uIdx) lo = mid; else hi = mid; }
             const int sIdx = (lo << 5) + (int)__fns(sMaskB[lo], 0, uIdx - sOffB[lo] + 1);   // index into the 3a list
             const int i = posA(sIdx);
@@ -995,7 +977,7 @@ __global__ void __launch_bounds__(NQ_RGB_THREADS, 4) k_merge_rgb(NqImage* imgs, 
   // The serial phases (heap top, ordered replay) belong to logical warp 0. Several CTAs share an SM, and the hardware
   // places warp k of every CTA on the same scheduler: rotating the logical warp ids by the CTA index spreads the serial
   // warps of co-resident images over the four schedulers.
-  const int t = (int)((threadIdx.x + 32u * ((rot & 1) ? (blockIdx.x & 3u) : 0u)) & 127u);
+  const int t = (int)((threadIdx.x + 32u * (rot ? (blockIdx.x & 3u) : 0u)) & 127u);
   const unsigned lane = lane_id(), w = t >> 5;
   const int W = NQ_RGB_THREADS / 32;
   const int maxbins = I.maxbins, extbins = I.extbins;

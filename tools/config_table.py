@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Runs BASELINE.json's configs (and the three synthetic classes) once each on cuda:0 and prints a markdown table:
 device-resident wall time of nq_convert_batch_device, Mpixels/s and the per-stage device times.
-Usage: config_table.py [--big] > profiles/rNN_configs.md     (--big adds the 8192x8192 sweep of configs[4])"""
+Usage: config_table.py [--big | --big256] > profiles/rNN_configs.md     (--big adds the 8192x8192 sweep of configs[4],
+--big256 only its 256-colour dither-on rows)"""
 import os
 import sys
 import time
@@ -32,14 +33,14 @@ def _oracle_seconds():
 ORACLE_S = _oracle_seconds()
 
 
-def run(ctx, label, kind, cls, alpha, W, H, K, dither, batch):
+def run(ctx, label, kind, cls, alpha, W, H, K, dither, batch, reps=2):
     npix = W * H
     din = torch.empty(batch * npix, dtype=torch.int32, device="cuda")
     dout = torch.empty_like(din)
     ctx.synth_device(din.data_ptr(), batch, W, H, CLS[cls], ALPHA[alpha], 0x5EED0000)
     seeds = np.arange(batch, dtype=np.uint64) + 0xC0FFEE
     best = None
-    for rep in range(2):          # first run warms the workspace, the Gilbert order and the tables
+    for rep in range(reps):       # first run warms the workspace, the Gilbert order and the tables
         ctx.stage_times(reset=True)
         torch.cuda.synchronize()
         t0 = time.time()
@@ -60,6 +61,7 @@ def run(ctx, label, kind, cls, alpha, W, H, K, dither, batch):
 
 def main():
     big = "--big" in sys.argv
+    big256 = "--big256" in sys.argv     # only the 256-colour, dither-on rows of configs[4] (one repetition: no warm run)
     ctx = Context(0)
     print("| config | quantizer | colours | dither | class/alpha | size | images | bins | ms | Mpixels/s | oracle Mpixels/s (1 core) | GPU / oracle | stage ms (scan / histogram / sweep / merge / setup / dither) |")
     print("|---|---|---:|---|---|---|---:|---:|---:|---:|---:|---:|---|")
@@ -71,6 +73,9 @@ def main():
     for cls in ("smooth", "rand"):
         run(ctx, f"class {cls}", 1, cls, "opaque", 3840, 2160, 256, 1, 148)
         run(ctx, f"class {cls}", 0, cls, "opaque", 3840, 2160, 256, 1, 148)
+    if big256:
+        for kind in (1, 0):
+            run(ctx, "configs[4]", kind, "noisy", "opaque", 8192, 8192, 256, 1, 1, reps=1)
     if big:
         for kind in (1, 0):
             for K in (256, 64, 16, 2):

@@ -6,6 +6,10 @@ import hashlib, os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
 import torch
+from nquant_android_b200 import _lib
+if os.environ.get("NQ_AB_LIB"):          # an older build of the library, for an A/B in the same session
+    _lib.SO = os.path.abspath(os.environ["NQ_AB_LIB"])
+    _lib.SYMBOLS = []
 from nquant_android_b200.quantizer import Context
 
 
