@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
-"""A/B of k_merge_lab's switchable variants (NQ_MERGE_MODE bits, nq_api.cu): one device-resident batch per mode in one
-process, merge stage time + phase clocks, and a hash of all palettes (the modes must agree bit for bit).
+"""A/B of k_merge_lab variants: one device-resident batch per mode in one process, merge stage time + phase clocks, and a
+hash of all palettes (the modes must agree bit for bit). The modes are the NQ_MERGE_MODE bits of the experimental kernel
+kept as profiles/r2_merge_variants.diff (not applied: the shipped library ignores the variable, every mode is the shipped
+kernel); NQ_AB_LIB=path loads another build of the library instead, for an old-vs-new comparison in one session.
 Usage: merge_mode_probe.py W H batch mode[,mode...]"""
 import hashlib, os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
