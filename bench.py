@@ -289,12 +289,15 @@ def run_ours(a, rank, world, local_rank):
     #      it is the headline line itself when --batch equals it)
     strong = None
     if world > 1 and a.strong_batch > 0 and a.strong_batch // world >= 1:
-        m = min(n, a.strong_batch // world)
+        from nquant_android_b200.sharding import shard_range
+        spans = [shard_range(a.strong_batch, r, world) for r in range(world)]       # balanced contiguous split of the one batch
+        per_rank = [min(n, e - b) for b, e in spans]
+        m = per_rank[rank]
         for _ in range(max(1, a.warmup // 2)):
             step_device(m)
         sms = max_over_ranks(timed(lambda: step_device(m), a.steps))
-        strong = {"scaling": "strong", "global_batch_images": m * world, "images_per_gpu": m, "ms_per_step": sms / a.steps,
-                  "value": world * m * npix * a.steps / (sms / 1e3) / 1e6, "unit": "Mpixels/s",
+        strong = {"scaling": "strong", "global_batch_images": sum(per_rank), "images_per_gpu": max(per_rank), "ms_per_step": sms / a.steps,
+                  "value": sum(per_rank) * npix * a.steps / (sms / 1e3) / 1e6, "unit": "Mpixels/s",
                   "note": "rank r converts the first m images of its own shard (same synthetic class; the images of a batch are independent)"}
 
     # ---- end to end: pinned host buffers through nq_convert_batch
