@@ -48,6 +48,10 @@ def run(L, w, h, nmax, cls, alpha, seg, warm, cells=1, seed=0xC0FFEE, img_seed=0
     (320, 180, 128, "noisy", "opaque", 2048, 512, 1),
     (173, 211, 200, "noisy", "opaque", 1000, 300, 1),        # ragged sizes, warm-up too short for some segments: re-runs
     (256, 256, 128, "smooth", "opaque", 4096, 1024, 1),      # DITHER_MAX 9 (weight >= .015), ArrayDeque because of <= 128 colours
+    (97, 1, 256, "noisy", "opaque", 64, 16, 1),              # a single row: the curve degenerates to a line, two short segments
+    (640, 360, 256, "noisy", "opaque", 8192, 1024, 1),       # the production segment length and warm-up
+    (333, 127, 65, "rand", "opaque", 1024, 256, 1),          # just above the 64-colour gate; 9 memo patches, 11 rounds
+    (256, 256, 256, "noisy", "opaque", 512, 64, 1),          # warm-up far too short: more than two runs per segment
 ])
 def test_spec_pipeline_matches_sequential_oracle(lib, w, h, nmax, cls, alpha, seg, warm, cells):
     r = run(lib, w, h, nmax, cls, alpha, seg, warm, cells)
